@@ -1,0 +1,198 @@
+/*
+ * bhw.h - C ABI of the B200-native window-coefficient generator.
+ *
+ * Drop-in boundary for the table-generation path of hukenovs/blackman_harris_win.
+ * The reference has no FFI; its "interface" is (i) the VHDL entity generics and
+ * ports and (ii) three small C/C++ model functions.  Every entry point below
+ * cites the reference interface it replaces (paths relative to the reference
+ * checkout).  Plain C types only: no torch, no C++ types, no exceptions.
+ *
+ * Conventions
+ *   - All functions return 0 (BHW_OK) or a negative bhw_status code; nothing
+ *     aborts or throws.  bhw_strerror() names a code.
+ *   - "device" pointers are CUDA device pointers on the *current* device of
+ *     the calling thread; "stream" is a cudaStream_t passed as void* (NULL =
+ *     legacy default stream).  Calls are stream-ordered and do not synchronise
+ *     unless the name ends in _host.
+ *   - Output elements are sign-extended two's complement: int32_t when
+ *     dat_width <= 32, int64_t otherwise (bhw_elem_bytes()).  Index order is
+ *     the entity's phase order: out[j] = DT_WIN for phase (n0 + j +
+ *     stream_offset) mod 2^phi_width.
+ *   - The library is re-entrant; its only persistent state is a per-device
+ *     workspace/trig-table cache (bhw_cache_clear() drops it).
+ */
+#ifndef BHW_H_
+#define BHW_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHW_VERSION 0x000100 /* 0.1.0 */
+#define BHW_MAX_TERMS 7
+
+/* ---- status codes ------------------------------------------------------ */
+typedef enum bhw_status {
+  BHW_OK = 0,
+  BHW_E_NULL = -1,        /* a required pointer is NULL                       */
+  BHW_E_WIN_TYPE = -2,    /* win_type is not 2,3,4,5,7                        */
+  BHW_E_SIN_TYPE = -3,    /* unknown sin_type, or not available for the entity
+                             (4/5/7-term have no TAYLOR: src/bh_win_4term.vhd:57-61) */
+  BHW_E_MODEL = -4,       /* unknown model, or model/sin_type/op mismatch     */
+  BHW_E_PHI_WIDTH = -5,   /* phi_width outside the supported range            */
+  BHW_E_DAT_WIDTH = -6,   /* dat_width outside the range of the sin source    */
+  BHW_E_PRECISION = -7,   /* cordic_dds PRECISION outside 1..7 or W > 49      */
+  BHW_E_LUT_SIZE = -8,    /* TAYLOR LUT_SIZE invalid (STAGE > 15, width
+                             overflow of the DSP slice, or the mis-aligned
+                             3-term case PHI_WIDTH-LUT_SIZE == 3)             */
+  BHW_E_COEFF = -9,       /* an AAk does not fit dat_width bits               */
+  BHW_E_RANGE = -10,      /* n0/count/flat range outside the window / batch   */
+  BHW_E_ELEM = -11,       /* mixed or wrong output element size in a batch    */
+  BHW_E_CUDA = -12,       /* a CUDA runtime call failed (bhw_last_cuda_error) */
+  BHW_E_NO_DEVICE = -13,  /* no CUDA device / device index out of range       */
+  BHW_E_ALLOC = -14,      /* workspace allocation failed                      */
+  BHW_E_VARIANT = -15,    /* bhw_quantize: unknown variant or rule            */
+  BHW_E_ARG = -16         /* any other invalid argument                       */
+} bhw_status;
+
+/* ---- enumerations mirroring the generics ------------------------------- */
+/* WIN_TYPE generic of win_selector (src/win_selector.vhd:64,93-199).  The
+ * value is the number of terms, i.e. the entity that is instantiated. */
+enum {
+  BHW_WIN_HAMMING = 2, /* "HAMMING" -> hamming_win  (src/hamming_win.vhd:60-82)  */
+  BHW_WIN_BH3TERM = 3, /* "BH3TERM" -> bh_win_3term (src/bh_win_3term.vhd:68-90) */
+  BHW_WIN_BH4TERM = 4, /* "BH4TERM" -> bh_win_4term (src/bh_win_4term.vhd:56-75) */
+  BHW_WIN_BH5TERM = 5, /* "BH5TERM" -> bh_win_5term (src/bh_win_5term.vhd:70-90) */
+  BHW_WIN_BH7TERM = 7  /* "BH7TERM" -> bh_win_7term (src/bh_win_7term.vhd:58-80) */
+};
+
+/* SIN_TYPE generic (src/win_selector.vhd:65) plus the two pin-compatible
+ * CORDIC entities that can be swapped in for cordic_dds. */
+enum {
+  BHW_SIN_CORDIC = 0,        /* cordic_dds        (src/cordic_dds.vhd:77-92)        */
+  BHW_SIN_TAYLOR = 1,        /* taylor_sincos     (src/taylor_sincos.vhd:65-81)     */
+  BHW_SIN_CORDIC48 = 2,      /* cordic_dds48      (src/cordic_dds48.vhd:91-105)     */
+  BHW_SIN_CORDIC_SCALED = 3  /* cordic_dds_scaled (src/cordic_dds_scaled.vhd:81-95) */
+};
+
+/* Which of the reference's three (mutually non-bit-identical) models the
+ * integers must equal. */
+enum {
+  BHW_MODEL_RTL = 0, /* the VHDL entities (src/ tree)                               */
+  BHW_MODEL_HLS = 1, /* hls/windows/win_function.cpp + hls/cordic/cordic.cpp      */
+  BHW_MODEL_CPP = 2  /* cpp/cordic_sincos.cpp (sin/cos table only: bhw_sincos)    */
+};
+
+/* Evaluation strategy (results are identical; this is a performance knob). */
+enum {
+  BHW_ALGO_AUTO = 0,
+  BHW_ALGO_DIRECT = 1, /* one thread per sample, every k*phi term evaluated in registers */
+  BHW_ALGO_TABLE = 2   /* sin/cos source evaluated once per distinct phase, then gathered */
+};
+
+/* ---- the descriptor: one field per generic / port ---------------------- */
+/* Mirrors win_selector's generic list and AA0..AA6 ports
+ * (src/win_selector.vhd:60-87).  For BHW_MODEL_HLS, phi_width/dat_width are
+ * NPHASE/NWIDTH (hls/windows/win_function.h:51-52) and aa[] are the a_k
+ * integers the HLS functions derive from their double constants
+ * (hls/windows/win_function.cpp:176-177 etc.; see bhw_quantize). */
+typedef struct bhw_desc {
+  int32_t win_type;      /* BHW_WIN_*     (WIN_TYPE)                               */
+  int32_t sin_type;      /* BHW_SIN_*     (SIN_TYPE / entity swap)                 */
+  int32_t model;         /* BHW_MODEL_*                                            */
+  int32_t phi_width;     /* PHI_WIDTH: window length N = 2^phi_width, 4..26        */
+  int32_t dat_width;     /* DAT_WIDTH: bits of AAk and DT_WIN                      */
+  int32_t precision;     /* cordic_dds PRECISION generic; 0 means the entity
+                            default 1 (src/cordic_dds.vhd:79). Ignored elsewhere.  */
+  int32_t lut_size;      /* LUT_SIZE (TAYLOR only); 0 means the entity default 9
+                            (src/hamming_win.vhd:67)                               */
+  int32_t stream_offset; /* 0: out[j] = w[n0+j]; 1: the DT_VLD-gated order
+                            w[1], w[2], ..., w[N-1], w[0] (DESIGN.md "stream order") */
+  int32_t algo;          /* BHW_ALGO_*                                             */
+  int32_t reserved;      /* must be 0 (XSERIES has no numeric effect)              */
+  int64_t aa[BHW_MAX_TERMS]; /* raw two's-complement AA0..AA6 port values; terms
+                                beyond win_type are ignored                        */
+} bhw_desc;
+
+/* ---- helpers ----------------------------------------------------------- */
+const char* bhw_strerror(int status);
+int bhw_version(void);
+
+/* Check a descriptor exactly as the generators do.  Rejections correspond to
+ * configurations the reference cannot elaborate or documents as invalid. */
+int bhw_validate(const bhw_desc* d);
+
+/* 4 or 8: bytes per output element for this descriptor. */
+int bhw_elem_bytes(const bhw_desc* d);
+
+/* Coefficient front end.  The reference leaves quantisation to the caller; the
+ * rules it uses itself are in src/tb/tb_windows.vhd:75-127 (rule BHW_RULE_TB)
+ * and hls/windows/win_function.cpp:176-355 (rule BHW_RULE_HLS).
+ * variant: 1 Hamming, 2 Hann, 3 Blackman, 4 Blackman-Harris-3, 5 Nuttall,
+ * 6 Blackman-Harris-4, 7 Blackman-Nuttall, 8 Flat-top, 9 Blackman-Harris-5,
+ * 10 Blackman-Harris-7 (README.md:30-41).  Writes aa_out[0..6] (unused = 0)
+ * and *win_type (2,3,4,5,7). */
+enum { BHW_RULE_TB = 0, BHW_RULE_HLS = 1 };
+int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS],
+                 int32_t* win_type);
+/* Real-valued coefficients of a variant as the reference spells them
+ * (for rule TB; rule HLS halves variant 3: win_function.cpp:206-208). */
+int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS], int32_t* nterms);
+
+/* ---- generation: one window ------------------------------------------- */
+/* Replaces: one win_selector instance streaming `count` DT_WIN words
+ * (src/win_selector.vhd:60-87) / the per-sample loop around
+ * win_function(win_type, i, &out) (hls/windows/window_test.cpp:93,193,
+ * hls/windows/win_function.h:65-69).  out_dev: device buffer of `count`
+ * elements. Range: n0 + count <= 2^phi_width. */
+int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, void* stream);
+
+/* Same with a HOST output buffer: generates on the current device and copies
+ * back (pinned staging, chunked, copy overlapped with generation).
+ * Synchronises before returning. */
+int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t count);
+
+/* ---- generation: a batch of windows, sharded by flat sample range ------ */
+/* The batch is the concatenation of the nwin full windows in order; "flat"
+ * indices address that concatenation.  Writes flat samples
+ * [flat_begin, flat_begin+flat_count) to out_dev[0 .. flat_count).  All
+ * windows in a batch must share one element size.  This is the sharding
+ * primitive: rank r of R calls it with its contiguous slice
+ * (bhw_shard_range) - no collective is involved. */
+int bhw_batch_total(const bhw_desc* descs, int nwin, uint64_t* total_samples);
+int bhw_shard_range(uint64_t total_samples, int rank, int nranks, uint64_t* begin,
+                    uint64_t* count);
+int bhw_generate_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin,
+                       uint64_t flat_count, void* out_dev, void* stream);
+int bhw_generate_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin,
+                            uint64_t flat_count, void* out_host);
+/* Single-process multi-GPU form: device g (0..ngpus-1) receives shard g of the
+ * flat range in outs_dev[g] (allocated by the caller on device g, at least
+ * the bhw_shard_range count).  Synchronises all devices before returning. */
+int bhw_generate_batch_multi(const bhw_desc* descs, int nwin, int ngpus, void* const* outs_dev);
+
+/* ---- sin/cos tables (the DDS entities on their own) -------------------- */
+/* Replaces: cordic_dds / cordic_dds48 / cordic_dds_scaled / taylor_sincos
+ * driven by a free-running phase counter (ports PH_IN -> DT_SIN, DT_COS:
+ * src/cordic_dds.vhd:83-91; taylor: src/taylor_sincos.vhd:73-80), the HLS
+ * cordic(phi, &cos, &sin) (hls/cordic/cordic.h:58-62) and the C++
+ * cordic(theta, lut, &s, &c) (cpp/cordic_sincos.cpp:10).  win_type/aa are
+ * ignored.  Either output may be NULL.  Elements as for bhw_generate. */
+int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t n0,
+               uint64_t count, void* stream);
+
+/* ---- cache / introspection --------------------------------------------- */
+int bhw_cache_clear(void);             /* free workspaces and cached trig tables  */
+int bhw_set_table_cache(int enabled);  /* 1 (default): keep trig tables between
+                                          calls; 0: rebuild them in every call   */
+uint64_t bhw_launch_count(void);       /* kernels launched by this library so far */
+const char* bhw_last_cuda_error(void); /* text of the last CUDA failure           */
+int bhw_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHW_H_ */

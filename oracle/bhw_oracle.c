@@ -1,0 +1,526 @@
+/*
+ * bhw_oracle.c - plain-C restatement of the reference's window-generation path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see bhw_oracle.h).  Every function follows the
+ * reference file:line it cites; nothing here is shared with the CUDA product.
+ * All arithmetic is done in int64_t / __int128 with explicit wrap ("sx") to the
+ * bit width the reference signal has, so the code reads like the RTL/C++ it
+ * restates rather than like an optimised implementation.
+ *
+ * Parity: HLS and CPP models are pinned against the compiled reference
+ * (oracle/_ref); the RTL model is unpinned by the reference (no simulator, no
+ * golden files) and anchored by oracle/rtl_bitvec.py + tests/golden KATs.
+ */
+#include "bhw_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef __int128 i128;
+
+/* wrap v to a b-bit two's-complement value, 1 <= b <= 64 */
+static inline int64_t sx(int64_t v, int b) {
+  if (b >= 64) return v;
+  uint64_t m = 1ull << (b - 1);
+  uint64_t x = (uint64_t)v & ((m << 1) - 1);
+  return (int64_t)((x ^ m) - m);
+}
+static inline int64_t sx128(i128 v, int b) { return sx((int64_t)v, b); } /* b <= 64: low bits suffice */
+
+/* atan ROM with pi/4 -> 2^46: src/cordic_dds.vhd:104-117 (same constants in
+ * hls/cordic/cordic.cpp:57-70, hls/windows/win_function.cpp:59-72). */
+static const int64_t ROM4[48] = {
+    0x400000000000, 0x25C80A3B3BE6, 0x13F670B6BDC7, 0x0A2223A83BBB, 0x05161A861CB1, 0x028BAFC2B209,
+    0x0145EC3CB850, 0x00A2F8AA23A9, 0x00517CA68DA2, 0x0028BE5D7661, 0x00145F300123, 0x000A2F982950,
+    0x000517CC19C0, 0x00028BE60D83, 0x000145F306D6, 0x0000A2F9836D, 0x0000517CC1B7, 0x000028BE60DC,
+    0x0000145F306E, 0x00000A2F9837, 0x00000517CC1B, 0x0000028BE60E, 0x00000145F307, 0x000000A2F983,
+    0x000000517CC2, 0x00000028BE61, 0x000000145F30, 0x0000000A2F98, 0x0000000517CC, 0x000000028BE6,
+    0x0000000145F3, 0x00000000A2FA, 0x00000000517D, 0x0000000028BE, 0x00000000145F, 0x000000000A30,
+    0x000000000518, 0x00000000028C, 0x000000000146, 0x0000000000A3, 0x000000000051, 0x000000000029,
+    0x000000000014, 0x00000000000A, 0x000000000005, 0x000000000003, 0x000000000001, 0x000000000000};
+/* atan ROM with pi/4 -> 2^45: src/cordic_dds48.vhd:115-128,
+ * src/cordic_dds_scaled.vhd:117-130, cpp/cordic_sincos.cpp:97-110.
+ * Independently rounded: not ROM4 >> 1. */
+static const int64_t ROM2[48] = {
+    0x200000000000, 0x12E4051D9DF3, 0x09FB385B5EE4, 0x051111D41DDE, 0x028B0D430E59, 0x0145D7E15904,
+    0x00A2F61E5C28, 0x00517C5511D4, 0x0028BE5346D1, 0x00145F2EBB31, 0x000A2F980092, 0x000517CC14A8,
+    0x00028BE60CE0, 0x000145F306C1, 0x0000A2F9836B, 0x0000517CC1B7, 0x000028BE60DC, 0x0000145F306E,
+    0x00000A2F9837, 0x00000517CC1B, 0x0000028BE60E, 0x00000145F307, 0x000000A2F983, 0x000000517CC2,
+    0x00000028BE61, 0x000000145F30, 0x0000000A2F98, 0x0000000517CC, 0x000000028BE6, 0x0000000145F3,
+    0x00000000A2FA, 0x00000000517D, 0x0000000028BE, 0x00000000145F, 0x000000000A30, 0x000000000518,
+    0x00000000028C, 0x000000000146, 0x0000000000A3, 0x000000000051, 0x000000000029, 0x000000000014,
+    0x00000000000A, 0x000000000005, 0x000000000003, 0x000000000001, 0x000000000001, 0x000000000000};
+static const int64_t GAIN_A = 0x4DBA76D421AF; /* src/cordic_dds.vhd:97 */
+static const int64_t GAIN_B = 0x26DD3B6A10D8; /* src/cordic_dds48.vhd:110, cpp/cordic_sincos.cpp:21 */
+
+/* output-side quadrant fix shared by cordic_dds (src/cordic_dds.vhd:232-246)
+ * and taylor_sincos (src/taylor_sincos.vhd:237-255): negation is not(v)+1 in
+ * dw bits. */
+static void quad_fix(int q, int64_t s, int64_t c, int dw, int64_t* so, int64_t* co) {
+  switch (q & 3) {
+    case 0: *so = s; *co = c; break;
+    case 1: *so = c; *co = sx(~s + 1, dw); break;
+    case 2: *so = sx(~s + 1, dw); *co = sx(~c + 1, dw); break;
+    default: *so = sx(~c + 1, dw); *co = s; break;
+  }
+}
+
+/* ---- (A) cordic_dds: src/cordic_dds.vhd:97-249 --------------------------- */
+void orc_cordic_dds(int pw, int dw, int prec, uint64_t ph, int64_t* s, int64_t* c) {
+  const int w = dw + prec;                      /* sigX/Y/Z width :134-135 */
+  const int64_t gain = GAIN_A >> (49 - w);      /* "0" & GAIN48(47 downto 48-w+1) :98 */
+  ph &= (1ull << pw) - 1;
+  const int q = (int)(ph >> (pw - 2));          /* quadz1/quadz2 :170-172 */
+  const uint64_t t = ph & ((1ull << (pw - 2)) - 1); /* init_t :179 */
+  int64_t z;
+  if (pw >= dw) z = (int64_t)((t >> (pw - dw)) << prec); /* xPHI_LESS :159-162 */
+  else z = (int64_t)(t << (dw - pw + prec));             /* xPHI_MORE :163-166 */
+  z = sx(z, w);
+  int64_t x = gain, y = 0;                      /* :177-178 */
+  for (int i = 0; i <= dw - 2; i++) {           /* lpXY / lpZ :197-213 */
+    const int64_t rom = ROM4[i] >> (49 - w);    /* func_atan :123-131 */
+    int64_t xn, yn, zn;
+    if (z < 0) { xn = x + (y >> i); yn = y - (x >> i); zn = z + rom; }
+    else       { xn = x - (y >> i); yn = y + (x >> i); zn = z - rom; }
+    x = sx(xn, w); y = sx(yn, w); z = sx(zn, w);
+  }
+  const int64_t ds = sx(y >> prec, dw);         /* dat_sin :218 */
+  const int64_t dc = sx(x >> prec, dw);         /* dat_cos :219 */
+  quad_fix(q, ds, dc, dw, s, c);
+}
+
+/* ---- (B)/(C) cordic_dds48 and cordic_dds_scaled -------------------------- */
+/* one algorithm, parameters (size, dwph): src/cordic_dds48.vhd:110-259,
+ * src/cordic_dds_scaled.vhd:100-285 */
+static void cordic_inq(int pw, int dw, int size, int dwph, uint64_t ph, int64_t* s, int64_t* c) {
+  const int64_t g = GAIN_B >> (48 - size);      /* GAIN32 = GAIN48(47 downto 48-size) :110-111 */
+  ph &= (1ull << pw) - 1;
+  const int q = (int)(ph >> (pw - 2));
+  const uint64_t low = ph & ((1ull << (pw - 2)) - 1);
+  uint64_t t; int64_t x, y;
+  switch (q) {                                  /* pr_phi / pr_xy: dds48 :170-216, scaled :196-242 */
+    case 1:  t = low;                         x = 0; y = sx(~g + 1, size); break;
+    case 2:  t = low | (3ull << (pw - 2));    x = 0; y = g; break;
+    default: t = ph;                          x = g; y = 0; break;
+  }
+  /* init_z: phase left-aligned in dwph bits (dds48 :164-165; scaled :186-192) */
+  int64_t z = sx((int64_t)(t << (dwph - pw)), dwph);
+  for (int i = 0; i <= dw - 1; i++) {           /* xl: DW iterations of X/Y (dds48 :234-242) */
+    int64_t xn, yn;
+    if (z >= 0) { xn = x + (y >> i); yn = y - (x >> i); }
+    else        { xn = x - (y >> i); yn = y + (x >> i); }
+    if (i <= dw - 2) {                          /* xp: Z advances only DW-1 times (:244-250) */
+      const int64_t rom = ROM2[i] >> (48 - dwph);
+      z = sx(z < 0 ? z + rom : z - rom, dwph);
+    }
+    x = sx(xn, size); y = sx(yn, size);
+  }
+  *s = sx(y >> (size - dw), dw);                /* top DW bits (dds48 :257-258) */
+  *c = sx(x >> (size - dw), dw);
+}
+void orc_cordic_dds48(int pw, int dw, uint64_t ph, int64_t* s, int64_t* c) {
+  cordic_inq(pw, dw, 48, 48, ph, s, c);
+}
+static const int SEL_SIZE[25] = {15, 15, 15, 18, 21, 22, 23, 26, 30, 31, 32, 33, 38,
+                                 38, 38, 42, 42, 45, 47, 47, 47, 48, 48, 48, 48}; /* scaled :102-107 */
+void orc_cordic_dds_scaled(int pw, int dw, uint64_t ph, int64_t* s, int64_t* c) {
+  const int size = SEL_SIZE[dw - 8];
+  const int dwph = size < pw ? pw : size;       /* func_width :132-143 */
+  cordic_inq(pw, dw, size, dwph, ph, s, c);
+}
+
+/* ---- (E) taylor_sincos + tay1_order -------------------------------------- */
+/* rom_calculate: src/taylor_sincos.vhd:91-111.  VHDL INTEGER(real) rounds to
+ * nearest; llround() differs only on exact .5 ties, which only ii = 0 could
+ * produce and that entry is an exact integer. */
+void orc_taylor_rom(int dw, int lut, int64_t* rom_cos, int64_t* rom_sin) {
+  const int depth = 1 << lut;
+  const double amp = ldexp(1.0, dw - 1) - 1.0;
+  for (int ii = 0; ii < depth; ii++) {
+    const double pi_new = ((double)ii * M_PI) / (2.0 * (double)depth);
+    rom_cos[ii] = sx(llround(amp * cos(pi_new)), dw);
+    rom_sin[ii] = sx(llround(amp * sin(pi_new)), dw);
+  }
+}
+static void taylor_core(int pw, int dw, int lut, const int64_t* rc, const int64_t* rs, uint64_t cnt,
+                        int64_t* s, int64_t* c) {
+  cnt &= (1ull << pw) - 1;
+  const int q = (int)(cnt >> (pw - 2));                         /* :141 */
+  const uint64_t t = cnt & ((1ull << (pw - 2)) - 1);
+  const int d = pw - lut;
+  int64_t ms, mc;
+  if (d < 2) {                                                  /* xGEN_LESS :157-161 */
+    const uint64_t addr = (t << (lut - pw + 2)) & ((1ull << lut) - 1);
+    mc = rc[addr]; ms = rs[addr];
+  } else if (d == 2) {                                          /* xGEN_EQ :164-167 */
+    mc = rc[t]; ms = rs[t];
+  } else {                                                      /* xGEN_MORE :169-217 */
+    const uint64_t addr = t >> (pw - lut - 2);                  /* cnt(PW-3 downto PW-LUT-2) :190 */
+    const int64_t acnt = (int64_t)(t & ((1ull << (pw - lut - 2)) - 1)); /* :191 */
+    const int stage = pw - lut - 3;                             /* :200 */
+    const int64_t c0 = rc[addr], s0 = rs[addr];
+    /* tay1_order: ramb_pi, mpi (src/tay1_order.vhd:130-147), XSHIFT (:112) */
+    const int64_t ramb_pi = (int64_t)round(M_PI * ldexp(1.0, 17 - stage));
+    const int64_t mpi = (ramb_pi * acnt) & 0xFFFFFF;
+    const int xs = 19 + lut;
+    if (dw < 19) {  /* DSP48 MACC: C -/+ A*B, slice [xs+dw-1:xs] (:180-504) */
+      mc = sx128((((i128)c0 << xs) - (i128)mpi * s0) >> xs, dw);
+      ms = sx128((((i128)s0 << xs) + (i128)mpi * c0) >> xs, dw);
+    } else {        /* wide multiplier + add/sub + saturation (:506-617) */
+      const int64_t m1 = sx128(((i128)s0 * mpi) >> xs, dw);     /* mlt1_bb :585 */
+      const int64_t m2 = sx128(((i128)c0 * mpi) >> xs, dw);     /* mlt2_bb :586 */
+      const int64_t cp = sx(c0 - m1, dw);                       /* cos_pdt :595 */
+      const int64_t sp = sx(s0 + m2, dw);                       /* sin_pdt :596 */
+      const int64_t sat = ((int64_t)1 << (dw - 1)) - 1;
+      mc = cp < 0 ? sat : cp;                                   /* pr_rnd :602-617 */
+      ms = sp < 0 ? sat : sp;
+    }
+  }
+  quad_fix(q, ms, mc, dw, s, c);                                /* pr_quad :237-255 */
+}
+void orc_taylor_sincos(int pw, int dw, int lut, uint64_t cnt, int64_t* s, int64_t* c) {
+  const int depth = 1 << lut;
+  int64_t* rc = (int64_t*)malloc(sizeof(int64_t) * 2 * depth);
+  orc_taylor_rom(dw, lut, rc, rc + depth);
+  taylor_core(pw, dw, lut, rc, rc + depth, cnt, s, c);
+  free(rc);
+}
+
+/* ---- (F) HLS cordic: hls/windows/win_function.cpp:47-156 ------------------ */
+/* (identical text in hls/cordic/cordic.cpp:45-154) */
+void orc_hls_cordic(int np, int nw, uint64_t phi, int64_t* s, int64_t* c) {
+  const int w = nw + 2;                                         /* dat_t: win_function.h:61 */
+  const int64_t gain = sx(GAIN_B >> (46 - nw), w);              /* GAIN48 :83 */
+  phi &= (1ull << np) - 1;
+  const int q = (int)(phi >> (np - 2));                         /* quadrant :86 */
+  const int64_t t = (int64_t)(phi & ((1ull << (np - 2)) - 1));  /* init_t :88 */
+  int64_t z;
+  if (np - 1 < nw) z = sx(t << (nw - np + 2), w);               /* :91-92 */
+  else z = sx((t >> (np - nw)) << 2, w);                        /* :94-95 */
+  int64_t x = gain, y = 0;
+  for (int k = 0; k < nw; k++) {                                /* stg :110-125 */
+    /* lut_angle has NW-1 entries (:74-80); the last pass reads one past the
+     * end, which only feeds z[NW] - never used - so any value works here. */
+    const int64_t lut = k < nw - 1 ? sx((ROM4[k] >> (47 - nw)) & 0xFFFFFFFFFFll, w) : 0;
+    int64_t xn, yn, zn;
+    if (z < 0) { xn = x + (y >> k); yn = y - (x >> k); zn = z + lut; }
+    else       { xn = x - (y >> k); yn = y + (x >> k); zn = z - lut; }
+    x = sx(xn, w); y = sx(yn, w); z = sx(zn, w);
+  }
+  const int64_t oc = x >> 2, os = y >> 2;                       /* :128-129 */
+  int64_t dc, ds;
+  switch (q) {                                                  /* :135-154, in dat_t */
+    case 0: ds = os; dc = oc; break;
+    case 1: ds = oc; dc = sx(~os + 1, w); break;
+    case 2: ds = sx(~os + 1, w); dc = sx(~oc + 1, w); break;
+    default: ds = sx(~oc + 1, w); dc = os; break;
+  }
+  *c = sx(dc, nw);                                              /* win_t truncation :153-154 */
+  *s = sx(ds, nw);
+}
+
+/* ---- (G) plain C++ cordic: cpp/cordic_sincos.cpp:10-92 -------------------- */
+void orc_cpp_cordic(int pw, int dw, int theta, int* s, int* c) {
+  const int precision = 1;                                      /* :12 */
+  const long long gain = GAIN_B >> (48 - dw - 2);               /* GAIN32 :21-22 */
+  const int q = theta >> (pw - 2);                              /* :25 */
+  const long long t = theta & (~(0x3 << (pw - 2)));             /* :27 */
+  long long z;
+  if (pw - 1 < dw) z = t << (dw - pw + precision);              /* :31-33 */
+  else z = (t >> (pw - dw)) << precision;                       /* :34-36 */
+  long long x = gain, y = 0;
+  for (int k = 0; k < dw; k++) {                                /* :49-63 */
+    /* lut_angle has DW-1 entries (:13-18); pass DW-1 reads past the end and
+     * only produces z[DW], which is never used. */
+    const long long lut = k < dw - 1 ? ((ROM2[k] >> (48 - dw - precision)) & 0xFFFFFFFFFFFFll) : 0;
+    long long xn, yn;
+    if (z < 0) { xn = x + (y >> k); yn = y - (x >> k); z = z + lut; }
+    else       { xn = x - (y >> k); yn = y + (x >> k); z = z - lut; }
+    x = xn; y = yn;
+  }
+  const long long oc = x >> 2, os = y >> 2;                     /* :64-65 */
+  long long dc, ds;
+  switch (q) {                                                  /* ones' complement, :70-86 */
+    case 0: ds = os; dc = oc; break;
+    case 1: ds = oc; dc = ~os; break;
+    case 2: ds = ~os; dc = ~oc; break;
+    default: ds = ~oc; dc = os; break;
+  }
+  *c = (int)dc; *s = (int)ds;                                   /* :89-90 */
+}
+
+/* ---- descriptor handling -------------------------------------------------- */
+static int eff_prec(const bhw_desc* d) { return d->precision == 0 ? 1 : d->precision; }
+static int eff_lut(const bhw_desc* d) { return d->lut_size == 0 ? 9 : d->lut_size; }
+
+static int validate_source(const bhw_desc* d, int for_window) {
+  const int pw = d->phi_width, dw = d->dat_width;
+  if (pw < 4 || pw > 30) return BHW_E_PHI_WIDTH;
+  switch (d->model) {
+    case BHW_MODEL_RTL:
+      switch (d->sin_type) {
+        case BHW_SIN_CORDIC: {
+          const int p = eff_prec(d);
+          if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
+          if (p < 1 || p > 7 || dw + p > 49) return BHW_E_PRECISION;
+          if (for_window && p != 1) return BHW_E_PRECISION; /* windows never override it: src/hamming_win.vhd:153-157 */
+          return BHW_OK;
+        }
+        case BHW_SIN_CORDIC48:
+          if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
+          return BHW_OK;
+        case BHW_SIN_CORDIC_SCALED:
+          if (dw < 8 || dw > 32) return BHW_E_DAT_WIDTH;
+          return BHW_OK;
+        case BHW_SIN_TAYLOR: {
+          const int lut = eff_lut(d);
+          if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;
+          if (lut < 1 || lut > 16) return BHW_E_LUT_SIZE;
+          const int nunits = (for_window && d->win_type == BHW_WIN_BH3TERM) ? 2 : 1;
+          if (for_window && d->win_type != BHW_WIN_HAMMING && d->win_type != BHW_WIN_BH3TERM)
+            return BHW_E_SIN_TYPE;
+          if (nunits == 2 && pw - lut == 3) return BHW_E_LUT_SIZE; /* src/bh_win_3term.vhd:30-31 */
+          for (int u = 0; u < nunits; u++) {
+            const int dd = (pw - u) - lut;
+            if (dd > 2) {
+              if (dd - 3 > 15) return BHW_E_LUT_SIZE;           /* cnt_exp is 16 bits: tay1_order.vhd:116-127 */
+              if (dw < 19 && 19 + lut + dw > 48) return BHW_E_LUT_SIZE; /* slice of a 48-bit P */
+              if (dw > 18 && 19 + lut + dw > 62) return BHW_E_LUT_SIZE; /* slice of a 62-bit product */
+            }
+          }
+          return BHW_OK;
+        }
+        default: return BHW_E_SIN_TYPE;
+      }
+    case BHW_MODEL_HLS:
+      if (d->sin_type != BHW_SIN_CORDIC) return BHW_E_SIN_TYPE;
+      if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;
+      if (pw > dw + 2) return BHW_E_PHI_WIDTH;  /* init_t no longer fits dat_t */
+      return BHW_OK;
+    case BHW_MODEL_CPP:
+      if (for_window) return BHW_E_MODEL;
+      if (d->sin_type != BHW_SIN_CORDIC) return BHW_E_SIN_TYPE;
+      if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;
+      return BHW_OK;
+    default: return BHW_E_MODEL;
+  }
+}
+
+int orc_validate(const bhw_desc* d) {
+  if (!d) return BHW_E_NULL;
+  const int m = d->win_type;
+  if (m != 2 && m != 3 && m != 4 && m != 5 && m != 7) return BHW_E_WIN_TYPE;
+  int st = validate_source(d, 1);
+  if (st) return st;
+  if (d->stream_offset != 0 && d->stream_offset != 1) return BHW_E_ARG;
+  if (d->reserved != 0) return BHW_E_ARG;
+  const int dw = d->dat_width;
+  for (int k = 0; k < m; k++) {
+    const int64_t v = d->aa[k];
+    if (dw < 63) {
+      if (v < -((int64_t)1 << (dw - 1)) || v >= ((int64_t)1 << dw)) return BHW_E_COEFF;
+      if (d->model == BHW_MODEL_HLS && v >= ((int64_t)1 << (dw - 1))) return BHW_E_COEFF;
+    }
+  }
+  return BHW_OK;
+}
+
+typedef struct {
+  const bhw_desc* d;
+  int64_t* rom[2]; /* Taylor ROMs of unit 1 (pw) and, for 3-term, unit 2 (pw-1): same table, kept once */
+} ctx_t;
+
+/* cos of harmonic k at sample n, per the entity's wiring */
+static int64_t harmonic_cos(const ctx_t* cx, int k, uint64_t n) {
+  const bhw_desc* d = cx->d;
+  const int pw = d->phi_width, dw = d->dat_width;
+  int64_t s, c;
+  if (d->model == BHW_MODEL_HLS) {            /* cordic(k*i, ...): win_function.cpp:361-366 */
+    orc_hls_cordic(pw, dw, (uint64_t)k * n, &s, &c);
+    return c;
+  }
+  switch (d->sin_type) {
+    case BHW_SIN_CORDIC:                      /* ph_in_k += k: src/bh_win_7term.vhd:176-197 */
+      orc_cordic_dds(pw, dw, eff_prec(d), (uint64_t)k * n, &s, &c); break;
+    case BHW_SIN_CORDIC48: orc_cordic_dds48(pw, dw, (uint64_t)k * n, &s, &c); break;
+    case BHW_SIN_CORDIC_SCALED: orc_cordic_dds_scaled(pw, dw, (uint64_t)k * n, &s, &c); break;
+    default: {                                /* TAYLOR: each unit owns a +1 counter; the 2nd
+                                                 harmonic is a PHASE_WIDTH-1 unit
+                                                 (src/bh_win_3term.vhd:205-234) */
+      const int lut = eff_lut(d), depth = 1 << lut;
+      taylor_core(pw - (k - 1), dw, lut, cx->rom[0], cx->rom[0] + depth, n, &s, &c);
+    }
+  }
+  return c;
+}
+
+static int64_t window_sample(const ctx_t* cx, uint64_t n) {
+  const bhw_desc* d = cx->d;
+  const int m = d->win_type, dw = d->dat_width;
+  if (d->model == BHW_MODEL_HLS) {
+    /* m_k = (a_k*c_k) >> (NW-2), out = (win_t)(a0 - m1 + m2 - ...):
+     * hls/windows/win_function.cpp:182,197,222-225,271-275,327-332,368-375 */
+    i128 acc = d->aa[0];
+    for (int k = 1; k < m; k++) {
+      const i128 mk = ((i128)d->aa[k] * harmonic_cos(cx, k, n)) >> (dw - 2);
+      acc += (k & 1) ? -mk : mk;
+    }
+    return sx128(acc, dw);
+  }
+  /* RTL tail, identical in all five entities (src/hamming_win.vhd:192-231,
+   * src/bh_win_3term.vhd:258-306, bh_win_4term.vhd:225-280, bh_win_5term.vhd:
+   * 281-347, bh_win_7term.vhd:350-438) */
+  int64_t b[BHW_MAX_TERMS];
+  b[0] = sx(d->aa[0], dw);                                    /* dsp_b0 <= AA0 */
+  for (int k = 1; k < m; k++) {
+    const i128 p = (i128)sx(d->aa[k], dw) * harmonic_cos(cx, k, n); /* int_multNxN_dsp48.vhd:105 */
+    const int64_t r = sx128(p >> (dw - 2), dw + 1);           /* mult_p(2DW-2 downto DW-2) */
+    b[k] = sx((r >> 1) + (r & 1), dw);                        /* pr_rnd: +1 when bit0 set */
+  }
+  if (m == 2) {
+    const int64_t pp = sx(b[0] - b[1], dw + 1);               /* hamming_win.vhd:214 */
+    return sx((pp >> 1) + (pp & 1), dw);                      /* :220-228 */
+  }
+  int64_t sum = 0;
+  for (int k = 0; k < m; k++) sum += (k & 1) ? -b[k] : b[k];
+  const int64_t pp = sx(sum, dw + 2);                         /* dsp_pp is DW+2 bits */
+  return sx((pp >> 2) + ((pp >> 1) & 1), dw);                 /* rounds on bit 1: bh_win_3term.vhd:295-306 */
+}
+
+static int ctx_init(ctx_t* cx, const bhw_desc* d) {
+  cx->d = d; cx->rom[0] = cx->rom[1] = NULL;
+  if (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR) {
+    const int depth = 1 << eff_lut(d);
+    cx->rom[0] = (int64_t*)malloc(sizeof(int64_t) * 2 * depth);
+    if (!cx->rom[0]) return BHW_E_ALLOC;
+    orc_taylor_rom(d->dat_width, eff_lut(d), cx->rom[0], cx->rom[0] + depth);
+  }
+  return BHW_OK;
+}
+static void ctx_free(ctx_t* cx) { free(cx->rom[0]); }
+
+int orc_window(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
+  int st = orc_validate(d);
+  if (st) return st;
+  if (!out && count) return BHW_E_NULL;
+  const uint64_t N = 1ull << d->phi_width;
+  if (n0 > N || count > N - n0) return BHW_E_RANGE;
+  ctx_t cx;
+  if ((st = ctx_init(&cx, d))) return st;
+  for (uint64_t j = 0; j < count; j++)
+    out[j] = window_sample(&cx, (n0 + j + (uint64_t)d->stream_offset) & (N - 1));
+  ctx_free(&cx);
+  return BHW_OK;
+}
+
+int orc_window_i32(const bhw_desc* d, uint64_t n0, uint64_t count, int32_t* out) {
+  int st = orc_validate(d);
+  if (st) return st;
+  if (d->dat_width > 32) return BHW_E_ELEM;
+  const uint64_t N = 1ull << d->phi_width;
+  if (n0 > N || count > N - n0) return BHW_E_RANGE;
+  ctx_t cx;
+  if ((st = ctx_init(&cx, d))) return st;
+  for (uint64_t j = 0; j < count; j++)
+    out[j] = (int32_t)window_sample(&cx, (n0 + j + (uint64_t)d->stream_offset) & (N - 1));
+  ctx_free(&cx);
+  return BHW_OK;
+}
+
+typedef struct { const bhw_desc* d; uint64_t n0, count; int64_t* out; int st; } job_t;
+static void* mt_worker(void* p) {
+  job_t* j = (job_t*)p;
+  j->st = orc_window(j->d, j->n0, j->count, j->out);
+  return NULL;
+}
+int orc_window_mt(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256]; job_t jobs[256];
+  const uint64_t per = (count + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
+  int used = 0;
+  for (int i = 0; i < nthreads; i++) {
+    const uint64_t b = per * (uint64_t)i;
+    if (b >= count) break;
+    const uint64_t c = count - b < per ? count - b : per;
+    jobs[i] = (job_t){d, n0 + b, c, out + b, 0};
+    pthread_create(&th[i], NULL, mt_worker, &jobs[i]);
+    used++;
+  }
+  int st = BHW_OK;
+  for (int i = 0; i < used; i++) { pthread_join(th[i], NULL); if (jobs[i].st) st = jobs[i].st; }
+  return st;
+}
+
+int orc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, int64_t* out_cos) {
+  if (!d) return BHW_E_NULL;
+  int st = validate_source(d, 0);
+  if (st) return st;
+  const int pw = d->phi_width, dw = d->dat_width;
+  const uint64_t N = 1ull << pw;
+  if (n0 > N || count > N - n0) return BHW_E_RANGE;
+  ctx_t cx;
+  if ((st = ctx_init(&cx, d))) return st;
+  for (uint64_t j = 0; j < count; j++) {
+    const uint64_t n = (n0 + j) & (N - 1);
+    int64_t s = 0, c = 0;
+    if (d->model == BHW_MODEL_HLS) orc_hls_cordic(pw, dw, n, &s, &c);
+    else if (d->model == BHW_MODEL_CPP) { int si, ci; orc_cpp_cordic(pw, dw, (int)n, &si, &ci); s = si; c = ci; }
+    else switch (d->sin_type) {
+      case BHW_SIN_CORDIC: orc_cordic_dds(pw, dw, eff_prec(d), n, &s, &c); break;
+      case BHW_SIN_CORDIC48: orc_cordic_dds48(pw, dw, n, &s, &c); break;
+      case BHW_SIN_CORDIC_SCALED: orc_cordic_dds_scaled(pw, dw, n, &s, &c); break;
+      default: { const int depth = 1 << eff_lut(d);
+                 taylor_core(pw, dw, eff_lut(d), cx.rom[0], cx.rom[0] + depth, n, &s, &c); }
+    }
+    if (out_sin) out_sin[j] = s;
+    if (out_cos) out_cos[j] = c;
+  }
+  ctx_free(&cx);
+  return BHW_OK;
+}
+
+/* ---- coefficient rules ---------------------------------------------------- */
+/* variants per README.md:30-41; values per the entity headers */
+static const double COEF[10][7] = {
+    {0.5434783, 1.0 - 0.5434783},                              /* 1 Hamming   tb :123-124 */
+    {0.5, 0.5},                                                /* 2 Hann      hamming_win.vhd:14-16 */
+    {0.42, 0.5, 0.08},                                         /* 3 Blackman  tb :114-116 */
+    {0.4243801, 0.4973406, 0.0782793},                         /* 4 BH3       bh_win_3term.vhd:20 */
+    {0.355768, 0.487396, 0.144323, 0.012604},                  /* 5 Nuttall   bh_win_4term.vhd:16-17 */
+    {0.35875, 0.48829, 0.14128, 0.01168},                      /* 6 BH4       tb :103-106 */
+    {0.3635819, 0.4891775, 0.1365995, 0.0106411},              /* 7 B-Nuttall bh_win_4term.vhd:18-19 */
+    {1.000, 1.930, 1.290, 0.388, 0.030},                       /* 8 Flat-top  tb :90-94 */
+    {0.3232153788877343, 0.4714921439576260, 0.1755341299601972, 0.0284969901061499,
+     0.0012613570882927},                                      /* 9 BH5       bh_win_5term.vhd:14-19 */
+    {0.271220360585039, 0.433444612327442, 0.218004122892930, 0.065785343295606,
+     0.010761867305342, 0.000770012710581, 0.000013680883060}};/* 10 BH7      tb :67-73 */
+static const int NTERMS[10] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7};
+
+int orc_quantize(int variant, int rule, int dw, int64_t aa[7], int32_t* win_type) {
+  if (variant < 1 || variant > 10 || (rule != BHW_RULE_TB && rule != BHW_RULE_HLS)) return BHW_E_VARIANT;
+  if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
+  const int m = NTERMS[variant - 1];
+  double scale;
+  if (rule == BHW_RULE_TB) {        /* src/tb/tb_windows.vhd:75-127 */
+    switch (m) {
+      case 2: case 7: scale = ldexp(1.0, dw - 1) - 1.0; break; /* :75-81, :126-127 */
+      case 3: scale = ldexp(1.0, dw) - 16.0; break;            /* :118-120 */
+      case 4: scale = ldexp(1.0, dw) - 1.0; break;             /* :108-111 */
+      default: scale = ldexp(1.0, dw - 2) - 1.0; break;        /* 5-term :96-100 */
+    }
+  } else {                          /* hls/windows/win_function.cpp:176-355 */
+    scale = (m >= 5) ? ldexp(1.0, dw - 2) - 1.0 : ldexp(1.0, dw - 1) - 1.0;
+  }
+  for (int k = 0; k < 7; k++) aa[k] = 0;
+  for (int k = 0; k < m; k++) {
+    double a = COEF[variant - 1][k];
+    if (rule == BHW_RULE_HLS && variant == 3) a *= 0.5;        /* 0.21/0.25/0.04: :206-208 */
+    if (rule == BHW_RULE_HLS && variant == 1 && k == 1) a = 1 - 0.5434783; /* :174 */
+    aa[k] = (int64_t)round(a * scale);                         /* VHDL integer(): nearest; C round() */
+  }
+  if (win_type) *win_type = m;
+  return BHW_OK;
+}

@@ -1,0 +1,46 @@
+/*
+ * bhw_oracle.h - CPU restatement of the reference's window-generation path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (blackman_harris_win_b200/,
+ * include/) links, imports or calls this; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may.
+ *
+ * Parity status: the HLS-model and CPP-model functions are pinned against the
+ * reference's own C++ compiled here (oracle/_ref, see oracle/Makefile).  The
+ * RTL-model functions have NO executable reference in this image (no VHDL
+ * simulator): they are "parity unpinned" by the reference and are anchored by
+ * an independent bit-vector restatement (oracle/rtl_bitvec.py) and the
+ * known-answer hashes in tests/golden/.
+ */
+#ifndef BHW_ORACLE_H_
+#define BHW_ORACLE_H_
+#include <stdint.h>
+#include "../include/bhw.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* sin/cos sources: phase in, (sin, cos) out as sign-extended DATA_WIDTH-bit ints */
+void orc_cordic_dds(int pw, int dw, int prec, uint64_t ph, int64_t* s, int64_t* c);
+void orc_cordic_dds48(int pw, int dw, uint64_t ph, int64_t* s, int64_t* c);
+void orc_cordic_dds_scaled(int pw, int dw, uint64_t ph, int64_t* s, int64_t* c);
+void orc_taylor_sincos(int pw, int dw, int lut, uint64_t cnt, int64_t* s, int64_t* c);
+void orc_taylor_rom(int dw, int lut, int64_t* rom_cos, int64_t* rom_sin); /* 2^lut entries each */
+void orc_hls_cordic(int np, int nw, uint64_t phi, int64_t* s, int64_t* c);
+void orc_cpp_cordic(int pw, int dw, int theta, int* s, int* c);
+
+/* whole-descriptor entry points (same descriptor as the product ABI) */
+int orc_validate(const bhw_desc* d);
+int orc_window(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out);
+int orc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, int64_t* out_cos);
+int orc_quantize(int variant, int rule, int dat_width, int64_t aa_out[7], int32_t* win_type);
+
+/* multi-threaded fill used by bench.py's CPU legs (pthreads, one contiguous slice per thread) */
+int orc_window_mt(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int nthreads);
+int orc_window_i32(const bhw_desc* d, uint64_t n0, uint64_t count, int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

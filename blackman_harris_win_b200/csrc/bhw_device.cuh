@@ -1,0 +1,366 @@
+// bhw_device.cuh - per-thread arithmetic of the kernels.
+//
+// Every kernel in bhw_kernels.cu is a thin index-mapping wrapper around a "body" function in
+// this header.  Under nvcc the bodies are __device__ only; tests/hostcheck compiles the very same
+// text with g++ (BHW_HD = static inline) to compare it with the oracle on a machine without a
+// GPU.  That host build is test infrastructure only: the shipped library contains no CPU path.
+//
+// "Generic" bodies cover every legal descriptor in 64-bit registers with explicit wraps to the
+// reference's signal widths (BHW_ALGO_DIRECT, DAT_WIDTH > 32, bhw_sincos, exotic widths).
+// "Fast" bodies are the 32-bit specialisations used by the table path.
+#pragma once
+#include <stdint.h>
+
+#include "bhw_internal.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define BHW_HD __device__ __forceinline__
+#define BHW_CONSTANT __constant__
+#else
+#define BHW_HD static inline
+#define BHW_CONSTANT static const
+#endif
+
+namespace bhw {
+
+struct I2 { int32_t x, y; };  // (cos, sin) ROM word of taylor_sincos
+
+// Two 48-entry x 48-bit atan tables, independently rounded in the reference:
+// [0] pi/4 -> 2^46 (src/cordic_dds.vhd:104-117; also hls/cordic/cordic.cpp:57-70),
+// [1] pi/4 -> 2^45 (src/cordic_dds48.vhd:115-128; also cpp/cordic_sincos.cpp:97-110).
+BHW_CONSTANT int64_t c_atan[2][48] = {
+    {0x400000000000ll, 0x25C80A3B3BE6ll, 0x13F670B6BDC7ll, 0x0A2223A83BBBll, 0x05161A861CB1ll,
+     0x028BAFC2B209ll, 0x0145EC3CB850ll, 0x00A2F8AA23A9ll, 0x00517CA68DA2ll, 0x0028BE5D7661ll,
+     0x00145F300123ll, 0x000A2F982950ll, 0x000517CC19C0ll, 0x00028BE60D83ll, 0x000145F306D6ll,
+     0x0000A2F9836Dll, 0x0000517CC1B7ll, 0x000028BE60DCll, 0x0000145F306Ell, 0x00000A2F9837ll,
+     0x00000517CC1Bll, 0x0000028BE60Ell, 0x00000145F307ll, 0x000000A2F983ll, 0x000000517CC2ll,
+     0x00000028BE61ll, 0x000000145F30ll, 0x0000000A2F98ll, 0x0000000517CCll, 0x000000028BE6ll,
+     0x0000000145F3ll, 0x00000000A2FAll, 0x00000000517Dll, 0x0000000028BEll, 0x00000000145Fll,
+     0x000000000A30ll, 0x000000000518ll, 0x00000000028Cll, 0x000000000146ll, 0x0000000000A3ll,
+     0x000000000051ll, 0x000000000029ll, 0x000000000014ll, 0x00000000000All, 0x000000000005ll,
+     0x000000000003ll, 0x000000000001ll, 0x000000000000ll},
+    {0x200000000000ll, 0x12E4051D9DF3ll, 0x09FB385B5EE4ll, 0x051111D41DDEll, 0x028B0D430E59ll,
+     0x0145D7E15904ll, 0x00A2F61E5C28ll, 0x00517C5511D4ll, 0x0028BE5346D1ll, 0x00145F2EBB31ll,
+     0x000A2F980092ll, 0x000517CC14A8ll, 0x00028BE60CE0ll, 0x000145F306C1ll, 0x0000A2F9836Bll,
+     0x0000517CC1B7ll, 0x000028BE60DCll, 0x0000145F306Ell, 0x00000A2F9837ll, 0x00000517CC1Bll,
+     0x0000028BE60Ell, 0x00000145F307ll, 0x000000A2F983ll, 0x000000517CC2ll, 0x00000028BE61ll,
+     0x000000145F30ll, 0x0000000A2F98ll, 0x0000000517CCll, 0x000000028BE6ll, 0x0000000145F3ll,
+     0x00000000A2FAll, 0x00000000517Dll, 0x0000000028BEll, 0x00000000145Fll, 0x000000000A30ll,
+     0x000000000518ll, 0x00000000028Cll, 0x000000000146ll, 0x0000000000A3ll, 0x000000000051ll,
+     0x000000000029ll, 0x000000000014ll, 0x00000000000All, 0x000000000005ll, 0x000000000003ll,
+     0x000000000001ll, 0x000000000001ll, 0x000000000000ll}};
+
+// wrap to b-bit two's complement, 1 <= b <= 64 (resp. 32)
+BHW_HD int64_t wrapb(int64_t v, int b) {
+  const int sh = 64 - b;
+  return (int64_t)((uint64_t)v << sh) >> sh;
+}
+BHW_HD int32_t wrapb32(int32_t v, int b) {
+  const int sh = 32 - b;
+  return (int32_t)((uint32_t)v << sh) >> sh;
+}
+
+// ============================================================================================
+// Generic (64-bit) sources
+// ============================================================================================
+
+// The shift-add core: returns the un-fixed (sin, cos) pair.  q/low are the quadrant bits and the
+// remaining phase bits of a pw-bit phase.
+BHW_HD void cordic_core_generic(const SrcParams& p, int q, uint64_t low, int64_t& vs, int64_t& vc) {
+  const int pw = p.pw;
+  const bool inq = p.kind == SRC_INQ;
+  int64_t x = p.gain, y = 0, z;
+  if (inq) {
+    // quadrant folded into the start vector and the phase sign (src/cordic_dds48.vhd:170-216)
+    uint64_t t = low | ((uint64_t)q << (pw - 2));
+    if (q == 1) { t = low; x = 0; y = wrapb(-p.gain, p.w); }
+    else if (q == 2) { t = low | (3ull << (pw - 2)); x = 0; y = p.gain; }
+    z = wrapb((int64_t)(t << p.z_lshift), p.zw);
+  } else {
+    z = wrapb((int64_t)((low >> p.z_rshift) << p.z_lshift), p.zw);
+  }
+  for (int i = 0; i < p.n_xy; ++i) {
+    const bool zneg = z < 0;
+    const bool cw = inq ? !zneg : zneg;  // cw: x += y>>i, y -= x>>i; opposite sense in dds48 (:234-242)
+    const int64_t xs = x >> i, ys = y >> i;
+    const int64_t xn = cw ? x + ys : x - ys;
+    const int64_t yn = cw ? y - xs : y + xs;
+    if (i < p.n_z) {
+      const int64_t r = (c_atan[p.rom_sel][i] >> p.rom_shift) & p.rom_mask;
+      z = wrapb(zneg ? z + r : z - r, p.zw);
+    }
+    x = wrapb(xn, p.w);
+    y = wrapb(yn, p.w);
+  }
+  vs = y >> p.out_shift;
+  vc = x >> p.out_shift;
+}
+
+// taylor_sincos ROM look-up + tay1_order first-order correction, before the quadrant fix.
+// rom[i] = (cos_i, sin_i), quarter wave, built on the host (src/taylor_sincos.vhd:91-111).
+BHW_HD void taylor_core_generic(const SrcParams& p, const I2* rom, uint32_t t, int64_t& vs, int64_t& vc) {
+  const int dw = p.dw;
+  if (p.tay_mode == TAY_LESS || p.tay_mode == TAY_EQ) {
+    const I2 e = rom[p.tay_mode == TAY_LESS ? (t << p.tay_ashift) : t];
+    vc = e.x; vs = e.y;
+    return;
+  }
+  const I2 e = rom[t >> p.tay_ashift];
+  const int64_t c0 = e.x, s0 = e.y;
+  const int64_t acnt = t & ((1u << p.tay_cbits) - 1);
+  const int64_t mpi = (p.tay_pi * acnt) & 0xFFFFFF;  // 24-bit ROM word (src/tay1_order.vhd:136-147)
+  const int xs = p.tay_xs;
+  if (p.tay_mode == TAY_DSP) {
+    // P = C -/+ A*B, result = P[xs+dw-1 : xs] (src/tay1_order.vhd:245,316,501-502)
+    vc = wrapb(((c0 << xs) - mpi * s0) >> xs, dw);
+    vs = wrapb(((s0 << xs) + mpi * c0) >> xs, dw);
+  } else {
+    const int64_t m1 = wrapb((s0 * mpi) >> xs, dw);                       // :585
+    const int64_t m2 = wrapb((c0 * mpi) >> xs, dw);                       // :586
+    const int64_t cp = wrapb(c0 - m1, dw), sp = wrapb(s0 + m2, dw);        // :595-596
+    const int64_t sat = ((int64_t)1 << (dw - 1)) - 1;
+    vc = cp < 0 ? sat : cp;                                               // negative -> max positive (:602-617)
+    vs = sp < 0 ? sat : sp;
+  }
+}
+
+// Output-side quadrant fix.  negw > 0: not(v)+1 in negw bits (src/cordic_dds.vhd:232-246,
+// src/taylor_sincos.vhd:237-255, hls/windows/win_function.cpp:135-154); negw == 0: ~v
+// (cpp/cordic_sincos.cpp:70-86).
+BHW_HD void quadrant_fix(int q, int negw, int64_t vs, int64_t vc, int64_t& so, int64_t& co) {
+  const int64_t ns = negw ? wrapb(-vs, negw) : ~vs;
+  const int64_t nc = negw ? wrapb(-vc, negw) : ~vc;
+  switch (q) {
+    case 0: so = vs; co = vc; break;
+    case 1: so = vc; co = ns; break;
+    case 2: so = ns; co = nc; break;
+    default: so = nc; co = vs; break;
+  }
+}
+
+BHW_HD void eval_source_generic(const SrcParams& p, const I2* rom, uint64_t ph, int64_t& s, int64_t& c) {
+  const int pw = p.pw;
+  ph &= (1ull << pw) - 1;
+  const int q = (int)(ph >> (pw - 2));
+  const uint64_t low = ph & ((1ull << (pw - 2)) - 1);
+  int64_t vs, vc;
+  if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom, (uint32_t)low, vs, vc);
+  else cordic_core_generic(p, q, low, vs, vc);
+  if (p.kind != SRC_INQ) quadrant_fix(q, p.negw, vs, vc, vs, vc);
+  s = wrapb(vs, p.outw);
+  c = wrapb(vc, p.outw);
+}
+
+// Window tails.  cosv[k] is the DW-bit cosine of harmonic k (index 0 unused).
+BHW_HD int64_t tail_generic(const WinParams& wp, const int64_t* cosv) {
+  const int dw = wp.dw, m = wp.m;
+  if (wp.tail == TAIL_HLS) {
+    // m_k = (a_k*c_k) >> (NW-2); out = (win_t)(a0 - m1 + m2 - ...) (win_function.cpp:182,225,275,332,375)
+    int64_t acc = wp.aa[0];
+    for (int k = 1; k < m; ++k) {
+      const int64_t mk = (wp.aa[k] * cosv[k]) >> (dw - 2);  // |a|,|c| <= 2^31: fits 64 bits
+      acc += (k & 1) ? -mk : mk;
+    }
+    return wrapb(acc, dw);
+  }
+  // RTL: p = AAk*cos_k (src/int_multNxN_dsp48.vhd:105); r = p[2DW-2:DW-2]; b = (r>>1)+(r&1) in DW bits
+  int64_t sum = wp.aa[0];
+  for (int k = 1; k < m; ++k) {
+    int64_t r;
+    if (dw <= 32) r = wrapb((wp.aa[k] * cosv[k]) >> (dw - 2), dw + 1);
+    else r = wrapb((int64_t)(((__int128)wp.aa[k] * (__int128)cosv[k]) >> (dw - 2)), dw + 1);
+    const int64_t b = wrapb((r >> 1) + (r & 1), dw);
+    sum += (k & 1) ? -b : b;
+  }
+  if (wp.tail == TAIL_RTL2) {
+    const int64_t pp = wrapb(sum, dw + 1);         // src/hamming_win.vhd:214
+    return wrapb((pp >> 1) + (pp & 1), dw);        // :220-228
+  }
+  const int64_t pp = wrapb(sum, dw + 2);           // dsp_pp (src/bh_win_3term.vhd:286-288 ...)
+  return wrapb((pp >> 2) + ((pp >> 1) & 1), dw);   // rounds on bit 1 (:295-306)
+}
+
+// One output sample of BHW_ALGO_DIRECT: every k*phi term evaluated in registers.
+BHW_HD int64_t direct_sample_generic(const WinParams& wp, const SrcParams* src, const I2* rom, uint64_t n) {
+  int64_t cosv[BHW_MAX_TERMS];
+  cosv[0] = 0;
+  for (int k = 1; k < wp.m; ++k) {
+    const TermParams& t = wp.term[k - 1];
+    const uint64_t ph = ((uint64_t)t.kmul * n) & t.ph_mask;
+    int64_t s;
+    eval_source_generic(src[t.src], rom, ph, s, cosv[k]);
+  }
+  return tail_generic(wp, cosv);
+}
+
+// ============================================================================================
+// Trig-table builder bodies (BHW_ALGO_TABLE, stage 1)
+// ============================================================================================
+// A table holds one full period of the source's cosine output, one int32 per *distinct*
+// phase: value(ph) = T[ph >> drop] where `drop` counts the low phase bits the source ignores
+// (cordic_dds with PHASE_WIDTH > DATA_WIDTH only looks at the top DATA_WIDTH phase bits,
+// src/cordic_dds.vhd:159-162).  The job's source is the canonical one with those bits removed.
+// For the output-quadrant sources one core evaluation yields the four entries
+// e, e+Q, e+2Q, e+3Q (Q = entries/4): cos = c, -s, -c, s (negations wrap in negw bits).
+
+struct TabJob {
+  SrcParams sp;         // canonical source: phase width reduced so that no phase bit is ignored
+  int32_t* tab;         // the table (device memory), `entries` int32 words
+  uint32_t entries;     // 2^sp.pw
+  uint32_t fast;        // 1: the 32-bit fast core is exact for this source
+  uint32_t work_begin;  // prefix sum of work items (threads) over the jobs of a launch
+  uint32_t work;        // work items of this job: entries/4, or entries for SRC_INQ
+  uint32_t rom_off;     // Taylor ROM offset (I2 units) in the rom buffer
+  uint32_t pad;
+};
+
+// 32-bit CORDIC for output-quadrant sources whose registers fit int32 and never wrap:
+// SRC_DDS with 8 <= DW, DW+PRECISION <= 32 and SRC_HLS with 8 <= NW <= 30.  Amplitude is a
+// quarter of the register range, so x, y, z stay inside W-1 bits and the reference's wraps are
+// no-ops (DESIGN.md "no-wrap argument").  z0 >= 0, so stage 0 always takes the z >= 0 branch.
+BHW_HD void cordic_core_fast32(const SrcParams& p, uint32_t low, int32_t& vs, int32_t& vc) {
+  int32_t z = (int32_t)((low >> p.z_rshift) << p.z_lshift);
+  const int32_t g = (int32_t)p.gain;
+  int32_t x = g, y = g;  // stage 0: x - (0>>0), 0 + (x>>0)
+  z -= (int32_t)((c_atan[p.rom_sel][0] >> p.rom_shift) & p.rom_mask);
+  const int n_xy = p.n_xy, n_z = p.n_z;
+#pragma unroll 4
+  for (int i = 1; i < n_xy; ++i) {
+    const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
+    const int32_t xs = x >> i, ys = y >> i;
+    x -= d * ys;                      // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
+    y += d * xs;                      // z<0: y - (x>>i)
+    if (i < n_z) z -= d * (int32_t)((c_atan[p.rom_sel][i] >> p.rom_shift) & p.rom_mask);
+  }
+  vs = y >> p.out_shift;
+  vc = x >> p.out_shift;
+}
+
+// Work item `e` of a table job -> table entries.
+BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
+  const SrcParams& p = job.sp;
+  int32_t* T = job.tab;
+  if (p.kind == SRC_INQ) {  // one phase per item, no output symmetry
+    int64_t s, c;
+    eval_source_generic(p, rom, (uint64_t)e, s, c);
+    T[e] = (int32_t)c;
+    return;
+  }
+  const uint32_t low = e;
+  int64_t vs, vc;
+  if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom + job.rom_off, low, vs, vc);
+  else if (job.fast) { int32_t s32, c32; cordic_core_fast32(p, low, s32, c32); vs = s32; vc = c32; }
+  else cordic_core_generic(p, 0, low, vs, vc);
+  const uint32_t Q = job.entries >> 2;
+  const int64_t ns = wrapb(-vs, p.negw), nc = wrapb(-vc, p.negw);
+  T[e] = (int32_t)wrapb(vc, p.outw);           // quadrant 0: cos =  c
+  T[e + Q] = (int32_t)wrapb(ns, p.outw);       // quadrant 1: cos = -s
+  T[e + 2 * Q] = (int32_t)wrapb(nc, p.outw);   // quadrant 2: cos = -c
+  T[e + 3 * Q] = (int32_t)wrapb(vs, p.outw);   // quadrant 3: cos =  s
+}
+
+// ============================================================================================
+// Window synthesis bodies (BHW_ALGO_TABLE, stage 2)
+// ============================================================================================
+// Per window, resolved for the 32-bit fast tail (DAT_WIDTH <= 32):
+//   phase32_k(n) = n * kstep[k]  (mod 2^32)  - the harmonic's phase left-aligned in 32 bits, so
+//                                              the modulo 2^PHI_WIDTH of the RTL counter is free
+//   cos_k       = tabp[k][phase32_k >> idx_rsh[k]]
+//   RTL  : b_k  = (AAk*cos_k + 2^(DW-2)) >> (DW-1)          == (r>>1)+(r&1), r = p[2DW-2:DW-2]
+//          S    = acc0 + sum_k b_k * mul[k]                  (mod 2^32), mul[k] = -/+ 2^sh
+//          out  = S >> fin_shift                             (arithmetic)
+//          With sh = 32-(DW+2) (31-DW for the 2-term entity) the mod-2^32 wrap of S *is* the
+//          wrap of dsp_pp, acc0 carries AA0 and the rounding increment, and the final
+//          arithmetic shift delivers the DW-bit wrap of DT_WIN.
+//   HLS  : m_k  = (a_k*cos_k) >> (NW-2); S = (a0<<sh) + sum -/+ m_k<<sh, sh = 32-NW; out = S >> sh.
+struct WinRec {
+  uint32_t flags;        // WR_*
+  uint32_t m;            // terms
+  uint32_t dw;
+  uint32_t pw;
+  int32_t acc0;          // initial accumulator (32-bit form)
+  int32_t fin_shift;     // final arithmetic shift (32-bit form)
+  int32_t bshift;        // RTL: DW-1 ; HLS: NW-2
+  int32_t rnd;           // RTL: 2^(DW-2) ; HLS: 0
+  int32_t aa[BHW_MAX_TERMS];       // AA1.. in [1..m-1]; aa[0] = AA0
+  int32_t mul[BHW_MAX_TERMS];      // mul[k], k = 1..m-1
+  uint32_t kstep[BHW_MAX_TERMS];   // kstep[k], k = 1..m-1
+  uint32_t idx_rsh[BHW_MAX_TERMS];
+  uint32_t n_first;      // n of the window's first flat sample (stream offset folded in)
+  uint32_t gen_idx;      // index into the generic-parameter array when WR_GENERIC
+  uint32_t pad[2];
+  const int32_t* tabp[BHW_MAX_TERMS];  // tabp[k], k = 1..m-1: trig table of harmonic k
+  uint32_t pad2[2];
+};
+static_assert(sizeof(WinRec) == 224, "WinRec is copied to shared memory as 56 words");
+enum : uint32_t {
+  WR_WIDE = 1u,     // products need 64 bits (DW > 16)
+  WR_ACC64 = 2u,    // accumulator needs more than 32 bits (RTL DW 31..32): 64-bit tail
+  WR_HLS = 4u,      // HLS tail
+  WR_RTL2 = 8u,     // 2-term entity
+  WR_GENERIC = 16u  // fall back to the generic 64-bit body (direct evaluation)
+};
+
+// fast tail, one sample, 32-bit accumulator (unsigned arithmetic: the wrap is intended).
+// WIDE selects the 64-bit product.
+template <int M, bool WIDE>
+BHW_HD int32_t synth_sample32(const WinRec& r, uint32_t n) {
+  uint32_t S = (uint32_t)r.acc0;
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t ph = n * r.kstep[k];
+    const int32_t c = r.tabp[k][ph >> r.idx_rsh[k]];
+    int32_t b;
+    if (WIDE) b = (int32_t)(((int64_t)r.aa[k] * c + (int64_t)r.rnd) >> r.bshift);
+    else b = (r.aa[k] * c + r.rnd) >> r.bshift;
+    S += (uint32_t)b * (uint32_t)r.mul[k];
+  }
+  return (int32_t)S >> r.fin_shift;
+}
+
+// fast tail for RTL DW 31..32: 64-bit sum, then the entity's rounding on bit 0 / bit 1.
+template <int M>
+BHW_HD int32_t synth_sample64(const WinRec& r, uint32_t n) {
+  int64_t S = r.aa[0];
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t ph = n * r.kstep[k];
+    const int32_t c = r.tabp[k][ph >> r.idx_rsh[k]];
+    const int32_t b = (int32_t)wrapb(((int64_t)r.aa[k] * c + (int64_t)r.rnd) >> r.bshift, (int)r.dw);
+    S += (k & 1) ? -(int64_t)b : (int64_t)b;
+  }
+  if (r.flags & WR_RTL2) {
+    const int64_t pp = wrapb(S, (int)r.dw + 1);
+    return (int32_t)wrapb((pp >> 1) + (pp & 1), (int)r.dw);
+  }
+  const int64_t pp = wrapb(S, (int)r.dw + 2);
+  return (int32_t)wrapb((pp >> 2) + ((pp >> 1) & 1), (int)r.dw);
+}
+
+template <int M>
+BHW_HD int32_t synth_sample_m(const WinRec& r, uint32_t n) {
+  if (r.flags & WR_ACC64) return synth_sample64<M>(r, n);
+  if (r.flags & WR_WIDE) return synth_sample32<M, true>(r, n);
+  return synth_sample32<M, false>(r, n);
+}
+
+BHW_HD int32_t synth_sample(const WinRec& r, uint32_t n) {
+  switch (r.m) {
+    case 2: return synth_sample_m<2>(r, n);
+    case 3: return synth_sample_m<3>(r, n);
+    case 4: return synth_sample_m<4>(r, n);
+    case 5: return synth_sample_m<5>(r, n);
+    default: return synth_sample_m<7>(r, n);
+  }
+}
+
+// Parameters of windows that take the generic body inside a batch launch.
+struct GenRec {
+  WinParams wp;
+  SrcParams src[2];
+  uint32_t rom_off;  // Taylor ROM offset (I2 units); both units of a 3-term window share one ROM
+  uint32_t pad[3];
+};
+
+}  // namespace bhw

@@ -1,0 +1,46 @@
+// bhw_launch.h - kernel argument blocks and launcher prototypes (bhw_kernels.cu <-> bhw_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bhw_device.cuh"
+
+namespace bhw {
+
+struct SynthArgs {
+  const WinRec* recs;        // [nrec] distinct window records
+  const uint32_t* win_rec;   // [nwin] record of each window; NULL: record 0 for every window
+  const uint64_t* flat_off;  // [nwin+1] first flat sample of each window; unused when uniform_pw >= 0
+  const GenRec* gens;        // parameters of WR_GENERIC windows
+  const I2* rom;             // Taylor ROM words (generic body only)
+  void* out;                 // int32 output, element 0 = flat sample flat_begin
+  uint64_t flat_begin;
+  uint64_t flat_count;
+  int32_t nwin;
+  int32_t uniform_pw;        // >= 0: every window has 2^uniform_pw samples (no search needed)
+};
+
+struct DirectArgs {
+  WinParams wp;
+  SrcParams src[2];
+  const I2* rom;              // Taylor ROM (global)
+  uint32_t rom_smem_entries;  // > 0: copy that many ROM words to shared memory first
+  uint32_t pad;
+  uint64_t n_first;           // n of output element 0 (stream offset folded in)
+  uint64_t count;
+};
+
+struct SinCosArgs {
+  SrcParams src;
+  const I2* rom;
+  uint64_t n_first;
+  uint64_t count;
+};
+
+cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total_work, const I2* rom_dev,
+                               cudaStream_t stream);
+cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
+cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
+cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream);
+
+}  // namespace bhw

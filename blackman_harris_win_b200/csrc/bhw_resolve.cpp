@@ -1,0 +1,368 @@
+// bhw_resolve.cpp - host-side half of the ABI that needs no GPU: descriptor validation, resolution
+// of the entity generics into kernel parameter blocks, and the coefficient front end.
+#include <math.h>
+#include <string.h>
+
+#include "bhw_internal.h"
+
+namespace bhw {
+
+static inline int eff_prec(const bhw_desc* d) { return d->precision == 0 ? 1 : d->precision; }
+static inline int eff_lut(const bhw_desc* d) { return d->lut_size == 0 ? 9 : d->lut_size; }
+
+// internal width table of cordic_dds_scaled, DATA_WIDTH 8..32 (src/cordic_dds_scaled.vhd:102-107)
+static const int kScaledSize[25] = {15, 15, 15, 18, 21, 22, 23, 26, 30, 31, 32, 33, 38,
+                                    38, 38, 42, 42, 45, 47, 47, 47, 48, 48, 48, 48};
+
+static const int64_t kGainDds = 0x4DBA76D421AFll;  // src/cordic_dds.vhd:97
+static const int64_t kGainInq = 0x26DD3B6A10D8ll;  // src/cordic_dds48.vhd:110, win_function.cpp:83
+
+static int check_taylor_unit(int pw, int dw, int lut) {
+  const int d = pw - lut;
+  if (pw < 3) return BHW_E_PHI_WIDTH;
+  if (d > 2) {
+    if (d - 3 > 15) return BHW_E_LUT_SIZE;                      // cnt_exp is 16 bits (tay1_order.vhd:116-127)
+    if (dw < 19 && 19 + lut + dw > 48) return BHW_E_LUT_SIZE;   // slice of the 48-bit P (:501-502)
+    if (dw > 18 && 19 + lut + dw > 62) return BHW_E_LUT_SIZE;   // slice of the 62-bit product (:585-586)
+  }
+  return BHW_OK;
+}
+
+int validate_desc(const bhw_desc* d, bool for_window) {
+  if (!d) return BHW_E_NULL;
+  const int pw = d->phi_width, dw = d->dat_width;
+  if (for_window) {
+    const int m = d->win_type;
+    if (m != 2 && m != 3 && m != 4 && m != 5 && m != 7) return BHW_E_WIN_TYPE;
+  }
+  if (pw < 4 || pw > 30) return BHW_E_PHI_WIDTH;
+  switch (d->model) {
+    case BHW_MODEL_RTL:
+      switch (d->sin_type) {
+        case BHW_SIN_CORDIC: {
+          const int p = eff_prec(d);
+          if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
+          if (p < 1 || p > 7 || dw + p > 49) return BHW_E_PRECISION;
+          // the window entities never override PRECISION (src/hamming_win.vhd:153-157)
+          if (for_window && p != 1) return BHW_E_PRECISION;
+          break;
+        }
+        case BHW_SIN_CORDIC48:
+          if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
+          break;
+        case BHW_SIN_CORDIC_SCALED:
+          if (dw < 8 || dw > 32) return BHW_E_DAT_WIDTH;
+          break;
+        case BHW_SIN_TAYLOR: {
+          const int lut = eff_lut(d);
+          if (for_window && d->win_type != BHW_WIN_HAMMING && d->win_type != BHW_WIN_BH3TERM)
+            return BHW_E_SIN_TYPE;  // 4/5/7-term entities have no SIN_TYPE (src/bh_win_4term.vhd:57-61)
+          if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;  // ROM built through VHDL INTEGER
+          if (lut < 1 || lut > 16) return BHW_E_LUT_SIZE;
+          int st = check_taylor_unit(pw, dw, lut);
+          if (st) return st;
+          if (for_window && d->win_type == BHW_WIN_BH3TERM) {
+            // "must set LUT_SIZE < (PHASE_WIDTH - 3)": the two units would sit in different
+            // latency branches (src/bh_win_3term.vhd:30-31,221-233)
+            if (pw - lut == 3) return BHW_E_LUT_SIZE;
+            if ((st = check_taylor_unit(pw - 1, dw, lut))) return st;
+          }
+          break;
+        }
+        default:
+          return BHW_E_SIN_TYPE;
+      }
+      break;
+    case BHW_MODEL_HLS:
+      if (d->sin_type != BHW_SIN_CORDIC) return BHW_E_SIN_TYPE;
+      if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;
+      if (pw > dw + 2) return BHW_E_PHI_WIDTH;  // init_t would be truncated by dat_t (win_function.cpp:88)
+      break;
+    case BHW_MODEL_CPP:
+      if (for_window) return BHW_E_MODEL;  // cpp/ has no window model
+      if (d->sin_type != BHW_SIN_CORDIC) return BHW_E_SIN_TYPE;
+      if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;
+      break;
+    default:
+      return BHW_E_MODEL;
+  }
+  if (d->algo < BHW_ALGO_AUTO || d->algo > BHW_ALGO_TABLE) return BHW_E_ARG;
+  if (!for_window) return BHW_OK;
+  if (d->stream_offset != 0 && d->stream_offset != 1) return BHW_E_ARG;
+  if (d->reserved != 0) return BHW_E_ARG;
+  for (int k = 0; k < d->win_type; k++) {
+    const int64_t v = d->aa[k];
+    // an AAk port is DAT_WIDTH raw bits: accept the signed or the unsigned reading of them
+    if (v < -((int64_t)1 << (dw - 1)) || v >= ((int64_t)1 << dw)) return BHW_E_COEFF;
+    // the HLS a_k are plain non-wrapping integers below 2^(NWIDTH-1)
+    if (d->model == BHW_MODEL_HLS && v >= ((int64_t)1 << (dw - 1))) return BHW_E_COEFF;
+  }
+  return BHW_OK;
+}
+
+int resolve_source(const bhw_desc* d, int unit, SrcParams* sp) {
+  memset(sp, 0, sizeof(*sp));
+  const int pw = d->phi_width - unit, dw = d->dat_width;
+  sp->pw = pw;
+  sp->dw = dw;
+  sp->rom_mask = -1;
+  if (d->model == BHW_MODEL_HLS) {
+    sp->kind = SRC_HLS;
+    sp->w = sp->zw = dw + 2;                 // dat_t
+    sp->n_xy = dw;                           // NWIDTH passes
+    sp->n_z = dw - 1;                        // lut_angle[NWIDTH-1]
+    sp->rom_sel = 0;
+    sp->rom_shift = 47 - dw;
+    sp->rom_mask = 0xFFFFFFFFFFll;
+    sp->gain = kGainInq >> (46 - dw);
+    if (pw - 1 < dw) { sp->z_rshift = 0; sp->z_lshift = dw - pw + 2; }
+    else { sp->z_rshift = pw - dw; sp->z_lshift = 2; }
+    sp->out_shift = 2;
+    sp->negw = dw + 2;
+    sp->outw = dw;
+    return BHW_OK;
+  }
+  if (d->model == BHW_MODEL_CPP) {
+    sp->kind = SRC_CPP;
+    sp->w = sp->zw = 64;                     // long long, never wraps
+    sp->n_xy = dw;
+    sp->n_z = dw - 1;
+    sp->rom_sel = 1;
+    sp->rom_shift = 47 - dw;
+    sp->rom_mask = 0xFFFFFFFFFFFFll;
+    sp->gain = kGainInq >> (46 - dw);
+    if (pw - 1 < dw) { sp->z_rshift = 0; sp->z_lshift = dw - pw + 1; }
+    else { sp->z_rshift = pw - dw; sp->z_lshift = 1; }
+    sp->out_shift = 2;
+    sp->negw = 0;                            // ones' complement
+    sp->outw = 32;                           // int(dat_c)
+    return BHW_OK;
+  }
+  switch (d->sin_type) {
+    case BHW_SIN_CORDIC: {
+      const int p = eff_prec(d), w = dw + p;
+      sp->kind = SRC_DDS;
+      sp->w = sp->zw = w;
+      sp->n_xy = sp->n_z = dw - 1;
+      sp->rom_sel = 0;
+      sp->rom_shift = 49 - w;
+      sp->gain = kGainDds >> (49 - w);
+      if (pw >= dw) { sp->z_rshift = pw - dw; sp->z_lshift = p; }
+      else { sp->z_rshift = 0; sp->z_lshift = dw - pw + p; }
+      sp->out_shift = p;
+      sp->negw = dw;
+      sp->outw = dw;
+      return BHW_OK;
+    }
+    case BHW_SIN_CORDIC48:
+    case BHW_SIN_CORDIC_SCALED: {
+      const int size = d->sin_type == BHW_SIN_CORDIC48 ? 48 : kScaledSize[dw - 8];
+      const int dwph = d->sin_type == BHW_SIN_CORDIC48 ? 48 : (size < pw ? pw : size);
+      sp->kind = SRC_INQ;
+      sp->w = size;
+      sp->zw = dwph;
+      sp->n_xy = dw;
+      sp->n_z = dw - 1;
+      sp->rom_sel = 1;
+      sp->rom_shift = 48 - dwph;
+      sp->gain = kGainInq >> (48 - size);
+      sp->z_rshift = 0;
+      sp->z_lshift = dwph - pw;
+      sp->out_shift = size - dw;
+      sp->negw = size;                       // used for the -GAIN start vector
+      sp->outw = dw;
+      return BHW_OK;
+    }
+    case BHW_SIN_TAYLOR: {
+      const int lut = eff_lut(d), dd = pw - lut;
+      sp->kind = SRC_TAYLOR;
+      sp->w = sp->zw = dw;
+      sp->lut = lut;
+      sp->negw = dw;
+      sp->outw = dw;
+      sp->tay_xs = 19 + lut;
+      if (dd < 2) { sp->tay_mode = TAY_LESS; sp->tay_ashift = lut - pw + 2; }
+      else if (dd == 2) { sp->tay_mode = TAY_EQ; sp->tay_ashift = 0; }
+      else {
+        sp->tay_mode = dw < 19 ? TAY_DSP : TAY_WIDE;
+        sp->tay_ashift = pw - lut - 2;
+        sp->tay_cbits = pw - lut - 2;
+        const int stage = pw - lut - 3;
+        sp->tay_pi = (int64_t)round(M_PI * ldexp(1.0, 17 - stage));  // tay1_order.vhd:131
+      }
+      return BHW_OK;
+    }
+  }
+  return BHW_E_SIN_TYPE;
+}
+
+TabLookup table_lookup_for(const SrcParams& sp) {
+  TabLookup t;
+  const uint32_t n = 1u << sp.pw;
+  if (sp.kind == SRC_INQ) {  // no output symmetry: one entry per phase
+    t.idx_mask = n - 1; t.idx_shift = 0; t.neg_bit = 0; t.entries = n;
+    return t;
+  }
+  // half a period; phases that differ only in bits the source drops share an entry
+  int drop = sp.kind == SRC_TAYLOR ? 0 : sp.z_rshift;
+  if (sp.kind == SRC_TAYLOR && sp.tay_mode == TAY_LESS) drop = 0;
+  t.idx_mask = (n >> 1) - 1;
+  t.idx_shift = (uint32_t)drop;
+  t.neg_bit = n >> 1;
+  t.entries = (n >> 1) >> drop;
+  return t;
+}
+
+int resolve_window(const bhw_desc* d, WinParams* wp, SrcParams src[2]) {
+  int st = validate_desc(d, true);
+  if (st) return st;
+  memset(wp, 0, sizeof(*wp));
+  const int m = d->win_type, dw = d->dat_width, pw = d->phi_width;
+  wp->m = m; wp->dw = dw; wp->pw = pw;
+  wp->stream_offset = d->stream_offset;
+  wp->elem64 = dw > 32;
+  wp->tail = d->model == BHW_MODEL_HLS ? TAIL_HLS : (m == 2 ? TAIL_RTL2 : TAIL_RTLM);
+  for (int k = 0; k < m; k++) {
+    const int sh = 64 - dw;
+    wp->aa[k] = (int64_t)((uint64_t)d->aa[k] << sh) >> sh;  // raw bits -> signed
+  }
+  if ((st = resolve_source(d, 0, &src[0]))) return st;
+  wp->nsrc = 1;
+  const bool taylor = d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR;
+  if (taylor && m == 3) {
+    if ((st = resolve_source(d, 1, &src[1]))) return st;
+    wp->nsrc = 2;
+  }
+  for (int k = 1; k < m; k++) {
+    TermParams& t = wp->term[k - 1];
+    if (taylor) {  // every unit owns a +1 counter; harmonic 2 is a PHASE_WIDTH-1 unit (bh_win_3term.vhd:221-233)
+      t.kmul = 1; t.src = k - 1; t.ph_mask = (1u << (pw - (k - 1))) - 1;
+    } else {       // ph_in_k += k (src/bh_win_7term.vhd:176-197); HLS: cordic(k*i) (win_function.cpp:361-366)
+      t.kmul = (uint32_t)k; t.src = 0; t.ph_mask = (1u << pw) - 1;
+    }
+  }
+  return BHW_OK;
+}
+
+// ---- coefficient front end -----------------------------------------------------------------
+// Real-valued sets as the reference spells them (README.md:30-41 for the list of variants).
+static const double kCoef[10][BHW_MAX_TERMS] = {
+    {0.5434783, 1.0 - 0.5434783},                        // Hamming       src/tb/tb_windows.vhd:123-124
+    {0.5, 0.5},                                          // Hann          src/hamming_win.vhd:14-16
+    {0.42, 0.5, 0.08},                                   // Blackman      src/tb/tb_windows.vhd:114-116
+    {0.4243801, 0.4973406, 0.0782793},                   // BH 3-term     src/bh_win_3term.vhd:20
+    {0.355768, 0.487396, 0.144323, 0.012604},            // Nuttall       src/bh_win_4term.vhd:16-17
+    {0.35875, 0.48829, 0.14128, 0.01168},                // BH 4-term     src/tb/tb_windows.vhd:103-106
+    {0.3635819, 0.4891775, 0.1365995, 0.0106411},        // Blackman-Nuttall src/bh_win_4term.vhd:18-19
+    {1.000, 1.930, 1.290, 0.388, 0.030},                 // Flat-top      src/tb/tb_windows.vhd:90-94
+    {0.3232153788877343, 0.4714921439576260, 0.1755341299601972, 0.0284969901061499,
+     0.0012613570882927},                                // BH 5-term     src/bh_win_5term.vhd:14-19
+    {0.271220360585039, 0.433444612327442, 0.218004122892930, 0.065785343295606, 0.010761867305342,
+     0.000770012710581, 0.000013680883060}};             // BH 7-term     src/tb/tb_windows.vhd:67-73
+static const int kTerms[10] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7};
+
+static int variant_coeffs(int variant, int rule, double a[BHW_MAX_TERMS], int* nterms) {
+  if (variant < 1 || variant > 10) return BHW_E_VARIANT;
+  if (rule != BHW_RULE_TB && rule != BHW_RULE_HLS) return BHW_E_VARIANT;
+  const int m = kTerms[variant - 1];
+  for (int k = 0; k < BHW_MAX_TERMS; k++) a[k] = k < m ? kCoef[variant - 1][k] : 0.0;
+  if (rule == BHW_RULE_HLS && variant == 3)  // the HLS Blackman uses 0.21/0.25/0.04 (win_function.cpp:206-208)
+    for (int k = 0; k < m; k++) a[k] *= 0.5;
+  *nterms = m;
+  return BHW_OK;
+}
+
+}  // namespace bhw
+
+using namespace bhw;
+
+extern "C" {
+
+int bhw_version(void) { return BHW_VERSION; }
+
+const char* bhw_strerror(int s) {
+  switch (s) {
+    case BHW_OK: return "ok";
+    case BHW_E_NULL: return "null pointer";
+    case BHW_E_WIN_TYPE: return "win_type must be 2, 3, 4, 5 or 7";
+    case BHW_E_SIN_TYPE: return "sin_type unknown or not available for this entity/model";
+    case BHW_E_MODEL: return "model unknown or not applicable to this call";
+    case BHW_E_PHI_WIDTH: return "phi_width out of range";
+    case BHW_E_DAT_WIDTH: return "dat_width out of range for this sin/cos source";
+    case BHW_E_PRECISION: return "cordic_dds PRECISION out of range";
+    case BHW_E_LUT_SIZE: return "TAYLOR LUT_SIZE invalid for this PHI_WIDTH/DAT_WIDTH";
+    case BHW_E_COEFF: return "coefficient does not fit dat_width bits";
+    case BHW_E_RANGE: return "sample range outside the window or batch";
+    case BHW_E_ELEM: return "output element size mismatch";
+    case BHW_E_CUDA: return "CUDA runtime error";
+    case BHW_E_NO_DEVICE: return "no usable CUDA device";
+    case BHW_E_ALLOC: return "allocation failed";
+    case BHW_E_VARIANT: return "unknown window variant or quantisation rule";
+    case BHW_E_ARG: return "invalid argument";
+    default: return "unknown status";
+  }
+}
+
+int bhw_validate(const bhw_desc* d) { return validate_desc(d, true); }
+
+int bhw_elem_bytes(const bhw_desc* d) { return d && d->dat_width > 32 ? 8 : 4; }
+
+int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS], int32_t* nterms) {
+  if (!a_out) return BHW_E_NULL;
+  int m = 0;
+  int st = variant_coeffs(variant, rule, a_out, &m);
+  if (st) return st;
+  if (nterms) *nterms = m;
+  return BHW_OK;
+}
+
+int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS], int32_t* win_type) {
+  if (!aa_out) return BHW_E_NULL;
+  double a[BHW_MAX_TERMS];
+  int m = 0;
+  int st = variant_coeffs(variant, rule, a, &m);
+  if (st) return st;
+  if (dat_width < 4 || dat_width > 48) return BHW_E_DAT_WIDTH;
+  double scale;
+  if (rule == BHW_RULE_TB) {
+    // integer(a * S) with S per entity: src/tb/tb_windows.vhd:75-81 (7-term), :96-100 (5-term),
+    // :108-111 (4-term), :118-120 (3-term), :126-127 (2-term)
+    if (m == 3) scale = ldexp(1.0, dat_width) - 16.0;
+    else if (m == 4) scale = ldexp(1.0, dat_width) - 1.0;
+    else if (m == 5) scale = ldexp(1.0, dat_width - 2) - 1.0;
+    else scale = ldexp(1.0, dat_width - 1) - 1.0;
+  } else {
+    // round(a * (2^(NW-1)-1)) for types 1-4, 2^(NW-2)-1 for 5 and 7 (win_function.cpp:176-355)
+    scale = m >= 5 ? ldexp(1.0, dat_width - 2) - 1.0 : ldexp(1.0, dat_width - 1) - 1.0;
+  }
+  for (int k = 0; k < BHW_MAX_TERMS; k++) aa_out[k] = k < m ? (int64_t)round(a[k] * scale) : 0;
+  if (win_type) *win_type = m;
+  return BHW_OK;
+}
+
+int bhw_batch_total(const bhw_desc* descs, int nwin, uint64_t* total) {
+  if (!descs || !total) return BHW_E_NULL;
+  if (nwin < 0) return BHW_E_ARG;
+  uint64_t t = 0;
+  for (int i = 0; i < nwin; i++) {
+    if (descs[i].phi_width < 4 || descs[i].phi_width > 30) return BHW_E_PHI_WIDTH;
+    t += 1ull << descs[i].phi_width;
+  }
+  *total = t;
+  return BHW_OK;
+}
+
+// Contiguous, balanced shards whose boundaries are multiples of 4 samples (one 128-bit store)
+// whenever the total allows it.
+int bhw_shard_range(uint64_t total, int rank, int nranks, uint64_t* begin, uint64_t* count) {
+  if (!begin || !count) return BHW_E_NULL;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return BHW_E_ARG;
+  const uint64_t quads = total / 4, rem = total % 4;
+  const uint64_t q0 = quads * (uint64_t)rank / (uint64_t)nranks;
+  const uint64_t q1 = quads * (uint64_t)(rank + 1) / (uint64_t)nranks;
+  *begin = q0 * 4;
+  *count = (q1 - q0) * 4 + (rank == nranks - 1 ? rem : 0);
+  return BHW_OK;
+}
+
+}  // extern "C"

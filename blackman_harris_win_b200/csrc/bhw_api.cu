@@ -1,5 +1,5 @@
-// bhw_api.cu - the GPU half of the C ABI (include/bhw.h): planning, trig-table cache,
-// descriptor upload, launches, host-buffer pipelines and the single-process multi-GPU form.
+// bhw_api.cu - the GPU half of the C ABI (include/bhw.h): plans, trig tables, sine ROM cache,
+// launches, the host-buffer pipeline and the single-process multi-GPU form.
 //
 // There is deliberately no CPU evaluation path in this file: every generate/sincos entry point
 // ends in a kernel launch or returns an error.
@@ -10,6 +10,8 @@
 
 #include <atomic>
 #include <map>
+#include <new>
+#include <unordered_map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -34,27 +36,64 @@ static int cuda_fail(cudaError_t e, const char* where) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
-// ---- per-device persistent state -------------------------------------------------------------
-struct CachedTable {
-  int32_t* ptr = nullptr;
-  uint32_t entries = 0;
-  cudaEvent_t ready = nullptr;  // recorded after the build, waited on by consumers
+// ---- optional per-kernel timing (bhw_timing_*) -------------------------------------------------
+struct TimedSpan { int cls; int dev; cudaEvent_t a, b; };
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+static std::vector<TimedSpan> g_spans;                 // recorded, not yet read
+static std::vector<cudaEvent_t> g_event_pool[64];      // reusable events per device
+static double g_time_ms[BHW_KERNEL_CLASSES] = {0, 0, 0, 0};
+static uint64_t g_time_n[BHW_KERNEL_CLASSES] = {0, 0, 0, 0};
+
+static cudaEvent_t pool_event(int dev) {
+  if (!g_event_pool[dev].empty()) { cudaEvent_t e = g_event_pool[dev].back(); g_event_pool[dev].pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return e;
+}
+
+// Brackets one launch with events on its stream when timing is on.
+struct LaunchTimer {
+  TimedSpan sp{0, 0, nullptr, nullptr};
+  cudaStream_t stream;
+  bool on;
+  LaunchTimer(int cls, cudaStream_t s) : stream(s), on(g_timing.load() != 0) {
+    if (!on) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { on = false; return; }
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    sp.cls = cls; sp.dev = dev; sp.a = pool_event(dev); sp.b = pool_event(dev);
+    if (!sp.a || !sp.b) { on = false; return; }
+    cudaEventRecord(sp.a, stream);
+  }
+  ~LaunchTimer() {
+    if (!on) return;
+    cudaEventRecord(sp.b, stream);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_spans.push_back(sp);
+  }
 };
+
+// ---- per-device persistent state -------------------------------------------------------------
 struct CachedRom {
   I2* ptr = nullptr;
   uint32_t entries = 0;
 };
+struct HostPipe {  // staging of the *_host entry points: two device chunks, two streams
+  cudaStream_t s_gen = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  char* buf[2] = {nullptr, nullptr};
+  size_t buf_bytes = 0;
+};
 struct DeviceState {
-  std::mutex call_mu;  // serialises table-path calls on a device while the cache is in use
   std::mutex mu;
-  std::map<std::string, CachedTable> tables;  // key: bytes of the canonical SrcParams
-  std::map<uint32_t, CachedRom> roms;         // key: dw << 8 | lut
+  std::map<uint32_t, CachedRom> roms;  // key: dw << 8 | lut
+  std::mutex pipe_mu;                  // one host-buffer call at a time per device
+  HostPipe pipe;
 };
 static DeviceState g_dev[64];
 
-static std::string key_of(const SrcParams& sp) { return std::string((const char*)&sp, sizeof(sp)); }
-
-static int get_rom(int dev, int dw, int lut, cudaStream_t stream, const I2** out) {
+static int get_rom(int dev, int dw, int lut, const I2** out) {
   DeviceState& ds = g_dev[dev];
   std::lock_guard<std::mutex> lk(ds.mu);
   const uint32_t key = ((uint32_t)dw << 8) | (uint32_t)lut;
@@ -70,34 +109,55 @@ static int get_rom(int dev, int dw, int lut, cudaStream_t stream, const I2** out
     if (e != cudaSuccess) { cudaFree(cr.ptr); return cuda_fail(e, "cudaMemcpy(rom)"); }
     it = ds.roms.emplace(key, cr).first;
   }
-  (void)stream;
   *out = it->second.ptr;
   return BHW_OK;
 }
 
-// ---- one batch call --------------------------------------------------------------------------
+static int current_device(int* dev) {
+  cudaError_t e = cudaGetDevice(dev);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return BHW_E_NO_DEVICE; }
+  if (*dev < 0 || *dev >= 64) return BHW_E_NO_DEVICE;
+  return BHW_OK;
+}
+
+}  // namespace bhw
+
+// ---- the plan object ---------------------------------------------------------------------------
 struct PlanTable {
-  SrcParams canon;
+  bhw::SrcParams canon;
   uint32_t drop;
   uint32_t entries;
   int32_t* ptr;
-  bool build;       // must be built in this call
-  bool transient;   // free after the call (cache disabled)
 };
 
-struct Plan {
-  std::vector<WinRec> recs;
-  std::vector<GenRec> gens;
+struct bhw_plan {
+  int dev = 0;
+  int nwin = 0;
+  bool elem64 = false;
+  bool transient = false;        // one-shot plan: device memory comes from / returns to the stream pool
+  uint64_t total = 0;            // flat samples of the whole batch
+  // DAT_WIDTH <= 32: table + synthesis path
+  std::vector<bhw::WinRec> recs;
+  std::vector<bhw::GenRec> gens;
   std::vector<uint32_t> win_rec;
   std::vector<uint64_t> flat_off;
   std::vector<PlanTable> tables;
-  std::vector<TabJob> jobs;
-  const I2* rom = nullptr;  // at most one Taylor ROM (DW, LUT) per call is supported per window set
+  std::vector<bhw::TabJob> jobs;
+  const bhw::I2* rom = nullptr;  // at most one Taylor (DW, LUT_SIZE) ROM per plan
   int uniform_pw = -1;
   bool all_same = false;
+  char* blob_dev = nullptr;      // [recs][gens][jobs][flat_off][win_rec]
+  size_t o_recs = 0, o_gens = 0, o_jobs = 0, o_off = 0, o_wr = 0;
+  uint32_t table_work = 0;
+  bool tables_built = false;
+  // DAT_WIDTH > 32: one direct launch per window
+  std::vector<bhw::DirectArgs> wins64;
+  std::mutex mu;
 };
 
-static int find_or_add_table(int dev, Plan& plan, const SrcParams& sp, cudaStream_t stream, int* index) {
+namespace bhw {
+
+static int find_or_add_table(bhw_plan& plan, const SrcParams& sp, int* index) {
   uint32_t drop;
   const SrcParams canon = canonical_source(sp, &drop);
   for (size_t i = 0; i < plan.tables.size(); i++)
@@ -107,84 +167,100 @@ static int find_or_add_table(int dev, Plan& plan, const SrcParams& sp, cudaStrea
   pt.drop = drop;
   pt.entries = 1u << canon.pw;
   pt.ptr = nullptr;
-  pt.build = true;
-  pt.transient = !g_cache_enabled.load();
-  const size_t bytes = (size_t)pt.entries * sizeof(int32_t);
-  if (pt.transient) {
-    BHW_CUDA(cudaMallocAsync((void**)&pt.ptr, bytes, stream));
-  } else {
-    DeviceState& ds = g_dev[dev];
-    std::lock_guard<std::mutex> lk(ds.mu);
-    auto it = ds.tables.find(key_of(canon));
-    if (it != ds.tables.end()) {
-      pt.ptr = it->second.ptr;
-      pt.build = false;
-      BHW_CUDA(cudaStreamWaitEvent(stream, it->second.ready, 0));
-    } else {
-      CachedTable ct;
-      ct.entries = pt.entries;
-      BHW_CUDA(cudaMalloc((void**)&ct.ptr, bytes));
-      cudaError_t e = cudaEventCreateWithFlags(&ct.ready, cudaEventDisableTiming);
-      if (e != cudaSuccess) { cudaFree(ct.ptr); return cuda_fail(e, "cudaEventCreate"); }
-      ds.tables.emplace(key_of(canon), ct);
-      pt.ptr = ct.ptr;
-    }
-  }
   plan.tables.push_back(pt);
   *index = (int)plan.tables.size() - 1;
   return BHW_OK;
 }
 
-static int plan_batch(int dev, const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
-                      cudaStream_t stream, Plan& plan) {
+static void plan_free_device(bhw_plan& plan, cudaStream_t stream) {
+  for (auto& pt : plan.tables)
+    if (pt.ptr) { if (plan.transient) cudaFreeAsync(pt.ptr, stream); else cudaFree(pt.ptr); pt.ptr = nullptr; }
+  if (plan.blob_dev) {
+    if (plan.transient) cudaFreeAsync(plan.blob_dev, stream); else cudaFree(plan.blob_dev);
+    plan.blob_dev = nullptr;
+  }
+}
+
+static cudaError_t plan_alloc(bhw_plan& plan, void** p, size_t bytes, cudaStream_t stream) {
+  return plan.transient ? cudaMallocAsync(p, bytes, stream) : cudaMalloc(p, bytes);
+}
+
+// Resolve a batch into `plan` and make it resident on the current device.  [hint_begin,
+// hint_begin+hint_count) is the flat range the caller is going to execute (the whole batch for
+// persistent plans): windows outside it get no tables, and BHW_ALGO_AUTO sends a short request
+// into a long window through the direct body instead of building a table for it.
+static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t hint_begin,
+                      uint64_t hint_count, cudaStream_t stream) {
+  int st = current_device(&plan.dev);
+  if (st) return st;
+  plan.nwin = nwin;
+  bool any64 = false, any32 = false;
+  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
+  if (any64 && any32) return BHW_E_ELEM;
+  plan.elem64 = any64;
   plan.flat_off.resize((size_t)nwin + 1);
-  plan.win_rec.resize((size_t)nwin);
-  // pass 1: flat offsets; windows with a byte-identical descriptor share one record
-  std::vector<int> rec_desc;       // descriptor index that defines record i
-  std::vector<uint64_t> rec_used;  // requested samples that fall into windows of record i
   uint64_t off = 0;
+  for (int w = 0; w < nwin; w++) {
+    if (descs[w].phi_width < 4 || descs[w].phi_width > 30) return BHW_E_PHI_WIDTH;
+    plan.flat_off[w] = off;
+    off += 1ull << descs[w].phi_width;
+  }
+  plan.flat_off[nwin] = off;
+  plan.total = off;
+  if (hint_begin > off || hint_count > off - hint_begin) return BHW_E_RANGE;
+  const uint64_t hint_end = hint_begin + hint_count;
+
+  if (plan.elem64) {
+    // DAT_WIDTH > 32: window by window through the direct kernel
+    plan.wins64.resize((size_t)nwin);
+    for (int w = 0; w < nwin; w++) {
+      DirectArgs& a = plan.wins64[(size_t)w];
+      memset(&a, 0, sizeof(a));
+      if ((st = resolve_window(&descs[w], &a.wp, a.src))) return st;
+    }
+    return BHW_OK;
+  }
+
+  // pass 1: windows with a byte-identical descriptor share one record
+  plan.win_rec.resize((size_t)nwin);
+  std::vector<int> rec_desc;       // descriptor index that defines record i
+  std::vector<uint64_t> rec_used;  // hinted samples that fall into windows of record i
+  std::unordered_map<std::string, int> seen;
   const int pw0 = descs[0].phi_width;
   bool uniform = true;
-  const uint64_t req_end = flat_begin + flat_count;
   for (int w = 0; w < nwin; w++) {
     const bhw_desc& d = descs[w];
-    plan.flat_off[w] = off;
-    if (d.phi_width < 4 || d.phi_width > 30) return BHW_E_PHI_WIDTH;
-    const uint64_t N = 1ull << d.phi_width;
     if (d.phi_width != pw0) uniform = false;
-    const uint64_t lo = off > flat_begin ? off : flat_begin;
-    const uint64_t hi = off + N < req_end ? off + N : req_end;
+    const uint64_t b = plan.flat_off[w], e = plan.flat_off[w + 1];
+    const uint64_t lo = b > hint_begin ? b : hint_begin;
+    const uint64_t hi = e < hint_end ? e : hint_end;
     const uint64_t used = lo < hi ? hi - lo : 0;
-    off += N;
-    int ri = -1;
+    int ri;
     if (w > 0 && !memcmp(&d, &descs[w - 1], sizeof(d))) ri = (int)plan.win_rec[w - 1];
-    else
-      for (size_t i = 0; i < rec_desc.size(); i++)
-        if (!memcmp(&d, &descs[rec_desc[i]], sizeof(d))) { ri = (int)i; break; }
-    if (ri < 0) { ri = (int)rec_desc.size(); rec_desc.push_back(w); rec_used.push_back(0); }
+    else {
+      auto ins = seen.emplace(std::string((const char*)&d, sizeof(d)), (int)rec_desc.size());
+      ri = ins.first->second;
+      if (ins.second) { rec_desc.push_back(w); rec_used.push_back(0); }
+    }
     plan.win_rec[w] = (uint32_t)ri;
     rec_used[(size_t)ri] += used;
   }
-  plan.flat_off[nwin] = off;
-  if (flat_begin > off || flat_count > off - flat_begin) return BHW_E_RANGE;
   plan.uniform_pw = uniform ? pw0 : -1;
   plan.all_same = rec_desc.size() == 1;
 
-  // pass 2: validate + resolve every distinct descriptor (touched by the request or not), and
-  // give the touched ones their trig tables
+  // pass 2: validate + resolve every distinct descriptor, give the used ones their trig tables
+  struct TabRef { int rec, k, tab; };
+  std::vector<TabRef> refs;
+  plan.recs.reserve(rec_desc.size());
   for (size_t i = 0; i < rec_desc.size(); i++) {
     const bhw_desc& d = descs[rec_desc[i]];
     WinParams wp; SrcParams src[2];
-    int st = resolve_window(&d, &wp, src);
-    if (st) return st;
-    if (wp.elem64) return BHW_E_ELEM;  // 64-bit windows go through the per-window direct path
+    if ((st = resolve_window(&d, &wp, src))) return st;
     WinRec r;
     memset(&r, 0, sizeof(r));
     r.n_first = (uint32_t)wp.stream_offset;
     bool generic = d.algo == BHW_ALGO_DIRECT || !fast_tail_exact(wp);
     if (!generic && d.algo == BHW_ALGO_AUTO && rec_used[i]) {
-      // a short request into a long window: building the table would cost more than evaluating
-      // the requested samples directly
       uint64_t table_work = 0;
       for (int u = 0; u < wp.nsrc; u++) {
         uint32_t drop;
@@ -203,8 +279,8 @@ static int plan_batch(int dev, const bhw_desc* descs, int nwin, uint64_t flat_be
       plan.gens.push_back(g);
       if (src[0].kind == SRC_TAYLOR && rec_used[i]) {
         const I2* rom = nullptr;
-        if ((st = get_rom(dev, src[0].dw, src[0].lut, stream, &rom))) return st;
-        if (plan.rom && plan.rom != rom) return BHW_E_ARG;  // one Taylor (DW, LUT_SIZE) per call
+        if ((st = get_rom(plan.dev, src[0].dw, src[0].lut, &rom))) return st;
+        if (plan.rom && plan.rom != rom) return BHW_E_ARG;  // one Taylor (DW, LUT_SIZE) per batch
         plan.rom = rom;
       }
     } else {
@@ -214,20 +290,21 @@ static int plan_batch(int dev, const bhw_desc* descs, int nwin, uint64_t flat_be
           const TermParams& t = wp.term[k - 1];
           const SrcParams& sp = src[t.src];
           int ti;
-          if ((st = find_or_add_table(dev, plan, sp, stream, &ti))) return st;
-          const PlanTable& pt = plan.tables[(size_t)ti];
-          r.tabp[k] = pt.ptr;
+          if ((st = find_or_add_table(plan, sp, &ti))) return st;
           r.kstep[k] = t.kmul << (32 - sp.pw);
-          r.idx_rsh[k] = (uint32_t)(32 - (sp.pw - (int)pt.drop));
+          r.idx_rsh[k] = (uint32_t)(32 - (sp.pw - (int)plan.tables[(size_t)ti].drop));
+          refs.push_back({(int)i, k, ti});
         }
       }
     }
     plan.recs.push_back(r);
   }
+
+  // device memory: tables, then the metadata blob (records carry the table pointers)
   uint32_t work = 0;
-  for (size_t i = 0; i < plan.tables.size(); i++) {
-    PlanTable& pt = plan.tables[i];
-    if (!pt.build) continue;
+  for (auto& pt : plan.tables) {
+    cudaError_t e = plan_alloc(plan, (void**)&pt.ptr, (size_t)pt.entries * sizeof(int32_t), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "alloc(trig table)");
     TabJob j;
     memset(&j, 0, sizeof(j));
     j.sp = pt.canon;
@@ -236,123 +313,232 @@ static int plan_batch(int dev, const bhw_desc* descs, int nwin, uint64_t flat_be
     j.fast = fast32_ok(pt.canon) ? 1u : 0u;
     j.work_begin = work;
     j.work = pt.canon.kind == SRC_INQ ? pt.entries : pt.entries / 4;
-    j.rom_off = 0;
     if (pt.canon.kind == SRC_TAYLOR) {
       const I2* rom = nullptr;
-      int st = get_rom(dev, pt.canon.dw, pt.canon.lut, stream, &rom);
-      if (st) return st;
-      if (plan.rom && plan.rom != rom) return BHW_E_ARG;  // one Taylor (DW, LUT_SIZE) per call
+      if ((st = get_rom(plan.dev, pt.canon.dw, pt.canon.lut, &rom))) return st;
+      if (plan.rom && plan.rom != rom) return BHW_E_ARG;  // one Taylor (DW, LUT_SIZE) per batch
       plan.rom = rom;
     }
     work += j.work;
     plan.jobs.push_back(j);
   }
-  return BHW_OK;
-}
+  plan.table_work = work;
+  for (const TabRef& tr : refs) plan.recs[(size_t)tr.rec].tabp[tr.k] = plan.tables[(size_t)tr.tab].ptr;
 
-static int current_device(int* dev) {
-  cudaError_t e = cudaGetDevice(dev);
-  if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return BHW_E_NO_DEVICE; }
-  if (*dev < 0 || *dev >= 64) return BHW_E_NO_DEVICE;
-  return BHW_OK;
-}
-
-static void release_transient(Plan& plan, cudaStream_t stream) {
-  for (auto& pt : plan.tables)
-    if (pt.transient && pt.ptr) { cudaFreeAsync(pt.ptr, stream); pt.ptr = nullptr; }
-}
-
-// Forget cached tables that were planned but whose build launch never happened.
-static void drop_unbuilt(int dev, Plan& plan) {
-  DeviceState& ds = g_dev[dev];
-  std::lock_guard<std::mutex> lk(ds.mu);
-  for (auto& pt : plan.tables)
-    if (pt.build && !pt.transient) {
-      auto it = ds.tables.find(key_of(pt.canon));
-      if (it != ds.tables.end()) {
-        cudaFree(it->second.ptr);
-        cudaEventDestroy(it->second.ready);
-        ds.tables.erase(it);
-      }
-    }
-}
-
-// The table-path executor: upload the call's metadata in one copy, build missing tables in one
-// launch, synthesise the flat range in one launch.
-static int run_batch_i32(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
-                         void* out_dev, cudaStream_t stream) {
-  int dev;
-  int st = current_device(&dev);
-  if (st) return st;
-  // a cached table is visible to other threads from the moment it is planned, so planning and
-  // the build launch of one call must not interleave with another call on the same device
-  std::unique_lock<std::mutex> call_lock(g_dev[dev].call_mu, std::defer_lock);
-  if (g_cache_enabled.load()) call_lock.lock();
-  Plan plan;
-  st = plan_batch(dev, descs, nwin, flat_begin, flat_count, stream, plan);
-  if (st) { release_transient(plan, stream); drop_unbuilt(dev, plan); return st; }
-  if (!flat_count) { release_transient(plan, stream); return BHW_OK; }
-
-  // one metadata blob: [recs][gens][jobs][flat_off][win_rec]
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-  const size_t o_recs = 0;
-  const size_t o_gens = align16(o_recs + plan.recs.size() * sizeof(WinRec));
-  const size_t o_jobs = align16(o_gens + plan.gens.size() * sizeof(GenRec));
-  const size_t o_off = align16(o_jobs + plan.jobs.size() * sizeof(TabJob));
-  const bool need_off = plan.uniform_pw < 0;
-  const size_t o_wr = align16(o_off + (need_off ? plan.flat_off.size() * sizeof(uint64_t) : 0));
-  const bool need_wr = !plan.all_same;
-  const size_t total = align16(o_wr + (need_wr ? plan.win_rec.size() * sizeof(uint32_t) : 0));
+  const bool need_off = plan.uniform_pw < 0, need_wr = !plan.all_same;
+  plan.o_recs = 0;
+  plan.o_gens = align16(plan.o_recs + plan.recs.size() * sizeof(WinRec));
+  plan.o_jobs = align16(plan.o_gens + plan.gens.size() * sizeof(GenRec));
+  plan.o_off = align16(plan.o_jobs + plan.jobs.size() * sizeof(TabJob));
+  plan.o_wr = align16(plan.o_off + (need_off ? plan.flat_off.size() * sizeof(uint64_t) : 0));
+  const size_t total = align16(plan.o_wr + (need_wr ? plan.win_rec.size() * sizeof(uint32_t) : 0));
   std::vector<char> blob(total);
-  memcpy(blob.data() + o_recs, plan.recs.data(), plan.recs.size() * sizeof(WinRec));
-  if (!plan.gens.empty()) memcpy(blob.data() + o_gens, plan.gens.data(), plan.gens.size() * sizeof(GenRec));
-  if (!plan.jobs.empty()) memcpy(blob.data() + o_jobs, plan.jobs.data(), plan.jobs.size() * sizeof(TabJob));
-  if (need_off) memcpy(blob.data() + o_off, plan.flat_off.data(), plan.flat_off.size() * sizeof(uint64_t));
-  if (need_wr) memcpy(blob.data() + o_wr, plan.win_rec.data(), plan.win_rec.size() * sizeof(uint32_t));
-  char* blob_dev = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&blob_dev, total, stream);
-  if (e != cudaSuccess) {
-    release_transient(plan, stream);
-    drop_unbuilt(dev, plan);
-    return cuda_fail(e, "cudaMallocAsync(meta)");
-  }
-  bool built = plan.jobs.empty();
+  memcpy(blob.data() + plan.o_recs, plan.recs.data(), plan.recs.size() * sizeof(WinRec));
+  if (!plan.gens.empty()) memcpy(blob.data() + plan.o_gens, plan.gens.data(), plan.gens.size() * sizeof(GenRec));
+  if (!plan.jobs.empty()) memcpy(blob.data() + plan.o_jobs, plan.jobs.data(), plan.jobs.size() * sizeof(TabJob));
+  if (need_off) memcpy(blob.data() + plan.o_off, plan.flat_off.data(), plan.flat_off.size() * sizeof(uint64_t));
+  if (need_wr) memcpy(blob.data() + plan.o_wr, plan.win_rec.data(), plan.win_rec.size() * sizeof(uint32_t));
+  cudaError_t e = plan_alloc(plan, (void**)&plan.blob_dev, total, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "alloc(plan metadata)");
   // pageable source: the runtime stages it before returning, so `blob` may die with this frame
-  e = cudaMemcpyAsync(blob_dev, blob.data(), total, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess && !plan.jobs.empty()) {
-    const TabJob& last = plan.jobs.back();
-    e = launch_table_build((const TabJob*)(blob_dev + o_jobs), (int)plan.jobs.size(),
-                           last.work_begin + last.work, plan.rom, stream);
-    if (e == cudaSuccess) { g_launches++; built = true; }
-    if (e == cudaSuccess) {
-      DeviceState& ds = g_dev[dev];
-      std::lock_guard<std::mutex> lk(ds.mu);
-      for (auto& pt : plan.tables)
-        if (pt.build && !pt.transient) {
-          auto it = ds.tables.find(key_of(pt.canon));
-          if (it != ds.tables.end()) cudaEventRecord(it->second.ready, stream);
+  e = cudaMemcpyAsync(plan.blob_dev, blob.data(), total, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(plan metadata)");
+  if (!plan.transient) {
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize(plan)");
+  }
+  if (!need_off) { plan.flat_off.clear(); plan.flat_off.shrink_to_fit(); }
+  return BHW_OK;
+}
+
+static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
+                        cudaStream_t stream) {
+  if (flat_begin > plan.total || flat_count > plan.total - flat_begin) return BHW_E_RANGE;
+  if (!flat_count) return BHW_OK;
+  if (!out_dev) return BHW_E_NULL;
+  if (plan.elem64) {
+    uint64_t off = 0;
+    for (int w = 0; w < plan.nwin; w++) {
+      DirectArgs a = plan.wins64[(size_t)w];
+      const uint64_t N = 1ull << a.wp.pw;
+      const uint64_t lo = off > flat_begin ? off : flat_begin;
+      const uint64_t hi = off + N < flat_begin + flat_count ? off + N : flat_begin + flat_count;
+      if (lo < hi) {
+        a.n_first = (lo - off) + (uint64_t)a.wp.stream_offset;
+        a.count = hi - lo;
+        cudaError_t e;
+        {
+          LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
+          e = launch_direct_window(a, (int64_t*)out_dev + (lo - flat_begin), stream);
         }
+        if (e != cudaSuccess) return cuda_fail(e, "k_direct_window");
+        g_launches++;
+      }
+      off += N;
     }
+    return BHW_OK;
   }
-  if (e == cudaSuccess) {
-    SynthArgs a;
-    a.recs = (const WinRec*)(blob_dev + o_recs);
-    a.win_rec = need_wr ? (const uint32_t*)(blob_dev + o_wr) : nullptr;
-    a.flat_off = need_off ? (const uint64_t*)(blob_dev + o_off) : nullptr;
-    a.gens = (const GenRec*)(blob_dev + o_gens);
-    a.rom = plan.rom;
-    a.out = out_dev;
-    a.flat_begin = flat_begin;
-    a.flat_count = flat_count;
-    a.nwin = nwin;
-    a.uniform_pw = plan.uniform_pw;
+  std::lock_guard<std::mutex> lk(plan.mu);
+  cudaError_t e = cudaSuccess;
+  if (!plan.jobs.empty() && (!plan.tables_built || !g_cache_enabled.load())) {
+    LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
+    e = launch_table_build((const TabJob*)(plan.blob_dev + plan.o_jobs), (int)plan.jobs.size(),
+                           plan.table_work, plan.rom, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "k_table_build");
+    g_launches++;
+    plan.tables_built = true;
+  }
+  SynthArgs a;
+  a.recs = (const WinRec*)(plan.blob_dev + plan.o_recs);
+  a.win_rec = !plan.all_same ? (const uint32_t*)(plan.blob_dev + plan.o_wr) : nullptr;
+  a.flat_off = plan.uniform_pw < 0 ? (const uint64_t*)(plan.blob_dev + plan.o_off) : nullptr;
+  a.gens = (const GenRec*)(plan.blob_dev + plan.o_gens);
+  a.rom = plan.rom;
+  a.out = out_dev;
+  a.flat_begin = flat_begin;
+  a.flat_count = flat_count;
+  a.nwin = plan.nwin;
+  a.uniform_pw = plan.uniform_pw;
+  {
+    LaunchTimer tm(BHW_KERNEL_SYNTH, stream);
     e = launch_synth(a, stream);
-    if (e == cudaSuccess) g_launches++;
   }
-  cudaFreeAsync(blob_dev, stream);
-  release_transient(plan, stream);
-  if (!built) drop_unbuilt(dev, plan);
-  if (e != cudaSuccess) return cuda_fail(e, "launch");
+  if (e != cudaSuccess) return cuda_fail(e, "k_synth");
+  g_launches++;
+  return BHW_OK;
+}
+
+// windows touched by a flat range
+static int shard_windows(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
+                         int* first_win, int* nwin_touched, uint64_t* local_begin) {
+  uint64_t off = 0;
+  int first = -1, last = -1;
+  uint64_t first_off = 0;
+  const uint64_t end = flat_begin + flat_count;
+  for (int w = 0; w < nwin; w++) {
+    if (descs[w].phi_width < 4 || descs[w].phi_width > 30) return BHW_E_PHI_WIDTH;
+    const uint64_t N = 1ull << descs[w].phi_width;
+    if (flat_count && off < end && off + N > flat_begin) {
+      if (first < 0) { first = w; first_off = off; }
+      last = w;
+    }
+    off += N;
+  }
+  if (flat_begin > off || flat_count > off - flat_begin) return BHW_E_RANGE;
+  if (first < 0) { *first_win = 0; *nwin_touched = 0; *local_begin = 0; return BHW_OK; }
+  *first_win = first;
+  *nwin_touched = last - first + 1;
+  *local_begin = flat_begin - first_off;
+  return BHW_OK;
+}
+
+// One-shot: plan the touched windows from the stream's memory pool, execute, release.
+static int run_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
+                     cudaStream_t stream) {
+  if (!descs) return BHW_E_NULL;
+  if (nwin <= 0) return BHW_E_ARG;
+  if (!out_dev && flat_count) return BHW_E_NULL;
+  // validate every descriptor of the batch, touched or not: errors do not depend on the range
+  for (int w = 0; w < nwin; w++) {
+    int st = validate_desc(&descs[w], true);
+    if (st) return st;
+  }
+  bool any64 = false, any32 = false;
+  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
+  if (any64 && any32) return BHW_E_ELEM;
+  int first = 0, touched = 0;
+  uint64_t local = 0;
+  int st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
+  if (st) return st;
+  if (!touched) return BHW_OK;
+  bhw_plan plan;
+  plan.transient = true;
+  st = plan_build(plan, descs + first, touched, local, flat_count, stream);
+  if (!st) st = plan_execute(plan, local, flat_count, out_dev, stream);
+  plan_free_device(plan, stream);
+  return st;
+}
+
+// ---- host-buffer pipeline ----------------------------------------------------------------------
+static const uint64_t kHostChunkBytes = 64ull << 20;
+
+static cudaError_t pipe_ensure(HostPipe& p) {
+  cudaError_t e = cudaSuccess;
+  if (!p.s_gen && (e = cudaStreamCreateWithFlags(&p.s_gen, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  if (!p.s_copy && (e = cudaStreamCreateWithFlags(&p.s_copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  for (int i = 0; i < 2; i++) {
+    if (!p.ev_gen[i] && (e = cudaEventCreateWithFlags(&p.ev_gen[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (!p.ev_copy[i] && (e = cudaEventCreateWithFlags(&p.ev_copy[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (!p.buf[i] && (e = cudaMalloc((void**)&p.buf[i], kHostChunkBytes)) != cudaSuccess) return e;
+  }
+  p.buf_bytes = kHostChunkBytes;
+  return cudaSuccess;
+}
+
+static void pipe_release(HostPipe& p) {
+  for (int i = 0; i < 2; i++) {
+    if (p.buf[i]) cudaFree(p.buf[i]);
+    if (p.ev_gen[i]) cudaEventDestroy(p.ev_gen[i]);
+    if (p.ev_copy[i]) cudaEventDestroy(p.ev_copy[i]);
+  }
+  if (p.s_gen) cudaStreamDestroy(p.s_gen);
+  if (p.s_copy) cudaStreamDestroy(p.s_copy);
+  p = HostPipe();
+}
+
+// Generates chunk c on the compute stream while chunk c-1 drains to the host on the copy stream.
+// The batch is planned once; the device staging buffers and streams are kept per device.
+static int run_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
+                          void* out_host) {
+  if (!descs) return BHW_E_NULL;
+  if (nwin <= 0) return BHW_E_ARG;
+  if (!out_host && flat_count) return BHW_E_NULL;
+  for (int w = 0; w < nwin; w++) {
+    int st = validate_desc(&descs[w], true);
+    if (st) return st;
+  }
+  bool any64 = false, any32 = false;
+  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
+  if (any64 && any32) return BHW_E_ELEM;
+  const size_t esz = any64 ? 8 : 4;
+  int first = 0, touched = 0;
+  uint64_t local = 0;
+  int st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
+  if (st) return st;
+  if (!touched) return BHW_OK;
+  int dev;
+  if ((st = current_device(&dev))) return st;
+  DeviceState& ds = g_dev[dev];
+  std::lock_guard<std::mutex> pipe_lock(ds.pipe_mu);
+  HostPipe& p = ds.pipe;
+  cudaError_t e = pipe_ensure(p);
+  if (e != cudaSuccess) { pipe_release(p); return cuda_fail(e, "host pipeline setup"); }
+  bhw_plan plan;
+  plan.transient = true;
+  st = plan_build(plan, descs + first, touched, local, flat_count, p.s_gen);
+  const uint64_t chunk = p.buf_bytes / esz;
+  uint64_t done = 0;
+  for (int c = 0; !st && e == cudaSuccess && done < flat_count; c++) {
+    const int b = c & 1;
+    const uint64_t cnt = flat_count - done < chunk ? flat_count - done : chunk;
+    if (c >= 2 && (e = cudaStreamWaitEvent(p.s_gen, p.ev_copy[b], 0)) != cudaSuccess) break;  // buffer drained?
+    st = plan_execute(plan, local + done, cnt, p.buf[b], p.s_gen);
+    if (st) break;
+    if ((e = cudaEventRecord(p.ev_gen[b], p.s_gen)) != cudaSuccess) break;
+    if ((e = cudaStreamWaitEvent(p.s_copy, p.ev_gen[b], 0)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync((char*)out_host + done * esz, p.buf[b], cnt * esz, cudaMemcpyDeviceToHost,
+                             p.s_copy)) != cudaSuccess) break;
+    if ((e = cudaEventRecord(p.ev_copy[b], p.s_copy)) != cudaSuccess) break;
+    done += cnt;
+  }
+  plan_free_device(plan, p.s_gen);
+  cudaError_t e2 = cudaStreamSynchronize(p.s_gen);
+  if (e == cudaSuccess) e = e2;
+  e2 = cudaStreamSynchronize(p.s_copy);
+  if (e == cudaSuccess) e = e2;
+  if (st) return st;
+  if (e != cudaSuccess) return cuda_fail(e, "host pipeline");
   return BHW_OK;
 }
 
@@ -367,115 +553,20 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
   const uint64_t N = 1ull << d->phi_width;
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
   if (a.src[0].kind == SRC_TAYLOR) {
-    if ((st = get_rom(dev, a.src[0].dw, a.src[0].lut, stream, &a.rom))) return st;
+    if ((st = get_rom(dev, a.src[0].dw, a.src[0].lut, &a.rom))) return st;
     const uint32_t entries = 1u << a.src[0].lut;
     a.rom_smem_entries = entries * sizeof(I2) <= 32768 ? entries : 0;  // the sine LUT lives in shared memory
   }
   a.n_first = n0 + (uint64_t)d->stream_offset;
   a.count = count;
-  cudaError_t e = launch_direct_window(a, out_dev, stream);
+  if (!count) return BHW_OK;
+  cudaError_t e;
+  {
+    LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
+    e = launch_direct_window(a, out_dev, stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "k_direct_window");
-  if (count) g_launches++;
-  return BHW_OK;
-}
-
-static bool batch_is_elem64(const bhw_desc* descs, int nwin, bool* mixed) {
-  bool any64 = false, any32 = false;
-  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
-  *mixed = any64 && any32;
-  return any64;
-}
-
-static int run_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
-                     cudaStream_t stream) {
-  if (!descs) return BHW_E_NULL;
-  if (nwin <= 0) return BHW_E_ARG;
-  if (!out_dev && flat_count) return BHW_E_NULL;
-  bool mixed;
-  const bool e64 = batch_is_elem64(descs, nwin, &mixed);
-  if (mixed) return BHW_E_ELEM;
-  if (!e64) return run_batch_i32(descs, nwin, flat_begin, flat_count, out_dev, stream);
-  // DAT_WIDTH > 32: window by window through the direct kernel
-  uint64_t off = 0;
-  for (int w = 0; w < nwin; w++) {
-    int st = validate_desc(&descs[w], true);
-    if (st) return st;
-    off += 1ull << descs[w].phi_width;
-  }
-  if (flat_begin > off || flat_count > off - flat_begin) return BHW_E_RANGE;
-  off = 0;
-  for (int w = 0; w < nwin; w++) {
-    const uint64_t N = 1ull << descs[w].phi_width;
-    const uint64_t lo = off > flat_begin ? off : flat_begin;
-    const uint64_t hi = off + N < flat_begin + flat_count ? off + N : flat_begin + flat_count;
-    if (lo < hi) {
-      int st = run_direct(&descs[w], lo - off, hi - lo, (int64_t*)out_dev + (lo - flat_begin), stream);
-      if (st) return st;
-    }
-    off += N;
-  }
-  return BHW_OK;
-}
-
-// ---- host-buffer pipeline ----------------------------------------------------------------------
-// Generates chunk c on the compute stream while chunk c-1 drains to the host on the copy stream.
-static int run_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
-                          void* out_host) {
-  if (!descs) return BHW_E_NULL;
-  if (nwin <= 0) return BHW_E_ARG;
-  if (!out_host && flat_count) return BHW_E_NULL;
-  bool mixed;
-  const bool e64 = batch_is_elem64(descs, nwin, &mixed);
-  if (mixed) return BHW_E_ELEM;
-  const size_t esz = e64 ? 8 : 4;
-  if (!flat_count) {
-    // still validate
-    return run_batch(descs, nwin, flat_begin, 0, (void*)descs, nullptr);
-  }
-  const uint64_t chunk = flat_count < (16ull << 20) ? flat_count : (16ull << 20);  // samples per chunk
-  cudaStream_t s_gen = nullptr, s_copy = nullptr;
-  cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-  char* buf[2] = {nullptr, nullptr};
-  int st = BHW_OK;
-  cudaError_t e = cudaSuccess;
-  const int nbuf = flat_count > chunk ? 2 : 1;
-  do {
-    if ((e = cudaStreamCreateWithFlags(&s_gen, cudaStreamNonBlocking)) != cudaSuccess) break;
-    if ((e = cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking)) != cudaSuccess) break;
-    for (int i = 0; i < nbuf && e == cudaSuccess; i++) {
-      e = cudaMalloc((void**)&buf[i], chunk * esz);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_gen[i], cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming);
-    }
-    if (e != cudaSuccess) break;
-    uint64_t done = 0;
-    for (int c = 0; done < flat_count; c++) {
-      const int b = c % nbuf;
-      const uint64_t cnt = flat_count - done < chunk ? flat_count - done : chunk;
-      if (c >= nbuf) {  // buffer b must have drained before it is overwritten
-        if ((e = cudaStreamWaitEvent(s_gen, ev_copy[b], 0)) != cudaSuccess) break;
-      }
-      st = run_batch(descs, nwin, flat_begin + done, cnt, buf[b], s_gen);
-      if (st) break;
-      if ((e = cudaEventRecord(ev_gen[b], s_gen)) != cudaSuccess) break;
-      if ((e = cudaStreamWaitEvent(s_copy, ev_gen[b], 0)) != cudaSuccess) break;
-      if ((e = cudaMemcpyAsync((char*)out_host + done * esz, buf[b], cnt * esz, cudaMemcpyDeviceToHost,
-                               s_copy)) != cudaSuccess) break;
-      if ((e = cudaEventRecord(ev_copy[b], s_copy)) != cudaSuccess) break;
-      done += cnt;
-    }
-  } while (0);
-  if (s_gen) { cudaError_t e2 = cudaStreamSynchronize(s_gen); if (e == cudaSuccess) e = e2; }
-  if (s_copy) { cudaError_t e2 = cudaStreamSynchronize(s_copy); if (e == cudaSuccess) e = e2; }
-  for (int i = 0; i < 2; i++) {
-    if (buf[i]) cudaFree(buf[i]);
-    if (ev_gen[i]) cudaEventDestroy(ev_gen[i]);
-    if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
-  }
-  if (s_gen) cudaStreamDestroy(s_gen);
-  if (s_copy) cudaStreamDestroy(s_copy);
-  if (st) return st;
-  if (e != cudaSuccess) return cuda_fail(e, "host pipeline");
+  g_launches++;
   return BHW_OK;
 }
 
@@ -541,6 +632,57 @@ int bhw_generate_batch_multi(const bhw_desc* descs, int nwin, int ngpus, void* c
   return st;
 }
 
+int bhw_shard_windows(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
+                      int* first_win, int* nwin_touched, uint64_t* local_begin) {
+  if (!descs || !first_win || !nwin_touched || !local_begin) return BHW_E_NULL;
+  if (nwin <= 0) return BHW_E_ARG;
+  return shard_windows(descs, nwin, flat_begin, flat_count, first_win, nwin_touched, local_begin);
+}
+
+int bhw_plan_create(const bhw_desc* descs, int nwin, bhw_plan** plan_out) {
+  if (!descs || !plan_out) return BHW_E_NULL;
+  *plan_out = nullptr;
+  if (nwin <= 0) return BHW_E_ARG;
+  for (int w = 0; w < nwin; w++) {
+    int st = validate_desc(&descs[w], true);
+    if (st) return st;
+  }
+  bhw_plan* p = new (std::nothrow) bhw_plan();
+  if (!p) return BHW_E_ALLOC;
+  uint64_t total = 0;
+  int st = bhw_batch_total(descs, nwin, &total);
+  if (!st) st = plan_build(*p, descs, nwin, 0, total, nullptr);
+  if (st) { plan_free_device(*p, nullptr); delete p; return st; }
+  *plan_out = p;
+  return BHW_OK;
+}
+
+int bhw_plan_execute(bhw_plan* plan, uint64_t flat_begin, uint64_t flat_count, void* out_dev, void* stream) {
+  if (!plan) return BHW_E_NULL;
+  int dev;
+  int st = current_device(&dev);
+  if (st) return st;
+  if (dev != plan->dev) return BHW_E_ARG;
+  return plan_execute(*plan, flat_begin, flat_count, out_dev, (cudaStream_t)stream);
+}
+
+int bhw_plan_total(const bhw_plan* plan, uint64_t* total_samples) {
+  if (!plan || !total_samples) return BHW_E_NULL;
+  *total_samples = plan->total;
+  return BHW_OK;
+}
+
+int bhw_plan_destroy(bhw_plan* plan) {
+  if (!plan) return BHW_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != plan->dev) cudaSetDevice(plan->dev);
+  plan_free_device(*plan, nullptr);  // cudaFree waits for work that still uses the memory
+  if (prev != plan->dev) cudaSetDevice(prev);
+  delete plan;
+  return BHW_OK;
+}
+
 int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t n0, uint64_t count,
                void* stream) {
   if (!d) return BHW_E_NULL;
@@ -553,11 +695,15 @@ int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t
   SinCosArgs a;
   memset(&a, 0, sizeof(a));
   if ((st = resolve_source(d, 0, &a.src))) return st;
-  if (a.src.kind == SRC_TAYLOR && (st = get_rom(dev, a.src.dw, a.src.lut, (cudaStream_t)stream, &a.rom))) return st;
+  if (a.src.kind == SRC_TAYLOR && (st = get_rom(dev, a.src.dw, a.src.lut, &a.rom))) return st;
   a.n_first = n0;
   a.count = count;
   if (!count || (!out_sin_dev && !out_cos_dev)) return BHW_OK;
-  cudaError_t e = launch_sincos(a, out_sin_dev, out_cos_dev, d->dat_width > 32, (cudaStream_t)stream);
+  cudaError_t e;
+  {
+    LaunchTimer tm(BHW_KERNEL_SINCOS, (cudaStream_t)stream);
+    e = launch_sincos(a, out_sin_dev, out_cos_dev, d->dat_width > 32, (cudaStream_t)stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "k_sincos");
   g_launches++;
   return BHW_OK;
@@ -570,14 +716,14 @@ int bhw_cache_clear(void) {
   cudaGetDevice(&prev);
   for (int g = 0; g < ndev && g < 64; g++) {
     DeviceState& ds = g_dev[g];
+    std::lock_guard<std::mutex> pl(ds.pipe_mu);
     std::lock_guard<std::mutex> lk(ds.mu);
-    if (ds.tables.empty() && ds.roms.empty()) continue;
+    if (ds.roms.empty() && !ds.pipe.s_gen) continue;
     cudaSetDevice(g);
     cudaDeviceSynchronize();
-    for (auto& kv : ds.tables) { cudaFree(kv.second.ptr); cudaEventDestroy(kv.second.ready); }
     for (auto& kv : ds.roms) cudaFree(kv.second.ptr);
-    ds.tables.clear();
     ds.roms.clear();
+    pipe_release(ds.pipe);
   }
   cudaSetDevice(prev);
   return BHW_OK;
@@ -586,6 +732,48 @@ int bhw_cache_clear(void) {
 int bhw_set_table_cache(int enabled) {
   g_cache_enabled.store(enabled ? 1 : 0);
   return BHW_OK;
+}
+
+int bhw_timing_enable(int enabled) {
+  g_timing.store(enabled ? 1 : 0);
+  return BHW_OK;
+}
+
+// fold finished spans into the per-class totals (synchronises on each span's end event)
+static int timing_collect() {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int st = BHW_OK;
+  for (auto& sp : g_spans) {
+    cudaSetDevice(sp.dev);
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (e == cudaSuccess) { g_time_ms[sp.cls] += (double)ms; g_time_n[sp.cls]++; }
+    else st = cuda_fail(e, "timing");
+    g_event_pool[sp.dev].push_back(sp.a);
+    g_event_pool[sp.dev].push_back(sp.b);
+  }
+  g_spans.clear();
+  cudaSetDevice(prev);
+  return st;
+}
+
+int bhw_timing_reset(void) {
+  int st = timing_collect();
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int i = 0; i < BHW_KERNEL_CLASSES; i++) { g_time_ms[i] = 0; g_time_n[i] = 0; }
+  return st;
+}
+
+int bhw_timing_read(int kernel_class, double* total_ms, uint64_t* launches) {
+  if (kernel_class < 0 || kernel_class >= BHW_KERNEL_CLASSES) return BHW_E_ARG;
+  int st = timing_collect();
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (total_ms) *total_ms = g_time_ms[kernel_class];
+  if (launches) *launches = g_time_n[kernel_class];
+  return st;
 }
 
 uint64_t bhw_launch_count(void) { return g_launches.load(); }

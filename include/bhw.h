@@ -19,7 +19,8 @@
  *     the entity's phase order: out[j] = DT_WIN for phase (n0 + j +
  *     stream_offset) mod 2^phi_width.
  *   - The library is re-entrant; its only persistent state is a per-device
- *     workspace/trig-table cache (bhw_cache_clear() drops it).
+ *     cache of TAYLOR sine ROMs and of the *_host staging buffers
+ *     (bhw_cache_clear() drops it).  Trig tables belong to plans.
  */
 #ifndef BHW_H_
 #define BHW_H_
@@ -29,6 +30,13 @@
 
 #ifdef __cplusplus
 extern "C" {
+#endif
+
+/* every entry point is exported; the library is built with -fvisibility=hidden */
+#if defined(__GNUC__)
+#define BHW_API __attribute__((visibility("default")))
+#else
+#define BHW_API
 #endif
 
 #define BHW_VERSION 0x000100 /* 0.1.0 */
@@ -118,15 +126,15 @@ typedef struct bhw_desc {
 } bhw_desc;
 
 /* ---- helpers ----------------------------------------------------------- */
-const char* bhw_strerror(int status);
-int bhw_version(void);
+BHW_API const char* bhw_strerror(int status);
+BHW_API int bhw_version(void);
 
 /* Check a descriptor exactly as the generators do.  Rejections correspond to
  * configurations the reference cannot elaborate or documents as invalid. */
-int bhw_validate(const bhw_desc* d);
+BHW_API int bhw_validate(const bhw_desc* d);
 
 /* 4 or 8: bytes per output element for this descriptor. */
-int bhw_elem_bytes(const bhw_desc* d);
+BHW_API int bhw_elem_bytes(const bhw_desc* d);
 
 /* Coefficient front end.  The reference leaves quantisation to the caller; the
  * rules it uses itself are in src/tb/tb_windows.vhd:75-127 (rule BHW_RULE_TB)
@@ -136,11 +144,11 @@ int bhw_elem_bytes(const bhw_desc* d);
  * 10 Blackman-Harris-7 (README.md:30-41).  Writes aa_out[0..6] (unused = 0)
  * and *win_type (2,3,4,5,7). */
 enum { BHW_RULE_TB = 0, BHW_RULE_HLS = 1 };
-int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS],
+BHW_API int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS],
                  int32_t* win_type);
 /* Real-valued coefficients of a variant as the reference spells them
  * (for rule TB; rule HLS halves variant 3: win_function.cpp:206-208). */
-int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS], int32_t* nterms);
+BHW_API int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS], int32_t* nterms);
 
 /* ---- generation: one window ------------------------------------------- */
 /* Replaces: one win_selector instance streaming `count` DT_WIN words
@@ -148,12 +156,12 @@ int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS], int32
  * win_function(win_type, i, &out) (hls/windows/window_test.cpp:93,193,
  * hls/windows/win_function.h:65-69).  out_dev: device buffer of `count`
  * elements. Range: n0 + count <= 2^phi_width. */
-int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, void* stream);
+BHW_API int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, void* stream);
 
 /* Same with a HOST output buffer: generates on the current device and copies
  * back (pinned staging, chunked, copy overlapped with generation).
  * Synchronises before returning. */
-int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t count);
+BHW_API int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t count);
 
 /* ---- generation: a batch of windows, sharded by flat sample range ------ */
 /* The batch is the concatenation of the nwin full windows in order; "flat"
@@ -162,17 +170,39 @@ int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t c
  * windows in a batch must share one element size.  This is the sharding
  * primitive: rank r of R calls it with its contiguous slice
  * (bhw_shard_range) - no collective is involved. */
-int bhw_batch_total(const bhw_desc* descs, int nwin, uint64_t* total_samples);
-int bhw_shard_range(uint64_t total_samples, int rank, int nranks, uint64_t* begin,
+BHW_API int bhw_batch_total(const bhw_desc* descs, int nwin, uint64_t* total_samples);
+BHW_API int bhw_shard_range(uint64_t total_samples, int rank, int nranks, uint64_t* begin,
                     uint64_t* count);
-int bhw_generate_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin,
+BHW_API int bhw_generate_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin,
                        uint64_t flat_count, void* out_dev, void* stream);
-int bhw_generate_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin,
+BHW_API int bhw_generate_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin,
                             uint64_t flat_count, void* out_host);
 /* Single-process multi-GPU form: device g (0..ngpus-1) receives shard g of the
  * flat range in outs_dev[g] (allocated by the caller on device g, at least
  * the bhw_shard_range count).  Synchronises all devices before returning. */
-int bhw_generate_batch_multi(const bhw_desc* descs, int nwin, int ngpus, void* const* outs_dev);
+BHW_API int bhw_generate_batch_multi(const bhw_desc* descs, int nwin, int ngpus, void* const* outs_dev);
+
+/* Which windows of a batch a flat range touches: descs[*first_win .. *first_win + *nwin_touched)
+ * and the range's offset inside that sub-batch.  A rank that owns flat slice [begin, begin+count)
+ * can plan only those windows. */
+BHW_API int bhw_shard_windows(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
+                      int* first_win, int* nwin_touched, uint64_t* local_begin);
+
+/* ---- plans: resolve once, execute many times ------------------------------ */
+/* A plan is a batch resolved and resident on the current device: per-window records, trig-table
+ * storage and (for TAYLOR) the sine ROM.  It corresponds to the elaborated entity instances of
+ * the reference (generics fixed at elaboration, src/win_selector.vhd:61-70); executing it is the
+ * ENABLE burst.  bhw_plan_execute writes flat samples [flat_begin, flat_begin+flat_count) of the
+ * batch to out_dev, stream-ordered, without host-side planning work.  Trig tables are built by
+ * the first execute and kept, unless the table cache is off (bhw_set_table_cache(0)), in which
+ * case every execute rebuilds them.  A plan must be executed and destroyed on the device it was
+ * created on; concurrent executes of one plan must use one stream. */
+typedef struct bhw_plan bhw_plan;
+BHW_API int bhw_plan_create(const bhw_desc* descs, int nwin, bhw_plan** plan_out);
+BHW_API int bhw_plan_execute(bhw_plan* plan, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
+                     void* stream);
+BHW_API int bhw_plan_total(const bhw_plan* plan, uint64_t* total_samples);
+BHW_API int bhw_plan_destroy(bhw_plan* plan);
 
 /* ---- sin/cos tables (the DDS entities on their own) -------------------- */
 /* Replaces: cordic_dds / cordic_dds48 / cordic_dds_scaled / taylor_sincos
@@ -181,16 +211,33 @@ int bhw_generate_batch_multi(const bhw_desc* descs, int nwin, int ngpus, void* c
  * cordic(phi, &cos, &sin) (hls/cordic/cordic.h:58-62) and the C++
  * cordic(theta, lut, &s, &c) (cpp/cordic_sincos.cpp:10).  win_type/aa are
  * ignored.  Either output may be NULL.  Elements as for bhw_generate. */
-int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t n0,
+BHW_API int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t n0,
                uint64_t count, void* stream);
 
 /* ---- cache / introspection --------------------------------------------- */
-int bhw_cache_clear(void);             /* free workspaces and cached trig tables  */
-int bhw_set_table_cache(int enabled);  /* 1 (default): keep trig tables between
-                                          calls; 0: rebuild them in every call   */
-uint64_t bhw_launch_count(void);       /* kernels launched by this library so far */
-const char* bhw_last_cuda_error(void); /* text of the last CUDA failure           */
-int bhw_device_count(void);
+BHW_API int bhw_cache_clear(void);             /* free the cached sine ROMs and host-pipeline staging */
+BHW_API int bhw_set_table_cache(int enabled);  /* 1 (default): a plan builds its trig tables on its
+                                          first execute and keeps them; 0: every execute
+                                          rebuilds them (one-shot calls always build)        */
+BHW_API uint64_t bhw_launch_count(void);       /* kernels launched by this library so far */
+BHW_API const char* bhw_last_cuda_error(void); /* text of the last CUDA failure           */
+BHW_API int bhw_device_count(void);
+
+/* ---- per-kernel device timing (for bench.py's roofline line) ------------- */
+/* When enabled, every kernel launch of the library is bracketed by CUDA events recorded on the
+ * launching stream.  bhw_timing_read() synchronises those events and returns, for one kernel
+ * class, the number of launches and their summed device time since the last reset.  Off by
+ * default; costs two cudaEventRecord per launch when on. */
+enum {
+  BHW_KERNEL_TABLE_BUILD = 0, /* k_table_build: sin/cos source evaluated once per distinct phase */
+  BHW_KERNEL_SYNTH = 1,       /* k_synth*: gather + multiply/round/sum tail + store             */
+  BHW_KERNEL_DIRECT = 2,      /* k_direct*: one thread per sample, sources evaluated in registers */
+  BHW_KERNEL_SINCOS = 3,      /* k_sincos                                                        */
+  BHW_KERNEL_CLASSES = 4
+};
+BHW_API int bhw_timing_enable(int enabled);
+BHW_API int bhw_timing_reset(void);
+BHW_API int bhw_timing_read(int kernel_class, double* total_ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -276,11 +276,11 @@ static int validate_source(const bhw_desc* d, int for_window) {
           return BHW_OK;
         case BHW_SIN_TAYLOR: {
           const int lut = eff_lut(d);
+          if (for_window && d->win_type != BHW_WIN_HAMMING && d->win_type != BHW_WIN_BH3TERM)
+            return BHW_E_SIN_TYPE;                              /* src/bh_win_4term.vhd:57-61 */
           if (dw < 4 || dw > 32) return BHW_E_DAT_WIDTH;
           if (lut < 1 || lut > 16) return BHW_E_LUT_SIZE;
           const int nunits = (for_window && d->win_type == BHW_WIN_BH3TERM) ? 2 : 1;
-          if (for_window && d->win_type != BHW_WIN_HAMMING && d->win_type != BHW_WIN_BH3TERM)
-            return BHW_E_SIN_TYPE;
           if (nunits == 2 && pw - lut == 3) return BHW_E_LUT_SIZE; /* src/bh_win_3term.vhd:30-31 */
           for (int u = 0; u < nunits; u++) {
             const int dd = (pw - u) - lut;

@@ -1,0 +1,60 @@
+"""Shared descriptor sets for the parity tests (CPU hostcheck tier and GPU tier)."""
+import blackman_harris_win_b200 as bhw
+
+VARIANT_DW = {1: 16, 2: 16, 3: 16, 4: 16, 5: 17, 6: 17, 7: 17, 8: 24, 9: 24, 10: 32}
+
+# BASELINE.json configs 1-4: name -> descriptor factory
+def baseline_configs():
+    return {
+        "cfg1_hamming_n1024_dw16": bhw.make_desc(2, 10, 16, [17808, 14959]),
+        "cfg1_hann_n1024_dw16": bhw.make_desc(2, 10, 16, [16384, 16384]),
+        "cfg2_bh4_n65536_dw17": bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531]),
+        "cfg3_bh7_n1m_dw32_dds48": bhw.make_desc(
+            7, 20, 32, [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379],
+            sin_type=bhw.SIN_CORDIC48),
+        "cfg3_bh7_n1m_dw32_dds": bhw.make_desc(
+            7, 20, 32, [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379]),
+        "cfg4_blackman_taylor_n16m_dw24": bhw.make_desc(
+            3, 24, 24, [7046424, 8388600, 1342176], sin_type=bhw.SIN_TAYLOR, lut_size=9),
+    }
+
+
+def rtl_sweep(pws=(4, 5, 7, 10, 13), extra_dws=(8, 12, 20, 31, 32, 33, 47),
+              sin_types=(bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR)):
+    """Every variant x phase width x data width x sin source the library accepts."""
+    out = []
+    for v in range(1, 11):
+        for pw in pws:
+            for dw in sorted(set((VARIANT_DW[v],) + tuple(extra_dws))):
+                for st in sin_types:
+                    d = bhw.variant_desc(v, pw, dw, sin_type=st)
+                    if bhw.validate(d) == 0:
+                        out.append(d)
+    return out
+
+
+def hls_sweep(cfgs):
+    out = []
+    for (np_, nw) in cfgs:
+        for t, v in HLS_TYPES.items():
+            out.append((t, bhw.variant_desc(v, np_, nw, model=bhw.MODEL_HLS)))
+    return out
+
+
+HLS_TYPES = {1: 1, 2: 2, 3: 3, 4: 6, 5: 9, 7: 10}  # win_function win_type -> README variant
+
+
+def edge_coeff_descs():
+    """Coefficient edge cases: negative, unsigned reading of the port bits, the most negative
+    value (b_k can wrap), zeros, all-ones."""
+    out = []
+    for dw in (8, 16, 17, 24, 30, 31, 32):
+        lo, hi = -(1 << (dw - 1)), (1 << (dw - 1)) - 1
+        for m in (2, 3, 4, 5, 7):
+            out.append(bhw.make_desc(m, 9, dw, [hi] * m))
+            out.append(bhw.make_desc(m, 9, dw, [lo] * m))
+            out.append(bhw.make_desc(m, 9, dw, [lo if k & 1 else hi for k in range(m)]))
+            out.append(bhw.make_desc(m, 9, dw, [(1 << dw) - 1] * m))   # raw bits, unsigned reading
+            out.append(bhw.make_desc(m, 9, dw, [0] * m))
+            out.append(bhw.make_desc(m, 9, dw, [-3, 5, -7, 11, -13, 17, -19][:m]))
+    return out

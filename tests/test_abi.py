@@ -1,0 +1,131 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/bhw.h declares, and its
+GPU-free entry points (validation, quantisation, sharding arithmetic) behave.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import blackman_harris_win_b200 as bhw
+from blackman_harris_win_b200 import api
+import harness as H
+
+HDR = os.path.join(H.ROOT, "include", "bhw.h")
+
+
+def declared_symbols():
+    txt = open(HDR).read()
+    return sorted(set(re.findall(r"BHW_API\s+[\w\s\*]+?\b(bhw_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(bhw.lib_path())
+    decl = declared_symbols()
+    assert len(decl) >= 19
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in include/bhw.h but not exported"
+    assert sorted(api.ABI_SYMBOLS) == decl
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(bhw.BhwDesc) == 10 * 4 + 7 * 8
+    assert bhw.BhwDesc.aa.offset == 40
+
+
+def test_version_and_strerror():
+    assert bhw.lib().bhw_version() == 0x000100
+    assert bhw.strerror(0) == "ok"
+    for code in range(-16, 0):
+        assert bhw.strerror(code) not in ("", "unknown status")
+    assert bhw.strerror(-99) == "unknown status"
+
+
+def test_quantize_matches_reference_rules():
+    # src/tb/tb_windows.vhd:75-127 worked examples
+    assert bhw.quantize(1, bhw.RULE_TB, 16) == ([17808, 14959, 0, 0, 0, 0, 0], 2)
+    assert bhw.quantize(2, bhw.RULE_TB, 16) == ([16384, 16384, 0, 0, 0, 0, 0], 2)   # 16383.5 ties up
+    assert bhw.quantize(6, bhw.RULE_TB, 17)[0][:4] == [47022, 64001, 18518, 1531]
+    assert bhw.quantize(3, bhw.RULE_TB, 24)[0][:3] == [7046424, 8388600, 1342176]
+    assert bhw.quantize(10, bhw.RULE_TB, 32)[0] == [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379]
+    assert bhw.quantize(8, bhw.RULE_TB, 16)[0][:5] == [16383, 31619, 21134, 6357, 491]
+    for v in range(1, 11):
+        for rule in (0, 1):
+            for dw in (8, 16, 17, 24, 32, 40, 48):
+                assert bhw.quantize(v, rule, dw) == H.orc_quantize(v, rule, dw)
+    with pytest.raises(bhw.BhwError):
+        bhw.quantize(11, 0, 16)
+    with pytest.raises(bhw.BhwError):
+        bhw.quantize(1, 2, 16)
+    assert bhw.variant_coeffs(3, bhw.RULE_HLS) == [0.21, 0.25, 0.04]
+
+
+def test_validate_rejections():
+    ok = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
+    assert bhw.validate(ok) == 0
+    assert bhw.validate(ok.copy(win_type=6)) == -2
+    assert bhw.validate(ok.copy(sin_type=bhw.SIN_TAYLOR)) == -3          # 4-term has no TAYLOR
+    assert bhw.validate(ok.copy(sin_type=9)) == -3
+    assert bhw.validate(ok.copy(model=7)) == -4
+    assert bhw.validate(ok.copy(model=bhw.MODEL_CPP)) == -4              # cpp/ has no window model
+    assert bhw.validate(ok.copy(phi_width=3)) == -5
+    assert bhw.validate(ok.copy(dat_width=49)) == -6
+    assert bhw.validate(ok.copy(precision=2)) == -7
+    assert bhw.validate(ok.copy(aa=[1 << 17, 0, 0, 0])) == -9
+    assert bhw.validate(ok.copy(stream_offset=2)) == -16
+    assert bhw.validate(ok.copy(reserved=1)) == -16
+    t3 = bhw.make_desc(3, 12, 16, [1, 1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=9)
+    assert bhw.validate(t3) == -8                                         # PHI_WIDTH - LUT_SIZE == 3
+    assert bhw.validate(t3.copy(phi_width=13)) == 0
+    assert bhw.validate(bhw.make_desc(2, 30, 16, [1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=9)) == -8  # STAGE > 15
+    assert bhw.validate(bhw.make_desc(2, 10, 33, [1, 1], sin_type=bhw.SIN_TAYLOR)) == -6
+    assert bhw.validate(bhw.make_desc(2, 20, 16, [1, 1], model=bhw.MODEL_HLS)) == -5  # NP > NW+2
+    assert bhw.lib().bhw_validate(None) == -1
+
+
+def test_shard_ranges_partition_the_flat_range():
+    for total in (0, 1, 3, 4, 5, 1023, 1024, 134217712, (1 << 26) * 10 + 7):
+        for r in (1, 2, 3, 4, 8):
+            pos = 0
+            sizes = []
+            for k in range(r):
+                b, c = bhw.shard_range(total, k, r)
+                assert b == pos
+                if k < r - 1:
+                    assert b % 4 == 0 and c % 4 == 0     # 128-bit store alignment
+                pos += c
+                sizes.append(c)
+            assert pos == total
+            if total >= 4 * r:
+                assert max(sizes) - min(sizes) <= 4 + total % 4
+    with pytest.raises(bhw.BhwError):
+        bhw.shard_range(10, 2, 2)
+
+
+def test_batch_total():
+    ds = [bhw.make_desc(2, pw, 16, [1, 1]) for pw in range(4, 27)]
+    assert bhw.batch_total(ds) == 134217712            # sum 2^4..2^26
+    with pytest.raises(bhw.BhwError):
+        bhw.batch_total([bhw.make_desc(2, 31, 16, [1, 1])])
+
+
+def test_generate_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bhw.BhwError):
+        bhw.generate(bhw.make_desc(2, 10, 16, [17808, 14959]))
+    # the C entry point itself reports the missing device instead of computing on the CPU
+    import numpy as np
+    out = np.full(1024, 12345, np.int32)
+    st = bhw.lib().bhw_generate_host(C.byref(bhw.make_desc(2, 10, 16, [17808, 14959])), out.ctypes.data, 0, 1024)
+    assert st in (-12, -13) and (out == 12345).all()
+
+
+def test_win_selector_mirror():
+    w = bhw.WinSelector(PHI_WIDTH=16, DAT_WIDTH=17, WIN_TYPE="BH4TERM")
+    d = w.desc(AA0=47022, AA1=64001, AA2=18518, AA3=1531)
+    assert (d.win_type, d.phi_width, d.dat_width, d.sin_type) == (4, 16, 17, 0)
+    with pytest.raises(bhw.BhwError):
+        bhw.WinSelector(WIN_TYPE="BH6TERM")
+    with pytest.raises(bhw.BhwError):
+        bhw.WinSelector(WIN_TYPE="BH4TERM", SIN_TYPE="TAYLOR").desc(AA0=1)

@@ -1,0 +1,268 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle - bit-exact.
+Small/medium sizes compare every sample; the BASELINE full sizes are covered by (i) the oracle on
+all host threads where that takes seconds, (ii) the compiled reference models (oracle/_ref), and
+(iii) size-independent properties: the two independent evaluation strategies agree, any split of
+the range reproduces the whole, batches equal their windows, the DT_VLD order is a rotation."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import blackman_harris_win_b200 as bhw
+import cases
+import harness as H
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_window(d, n0=0, count=None):
+    return bhw.generate(d, n0, count).cpu().numpy().astype(np.int64)
+
+
+def both_algos(d):
+    yield "auto", d
+    yield "direct", d.copy(algo=bhw.ALGO_DIRECT)
+    if d.dat_width <= 32:
+        yield "table", d.copy(algo=bhw.ALGO_TABLE)
+
+
+def test_library_is_the_cuda_one():
+    import torch
+    assert torch.cuda.is_available()
+    assert os.path.exists(bhw.lib_path())
+    n0 = bhw.launch_count()
+    gpu_window(bhw.make_desc(2, 10, 16, [17808, 14959]))
+    assert bhw.launch_count() > n0
+
+
+def test_rtl_sweep_all_variants_widths_sources():
+    """Every variant x PHI_WIDTH x DAT_WIDTH x sin source, both strategies, every sample."""
+    descs = cases.rtl_sweep(pws=(4, 5, 7, 10, 13))
+    for d in descs:
+        want = H.orc_window(d)
+        for name, dd in both_algos(d):
+            assert np.array_equal(gpu_window(dd), want), (name, d)
+
+
+def test_hls_model_vs_oracle_and_compiled_reference():
+    cfgs = H.ref_configs("hls_win")
+    assert cfgs, "oracle/_ref is missing (it is built by __graft_entry__.build() and ships with the repo)"
+    for (np_, nw) in cfgs:
+        for t, v in cases.HLS_TYPES.items():
+            d = bhw.variant_desc(v, np_, nw, model=bhw.MODEL_HLS)
+            n = 1 << np_
+            cnt = min(n, 1 << 15)
+            ref = H.ref_hls_window(np_, nw, t, 0, cnt)
+            for name, dd in both_algos(d):
+                assert np.array_equal(gpu_window(dd, 0, cnt), ref), (name, np_, nw, t)
+            # the bhw.win_function mirror of the HLS entry point
+            assert np.array_equal(bhw.win_function(t, np_, nw, 0, cnt).cpu().numpy(), ref)
+
+
+def test_reference_hashes_full_size():
+    kat = json.load(open(os.path.join(GOLD, "reference_kat.json")))
+    for e in kat["hls_win"]:
+        d = bhw.variant_desc(cases.HLS_TYPES[e["type"]], e["nphase"], e["nwidth"], model=bhw.MODEL_HLS)
+        w = gpu_window(d)
+        assert [int(x) for x in w[:4]] == e["first"] and int(w[len(w) // 2]) == e["mid"]
+        if e["nphase"] <= 16 or (e["nphase"], e["nwidth"], e["type"]) == (20, 32, 7):
+            assert H.sha_lines(w) == e["sha256"], e
+
+
+def test_rtl_anchor_hashes():
+    rtl = json.load(open(os.path.join(GOLD, "rtl_kat.json")))
+    for e in rtl["windows"]:
+        d = bhw.make_desc(e["win_type"], e["phi_width"], e["dat_width"], e["aa"], sin_type=e["sin_type"],
+                          lut_size=e["lut_size"])
+        for name, dd in both_algos(d):
+            assert H.sha_lines(gpu_window(dd)) == e["sha256"], (name, e["name"])
+
+
+@pytest.mark.parametrize("name", list(cases.baseline_configs()))
+def test_baseline_configs_full_size(name):
+    """BASELINE.json configs 1-4 at their full sizes, every sample, oracle on all host threads."""
+    d = cases.baseline_configs()[name]
+    n = 1 << d.phi_width
+    want = H.orc_window(d, 0, n, threads=os.cpu_count() or 8)
+    got_auto = gpu_window(d)
+    assert np.array_equal(got_auto, want)
+    # the other strategy must agree too (direct is slow for 64-bit-limb sources: subsample there)
+    dd = d.copy(algo=bhw.ALGO_DIRECT)
+    if n <= 1 << 20:
+        assert np.array_equal(gpu_window(dd), want)
+    else:
+        for n0 in (0, n // 4 - 1000, n // 2 - 4096, n - 8192):
+            assert np.array_equal(gpu_window(dd, n0, 8192), want[n0:n0 + 8192])
+    # DT_VLD-gated order = rotation by one
+    assert np.array_equal(gpu_window(d.copy(stream_offset=1)), np.roll(want, -1))
+
+
+def test_large_windows_properties():
+    """N = 2^24 .. 2^26: strategies agree, splits reproduce the whole, spot ranges match the oracle."""
+    import torch
+    for v, pw, dw in ((1, 26, 16), (6, 25, 17), (9, 24, 24), (10, 24, 32)):
+        d = bhw.variant_desc(v, pw, dw)
+        n = 1 << pw
+        full = bhw.generate(d)
+        # spot ranges against the oracle
+        for n0 in (0, 12345, n // 2 - 2048, n - 4096):
+            assert np.array_equal(full[n0:n0 + 4096].cpu().numpy().astype(np.int64), H.orc_window(d, n0, 4096))
+        # ragged 3-way split equals the whole
+        cuts = [0, n // 3 + 1, n // 3 + 1 + 777, n]
+        parts = [bhw.generate(d, cuts[i], cuts[i + 1] - cuts[i]) for i in range(3)]
+        assert torch.equal(torch.cat(parts), full)
+        # direct strategy on sub-ranges
+        dd = d.copy(algo=bhw.ALGO_DIRECT)
+        for n0 in (0, n - 65536):
+            assert torch.equal(bhw.generate(dd, n0, 65536), full[n0:n0 + 65536])
+        # checksum-of-checksums identity between two layouts of the same data
+        assert int(full.to(torch.int64).sum()) == sum(int(p.to(torch.int64).sum()) for p in parts)
+        del full, parts
+
+
+def test_coefficient_edge_cases():
+    for d in cases.edge_coeff_descs():
+        want = H.orc_window(d)
+        for name, dd in both_algos(d):
+            assert np.array_equal(gpu_window(dd), want), (name, d)
+
+
+def test_taylor_modes():
+    for pw, lut in [(6, 6), (6, 5), (8, 6), (10, 7), (14, 9), (16, 9), (20, 9), (24, 9), (26, 10), (12, 1), (18, 16)]:
+        for dw in (8, 16, 18, 19, 24, 32):
+            for wt, aa in ((2, [100, 77]), (3, [90, 100, 17])):
+                amp = (1 << (dw - 1)) - 1
+                d = bhw.make_desc(wt, pw, dw, [a * amp // 128 for a in aa], sin_type=bhw.SIN_TAYLOR, lut_size=lut)
+                if bhw.validate(d):
+                    continue
+                n = 1 << pw
+                cnt = min(n, 1 << 14)
+                n0 = (n - cnt) // 2
+                want = H.orc_window(d, n0, cnt)
+                for name, dd in both_algos(d):
+                    assert np.array_equal(gpu_window(dd, n0, cnt), want), (name, d)
+
+
+def test_sincos_all_sources():
+    for model, st, pw, dw, prec in [(0, 0, 10, 16, 0), (0, 0, 12, 8, 3), (0, 0, 20, 32, 1), (0, 0, 9, 47, 2),
+                                    (0, 2, 10, 16, 0), (0, 2, 14, 47, 0), (0, 3, 10, 8, 0), (0, 3, 16, 32, 0),
+                                    (0, 3, 26, 12, 0), (0, 1, 14, 16, 0), (0, 1, 16, 24, 0), (1, 0, 10, 16, 0),
+                                    (1, 0, 18, 16, 0), (2, 0, 14, 12, 0), (2, 0, 10, 32, 0)]:
+        d = bhw.make_desc(2, pw, dw, sin_type=st, model=model, precision=prec)
+        cnt = min(1 << pw, 1 << 15)
+        s, c = bhw.sincos(d, 0, cnt)
+        ws, wc = H.orc_sincos(d, 0, cnt)
+        assert np.array_equal(s.cpu().numpy().astype(np.int64), ws), d
+        assert np.array_equal(c.cpu().numpy().astype(np.int64), wc), d
+    # the cpp model against the compiled cpp/cordic_sincos.cpp itself
+    for (pw, dw) in H.ref_configs("cpp"):
+        cnt = min(1 << pw, 1 << 15)
+        s, c = bhw.sincos(bhw.make_desc(2, pw, dw, model=bhw.MODEL_CPP), 0, cnt)
+        rs, rc = H.ref_cpp_cordic(pw, dw, 0, cnt)
+        assert np.array_equal(s.cpu().numpy(), rs) and np.array_equal(c.cpu().numpy(), rc)
+
+
+def test_batch_mixed_windows_and_ragged_ranges():
+    """win_selector sweep in miniature: all 10 variants x PHI_WIDTH 4..12 in one batch, read back
+    in ragged flat ranges (ranges that start/end mid-window, windows shorter than a tile)."""
+    descs = [bhw.variant_desc(v, pw, cases.VARIANT_DW[v]) for v in range(1, 11) for pw in range(4, 13)]
+    total = bhw.batch_total(descs)
+    want = H.orc_batch(descs, 0, total)
+    got = bhw.generate_batch(descs).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(7)
+    for _ in range(12):
+        b = int(rng.integers(0, total))
+        c = int(rng.integers(0, total - b + 1))
+        assert np.array_equal(bhw.generate_batch(descs, b, c).cpu().numpy().astype(np.int64), want[b:b + c])
+    assert bhw.generate_batch(descs, 5, 0).numel() == 0
+    # plans: execute == one-shot, repeatable, with and without the table cache
+    plan = bhw.Plan(descs)
+    for cache in (True, False, True):
+        bhw.set_table_cache(cache)
+        for _ in range(2):
+            assert np.array_equal(plan.execute().cpu().numpy().astype(np.int64), want)
+        assert np.array_equal(plan.execute(1000, 5000).cpu().numpy().astype(np.int64), want[1000:6000])
+    plan.destroy()
+    bhw.set_table_cache(True)
+
+
+def test_batch_int64_windows():
+    descs = [bhw.variant_desc(v, pw, 40) for v in (1, 6, 10) for pw in (4, 9)]
+    total = bhw.batch_total(descs)
+    want = H.orc_batch(descs, 0, total)
+    got = bhw.generate_batch(descs)
+    assert got.dtype.itemsize == 8 and np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(bhw.generate_batch(descs, 17, 600).cpu().numpy(), want[17:617])
+    with pytest.raises(bhw.BhwError):
+        bhw.generate_batch(descs + [bhw.variant_desc(1, 8, 16)])       # mixed element sizes
+
+
+def test_shards_reassemble():
+    """1/2/4/8-way sharding by flat sample range (what each rank of bench.py does) reproduces the
+    unsharded batch; shards are planned from their own windows only."""
+    import torch
+    descs = [bhw.variant_desc(6, 12, 17).copy(aa=[47022 - i, 64001 - i, 18518 + i, 1531 + i]) for i in range(37)]
+    total = bhw.batch_total(descs)
+    full = bhw.generate_batch(descs)
+    assert np.array_equal(full.cpu().numpy().astype(np.int64), H.orc_batch(descs, 0, total))
+    arr = bhw.desc_array(descs)
+    for world in (1, 2, 4, 8):
+        parts = []
+        for r in range(world):
+            b, c = bhw.shard_range(total, r, world)
+            first, touched, local = bhw.shard_windows(arr, b, c)
+            parts.append(bhw.generate_batch(descs[first:first + touched], local, c))
+        assert torch.equal(torch.cat(parts), full)
+
+
+def test_host_entry_points():
+    d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
+    want = H.orc_window(d)
+    assert np.array_equal(bhw.generate_host(d).astype(np.int64), want)
+    assert np.array_equal(bhw.generate_host(d, 1000, 3000).astype(np.int64), want[1000:4000])
+    # chunked pipeline: a window larger than one 64 MiB staging chunk
+    big = bhw.variant_desc(1, 25, 16)
+    host = bhw.generate_host(big)
+    dev = bhw.generate(big).cpu().numpy()
+    assert np.array_equal(host, dev)
+    d64 = bhw.variant_desc(10, 12, 40)
+    assert np.array_equal(bhw.generate_host(d64), H.orc_window(d64))
+    descs = [bhw.variant_desc(v, 10, cases.VARIANT_DW[v]) for v in range(1, 11)]
+    assert np.array_equal(bhw.generate_batch_host(descs).astype(np.int64), H.orc_batch(descs, 0, bhw.batch_total(descs)))
+
+
+def test_win_selector_and_errors():
+    w = bhw.WinSelector(PHI_WIDTH=10, DAT_WIDTH=16, WIN_TYPE="HAMMING")
+    assert np.array_equal(w.stream(AA0=17808, AA1=14959).cpu().numpy().astype(np.int64),
+                          H.orc_window(bhw.make_desc(2, 10, 16, [17808, 14959])))
+    wt = bhw.WinSelector(PHI_WIDTH=14, DAT_WIDTH=16, WIN_TYPE="BH3TERM", SIN_TYPE="TAYLOR", dt_vld_order=True)
+    d = wt.desc(AA0=27518, AA1=32760, AA2=5242)
+    assert np.array_equal(wt.stream(AA0=27518, AA1=32760, AA2=5242, host=True).astype(np.int64), H.orc_window(d))
+    good = bhw.make_desc(2, 10, 16, [17808, 14959])
+    with pytest.raises(bhw.BhwError):
+        bhw.generate(good, 1000, 100)                                     # past the end
+    with pytest.raises(bhw.BhwError):
+        bhw.generate(good.copy(dat_width=50))
+    import torch
+    out = torch.full((1024,), 7, dtype=torch.int32, device="cuda")
+    st = bhw.lib().bhw_generate(C.byref(good.copy(win_type=6)), out.data_ptr(), 0, 1024, None)
+    assert st == -2 and bool((out == 7).all())                            # errors write nothing
+
+
+def test_multi_gpu_single_process_form():
+    import torch
+    ng = torch.cuda.device_count()
+    descs = bhw.desc_array([bhw.variant_desc(6, 12, 17) for _ in range(9)])
+    total = bhw.batch_total(descs)
+    outs, ptrs = [], (C.c_void_p * ng)()
+    for g in range(ng):
+        b, c = bhw.shard_range(total, g, ng)
+        outs.append(torch.empty(c, dtype=torch.int32, device=f"cuda:{g}"))
+        ptrs[g] = outs[-1].data_ptr()
+    assert bhw.lib().bhw_generate_batch_multi(descs, len(descs), ng, ptrs) == 0
+    got = np.concatenate([o.cpu().numpy() for o in outs]).astype(np.int64)
+    assert np.array_equal(got, H.orc_batch(list(descs), 0, total))

@@ -1,0 +1,128 @@
+"""CPU tier: the kernels' per-thread bodies (csrc/bhw_device.cuh, compiled for the host by
+tests/hostcheck) against the oracle.  This is what can be said about kernel arithmetic without a
+GPU; the GPU tier (test_gpu_parity.py) repeats it through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import blackman_harris_win_b200 as bhw
+import cases
+import harness as H
+
+
+def hc_window(d, n0, cnt, which, force_generic_core=0):
+    out = np.empty(cnt, np.int64)
+    hc = H.hostcheck()
+    if which == "direct":
+        st = hc.hc_direct(C.byref(d), n0, cnt, out.ctypes.data_as(H.I64P))
+    else:
+        st = hc.hc_table(C.byref(d), n0, cnt, out.ctypes.data_as(H.I64P), force_generic_core)
+    return st, out
+
+
+def check(d, cnt_cap=2048):
+    n = 1 << d.phi_width
+    cnt = min(n, cnt_cap)
+    n0 = 0 if cnt == n else (n // 2 - cnt // 2)
+    want = H.orc_window(d, n0, cnt)
+    st, got = hc_window(d, n0, cnt, "direct")
+    assert st == 0 and np.array_equal(got, want), ("direct", d)
+    if d.dat_width <= 32:
+        for force in (0, 1):
+            st, got = hc_window(d, n0, cnt, "table", force)
+            assert st in (0, 1), d
+            if st == 0:
+                assert np.array_equal(got, want), ("table", force, d)
+
+
+def test_rtl_sweep_all_variants_widths_sources():
+    descs = cases.rtl_sweep()
+    assert len(descs) > 800
+    for d in descs:
+        check(d)
+
+
+def test_validation_agrees_with_oracle():
+    n = 0
+    for v in range(1, 11):
+        for pw in (3, 4, 12, 26, 30, 31):
+            for dw in (3, 4, 8, 18, 19, 32, 33, 47, 48, 49):
+                for st in range(0, 5):
+                    for model in (0, 1, 2, 3):
+                        for lut in (0, 1, 9, 12, 16, 17):
+                            try:
+                                aa, wt = bhw.quantize(v, 0, min(max(dw, 4), 48))
+                            except bhw.BhwError:
+                                continue
+                            d = bhw.make_desc(wt, pw, dw, aa, sin_type=st, model=model, lut_size=lut)
+                            a, b = bhw.validate(d), H.orc_window_status(d)
+                            assert (a == 0) == (b == 0), (d, a, b)
+                            n += 1
+    assert n > 5000
+
+
+def test_hls_model_bodies():
+    for (np_, nw) in [(4, 8), (6, 6), (8, 32), (10, 16), (10, 24), (12, 12), (14, 12), (16, 17), (18, 16), (13, 30), (13, 31)]:
+        for t, v in cases.HLS_TYPES.items():
+            check(bhw.variant_desc(v, np_, nw, model=bhw.MODEL_HLS))
+
+
+def test_coefficient_edge_cases():
+    for d in cases.edge_coeff_descs():
+        check(d, 512)
+    # the same through the other sources
+    for st in (bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR):
+        for d in cases.edge_coeff_descs()[::7]:
+            d2 = d.copy(sin_type=st)
+            if bhw.validate(d2) == 0:
+                check(d2, 512)
+
+
+def test_stream_offset_is_a_rotation():
+    for d in (bhw.make_desc(2, 8, 16, [17808, 14959]), bhw.make_desc(3, 14, 24, [7046424, 8388600, 1342176],
+                                                                  sin_type=bhw.SIN_TAYLOR)):
+        base = H.orc_window(d)
+        d1 = d.copy(stream_offset=1)
+        assert np.array_equal(H.orc_window(d1), np.roll(base, -1))
+        for which in ("direct", "table"):
+            st, got = hc_window(d1, 0, len(base), which)
+            assert st == 0 and np.array_equal(got, np.roll(base, -1))
+
+
+def test_taylor_modes():
+    # LESS (pw-lut<2), EQ (=2), DSP (dw<19) and WIDE (dw>18) branches, LUT 1..16
+    for pw, lut in [(6, 6), (6, 5), (8, 6), (10, 7), (14, 9), (16, 9), (20, 9), (24, 9), (26, 10), (12, 1), (18, 16)]:
+        for dw in (8, 16, 18, 19, 24, 32):
+            for wt, aa in ((2, [100, 77]), (3, [90, 100, 17])):
+                amp = (1 << (dw - 1)) - 1
+                d = bhw.make_desc(wt, pw, dw, [a * amp // 128 for a in aa], sin_type=bhw.SIN_TAYLOR, lut_size=lut)
+                if bhw.validate(d) == 0:
+                    check(d, 1024)
+
+
+def test_sincos_bodies_all_sources():
+    hc = H.hostcheck()
+    for model, st, pw, dw, prec in [(0, 0, 10, 16, 0), (0, 0, 12, 8, 3), (0, 0, 20, 32, 1), (0, 0, 9, 47, 2),
+                                    (0, 2, 10, 16, 0), (0, 2, 14, 47, 0), (0, 3, 10, 8, 0), (0, 3, 16, 32, 0),
+                                    (0, 3, 26, 12, 0), (0, 1, 14, 16, 0), (0, 1, 16, 24, 0), (1, 0, 10, 16, 0),
+                                    (1, 0, 18, 16, 0), (2, 0, 14, 12, 0), (2, 0, 10, 32, 0)]:
+        d = bhw.make_desc(2, pw, dw, sin_type=st, model=model, precision=prec)
+        cnt = min(1 << pw, 4096)
+        s, c = H.orc_sincos(d, 0, cnt)
+        gs, gc = np.empty(cnt, np.int64), np.empty(cnt, np.int64)
+        assert hc.hc_sincos(C.byref(d), 0, cnt, gs.ctypes.data_as(H.I64P), gc.ctypes.data_as(H.I64P)) == 0
+        assert np.array_equal(gs, s) and np.array_equal(gc, c), d
+
+
+def test_table_equals_harmonic_gather():
+    """cos_k[n] = C[(k*n) mod N]: the memoised table is the k=1 source sequence."""
+    hc = H.hostcheck()
+    for d in (bhw.make_desc(7, 12, 16, [1] * 7), bhw.make_desc(4, 18, 16, [1] * 4),
+              bhw.make_desc(5, 12, 24, [1] * 5, sin_type=bhw.SIN_CORDIC_SCALED)):
+        n = 1 << d.phi_width
+        tab = np.empty(n, np.int64)
+        for force in (0, 1):
+            assert hc.hc_table_cos(C.byref(d), tab.ctypes.data_as(H.I64P), force) == 0
+            _, c = H.orc_sincos(d)
+            assert np.array_equal(tab, c)

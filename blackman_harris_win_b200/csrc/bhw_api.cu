@@ -42,8 +42,8 @@ static std::atomic<int> g_timing{0};
 static std::mutex g_timing_mu;
 static std::vector<TimedSpan> g_spans;                 // recorded, not yet read
 static std::vector<cudaEvent_t> g_event_pool[64];      // reusable events per device
-static double g_time_ms[BHW_KERNEL_CLASSES] = {0, 0, 0, 0};
-static uint64_t g_time_n[BHW_KERNEL_CLASSES] = {0, 0, 0, 0};
+static double g_time_ms[BHW_KERNEL_CLASSES] = {0};
+static uint64_t g_time_n[BHW_KERNEL_CLASSES] = {0};
 
 static cudaEvent_t pool_event(int dev) {
   if (!g_event_pool[dev].empty()) { cudaEvent_t e = g_event_pool[dev].back(); g_event_pool[dev].pop_back(); return e; }
@@ -150,6 +150,15 @@ struct bhw_plan {
   size_t o_recs = 0, o_gens = 0, o_jobs = 0, o_off = 0, o_wr = 0;
   uint32_t table_work = 0;
   bool tables_built = false;
+  // runs of consecutive same-shape windows that the bank kernel can take whole
+  struct BankRun {
+    int w_begin, w_end;      // windows [w_begin, w_end)
+    uint64_t flat_off;       // flat sample of window w_begin
+    bhw::BankShape sh;
+    int tab_mode;
+    bool pair;
+  };
+  std::vector<BankRun> runs;
   // DAT_WIDTH > 32: one direct launch per window
   std::vector<bhw::DirectArgs> wins64;
   std::mutex mu;
@@ -183,6 +192,41 @@ static void plan_free_device(bhw_plan& plan, cudaStream_t stream) {
 
 static cudaError_t plan_alloc(bhw_plan& plan, void** p, size_t bytes, cudaStream_t stream) {
   return plan.transient ? cudaMallocAsync(p, bytes, stream) : cudaMalloc(p, bytes);
+}
+
+
+static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
+  plan.runs.clear();
+  uint64_t off = 0;
+  for (int w = 0; w < plan.nwin; w++) {
+    const uint32_t ri = plan.win_rec[(size_t)w];
+    const WinRec& r = plan.recs[ri];
+    const uint64_t N = 1ull << r.pw;
+    BankShape sh;
+    int mode = 0;
+    bool pair = false;
+    BankTableInfo ti[BHW_MAX_TERMS];
+    for (int k = 0; k < BHW_MAX_TERMS; k++) {
+      const int t = rec_tab[(size_t)ri * BHW_MAX_TERMS + (size_t)k];
+      ti[k].ptr = t < 0 ? nullptr : plan.tables[(size_t)t].ptr;
+      ti[k].entries = t < 0 ? 0 : plan.tables[(size_t)t].entries;
+      ti[k].kind = t < 0 ? 0 : plan.tables[(size_t)t].canon.kind;
+    }
+    if (bank_shape(r, ti, bank_smem_limit(), &sh, &mode, &pair)) {
+      if (!plan.runs.empty()) {
+        bhw_plan::BankRun& last = plan.runs.back();
+        if (last.w_end == w && last.tab_mode == mode && last.pair == pair && !memcmp(&last.sh, &sh, sizeof(sh))) {
+          last.w_end = w + 1;
+          off += N;
+          continue;
+        }
+      }
+      bhw_plan::BankRun run;
+      run.w_begin = w; run.w_end = w + 1; run.flat_off = off; run.sh = sh; run.tab_mode = mode; run.pair = pair;
+      plan.runs.push_back(run);
+    }
+    off += N;
+  }
 }
 
 // Resolve a batch into `plan` and make it resident on the current device.  [hint_begin,
@@ -259,7 +303,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     WinRec r;
     memset(&r, 0, sizeof(r));
     r.n_first = (uint32_t)wp.stream_offset;
-    bool generic = d.algo == BHW_ALGO_DIRECT || !fast_tail_exact(wp);
+    bool generic = d.algo == BHW_ALGO_DIRECT || fast_tail_mode(wp, src) == TAILMODE_GENERIC;
     if (!generic && d.algo == BHW_ALGO_AUTO && rec_used[i]) {
       uint64_t table_work = 0;
       for (int u = 0; u < wp.nsrc; u++) {
@@ -284,7 +328,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
         plan.rom = rom;
       }
     } else {
-      fill_fast_rec(wp, r);
+      fill_fast_rec(wp, src, r);
       if (rec_used[i]) {
         for (int k = 1; k < wp.m; k++) {
           const TermParams& t = wp.term[k - 1];
@@ -311,6 +355,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     j.tab = pt.ptr;
     j.entries = pt.entries;
     j.fast = fast32_ok(pt.canon) ? 1u : 0u;
+    j.tshift = (uint32_t)table_tshift(pt.canon);
     j.work_begin = work;
     j.work = pt.canon.kind == SRC_INQ ? pt.entries : pt.entries / 4;
     if (pt.canon.kind == SRC_TAYLOR) {
@@ -323,7 +368,12 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     plan.jobs.push_back(j);
   }
   plan.table_work = work;
-  for (const TabRef& tr : refs) plan.recs[(size_t)tr.rec].tabp[tr.k] = plan.tables[(size_t)tr.tab].ptr;
+  std::vector<int> rec_tab(plan.recs.size() * BHW_MAX_TERMS, -1);
+  for (const TabRef& tr : refs) {
+    plan.recs[(size_t)tr.rec].tabp[tr.k] = plan.tables[(size_t)tr.tab].ptr;
+    rec_tab[(size_t)tr.rec * BHW_MAX_TERMS + (size_t)tr.k] = tr.tab;
+  }
+  build_bank_runs(plan, rec_tab);
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const bool need_off = plan.uniform_pw < 0, need_wr = !plan.all_same;
@@ -395,18 +445,54 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   a.flat_off = plan.uniform_pw < 0 ? (const uint64_t*)(plan.blob_dev + plan.o_off) : nullptr;
   a.gens = (const GenRec*)(plan.blob_dev + plan.o_gens);
   a.rom = plan.rom;
-  a.out = out_dev;
-  a.flat_begin = flat_begin;
-  a.flat_count = flat_count;
   a.nwin = plan.nwin;
   a.uniform_pw = plan.uniform_pw;
-  {
-    LaunchTimer tm(BHW_KERNEL_SYNTH, stream);
-    e = launch_synth(a, stream);
+  // any flat sub-range through the general kernel
+  auto general = [&](uint64_t b, uint64_t e_) -> int {
+    if (b >= e_) return BHW_OK;
+    a.out = (int32_t*)out_dev + (b - flat_begin);
+    a.flat_begin = b;
+    a.flat_count = e_ - b;
+    cudaError_t ce;
+    {
+      LaunchTimer tm(BHW_KERNEL_SYNTH, stream);
+      ce = launch_synth(a, stream);
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "k_synth");
+    g_launches++;
+    return BHW_OK;
+  };
+  // whole windows of bank runs go to the bank kernel, everything in between to the general one
+  const uint64_t flat_end = flat_begin + flat_count;
+  uint64_t cursor = flat_begin;
+  for (const bhw_plan::BankRun& run : plan.runs) {
+    const uint32_t pw = run.sh.pw;
+    const uint64_t N = 1ull << pw;
+    const uint64_t rb = run.flat_off, re = rb + ((uint64_t)(run.w_end - run.w_begin) << pw);
+    if (re <= cursor) continue;
+    if (rb >= flat_end) break;
+    const uint64_t lo = rb > cursor ? rb : cursor, hi = re < flat_end ? re : flat_end;
+    const uint64_t wlo = (lo - rb + N - 1) >> pw, whi = (hi - rb) >> pw;  // whole windows [wlo, whi) of the run
+    if (whi <= wlo) continue;
+    const uint64_t bb = rb + (wlo << pw), be = rb + (whi << pw);
+    int st = general(cursor, bb);
+    if (st) return st;
+    BankArgs ba;
+    ba.sh = run.sh;
+    ba.recs = a.recs;
+    ba.win_rec = a.win_rec;
+    ba.out = (int32_t*)out_dev + (bb - flat_begin);
+    ba.w_first = (uint32_t)run.w_begin + (uint32_t)wlo;
+    ba.nwin = (uint32_t)(whi - wlo);
+    {
+      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, stream);
+      e = launch_synth_bank(ba, run.tab_mode, run.pair, stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "k_synth_bank");
+    g_launches++;
+    cursor = be;
   }
-  if (e != cudaSuccess) return cuda_fail(e, "k_synth");
-  g_launches++;
-  return BHW_OK;
+  return general(cursor, flat_end);
 }
 
 // windows touched by a flat range

@@ -212,7 +212,7 @@ struct TabJob {
   uint32_t work_begin;  // prefix sum of work items (threads) over the jobs of a launch
   uint32_t work;        // work items of this job: entries/4, or entries for SRC_INQ
   uint32_t rom_off;     // Taylor ROM offset (I2 units) in the rom buffer
-  uint32_t pad;
+  uint32_t tshift;      // entries are stored left-shifted by this much (see WinRec)
 };
 
 // 32-bit CORDIC for output-quadrant sources whose registers fit int32 and never wrap:
@@ -244,7 +244,7 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   if (p.kind == SRC_INQ) {  // one phase per item, no output symmetry
     int64_t s, c;
     eval_source_generic(p, rom, (uint64_t)e, s, c);
-    T[e] = (int32_t)c;
+    T[e] = (int32_t)(c * ((int64_t)1 << job.tshift));
     return;
   }
   const uint32_t low = e;
@@ -253,96 +253,101 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   else if (job.fast) { int32_t s32, c32; cordic_core_fast32(p, low, s32, c32); vs = s32; vc = c32; }
   else cordic_core_generic(p, 0, low, vs, vc);
   const uint32_t Q = job.entries >> 2;
+  const int64_t t = (int64_t)1 << job.tshift;
   const int64_t ns = wrapb(-vs, p.negw), nc = wrapb(-vc, p.negw);
-  T[e] = (int32_t)wrapb(vc, p.outw);           // quadrant 0: cos =  c
-  T[e + Q] = (int32_t)wrapb(ns, p.outw);       // quadrant 1: cos = -s
-  T[e + 2 * Q] = (int32_t)wrapb(nc, p.outw);   // quadrant 2: cos = -c
-  T[e + 3 * Q] = (int32_t)wrapb(vs, p.outw);   // quadrant 3: cos =  s
+  T[e] = (int32_t)(wrapb(vc, p.outw) * t);          // quadrant 0: cos =  c
+  T[e + Q] = (int32_t)(wrapb(ns, p.outw) * t);      // quadrant 1: cos = -s
+  T[e + 2 * Q] = (int32_t)(wrapb(nc, p.outw) * t);  // quadrant 2: cos = -c
+  T[e + 3 * Q] = (int32_t)(wrapb(vs, p.outw) * t);  // quadrant 3: cos =  s
 }
 
 // ============================================================================================
 // Window synthesis bodies (BHW_ALGO_TABLE, stage 2)
 // ============================================================================================
-// Per window, resolved for the 32-bit fast tail (DAT_WIDTH <= 32):
+// Per window, resolved for the 32-bit fast tail:
 //   phase32_k(n) = n * kstep[k]  (mod 2^32)  - the harmonic's phase left-aligned in 32 bits, so
 //                                              the modulo 2^PHI_WIDTH of the RTL counter is free
-//   cos_k       = tabp[k][phase32_k >> idx_rsh[k]]
-//   RTL  : b_k  = (AAk*cos_k + 2^(DW-2)) >> (DW-1)          == (r>>1)+(r&1), r = p[2DW-2:DW-2]
-//          S    = acc0 + sum_k b_k * mul[k]                  (mod 2^32), mul[k] = -/+ 2^sh
-//          out  = S >> fin_shift                             (arithmetic)
-//          With sh = 32-(DW+2) (31-DW for the 2-term entity) the mod-2^32 wrap of S *is* the
-//          wrap of dsp_pp, acc0 carries AA0 and the rounding increment, and the final
-//          arithmetic shift delivers the DW-bit wrap of DT_WIN.
-//   HLS  : m_k  = (a_k*cos_k) >> (NW-2); S = (a0<<sh) + sum -/+ m_k<<sh, sh = 32-NW; out = S >> sh.
+//   C2_k        = tabp[k][phase32_k >> idx_rsh[k]]   - the table stores cos << tshift
+//   RTL  : b_k  = (r>>1)+(r&1), r = (AAk*cos_k)[2DW-2:DW-2]  ==  floor((AAk*cos_k + 2^(DW-2)) / 2^(DW-1))
+//               = hi32(A_k*C2_k + 2^31)            with A_k = AAk << (32-DW), tshift = 1
+//          S    = AA0 + add + sum_k (-1)^k b_k     (mod 2^32), add = 2 (1 for the 2-term entity):
+//                 (pp>>2)+((pp>>1)&1) == (pp+2)>>2, (pp>>1)+(pp&1) == (pp+1)>>1
+//          out  = (S << lsh) >> rsh (arithmetic)   lsh = 30-DW (31-DW), rsh = 32-DW: the left shift
+//                 wraps S to the DW+2 (DW+1) bits of dsp_pp, the right shift drops the rounded-off
+//                 bits and sign-extends the DW-bit DT_WIN in one go.
+//   HLS  : m_k  = (a_k*cos_k) >> (NW-2) = hi32(A_k*C2_k), A_k = a_k << (32-NW), tshift = 2;
+//          out  = (S << (32-NW)) >> (32-NW).
+// `rc` is the low word of the 64-bit addend of the product (RTL 0x80000000, HLS 0).
 struct WinRec {
   uint32_t flags;        // WR_*
   uint32_t m;            // terms
   uint32_t dw;
   uint32_t pw;
-  int32_t acc0;          // initial accumulator (32-bit form)
-  int32_t fin_shift;     // final arithmetic shift (32-bit form)
-  int32_t bshift;        // RTL: DW-1 ; HLS: NW-2
-  int32_t rnd;           // RTL: 2^(DW-2) ; HLS: 0
-  int32_t aa[BHW_MAX_TERMS];       // AA1.. in [1..m-1]; aa[0] = AA0
-  int32_t mul[BHW_MAX_TERMS];      // mul[k], k = 1..m-1
+  int32_t S0;            // AA0 + add
+  int32_t lsh, rsh;      // final shifts
+  uint32_t rc;           // product rounding addend
+  int32_t A[BHW_MAX_TERMS];        // A[k], k = 1..m-1 (A[0] unused)
+  int32_t aa[BHW_MAX_TERMS];       // raw AA0.. (64-bit tail)
   uint32_t kstep[BHW_MAX_TERMS];   // kstep[k], k = 1..m-1
   uint32_t idx_rsh[BHW_MAX_TERMS];
   uint32_t n_first;      // n of the window's first flat sample (stream offset folded in)
   uint32_t gen_idx;      // index into the generic-parameter array when WR_GENERIC
-  uint32_t pad[2];
+  uint32_t tshift;       // left shift of the table entries
+  uint32_t pad;
   const int32_t* tabp[BHW_MAX_TERMS];  // tabp[k], k = 1..m-1: trig table of harmonic k
   uint32_t pad2[2];
 };
 static_assert(sizeof(WinRec) == 224, "WinRec is copied to shared memory as 56 words");
 enum : uint32_t {
-  WR_WIDE = 1u,     // products need 64 bits (DW > 16)
-  WR_ACC64 = 2u,    // accumulator needs more than 32 bits (RTL DW 31..32): 64-bit tail
+  WR_ACC64 = 2u,    // accumulator / shifts need more than 32 bits: 64-bit tail on table values
   WR_HLS = 4u,      // HLS tail
   WR_RTL2 = 8u,     // 2-term entity
   WR_GENERIC = 16u  // fall back to the generic 64-bit body (direct evaluation)
 };
 
-// fast tail, one sample, 32-bit accumulator (unsigned arithmetic: the wrap is intended).
-// WIDE selects the 64-bit product.
-template <int M, bool WIDE>
+// hi32(a*b + rc): one IMAD.WIDE with a 64-bit addend, high word taken
+BHW_HD int32_t mulhi_rc(int32_t a, int32_t b, uint32_t rc) {
+  return (int32_t)(((int64_t)a * (int64_t)b + (int64_t)(uint64_t)rc) >> 32);
+}
+
+// fast tail, one sample, 32-bit accumulator (the wraps are intended)
+template <int M>
 BHW_HD int32_t synth_sample32(const WinRec& r, uint32_t n) {
-  uint32_t S = (uint32_t)r.acc0;
+  uint32_t S = (uint32_t)r.S0;
 #pragma unroll
   for (int k = 1; k < M; ++k) {
     const uint32_t ph = n * r.kstep[k];
-    const int32_t c = r.tabp[k][ph >> r.idx_rsh[k]];
-    int32_t b;
-    if (WIDE) b = (int32_t)(((int64_t)r.aa[k] * c + (int64_t)r.rnd) >> r.bshift);
-    else b = (r.aa[k] * c + r.rnd) >> r.bshift;
-    S += (uint32_t)b * (uint32_t)r.mul[k];
+    const int32_t c2 = r.tabp[k][ph >> r.idx_rsh[k]];
+    const uint32_t b = (uint32_t)mulhi_rc(r.A[k], c2, r.rc);
+    S = (k & 1) ? S - b : S + b;
   }
-  return (int32_t)S >> r.fin_shift;
+  return (int32_t)(S << r.lsh) >> r.rsh;
 }
 
-// fast tail for RTL DW 31..32: 64-bit sum, then the entity's rounding on bit 0 / bit 1.
+// tail for RTL DW 31..32 (and TAYLOR DW 32): 64-bit sum, then the entity's rounding on bit 0 / bit 1.
 template <int M>
 BHW_HD int32_t synth_sample64(const WinRec& r, uint32_t n) {
+  const int dw = (int)r.dw;
   int64_t S = r.aa[0];
 #pragma unroll
   for (int k = 1; k < M; ++k) {
     const uint32_t ph = n * r.kstep[k];
-    const int32_t c = r.tabp[k][ph >> r.idx_rsh[k]];
-    const int32_t b = (int32_t)wrapb(((int64_t)r.aa[k] * c + (int64_t)r.rnd) >> r.bshift, (int)r.dw);
+    const int32_t c = r.tabp[k][ph >> r.idx_rsh[k]] >> r.tshift;
+    const int32_t b = (int32_t)wrapb(((int64_t)r.aa[k] * c + ((int64_t)1 << (dw - 2))) >> (dw - 1), dw);
     S += (k & 1) ? -(int64_t)b : (int64_t)b;
   }
   if (r.flags & WR_RTL2) {
-    const int64_t pp = wrapb(S, (int)r.dw + 1);
-    return (int32_t)wrapb((pp >> 1) + (pp & 1), (int)r.dw);
+    const int64_t pp = wrapb(S, dw + 1);
+    return (int32_t)wrapb((pp >> 1) + (pp & 1), dw);
   }
-  const int64_t pp = wrapb(S, (int)r.dw + 2);
-  return (int32_t)wrapb((pp >> 2) + ((pp >> 1) & 1), (int)r.dw);
+  const int64_t pp = wrapb(S, dw + 2);
+  return (int32_t)wrapb((pp >> 2) + ((pp >> 1) & 1), dw);
 }
 
 template <int M>
 BHW_HD int32_t synth_sample_m(const WinRec& r, uint32_t n) {
   if (r.flags & WR_ACC64) return synth_sample64<M>(r, n);
-  if (r.flags & WR_WIDE) return synth_sample32<M, true>(r, n);
-  return synth_sample32<M, false>(r, n);
+  return synth_sample32<M>(r, n);
 }
 
 BHW_HD int32_t synth_sample(const WinRec& r, uint32_t n) {
@@ -352,6 +357,86 @@ BHW_HD int32_t synth_sample(const WinRec& r, uint32_t n) {
     case 4: return synth_sample_m<4>(r, n);
     case 5: return synth_sample_m<5>(r, n);
     default: return synth_sample_m<7>(r, n);
+  }
+}
+
+// ============================================================================================
+// Bank synthesis body (k_synth_bank): whole windows of one shape
+// ============================================================================================
+// A "bank" is a run of windows that differ only in their AAk ports (and stream offset): same
+// entity, PHI_WIDTH, DAT_WIDTH and sin/cos source, hence the same trig tables and the same
+// constants below.  The kernel stages the tables in shared memory when they fit and gives every
+// lane *pairs* of samples (n, n + N/2): for the output-quadrant sources the table is exactly
+// antisymmetric over half a period, so cos_k(n + N/2) = (-1)^k cos_k(n) and one look-up serves
+// both samples - odd harmonics with the product negated, even harmonics unchanged:
+//   b(-P) = floor((-P + rc) / 2^32) = -hi32(P + rcn),  rcn = 2^32 - 1 - rc.
+// When even half a period does not fit, only the first half-period is staged (TAB_SMEM_HALF) and
+// the sign of a look-up in the second half moves into the coefficient: (-A) * C2 == A * (-C2).
+struct BankShape {
+  uint32_t m, pw;
+  uint32_t rc, rcn;
+  int32_t lsh, rsh;
+  uint32_t ntab;                        // distinct tables (1, or 2 for 3-term TAYLOR)
+  uint32_t smem_words;                  // staged words in total
+  uint32_t kstep[BHW_MAX_TERMS];
+  uint32_t idx_rsh[BHW_MAX_TERMS];      // full-period index = phase32 >> idx_rsh
+  uint32_t tsel[BHW_MAX_TERMS];         // which distinct table harmonic k reads
+  uint32_t toff[2];                     // word offset of distinct table u in the staged copy
+  uint32_t tentries[2];                 // entries of distinct table u (full period)
+  const int32_t* tab[2];                // distinct table u in global memory
+};
+enum : int { TAB_SMEM_FULL = 0, TAB_SMEM_HALF = 1, TAB_GLOBAL = 2 };
+constexpr int kBankTile = 128;          // samples per warp tile (per half when paired)
+
+// Do all 128 samples of the tile starting at sample nbase see, for every harmonic, a phase in one
+// and the same half-period?  (TAB_SMEM_HALF only; needs 127*kstep < 2^31, guaranteed by the host.)
+template <int M>
+BHW_HD bool bank_tile_sign_uniform(const BankShape& sh, uint32_t nbase) {
+  uint32_t diff = 0;
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t first = nbase * sh.kstep[k];
+    diff |= first ^ (first + (uint32_t)(kBankTile - 1) * sh.kstep[k]);
+  }
+  return (diff >> 31) == 0;
+}
+
+// One lane's share of a tile: samples n + 32*j (j = 0..3) -> va[j], and their partners half a
+// window later -> vb[j] when PAIR.  `tabs[u]` is distinct table u as the kernel sees it (staged
+// or global).  A[k] are the window's pre-shifted coefficients, S0 its initial accumulator.
+template <int M, int TAB, bool PAIR, bool LANE_SIGN>
+BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
+                           uint32_t n, uint32_t nbase, int32_t* va, int32_t* vb) {
+  uint32_t Sa[4], Sb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { Sa[j] = (uint32_t)S0; Sb[j] = (uint32_t)S0; }
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t ks = sh.kstep[k];
+    const int32_t* T = sh.tsel[k] ? tabs[1] : tabs[0];
+    const uint32_t ph0 = n * ks;
+    int32_t Ak = A[k];
+    if (TAB == TAB_SMEM_HALF && !LANE_SIGN) Ak = ((int32_t)(nbase * ks) < 0) ? -Ak : Ak;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t ph = ph0 + (uint32_t)(32 * j) * ks;
+      const uint32_t idx = TAB == TAB_SMEM_HALF ? ((ph << 1) >> (sh.idx_rsh[k] + 1)) : (ph >> sh.idx_rsh[k]);
+      const int32_t c2 = T[idx];
+      int32_t Ae = Ak;
+      if (TAB == TAB_SMEM_HALF && LANE_SIGN) Ae = ((int32_t)ph < 0) ? -Ak : Ak;
+      const int64_t P = (int64_t)Ae * (int64_t)c2;
+      const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
+      Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
+      if (PAIR) {
+        if (k & 1) Sb[j] += (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32);  // -(-1)*hi32(P+rcn)
+        else Sb[j] += ba;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    va[j] = (int32_t)(Sa[j] << sh.lsh) >> sh.rsh;
+    if (PAIR) vb[j] = (int32_t)(Sb[j] << sh.lsh) >> sh.rsh;
   }
 }
 

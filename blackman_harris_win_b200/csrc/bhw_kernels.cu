@@ -54,14 +54,10 @@ __device__ __forceinline__ void synth_tile(const WinRec& r, uint32_t n, int32_t*
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if ((uint32_t)(32 * j) < valid) out[32 * j] = synth_sample64<M>(r, n + 32 * j);
-  } else if (r.flags & WR_WIDE) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if ((uint32_t)(32 * j) < valid) out[32 * j] = synth_sample32<M, true>(r, n + 32 * j);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if ((uint32_t)(32 * j) < valid) out[32 * j] = synth_sample32<M, false>(r, n + 32 * j);
+      if ((uint32_t)(32 * j) < valid) out[32 * j] = synth_sample32<M>(r, n + 32 * j);
   }
 }
 
@@ -156,6 +152,72 @@ k_synth(SynthArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------
+// stage 2, bank form: whole windows of one shape (see BankShape in bhw_device.cuh)
+// -------------------------------------------------------------------------------------------
+// Persistent: one CTA per SM, each CTA owns a contiguous range of warp tiles, its warps take
+// consecutive tiles so that a CTA sweeps its output range front to back.  The trig tables are
+// staged in shared memory once per CTA (TAB_SMEM_*), gathers then cost one LDS each; with
+// TAB_GLOBAL they stay in L2/L1.  Stores are 128 B per warp instruction, streaming.
+constexpr int kBankThreads = 1024;
+constexpr int kBankWarps = kBankThreads / 32;
+
+template <int M, int TAB, bool PAIR>
+__global__ void __launch_bounds__(kBankThreads, 1)
+k_synth_bank(const __grid_constant__ BankArgs a) {
+  extern __shared__ __align__(16) int32_t s_tab[];
+  const BankShape& sh = a.sh;
+  const int32_t* tab0 = sh.tab[0];
+  const int32_t* tab1 = sh.tab[1];
+  if (TAB != TAB_GLOBAL) {
+    for (uint32_t u = 0; u < sh.ntab; ++u) {
+      const uint32_t words = sh.tentries[u] >> (TAB == TAB_SMEM_HALF ? 1 : 0);
+      const int4* src = reinterpret_cast<const int4*>(sh.tab[u]);
+      int4* dst = reinterpret_cast<int4*>(s_tab + sh.toff[u]);
+      for (uint32_t i = threadIdx.x; i < words / 4; i += kBankThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    tab0 = s_tab + sh.toff[0];
+    tab1 = s_tab + sh.toff[1];
+  }
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t pw = sh.pw;
+  const uint32_t log_tpw = pw - 7 - (PAIR ? 1 : 0);  // log2(tiles per window)
+  const uint32_t half = 1u << (pw - 1);
+  const uint64_t U = (uint64_t)a.nwin << log_tpw;
+  const uint64_t u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
+  uint32_t cur_w = 0xFFFFFFFFu, n_first = 0;
+  int32_t A[M], S0 = 0;
+#pragma unroll
+  for (int k = 0; k < M; ++k) A[k] = 0;
+  for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
+    const uint32_t w = (uint32_t)(u >> log_tpw);
+    const uint32_t t = (uint32_t)u & ((1u << log_tpw) - 1);
+    if (w != cur_w) {  // warp-uniform: the window's ports
+      const WinRec* r = a.recs + (a.win_rec ? __ldg(a.win_rec + a.w_first + w) : 0u);
+#pragma unroll
+      for (int k = 1; k < M; ++k) A[k] = __ldg(&r->A[k]);
+      S0 = __ldg(&r->S0);
+      n_first = __ldg(&r->n_first);
+      cur_w = w;
+    }
+    const uint32_t nbase = t * kBankTile + n_first;
+    const uint32_t n = nbase + lane;
+    const int32_t* tabs[2] = {tab0, tab1};
+    int32_t va[4], vb[4];
+    if (TAB == TAB_SMEM_HALF && !bank_tile_sign_uniform<M>(sh, nbase))
+      bank_lane_tile<M, TAB, PAIR, true>(sh, A, S0, tabs, n, nbase, va, vb);
+    else
+      bank_lane_tile<M, TAB, PAIR, false>(sh, A, S0, tabs, n, nbase, va, vb);
+    int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __stcs(o + 32 * j, va[j]);
+      if (PAIR) __stcs(o + half + 32 * j, vb[j]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // direct evaluation (one thread per sample) and the sin/cos entry
 // -------------------------------------------------------------------------------------------
 template <typename OutT>
@@ -226,6 +288,51 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
   const unsigned grid = grid_for((ntiles + kSynthWarps - 1) / kSynthWarps, 8);
   k_synth<<<grid, kSynthThreads, 0, stream>>>(a);
   return cudaGetLastError();
+}
+
+size_t bank_smem_limit() { return 192u * 1024u; }
+
+template <int M, int TAB, bool PAIR>
+static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_synth_bank<M, TAB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bank_smem_limit());
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  k_synth_bank<M, TAB, PAIR><<<grid, kBankThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int M>
+static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned grid, size_t smem,
+                                 cudaStream_t stream) {
+  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, true>(a, grid, smem, stream)
+                                        : launch_bank_t<M, TAB_SMEM_FULL, false>(a, grid, smem, stream);
+  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, true>(a, grid, smem, stream);
+  return pair ? launch_bank_t<M, TAB_GLOBAL, true>(a, grid, 0, stream)
+              : launch_bank_t<M, TAB_GLOBAL, false>(a, grid, 0, stream);
+}
+
+cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream) {
+  if (!a.nwin) return cudaSuccess;
+  if (tab == TAB_SMEM_HALF && !pair) return cudaErrorInvalidValue;
+  const uint32_t log_tpw = a.sh.pw - 7 - (pair ? 1 : 0);
+  const uint64_t units = (uint64_t)a.nwin << log_tpw;
+  const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;
+  const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());
+  const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);
+  switch (a.sh.m) {
+    case 2: return launch_bank_m<2>(a, tab, pair, grid, smem, stream);
+    case 3: return launch_bank_m<3>(a, tab, pair, grid, smem, stream);
+    case 4: return launch_bank_m<4>(a, tab, pair, grid, smem, stream);
+    case 5: return launch_bank_m<5>(a, tab, pair, grid, smem, stream);
+    case 7: return launch_bank_m<7>(a, tab, pair, grid, smem, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream) {

@@ -20,6 +20,15 @@ struct SynthArgs {
   int32_t uniform_pw;        // >= 0: every window has 2^uniform_pw samples (no search needed)
 };
 
+struct BankArgs {
+  BankShape sh;
+  const WinRec* recs;        // per-window records (A[k], S0, n_first are read)
+  const uint32_t* win_rec;   // record of each window; NULL: record 0 for every window
+  int32_t* out;              // sample 0 of window w_first
+  uint32_t w_first;          // first window of the launch (index into win_rec)
+  uint32_t nwin;             // whole windows to generate
+};
+
 struct DirectArgs {
   WinParams wp;
   SrcParams src[2];
@@ -40,6 +49,9 @@ struct SinCosArgs {
 cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total_work, const I2* rom_dev,
                                cudaStream_t stream);
 cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
+// tab: TAB_SMEM_FULL / TAB_SMEM_HALF / TAB_GLOBAL; pair: lanes own (n, n + N/2) sample pairs
+cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream);
+size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
 cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream);
 

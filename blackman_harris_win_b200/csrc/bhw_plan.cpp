@@ -41,48 +41,93 @@ void build_taylor_rom(int dw, int lut, std::vector<I2>& rom) {
   }
 }
 
-// Fill the 32-bit fast-tail record of a window (see the derivation above WinRec).
-void fill_fast_rec(const WinParams& wp, WinRec& r) {
+// Left shift applied to the entries of a source's trig table (WinRec comment): it lets the
+// synthesis kernels take the wanted product bits with a multiply-high.  1 for the RTL tail
+// (2 for the HLS tail) whenever the shifted cosine still fits 32 bits, else 0.
+int table_tshift(const SrcParams& sp) {
+  switch (sp.kind) {
+    case SRC_HLS: return sp.dw <= 30 ? 2 : 0;      // |cos| <= 2^(NW-2)+eps
+    case SRC_TAYLOR: return sp.dw <= 31 ? 1 : 0;   // |cos| <= 2^(DW-1)-1
+    default: return sp.dw <= 31 ? 1 : 0;           // CORDIC entities: |cos| <= 2^(DW-2)+eps (overshoots 2^(DW-2))
+  }
+}
+
+// Which synthesis tail reproduces the entity for this window.
+TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src) {
+  if (wp.dw > 32) return TAILMODE_GENERIC;
+  const int t = table_tshift(src[0]);
+  if (wp.tail == TAIL_HLS) return t == 2 ? TAILMODE_FAST32 : TAILMODE_GENERIC;
+  // AAk = -2^(DW-1) (k >= 1) is left to the generic body (b_k is computed there with the
+  // entity's own DW-bit wrap)
+  const int64_t lo = -((int64_t)1 << (wp.dw - 1));
+  for (int k = 1; k < wp.m; k++) if (wp.aa[k] == lo) return TAILMODE_GENERIC;
+  const int dmax = wp.tail == TAIL_RTL2 ? 31 : 30;  // dsp_pp (DW+1 / DW+2 bits) must fit 32 bits
+  return (t == 1 && wp.dw <= dmax) ? TAILMODE_FAST32 : TAILMODE_ACC64;
+}
+
+// Fill the tail record of a window (see the derivation above WinRec).
+void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r) {
   const int dw = wp.dw, m = wp.m;
+  const TailMode mode = fast_tail_mode(wp, src);
   r.m = (uint32_t)m; r.dw = (uint32_t)dw; r.pw = (uint32_t)wp.pw;
   r.flags = 0;
-  if (dw > 16) r.flags |= WR_WIDE;
+  r.tshift = (uint32_t)table_tshift(src[0]);
   for (int k = 0; k < m; k++) r.aa[k] = (int32_t)wp.aa[k];
+  if (wp.tail == TAIL_HLS) r.flags |= WR_HLS;
+  if (wp.tail == TAIL_RTL2) r.flags |= WR_RTL2;
+  if (mode == TAILMODE_ACC64) { r.flags |= WR_ACC64; return; }
+  const int ashift = 32 - dw;
+  for (int k = 1; k < m; k++) r.A[k] = (int32_t)((uint32_t)r.aa[k] << ashift);
   if (wp.tail == TAIL_HLS) {
-    const int sh = 32 - dw;
-    r.flags |= WR_HLS;
-    r.bshift = dw - 2; r.rnd = 0;
-    r.acc0 = (int32_t)((uint32_t)r.aa[0] << sh);
-    r.fin_shift = sh;
-    for (int k = 1; k < m; k++) r.mul[k] = (int32_t)((k & 1) ? (0u - (1u << sh)) : (1u << sh));
-    return;
+    r.rc = 0; r.S0 = r.aa[0]; r.lsh = 32 - dw; r.rsh = 32 - dw;
+  } else if (wp.tail == TAIL_RTL2) {
+    r.rc = 0x80000000u; r.S0 = (int32_t)((uint32_t)r.aa[0] + 1u); r.lsh = 31 - dw; r.rsh = 32 - dw;
+  } else {
+    r.rc = 0x80000000u; r.S0 = (int32_t)((uint32_t)r.aa[0] + 2u); r.lsh = 30 - dw; r.rsh = 32 - dw;
   }
-  r.bshift = dw - 1; r.rnd = 1 << (dw - 2);
-  if (wp.tail == TAIL_RTL2) {
-    r.flags |= WR_RTL2;
-    if (dw > 31) { r.flags |= WR_ACC64; return; }
-    const int sh = 31 - dw;  // dsp_pp is DW+1 bits; +1 = the round-half-up increment
-    r.acc0 = (int32_t)(((uint32_t)r.aa[0] << sh) + (1u << sh));
-    r.fin_shift = sh + 1;
-    r.mul[1] = (int32_t)(0u - (1u << sh));
-    return;
-  }
-  if (dw > 30) { r.flags |= WR_ACC64; return; }
-  const int sh = 30 - dw;    // dsp_pp is DW+2 bits; +2 = the increment of the bit-1 rounding
-  r.acc0 = (int32_t)(((uint32_t)r.aa[0] << sh) + (2u << sh));
-  r.fin_shift = sh + 2;
-  for (int k = 1; k < m; k++) r.mul[k] = (int32_t)((k & 1) ? (0u - (1u << sh)) : (1u << sh));
 }
 
-// Does the fast tail reproduce the entity for these coefficients?  The only case it does not is
-// AAk = -2^(DW-1) (k >= 1), where b_k can wrap to DW bits; such windows take the generic body.
-bool fast_tail_exact(const WinParams& wp) {
-  if (wp.dw > 32) return false;
-  if (wp.tail == TAIL_HLS) return true;
-  const int64_t lo = -((int64_t)1 << (wp.dw - 1));
-  for (int k = 1; k < wp.m; k++) if (wp.aa[k] == lo) return false;
+bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
+                int* tab_mode, bool* pair) {
+  if (r.flags & (WR_GENERIC | WR_ACC64)) return false;
+  if (r.pw < 7) return false;  // a window must hold at least one 128-sample tile
+  memset(sh, 0, sizeof(*sh));
+  sh->m = r.m; sh->pw = r.pw;
+  sh->rc = r.rc; sh->rcn = 0xFFFFFFFFu - r.rc;
+  sh->lsh = r.lsh; sh->rsh = r.rsh;
+  bool antisym = true, half_ok = true;
+  for (uint32_t k = 1; k < r.m; k++) {
+    if (!tk[k].ptr) return false;
+    uint32_t u = 0;
+    for (; u < sh->ntab; u++) if (sh->tab[u] == tk[k].ptr) break;
+    if (u == sh->ntab) {
+      if (sh->ntab == 2) return false;
+      sh->tab[u] = tk[k].ptr;
+      sh->tentries[u] = tk[k].entries;
+      sh->ntab++;
+    }
+    sh->kstep[k] = r.kstep[k];
+    sh->idx_rsh[k] = r.idx_rsh[k];
+    sh->tsel[k] = u;
+    // cordic_dds48 / cordic_dds_scaled fold the quadrant in at the input: their table is not
+    // antisymmetric over half a period
+    if (tk[k].kind == SRC_INQ) antisym = false;
+    if ((uint64_t)r.kstep[k] * (uint64_t)(kBankTile - 1) >= (1ull << 31)) half_ok = false;
+  }
+  size_t words = 0;
+  for (uint32_t u = 0; u < sh->ntab; u++) words += sh->tentries[u];
+  if (sh->ntab == 1) { sh->tab[1] = sh->tab[0]; sh->tentries[1] = sh->tentries[0]; }
+  const size_t limit = smem_limit_bytes / sizeof(int32_t);
+  const bool can_pair = antisym && r.pw >= 8;
+  if (words <= limit) { *tab_mode = TAB_SMEM_FULL; *pair = can_pair; }
+  else if (can_pair && half_ok && words / 2 <= limit) { *tab_mode = TAB_SMEM_HALF; *pair = true; }
+  else { *tab_mode = TAB_GLOBAL; *pair = can_pair; }
+  const int sh_half = *tab_mode == TAB_SMEM_HALF ? 1 : 0;
+  uint32_t off = 0;
+  for (uint32_t u = 0; u < sh->ntab; u++) { sh->toff[u] = off; off += sh->tentries[u] >> sh_half; }
+  if (sh->ntab == 1) sh->toff[1] = sh->toff[0];
+  sh->smem_words = *tab_mode == TAB_GLOBAL ? 0 : off;
   return true;
 }
-
 
 }  // namespace bhw

@@ -9,7 +9,16 @@ namespace bhw {
 SrcParams canonical_source(const SrcParams& sp, uint32_t* drop);
 bool fast32_ok(const SrcParams& sp);
 void build_taylor_rom(int dw, int lut, std::vector<I2>& rom);
-void fill_fast_rec(const WinParams& wp, WinRec& r);
-bool fast_tail_exact(const WinParams& wp);
+enum TailMode { TAILMODE_FAST32 = 0, TAILMODE_ACC64 = 1, TAILMODE_GENERIC = 2 };
+int table_tshift(const SrcParams& sp);
+TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src);
+void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r);
+
+// Trig table of one harmonic as the bank planner sees it.
+struct BankTableInfo { const int32_t* ptr; uint32_t entries; int32_t kind; };
+// Shape of a record for the bank kernel (tables_k[k] = table of harmonic k), the table placement
+// (TAB_*) and whether lanes take (n, n + N/2) pairs; false when the record cannot go there.
+bool bank_shape(const WinRec& r, const BankTableInfo* tables_k, size_t smem_limit_bytes, BankShape* sh,
+                int* tab_mode, bool* pair);
 
 }  // namespace bhw

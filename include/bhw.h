@@ -230,10 +230,11 @@ BHW_API int bhw_device_count(void);
  * default; costs two cudaEventRecord per launch when on. */
 enum {
   BHW_KERNEL_TABLE_BUILD = 0, /* k_table_build: sin/cos source evaluated once per distinct phase */
-  BHW_KERNEL_SYNTH = 1,       /* k_synth*: gather + multiply/round/sum tail + store             */
+  BHW_KERNEL_SYNTH = 1,       /* k_synth: any flat range of any batch (gather + tail + store)   */
   BHW_KERNEL_DIRECT = 2,      /* k_direct*: one thread per sample, sources evaluated in registers */
   BHW_KERNEL_SINCOS = 3,      /* k_sincos                                                        */
-  BHW_KERNEL_CLASSES = 4
+  BHW_KERNEL_SYNTH_BANK = 4,  /* k_synth_bank: whole windows of one shape, tables in shared memory */
+  BHW_KERNEL_CLASSES = 5
 };
 BHW_API int bhw_timing_enable(int enabled);
 BHW_API int bhw_timing_reset(void);

@@ -34,6 +34,7 @@ void build_table(const SrcParams& sp, const std::vector<I2>& rom, HostTable& t, 
   j.tab = t.data.data();
   j.entries = entries;
   j.fast = (!force_generic && fast32_ok(t.canon)) ? 1u : 0u;
+  j.tshift = (uint32_t)table_tshift(t.canon);
   j.work = t.canon.kind == SRC_INQ ? entries : entries / 4;
   for (uint32_t e = 0; e < j.work; e++) table_build_item(j, rom.data(), e);
 }
@@ -62,14 +63,14 @@ int hc_table(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int f
   WinParams wp; SrcParams src[2];
   int st = resolve_window(d, &wp, src);
   if (st) return st;
-  if (!fast_tail_exact(wp)) return 1;
+  if (fast_tail_mode(wp, src) == TAILMODE_GENERIC) return 1;
   std::vector<I2> rom;
   if (src[0].kind == SRC_TAYLOR) build_taylor_rom(src[0].dw, src[0].lut, rom);
   HostTable tabs[2];
   for (int u = 0; u < wp.nsrc; u++) build_table(src[u], rom, tabs[u], force_generic_core);
   WinRec r;
   memset(&r, 0, sizeof(r));
-  fill_fast_rec(wp, r);
+  fill_fast_rec(wp, src, r);
   r.n_first = (uint32_t)wp.stream_offset;
   for (int k = 1; k < wp.m; k++) {
     const TermParams& t = wp.term[k - 1];
@@ -79,6 +80,97 @@ int hc_table(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int f
     r.idx_rsh[k] = (uint32_t)(32 - (sp.pw - (int)tabs[t.src].drop));
   }
   for (uint64_t j = 0; j < count; j++) out[j] = synth_sample(r, (uint32_t)(n0 + j) + r.n_first);
+  return 0;
+}
+
+// Bank kernel body (k_synth_bank) for one whole window, with the kernel's tile/lane mapping.
+// force_mode: -1 = the planner's choice for `smem_limit` bytes, else TAB_* ; force_pair: -1/0/1.
+// Returns 1 when the window is not bank-eligible (or the forced combination is not legal).
+int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode, int force_pair) {
+  WinParams wp; SrcParams src[2];
+  int st = resolve_window(d, &wp, src);
+  if (st) return st;
+  if (fast_tail_mode(wp, src) != TAILMODE_FAST32) return 1;
+  std::vector<I2> rom;
+  if (src[0].kind == SRC_TAYLOR) build_taylor_rom(src[0].dw, src[0].lut, rom);
+  HostTable tabs[2];
+  for (int u = 0; u < wp.nsrc; u++) build_table(src[u], rom, tabs[u], 0);
+  WinRec r;
+  memset(&r, 0, sizeof(r));
+  fill_fast_rec(wp, src, r);
+  r.n_first = (uint32_t)wp.stream_offset;
+  BankTableInfo tk[BHW_MAX_TERMS];
+  memset(tk, 0, sizeof(tk));
+  for (int k = 1; k < wp.m; k++) {
+    const TermParams& t = wp.term[k - 1];
+    const SrcParams& sp = src[t.src];
+    r.tabp[k] = tabs[t.src].data.data();
+    r.kstep[k] = t.kmul << (32 - sp.pw);
+    r.idx_rsh[k] = (uint32_t)(32 - (sp.pw - (int)tabs[t.src].drop));
+    tk[k].ptr = r.tabp[k];
+    tk[k].entries = (uint32_t)tabs[t.src].data.size();
+    tk[k].kind = tabs[t.src].canon.kind;
+  }
+  BankShape sh;
+  int mode; bool pair;
+  if (!bank_shape(r, tk, smem_limit, &sh, &mode, &pair)) return 1;
+  if (force_pair == 1 && !pair) return 1;           // pairing needs an antisymmetric table
+  if (force_pair == 0) pair = false;
+  if (force_mode >= 0 && force_mode != mode) {
+    if (force_mode == TAB_SMEM_HALF) {
+      // legal only if the planner itself could have chosen it: re-plan with a limit that forces it
+      size_t words = 0;
+      for (uint32_t u = 0; u < sh.ntab; u++) words += sh.tentries[u];
+      if (!bank_shape(r, tk, (words / 2) * 4, &sh, &mode, &pair) || mode != TAB_SMEM_HALF) return 1;
+    } else if (force_mode == TAB_GLOBAL) {
+      if (!bank_shape(r, tk, 0, &sh, &mode, &pair) || mode != TAB_GLOBAL) return 1;
+      if (force_pair == 0) pair = false;
+    } else return 1;
+  }
+  if (mode == TAB_SMEM_HALF && !pair) return 1;
+  // "stage" the tables as the kernel does
+  std::vector<int32_t> staged(sh.smem_words ? sh.smem_words : 1);
+  const int32_t* tp[2] = {sh.tab[0], sh.tab[1]};
+  if (mode != TAB_GLOBAL) {
+    for (uint32_t u = 0; u < sh.ntab; u++) {
+      const uint32_t words = sh.tentries[u] >> (mode == TAB_SMEM_HALF ? 1 : 0);
+      memcpy(staged.data() + sh.toff[u], sh.tab[u], words * sizeof(int32_t));
+    }
+    tp[0] = staged.data() + sh.toff[0];
+    tp[1] = staged.data() + sh.toff[1];
+  }
+  const uint32_t pw = sh.pw, log_tpw = pw - 7 - (pair ? 1 : 0), half = 1u << (pw - 1);
+  for (uint32_t t = 0; t < (1u << log_tpw); t++) {
+    const uint32_t nbase = t * kBankTile + r.n_first;
+    for (uint32_t lane = 0; lane < 32; lane++) {
+      int32_t va[4], vb[4];
+      const uint32_t n = nbase + lane;
+#define HC_TILE(M, TAB, PAIR)                                                                      \
+      do {                                                                                         \
+        if (TAB == TAB_SMEM_HALF && !bank_tile_sign_uniform<M>(sh, nbase))                         \
+          bank_lane_tile<M, TAB, PAIR, true>(sh, r.A, r.S0, tp, n, nbase, va, vb);                 \
+        else                                                                                       \
+          bank_lane_tile<M, TAB, PAIR, false>(sh, r.A, r.S0, tp, n, nbase, va, vb);                \
+      } while (0)
+#define HC_MODE(M)                                                                                 \
+      do {                                                                                         \
+        if (mode == TAB_SMEM_FULL) { if (pair) HC_TILE(M, TAB_SMEM_FULL, true); else HC_TILE(M, TAB_SMEM_FULL, false); } \
+        else if (mode == TAB_SMEM_HALF) HC_TILE(M, TAB_SMEM_HALF, true);                           \
+        else { if (pair) HC_TILE(M, TAB_GLOBAL, true); else HC_TILE(M, TAB_GLOBAL, false); }       \
+      } while (0)
+      switch (sh.m) {
+        case 2: HC_MODE(2); break;
+        case 3: HC_MODE(3); break;
+        case 4: HC_MODE(4); break;
+        case 5: HC_MODE(5); break;
+        default: HC_MODE(7); break;
+      }
+      for (int j = 0; j < 4; j++) {
+        out[t * kBankTile + lane + 32 * j] = va[j];
+        if (pair) out[half + t * kBankTile + lane + 32 * j] = vb[j];
+      }
+    }
+  }
   return 0;
 }
 
@@ -109,7 +201,8 @@ int hc_table_cos(const bhw_desc* d, int64_t* out_cos, int force_generic_core) {
   HostTable t;
   build_table(src[0], rom, t, force_generic_core);
   const uint64_t N = 1ull << src[0].pw;
-  for (uint64_t ph = 0; ph < N; ph++) out_cos[ph] = t.data[ph >> t.drop];
+  const int ts = table_tshift(t.canon);
+  for (uint64_t ph = 0; ph < N; ph++) out_cos[ph] = t.data[ph >> t.drop] >> ts;
   return 0;
 }
 

@@ -126,3 +126,55 @@ def test_table_equals_harmonic_gather():
             assert hc.hc_table_cos(C.byref(d), tab.ctypes.data_as(H.I64P), force) == 0
             _, c = H.orc_sincos(d)
             assert np.array_equal(tab, c)
+
+
+def hc_bank(d, limit=192 * 1024, mode=-1, pair=-1):
+    n = 1 << d.phi_width
+    out = np.full(n, -(1 << 62), np.int64)
+    st = H.hostcheck().hc_bank(C.byref(d), out.ctypes.data_as(H.I64P), limit, mode, pair)
+    return st, out
+
+
+def test_bank_body_all_modes():
+    """k_synth_bank's lane/tile body in every table placement (staged full period, staged half
+    period with the sign folded into the coefficient, global) with and without (n, n+N/2) pairing."""
+    TAB_FULL, TAB_HALF, TAB_GLOBAL = 0, 1, 2
+    seen = set()
+    descs = []
+    for v in range(1, 11):
+        for pw in (7, 8, 9, 12, 14):
+            for dw in sorted({cases.VARIANT_DW[v], 12, 16, 24, 30}):
+                for st in (bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR):
+                    d = bhw.variant_desc(v, pw, dw, sin_type=st)
+                    if bhw.validate(d) == 0:
+                        descs.append(d)
+        for (np_, nw) in ((8, 16), (10, 24), (12, 12), (14, 17), (13, 30)):
+            if v in cases.HLS_TYPES.values():
+                descs.append(bhw.variant_desc(v, np_, nw, model=bhw.MODEL_HLS))
+    descs.append(bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531]))                 # cfg 2
+    descs.append(bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531], stream_offset=1))
+    descs.append(bhw.make_desc(3, 14, 16, [27518, 32760, 5242], sin_type=bhw.SIN_TAYLOR, stream_offset=1))
+    descs.append(bhw.make_desc(7, 12, 16, [-8887, 14203, -7143, 2156, -353, 25, -1]))
+    for d in descs:
+        want = H.orc_window(d)
+        for mode in (-1, TAB_FULL, TAB_HALF, TAB_GLOBAL):
+            for pair in (-1, 0, 1):
+                st, got = hc_bank(d, mode=mode, pair=pair)
+                assert st in (0, 1), d
+                if st == 0:
+                    seen.add((mode, pair))
+                    assert np.array_equal(got, want), (mode, pair, d)
+    # every legal combination was exercised
+    for combo in ((-1, -1), (TAB_FULL, 0), (TAB_FULL, 1), (TAB_HALF, 1), (TAB_GLOBAL, 0), (TAB_GLOBAL, 1)):
+        assert combo in seen, combo
+
+
+def test_bank_body_half_table_sign_boundaries():
+    """Staged half period: tiles that straddle a half-period boundary of some harmonic take the
+    per-lane sign path; all tiles of a long 7-term window must match."""
+    d = bhw.variant_desc(10, 16, 16)
+    st, got = hc_bank(d, limit=128 * 1024)
+    assert st == 0 and np.array_equal(got, H.orc_window(d))
+    d = bhw.variant_desc(9, 17, 24).copy(stream_offset=1)
+    st, got = hc_bank(d, mode=1)
+    assert st == 0 and np.array_equal(got, H.orc_window(d))

@@ -328,18 +328,22 @@ def run_cuda(args):
         if st:
             raise bhw.BhwError(st, "bhw_generate_batch_host")
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = (total * e2e_steps) / e2e_s / 1e9
-    if not torch.equal(host[: 1 << PHI_WIDTH], chk.cpu()):
-        raise SystemExit("bench.py: host-path output differs from the device path")
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        if not torch.equal(host[: 1 << PHI_WIDTH], chk.cpu()):
+            raise SystemExit("bench.py: host-path output differs from the device path")
+        e2e = {"value": (total * e2e_steps) / e2e_s / 1e9, "unit": UNIT, "steps": e2e_steps,
+               "h2d_bytes_per_step": _meta_bytes(touched), "d2h_bytes_per_step": count * 4,
+               "api": "bhw_generate_batch_host (pinned host output)"}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peaks = {}
@@ -377,10 +381,7 @@ def run_cuda(args):
                        "tables": "rebuilt every step (table cache off)",
                        "sharding": f"flat sample range, {world} rank(s), no collective"},
             "roofline": roof, "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
-                    "h2d_bytes_per_step": _meta_bytes(touched),
-                    "d2h_bytes_per_step": count * 4,
-                    "api": "bhw_generate_batch_host (pinned host output)"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
         }
         if world == 1 and not args.no_cpu:
@@ -407,7 +408,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "direct", "table"])
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=10, help="0 skips the host-buffer leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -210,7 +210,7 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
       const int t = rec_tab[(size_t)ri * BHW_MAX_TERMS + (size_t)k];
       ti[k].ptr = t < 0 ? nullptr : plan.tables[(size_t)t].ptr;
       ti[k].entries = t < 0 ? 0 : plan.tables[(size_t)t].entries;
-      ti[k].kind = t < 0 ? 0 : plan.tables[(size_t)t].canon.kind;
+      ti[k].antisym = t >= 0 && source_antisymmetric(plan.tables[(size_t)t].canon);
     }
     if (bank_shape(r, ti, bank_smem_limit(), &sh, &mode, &pair)) {
       if (!plan.runs.empty()) {

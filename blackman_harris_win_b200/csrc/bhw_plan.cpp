@@ -87,6 +87,21 @@ void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r) {
   }
 }
 
+bool source_antisymmetric(const SrcParams& sp) {
+  switch (sp.kind) {
+    case SRC_DDS:   // |value| <= 2^(DW-2) + a few LSB: far from -2^(DW-1) once DW >= 8; the quadrant
+    case SRC_HLS:   // fix negates with a wrap that is then exact (src/cordic_dds.vhd:232-246)
+      return sp.dw >= 8;
+    case SRC_TAYLOR:
+      // ROM-only branches: entries in [0, 2^(DW-1)-1].  DW > 18: tay1_order saturates negatives
+      // to 2^(DW-1)-1 (src/tay1_order.vhd:602-617), so again [0, 2^(DW-1)-1].  The DSP48 branch
+      // (DW < 19) wraps instead: sin + delta*cos can reach 2^(DW-1) = -2^(DW-1) - not provable.
+      return sp.tay_mode != TAY_DSP;
+    default:        // cordic_dds48 / cordic_dds_scaled fold the quadrant in at the input
+      return false;
+  }
+}
+
 bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
                 int* tab_mode, bool* pair) {
   if (r.flags & (WR_GENERIC | WR_ACC64)) return false;
@@ -109,9 +124,7 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
     sh->kstep[k] = r.kstep[k];
     sh->idx_rsh[k] = r.idx_rsh[k];
     sh->tsel[k] = u;
-    // cordic_dds48 / cordic_dds_scaled fold the quadrant in at the input: their table is not
-    // antisymmetric over half a period
-    if (tk[k].kind == SRC_INQ) antisym = false;
+    if (!tk[k].antisym) antisym = false;
     if ((uint64_t)r.kstep[k] * (uint64_t)(kBankTile - 1) >= (1ull << 31)) half_ok = false;
   }
   size_t words = 0;

@@ -15,7 +15,11 @@ TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src);
 void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r);
 
 // Trig table of one harmonic as the bank planner sees it.
-struct BankTableInfo { const int32_t* ptr; uint32_t entries; int32_t kind; };
+struct BankTableInfo { const int32_t* ptr; uint32_t entries; bool antisym; };
+// Is the source's cosine table provably antisymmetric over half a period, T[i + E/2] == -T[i]
+// as plain integers?  (It is whenever no entry can be the most negative DW-bit number, whose
+// negation wraps onto itself.)
+bool source_antisymmetric(const SrcParams& sp);
 // Shape of a record for the bank kernel (tables_k[k] = table of harmonic k), the table placement
 // (TAB_*) and whether lanes take (n, n + N/2) pairs; false when the record cannot go there.
 bool bank_shape(const WinRec& r, const BankTableInfo* tables_k, size_t smem_limit_bytes, BankShape* sh,

@@ -187,6 +187,7 @@ def hostcheck():
     L.hc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]
     L.hc_table_cos.argtypes = [D, I64P, C.c_int]
     L.hc_bank.argtypes = [D, I64P, C.c_uint64, C.c_int, C.c_int]
+    L.hc_source_antisymmetric.argtypes = [D]
     return L
 
 

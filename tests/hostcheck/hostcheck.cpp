@@ -109,7 +109,7 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
     r.idx_rsh[k] = (uint32_t)(32 - (sp.pw - (int)tabs[t.src].drop));
     tk[k].ptr = r.tabp[k];
     tk[k].entries = (uint32_t)tabs[t.src].data.size();
-    tk[k].kind = tabs[t.src].canon.kind;
+    tk[k].antisym = source_antisymmetric(tabs[t.src].canon);
   }
   BankShape sh;
   int mode; bool pair;
@@ -189,6 +189,15 @@ int hc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, 
     if (out_cos) out_cos[j] = c;
   }
   return 0;
+}
+
+// 1 if the planner treats the window's first source as antisymmetric over half a period
+int hc_source_antisymmetric(const bhw_desc* d) {
+  WinParams wp; SrcParams src[2];
+  int st = resolve_window(d, &wp, src);
+  if (st) return st;
+  uint32_t drop;
+  return source_antisymmetric(canonical_source(src[0], &drop)) ? 1 : 0;
 }
 
 // the cosine table of the window's first source, expanded to one value per phase

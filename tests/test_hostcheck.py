@@ -34,6 +34,12 @@ def check(d, cnt_cap=2048):
             assert st in (0, 1), d
             if st == 0:
                 assert np.array_equal(got, want), ("table", force, d)
+        if 7 <= d.phi_width <= 14:   # the bank kernel body, planner's own choice of placement
+            full = np.full(n, -(1 << 62), np.int64)
+            st = H.hostcheck().hc_bank(C.byref(d), full.ctypes.data_as(H.I64P), 192 * 1024, -1, -1)
+            assert st in (0, 1), d
+            if st == 0:
+                assert np.array_equal(full[n0:n0 + cnt], want), ("bank", d)
 
 
 def test_rtl_sweep_all_variants_widths_sources():
@@ -178,3 +184,28 @@ def test_bank_body_half_table_sign_boundaries():
     d = bhw.variant_desc(9, 17, 24).copy(stream_offset=1)
     st, got = hc_bank(d, mode=1)
     assert st == 0 and np.array_equal(got, H.orc_window(d))
+
+
+def test_antisymmetry_claim_holds_wherever_the_planner_relies_on_it():
+    """Pairing and the half-period table assume T[i + E/2] == -T[i]; check the claim against the
+    oracle's cosine sequence for every source the planner declares antisymmetric - and that the
+    planner does not declare the sources for which it is false (TAYLOR on the DSP48 branch)."""
+    hc = H.hostcheck()
+    claimed = refuted = 0
+    for st, model in ((bhw.SIN_CORDIC, 0), (bhw.SIN_CORDIC, 1), (bhw.SIN_TAYLOR, 0), (bhw.SIN_CORDIC48, 0),
+                      (bhw.SIN_CORDIC_SCALED, 0)):
+        for pw in (4, 6, 9, 12, 14):
+            for dw in (4, 5, 7, 8, 12, 16, 17, 18, 19, 24, 30):
+                for lut in ((0,) if st != bhw.SIN_TAYLOR else (1, 4, 9)):
+                    d = bhw.make_desc(2, pw, dw, [1, 1], sin_type=st, model=model, lut_size=lut)
+                    if bhw.validate(d):
+                        continue
+                    _, c = H.orc_sincos(d)
+                    half = len(c) // 2
+                    holds = bool(np.array_equal(c[:half], -c[half:]))
+                    if hc.hc_source_antisymmetric(C.byref(d)) == 1:
+                        claimed += 1
+                        assert holds, d
+                    elif not holds:
+                        refuted += 1
+    assert claimed > 100 and refuted > 0

@@ -384,11 +384,19 @@ struct BankShape {
   uint32_t toff[2];                     // word offset of distinct table u in the staged copy
   uint32_t tentries[2];                 // entries of distinct table u (full period)
   const int32_t* tab[2];                // distinct table u in global memory
+  // linear indexing: when no phase bit is dropped, index_k(n) = (n * lin_step[k]) mod entries, so
+  // inside a tile that crosses no boundary of the staged domain the index is affine in (lane, j)
+  uint32_t lin;                         // 1: every harmonic has an integer index step
+  uint32_t lin_step[BHW_MAX_TERMS];     // k for the CORDIC entities, 1 for a TAYLOR unit
+  uint32_t lin_dmask[BHW_MAX_TERMS];    // staged domain size - 1 (half a period with TAB_SMEM_HALF)
+  uint32_t lin_dbit[BHW_MAX_TERMS];     // TAB_SMEM_HALF: the index bit that selects the negated half
 };
 enum : int { TAB_SMEM_FULL = 0, TAB_SMEM_HALF = 1, TAB_GLOBAL = 2 };
-constexpr int kBankTile = 128;          // samples per warp tile (per half when paired)
+constexpr int kBankJ = 8;               // samples per lane and tile (per half when paired)
+constexpr int kBankTile = 32 * kBankJ;  // samples per warp tile (per half when paired)
+constexpr int kBankTileLog2 = 8;
 
-// Do all 128 samples of the tile starting at sample nbase see, for every harmonic, a phase in one
+// Do all samples of the tile starting at sample nbase see, for every harmonic, a phase in one
 // and the same half-period?  (TAB_SMEM_HALF only; needs 127*kstep < 2^31, guaranteed by the host.)
 template <int M>
 BHW_HD bool bank_tile_sign_uniform(const BankShape& sh, uint32_t nbase) {
@@ -401,15 +409,65 @@ BHW_HD bool bank_tile_sign_uniform(const BankShape& sh, uint32_t nbase) {
   return (diff >> 31) == 0;
 }
 
-// One lane's share of a tile: samples n + 32*j (j = 0..3) -> va[j], and their partners half a
+// Linear tiles.  Returns true when, for every harmonic, the 128 samples starting at nbase stay
+// inside one staged domain (no wrap of the table index, no sign change); base[k] is then the
+// index of sample nbase and bit k of *neg says whether the harmonic sits in the negated half.
+template <int M, int TAB>
+BHW_HD bool bank_tile_linear(const BankShape& sh, uint32_t nbase, uint32_t* base, uint32_t* neg) {
+  bool ok = true;
+  uint32_t ng = 0;
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t pos = nbase * sh.lin_step[k];
+    const uint32_t p = pos & sh.lin_dmask[k];
+    ok = ok && (p + (uint32_t)(kBankTile - 1) * sh.lin_step[k] <= sh.lin_dmask[k]);
+    base[k] = p;
+    if (TAB == TAB_SMEM_HALF) ng |= (pos & sh.lin_dbit[k]) ? (1u << k) : 0u;
+  }
+  *neg = ng;
+  return ok;
+}
+
+// One lane's share of a linear tile: the look-ups of harmonic k are T[base + step*(lane + 32*j)].
+template <int M, int TAB, bool PAIR>
+BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
+                               uint32_t lane, const uint32_t* base, uint32_t neg, int32_t* va, int32_t* vb) {
+  uint32_t Sa[kBankJ], Sb[kBankJ];
+#pragma unroll
+  for (int j = 0; j < kBankJ; ++j) { Sa[j] = (uint32_t)S0; Sb[j] = (uint32_t)S0; }
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t step = sh.lin_step[k];
+    const int32_t* T = (sh.tsel[k] ? tabs[1] : tabs[0]) + base[k] + step * lane;
+    const int32_t Ak = (TAB == TAB_SMEM_HALF && ((neg >> k) & 1u)) ? -A[k] : A[k];
+#pragma unroll
+    for (int j = 0; j < kBankJ; ++j) {
+      const int32_t c2 = T[(uint32_t)(32 * j) * step];
+      const int64_t P = (int64_t)Ak * (int64_t)c2;
+      const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
+      Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
+      if (PAIR) {
+        if (k & 1) Sb[j] += (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32);
+        else Sb[j] += ba;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kBankJ; ++j) {
+    va[j] = (int32_t)(Sa[j] << sh.lsh) >> sh.rsh;
+    if (PAIR) vb[j] = (int32_t)(Sb[j] << sh.lsh) >> sh.rsh;
+  }
+}
+
+// One lane's share of a tile: samples n + 32*j (j = 0..kBankJ-1) -> va[j], and their partners half a
 // window later -> vb[j] when PAIR.  `tabs[u]` is distinct table u as the kernel sees it (staged
 // or global).  A[k] are the window's pre-shifted coefficients, S0 its initial accumulator.
 template <int M, int TAB, bool PAIR, bool LANE_SIGN>
 BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
                            uint32_t n, uint32_t nbase, int32_t* va, int32_t* vb) {
-  uint32_t Sa[4], Sb[4];
+  uint32_t Sa[kBankJ], Sb[kBankJ];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { Sa[j] = (uint32_t)S0; Sb[j] = (uint32_t)S0; }
+  for (int j = 0; j < kBankJ; ++j) { Sa[j] = (uint32_t)S0; Sb[j] = (uint32_t)S0; }
 #pragma unroll
   for (int k = 1; k < M; ++k) {
     const uint32_t ks = sh.kstep[k];
@@ -418,7 +476,7 @@ BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, co
     int32_t Ak = A[k];
     if (TAB == TAB_SMEM_HALF && !LANE_SIGN) Ak = ((int32_t)(nbase * ks) < 0) ? -Ak : Ak;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kBankJ; ++j) {
       const uint32_t ph = ph0 + (uint32_t)(32 * j) * ks;
       const uint32_t idx = TAB == TAB_SMEM_HALF ? ((ph << 1) >> (sh.idx_rsh[k] + 1)) : (ph >> sh.idx_rsh[k]);
       const int32_t c2 = T[idx];
@@ -434,7 +492,7 @@ BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, co
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < kBankJ; ++j) {
     va[j] = (int32_t)(Sa[j] << sh.lsh) >> sh.rsh;
     if (PAIR) vb[j] = (int32_t)(Sb[j] << sh.lsh) >> sh.rsh;
   }

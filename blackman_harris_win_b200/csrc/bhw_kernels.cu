@@ -181,7 +181,7 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   }
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t pw = sh.pw;
-  const uint32_t log_tpw = pw - 7 - (PAIR ? 1 : 0);  // log2(tiles per window)
+  const uint32_t log_tpw = pw - kBankTileLog2 - (PAIR ? 1 : 0);  // log2(tiles per window)
   const uint32_t half = 1u << (pw - 1);
   const uint64_t U = (uint64_t)a.nwin << log_tpw;
   const uint64_t u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
@@ -203,14 +203,17 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     const uint32_t nbase = t * kBankTile + n_first;
     const uint32_t n = nbase + lane;
     const int32_t* tabs[2] = {tab0, tab1};
-    int32_t va[4], vb[4];
-    if (TAB == TAB_SMEM_HALF && !bank_tile_sign_uniform<M>(sh, nbase))
+    int32_t va[kBankJ], vb[kBankJ];
+    uint32_t lbase[M], lneg;
+    if (sh.lin && bank_tile_linear<M, TAB>(sh, nbase, lbase, &lneg))   // warp-uniform
+      bank_lane_tile_lin<M, TAB, PAIR>(sh, A, S0, tabs, lane, lbase, lneg, va, vb);
+    else if (TAB == TAB_SMEM_HALF)
       bank_lane_tile<M, TAB, PAIR, true>(sh, A, S0, tabs, n, nbase, va, vb);
     else
       bank_lane_tile<M, TAB, PAIR, false>(sh, A, S0, tabs, n, nbase, va, vb);
     int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kBankJ; ++j) {
       __stcs(o + 32 * j, va[j]);
       if (PAIR) __stcs(o + half + 32 * j, vb[j]);
     }
@@ -320,7 +323,7 @@ static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream) {
   if (!a.nwin) return cudaSuccess;
   if (tab == TAB_SMEM_HALF && !pair) return cudaErrorInvalidValue;
-  const uint32_t log_tpw = a.sh.pw - 7 - (pair ? 1 : 0);
+  const uint32_t log_tpw = a.sh.pw - kBankTileLog2 - (pair ? 1 : 0);
   const uint64_t units = (uint64_t)a.nwin << log_tpw;
   const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;
   const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());

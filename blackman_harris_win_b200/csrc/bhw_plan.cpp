@@ -105,7 +105,7 @@ bool source_antisymmetric(const SrcParams& sp) {
 bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
                 int* tab_mode, bool* pair) {
   if (r.flags & (WR_GENERIC | WR_ACC64)) return false;
-  if (r.pw < 7) return false;  // a window must hold at least one 128-sample tile
+  if (r.pw < (uint32_t)kBankTileLog2) return false;  // a window must hold at least one tile
   memset(sh, 0, sizeof(*sh));
   sh->m = r.m; sh->pw = r.pw;
   sh->rc = r.rc; sh->rcn = 0xFFFFFFFFu - r.rc;
@@ -131,7 +131,7 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
   for (uint32_t u = 0; u < sh->ntab; u++) words += sh->tentries[u];
   if (sh->ntab == 1) { sh->tab[1] = sh->tab[0]; sh->tentries[1] = sh->tentries[0]; }
   const size_t limit = smem_limit_bytes / sizeof(int32_t);
-  const bool can_pair = antisym && r.pw >= 8;
+  const bool can_pair = antisym && r.pw >= (uint32_t)kBankTileLog2 + 1;
   if (words <= limit) { *tab_mode = TAB_SMEM_FULL; *pair = can_pair; }
   else if (can_pair && half_ok && words / 2 <= limit) { *tab_mode = TAB_SMEM_HALF; *pair = true; }
   else { *tab_mode = TAB_GLOBAL; *pair = can_pair; }
@@ -140,6 +140,17 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
   for (uint32_t u = 0; u < sh->ntab; u++) { sh->toff[u] = off; off += sh->tentries[u] >> sh_half; }
   if (sh->ntab == 1) sh->toff[1] = sh->toff[0];
   sh->smem_words = *tab_mode == TAB_GLOBAL ? 0 : off;
+  // linear indexing: the harmonic's phase step is a whole number of table entries
+  sh->lin = 1;
+  for (uint32_t k = 1; k < r.m; k++) {
+    const uint32_t entries = sh->tentries[sh->tsel[k]];
+    const uint32_t per_entry = 1u << r.idx_rsh[k];           // phase32 units per table entry (idx_rsh >= 2)
+    if (r.kstep[k] % per_entry) { sh->lin = 0; break; }
+    sh->lin_step[k] = r.kstep[k] / per_entry;
+    sh->lin_dmask[k] = (entries >> sh_half) - 1;
+    sh->lin_dbit[k] = sh_half ? entries >> 1 : 0;
+    if ((uint64_t)sh->lin_step[k] * kBankTile > (entries >> sh_half)) { sh->lin = 0; break; }
+  }
   return true;
 }
 

@@ -86,7 +86,12 @@ int hc_table(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int f
 // Bank kernel body (k_synth_bank) for one whole window, with the kernel's tile/lane mapping.
 // force_mode: -1 = the planner's choice for `smem_limit` bytes, else TAB_* ; force_pair: -1/0/1.
 // Returns 1 when the window is not bank-eligible (or the forced combination is not legal).
+static uint64_t lin_tiles = 0;   // lane-tiles that took the linear path since the last reset
+uint64_t hc_lin_tiles(int reset) { const uint64_t v = lin_tiles; if (reset) lin_tiles = 0; return v; }
+
 int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode, int force_pair) {
+  const bool no_lin = force_pair >= 16;  // force_pair + 16: keep every tile on the general path
+  if (no_lin) force_pair -= 16;
   WinParams wp; SrcParams src[2];
   int st = resolve_window(d, &wp, src);
   if (st) return st;
@@ -139,15 +144,19 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
     tp[0] = staged.data() + sh.toff[0];
     tp[1] = staged.data() + sh.toff[1];
   }
-  const uint32_t pw = sh.pw, log_tpw = pw - 7 - (pair ? 1 : 0), half = 1u << (pw - 1);
+  const uint32_t pw = sh.pw, log_tpw = pw - kBankTileLog2 - (pair ? 1 : 0), half = 1u << (pw - 1);
   for (uint32_t t = 0; t < (1u << log_tpw); t++) {
     const uint32_t nbase = t * kBankTile + r.n_first;
     for (uint32_t lane = 0; lane < 32; lane++) {
-      int32_t va[4], vb[4];
+      int32_t va[kBankJ], vb[kBankJ];
       const uint32_t n = nbase + lane;
 #define HC_TILE(M, TAB, PAIR)                                                                      \
       do {                                                                                         \
-        if (TAB == TAB_SMEM_HALF && !bank_tile_sign_uniform<M>(sh, nbase))                         \
+        uint32_t lbase[M], lneg;                                                                   \
+        if (sh.lin && !no_lin && bank_tile_linear<M, TAB>(sh, nbase, lbase, &lneg)) {              \
+          bank_lane_tile_lin<M, TAB, PAIR>(sh, r.A, r.S0, tp, lane, lbase, lneg, va, vb);          \
+          lin_tiles++;                                                                             \
+        } else if (TAB == TAB_SMEM_HALF)                                                           \
           bank_lane_tile<M, TAB, PAIR, true>(sh, r.A, r.S0, tp, n, nbase, va, vb);                 \
         else                                                                                       \
           bank_lane_tile<M, TAB, PAIR, false>(sh, r.A, r.S0, tp, n, nbase, va, vb);                \
@@ -165,7 +174,7 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
         case 5: HC_MODE(5); break;
         default: HC_MODE(7); break;
       }
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < kBankJ; j++) {
         out[t * kBankTile + lane + 32 * j] = va[j];
         if (pair) out[half + t * kBankTile + lane + 32 * j] = vb[j];
       }

@@ -147,8 +147,9 @@ def test_bank_body_all_modes():
     TAB_FULL, TAB_HALF, TAB_GLOBAL = 0, 1, 2
     seen = set()
     descs = []
+    H.hostcheck().hc_lin_tiles(1)
     for v in range(1, 11):
-        for pw in (7, 8, 9, 12, 14):
+        for pw in (8, 9, 10, 12, 14):
             for dw in sorted({cases.VARIANT_DW[v], 12, 16, 24, 30}):
                 for st in (bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR):
                     d = bhw.variant_desc(v, pw, dw, sin_type=st)
@@ -164,12 +165,13 @@ def test_bank_body_all_modes():
     for d in descs:
         want = H.orc_window(d)
         for mode in (-1, TAB_FULL, TAB_HALF, TAB_GLOBAL):
-            for pair in (-1, 0, 1):
+            for pair in (-1, 0, 1, 15, 16, 17):      # +16: every tile on the non-linear path
                 st, got = hc_bank(d, mode=mode, pair=pair)
                 assert st in (0, 1), d
                 if st == 0:
-                    seen.add((mode, pair))
+                    seen.add((mode, pair if pair < 15 else pair - 16))
                     assert np.array_equal(got, want), (mode, pair, d)
+    assert H.hostcheck().hc_lin_tiles(0) > 10000     # the linear-tile path did run
     # every legal combination was exercised
     for combo in ((-1, -1), (TAB_FULL, 0), (TAB_FULL, 1), (TAB_HALF, 1), (TAB_GLOBAL, 0), (TAB_GLOBAL, 1)):
         assert combo in seen, combo

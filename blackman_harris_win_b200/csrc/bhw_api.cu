@@ -647,7 +647,14 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
   a.count = count;
   if (!count) return BHW_OK;
   cudaError_t e;
-  {
+  Direct32Args a32;
+  if (!a.wp.elem64 && direct32_params(a.wp, a.src, &a32.p)) {
+    // register-resident 32-bit stages, 128-bit stores
+    a32.n0 = n0;
+    a32.count = count;
+    LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
+    e = launch_direct32(a32, (int32_t*)out_dev, stream);
+  } else {
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct_window(a, out_dev, stream);
   }

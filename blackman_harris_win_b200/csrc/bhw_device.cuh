@@ -361,6 +361,68 @@ BHW_HD int32_t synth_sample(const WinRec& r, uint32_t n) {
 }
 
 // ============================================================================================
+// Register-resident 32-bit direct evaluation (BHW_ALGO_DIRECT fast path)
+// ============================================================================================
+// One thread per output sample, every k*phi term evaluated by fully unrolled shift-add stages in
+// int32 registers; the atan words arrive pre-sliced for this register width in the kernel
+// parameter block (constant bank).  Valid for the output-quadrant CORDICs whose registers fit
+// 32 bits without ever wrapping (fast32_ok(): cordic_dds with DW+PRECISION <= 32, the HLS cordic
+// with NW <= 30, both DW >= 8) combined with a 32-bit tail (TAILMODE_FAST32).
+struct Direct32Params {
+  int32_t m, pw;
+  int32_t n_xy, n_z;             // x/y stages, z stages
+  int32_t z_rshift, z_lshift;    // z0 = ((phase without quadrant bits) >> z_rshift) << z_lshift
+  int32_t out_shift;             // cos = x >> out_shift
+  int32_t tshift;                // the tail wants cos << tshift (WinRec comment)
+  int32_t gain;                  // x0
+  int32_t S0, lsh, rsh;          // tail constants (WinRec)
+  uint32_t rc;
+  uint32_t n_first;              // sample index of output element 0 (stream offset folded in)
+  int32_t A[BHW_MAX_TERMS];      // A[k], k = 1..m-1
+  uint32_t kmul[BHW_MAX_TERMS];  // phase step of harmonic k
+  int32_t rom[32];               // atan word of stage i, already shifted/masked for this width
+};
+
+// cos of a pw-bit phase by the unrolled CORDIC (src/cordic_dds.vhd:170-246 with the quadrant fix;
+// identical structure in hls/windows/win_function.cpp:86-154)
+BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
+  const int pw = p.pw;
+  const uint32_t q = ph >> (pw - 2);
+  const uint32_t low = ph & ((1u << (pw - 2)) - 1u);
+  int32_t z = (int32_t)((low >> p.z_rshift) << p.z_lshift);
+  int32_t x = p.gain, y = p.gain;  // stage 0 with z0 >= 0: x - (0>>0), 0 + (x>>0)
+  z -= p.rom[0];
+#pragma unroll
+  for (int i = 1; i < 32; ++i) {
+    if (i < p.n_xy) {              // uniform: the stage count is a kernel parameter
+      const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
+      const int32_t xs = x >> i, ys = y >> i;
+      x -= d * ys;                 // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
+      y += d * xs;                 // z<0: y - (x>>i)
+      if (i < p.n_z) z -= d * p.rom[i];
+    }
+  }
+  const int32_t vc = x >> p.out_shift, vs = y >> p.out_shift;
+  // quadrant fix for the cosine output: c, -s, -c, s.  |vc|,|vs| <= 2^(DW-2)+eps, so the
+  // reference's wrapped negation is the plain one
+  const int32_t v = (q & 1u) ? vs : vc;
+  return ((q + 1u) & 2u) ? -v : v;
+}
+
+template <int M>
+BHW_HD int32_t direct32_sample(const Direct32Params& p, uint32_t n) {
+  const uint32_t pmask = (1u << p.pw) - 1u;
+  uint32_t S = (uint32_t)p.S0;
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const int32_t c = direct32_cos(p, (p.kmul[k] * n) & pmask);
+    const uint32_t b = (uint32_t)mulhi_rc(p.A[k], c << p.tshift, p.rc);
+    S = (k & 1) ? S - b : S + b;
+  }
+  return (int32_t)(S << p.lsh) >> p.rsh;
+}
+
+// ============================================================================================
 // Bank synthesis body (k_synth_bank): whole windows of one shape
 // ============================================================================================
 // A "bank" is a run of windows that differ only in their AAk ports (and stream offset): same

@@ -242,6 +242,29 @@ k_direct_window(DirectArgs a, OutT* __restrict__ out) {
   }
 }
 
+// Register-resident 32-bit form: 4 consecutive samples per thread, one 128-bit store.
+template <int M>
+__global__ void __launch_bounds__(256)
+k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
+  const Direct32Params& p = a.p;
+  const uint64_t quads = (a.count + 3) / 4;
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads;
+       qd += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t j = qd * 4;
+    const uint32_t n = (uint32_t)(a.n0 + j) + p.n_first;  // taken modulo 2^pw inside
+    int32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = direct32_sample<M>(p, n + e);
+    if (aligned && j + 4 <= a.count) {
+      __stcs(reinterpret_cast<int4*>(out + j), make_int4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (j + e < a.count) out[j + e] = v[e];
+    }
+  }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_sincos(SinCosArgs a, OutT* __restrict__ out_sin, OutT* __restrict__ out_cos) {
@@ -344,6 +367,20 @@ cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t st
   const size_t smem = (size_t)a.rom_smem_entries * sizeof(I2);
   if (a.wp.elem64) k_direct_window<int64_t><<<grid, 256, smem, stream>>>(a, (int64_t*)out);
   else k_direct_window<int32_t><<<grid, 256, smem, stream>>>(a, (int32_t*)out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream) {
+  if (!a.count) return cudaSuccess;
+  const unsigned grid = grid_for(((a.count + 3) / 4 + 255) / 256, 8);
+  switch (a.p.m) {
+    case 2: k_direct32<2><<<grid, 256, 0, stream>>>(a, out); break;
+    case 3: k_direct32<3><<<grid, 256, 0, stream>>>(a, out); break;
+    case 4: k_direct32<4><<<grid, 256, 0, stream>>>(a, out); break;
+    case 5: k_direct32<5><<<grid, 256, 0, stream>>>(a, out); break;
+    case 7: k_direct32<7><<<grid, 256, 0, stream>>>(a, out); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

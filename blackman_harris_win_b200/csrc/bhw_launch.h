@@ -39,6 +39,12 @@ struct DirectArgs {
   uint64_t count;
 };
 
+struct Direct32Args {
+  Direct32Params p;
+  uint64_t n0;      // first sample (the stream offset lives in p.n_first)
+  uint64_t count;
+};
+
 struct SinCosArgs {
   SrcParams src;
   const I2* rom;
@@ -53,6 +59,7 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream);
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
+cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream);
 cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream);
 
 }  // namespace bhw

@@ -87,6 +87,30 @@ void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r) {
   }
 }
 
+bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* out) {
+  if (wp.nsrc != 1 || !fast32_ok(src[0])) return false;
+  if (fast_tail_mode(wp, src) != TAILMODE_FAST32) return false;
+  const SrcParams& sp = src[0];
+  if (sp.n_xy > 32 || sp.pw < 3) return false;
+  WinRec r;
+  memset(&r, 0, sizeof(r));
+  fill_fast_rec(wp, src, r);
+  Direct32Params& p = *out;
+  memset(&p, 0, sizeof(p));
+  p.m = wp.m; p.pw = sp.pw;
+  p.n_xy = sp.n_xy; p.n_z = sp.n_z;
+  p.z_rshift = sp.z_rshift; p.z_lshift = sp.z_lshift;
+  p.out_shift = sp.out_shift;
+  p.tshift = (int32_t)r.tshift;
+  p.gain = (int32_t)sp.gain;
+  p.S0 = r.S0; p.lsh = r.lsh; p.rsh = r.rsh; p.rc = r.rc;
+  p.n_first = (uint32_t)wp.stream_offset;
+  for (int k = 1; k < wp.m; k++) { p.A[k] = r.A[k]; p.kmul[k] = wp.term[k - 1].kmul; }
+  for (int i = 0; i < sp.n_z && i < 32; i++)
+    p.rom[i] = (int32_t)((c_atan[sp.rom_sel][i] >> sp.rom_shift) & sp.rom_mask);
+  return true;
+}
+
 bool source_antisymmetric(const SrcParams& sp) {
   switch (sp.kind) {
     case SRC_DDS:   // |value| <= 2^(DW-2) + a few LSB: far from -2^(DW-1) once DW >= 8; the quadrant

@@ -14,6 +14,10 @@ int table_tshift(const SrcParams& sp);
 TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src);
 void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r);
 
+// Parameters of the register-resident 32-bit direct kernel; false when the window needs the
+// generic 64-bit body (wide registers, input-quadrant CORDICs, TAYLOR, 64-bit tails).
+bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* out);
+
 // Trig table of one harmonic as the bank planner sees it.
 struct BankTableInfo { const int32_t* ptr; uint32_t entries; bool antisym; };
 // Is the source's cosine table provably antisymmetric over half a period, T[i + E/2] == -T[i]

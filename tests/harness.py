@@ -184,6 +184,7 @@ def hostcheck():
     D = P(BhwDesc)
     L.hc_direct.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
     L.hc_table.argtypes = [D, C.c_uint64, C.c_uint64, I64P, C.c_int]
+    L.hc_direct32.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
     L.hc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]
     L.hc_table_cos.argtypes = [D, I64P, C.c_int]
     L.hc_bank.argtypes = [D, I64P, C.c_uint64, C.c_int, C.c_int]

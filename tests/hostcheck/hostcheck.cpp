@@ -56,6 +56,26 @@ int hc_direct(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
   return 0;
 }
 
+// the 32-bit register-resident direct body (k_direct32); returns 1 when the window is not eligible
+int hc_direct32(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
+  WinParams wp; SrcParams src[2];
+  int st = resolve_window(d, &wp, src);
+  if (st) return st;
+  Direct32Params p;
+  if (wp.elem64 || !direct32_params(wp, src, &p)) return 1;
+  for (uint64_t j = 0; j < count; j++) {
+    const uint32_t n = (uint32_t)(n0 + j) + p.n_first;
+    switch (p.m) {
+      case 2: out[j] = direct32_sample<2>(p, n); break;
+      case 3: out[j] = direct32_sample<3>(p, n); break;
+      case 4: out[j] = direct32_sample<4>(p, n); break;
+      case 5: out[j] = direct32_sample<5>(p, n); break;
+      default: out[j] = direct32_sample<7>(p, n); break;
+    }
+  }
+  return 0;
+}
+
 // BHW_ALGO_TABLE bodies: stage 1 (tables) then stage 2 (synthesis), as bhw_api.cu plans them.
 // Returns 1 if the descriptor is not eligible for the fast tail (caller should expect the
 // generic body instead), negative on error.

@@ -21,6 +21,9 @@ def hc_window(d, n0, cnt, which, force_generic_core=0):
     return st, out
 
 
+DIRECT32_SEEN = []
+
+
 def check(d, cnt_cap=2048):
     n = 1 << d.phi_width
     cnt = min(n, cnt_cap)
@@ -28,6 +31,12 @@ def check(d, cnt_cap=2048):
     want = H.orc_window(d, n0, cnt)
     st, got = hc_window(d, n0, cnt, "direct")
     assert st == 0 and np.array_equal(got, want), ("direct", d)
+    got32 = np.empty(cnt, np.int64)
+    st = H.hostcheck().hc_direct32(C.byref(d), n0, cnt, got32.ctypes.data_as(H.I64P))
+    assert st in (0, 1), d
+    if st == 0:
+        DIRECT32_SEEN.append(1)
+        assert np.array_equal(got32, want), ("direct32", d)
     if d.dat_width <= 32:
         for force in (0, 1):
             st, got = hc_window(d, n0, cnt, "table", force)
@@ -47,6 +56,7 @@ def test_rtl_sweep_all_variants_widths_sources():
     assert len(descs) > 800
     for d in descs:
         check(d)
+    assert len(DIRECT32_SEEN) > 100      # the 32-bit direct body covered its share of the sweep
 
 
 def test_validation_agrees_with_oracle():

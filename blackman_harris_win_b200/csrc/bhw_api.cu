@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <atomic>
@@ -336,7 +337,9 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
           int ti;
           if ((st = find_or_add_table(plan, sp, &ti))) return st;
           r.kstep[k] = t.kmul << (32 - sp.pw);
-          r.idx_rsh[k] = (uint32_t)(32 - (sp.pw - (int)plan.tables[(size_t)ti].drop));
+          // full-period index = phase32 >> (32 - log2(entries)): windows whose PHI_WIDTH exceeds
+          // the source's input resolution share one table and simply drop more phase bits
+          r.idx_rsh[k] = (uint32_t)(32 - plan.tables[(size_t)ti].canon.pw);
           refs.push_back({(int)i, k, ti});
         }
       }
@@ -757,6 +760,23 @@ int bhw_plan_execute(bhw_plan* plan, uint64_t flat_begin, uint64_t flat_count, v
   if (st) return st;
   if (dev != plan->dev) return BHW_E_ARG;
   return plan_execute(*plan, flat_begin, flat_count, out_dev, (cudaStream_t)stream);
+}
+
+// undocumented: print how a plan is going to be executed (stderr)
+__attribute__((visibility("default"))) int bhw_plan_debug_dump(const bhw_plan* plan) {
+  if (!plan) return BHW_E_NULL;
+  fprintf(stderr, "plan: nwin=%d total=%llu recs=%zu tables=%zu jobs=%zu uniform_pw=%d all_same=%d elem64=%d\n", plan->nwin,
+          (unsigned long long)plan->total, plan->recs.size(), plan->tables.size(), plan->jobs.size(), plan->uniform_pw,
+          (int)plan->all_same, (int)plan->elem64);
+  for (size_t i = 0; i < plan->tables.size(); i++)
+    fprintf(stderr, "  table %zu: kind=%d pw=%d dw=%d entries=%u ptr=%p\n", i, plan->tables[i].canon.kind,
+            plan->tables[i].canon.pw, plan->tables[i].canon.dw, plan->tables[i].entries, (void*)plan->tables[i].ptr);
+  for (const bhw_plan::BankRun& r : plan->runs)
+    fprintf(stderr, "  run: windows [%d,%d) flat_off=%llu m=%u pw=%u mode=%d pair=%d lin=%u ntab=%u smem_words=%u tab0=%p entries0=%u "
+            "kstep1=%u idx_rsh1=%u\n", r.w_begin, r.w_end, (unsigned long long)r.flat_off, r.sh.m, r.sh.pw, r.tab_mode,
+            (int)r.pair, r.sh.lin, r.sh.ntab, r.sh.smem_words, (const void*)r.sh.tab[0], r.sh.tentries[0], r.sh.kstep[1],
+            r.sh.idx_rsh[1]);
+  return BHW_OK;
 }
 
 int bhw_plan_total(const bhw_plan* plan, uint64_t* total_samples) {

@@ -190,6 +190,47 @@ def test_batch_mixed_windows_and_ragged_ranges():
     bhw.set_table_cache(True)
 
 
+def test_batch_windows_sharing_one_table_at_different_phi_width():
+    """PHI_WIDTH > DAT_WIDTH: cordic_dds only sees the top DAT_WIDTH phase bits, so windows of
+    different lengths share one trig table and differ in how many phase bits they drop."""
+    for dw, m, v in ((8, 2, 1), (10, 4, 6), (12, 7, 10), (9, 3, 3)):
+        descs = [bhw.variant_desc(v, pw, dw) for pw in (6, 9, 10, 11, 12, 13, 14, 15, 9, 16)]
+        total = bhw.batch_total(descs)
+        want = H.orc_batch(descs, 0, total)
+        assert np.array_equal(bhw.generate_batch(descs).cpu().numpy().astype(np.int64), want), (dw, m)
+        plan = bhw.Plan(descs)
+        off = 0
+        for d in descs:      # window by window through the plan
+            n = 1 << d.phi_width
+            assert np.array_equal(plan.execute(off, n).cpu().numpy().astype(np.int64), want[off:off + n]), d
+            off += n
+        plan.destroy()
+    # HLS model, NPHASE up to NWIDTH + 2
+    descs = [bhw.variant_desc(6, np_, 12, model=bhw.MODEL_HLS) for np_ in (8, 11, 12, 13, 14)]
+    assert np.array_equal(bhw.generate_batch(descs).cpu().numpy().astype(np.int64),
+                          H.orc_batch(descs, 0, bhw.batch_total(descs)))
+
+
+def test_win_selector_sweep_all_variants_all_lengths():
+    """BASELINE config 5: all 10 variants x PHI_WIDTH 4..26 in one plan (1.34 G samples, 5.4 GB);
+    checked against the per-window one-shot path on the long windows (an independent route through
+    the planner) and against the oracle on every window up to 2^14 samples."""
+    import torch
+    descs = [bhw.variant_desc(v, pw, cases.VARIANT_DW[v]) for v in range(1, 11) for pw in range(4, 27)]
+    plan = bhw.Plan(descs)
+    out = plan.execute()
+    off = 0
+    for d in descs:
+        n = 1 << d.phi_width
+        if n <= 1 << 14:
+            assert np.array_equal(out[off:off + n].cpu().numpy().astype(np.int64), H.orc_window(d)), d
+        elif d.phi_width in (15, 17, 20, 22, 26):
+            assert torch.equal(out[off:off + n], bhw.generate(d)), d
+            assert np.array_equal(out[off + n - 4096:off + n].cpu().numpy().astype(np.int64), H.orc_window(d, n - 4096, 4096)), d
+        off += n
+    plan.destroy()
+
+
 def test_batch_int64_windows():
     descs = [bhw.variant_desc(v, pw, 40) for v in (1, 6, 10) for pw in (4, 9)]
     total = bhw.batch_total(descs)

@@ -392,15 +392,14 @@ BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
   int32_t z = (int32_t)((low >> p.z_rshift) << p.z_lshift);
   int32_t x = p.gain, y = p.gain;  // stage 0 with z0 >= 0: x - (0>>0), 0 + (x>>0)
   z -= p.rom[0];
-#pragma unroll
-  for (int i = 1; i < 32; ++i) {
-    if (i < p.n_xy) {              // uniform: the stage count is a kernel parameter
-      const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
-      const int32_t xs = x >> i, ys = y >> i;
-      x -= d * ys;                 // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
-      y += d * xs;                 // z<0: y - (x>>i)
-      if (i < p.n_z) z -= d * p.rom[i];
-    }
+  const int n_xy = p.n_xy, n_z = p.n_z;  // n_z == n_xy (cordic_dds) or n_xy - 1 (HLS: last atan word unused)
+#pragma unroll 4
+  for (int i = 1; i < n_xy; ++i) {
+    const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
+    const int32_t xs = x >> i, ys = y >> i;
+    x -= d * ys;                      // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
+    y += d * xs;                      // z<0: y - (x>>i)
+    z -= d * (i < n_z ? p.rom[i] : 0);
   }
   const int32_t vc = x >> p.out_shift, vs = y >> p.out_shift;
   // quadrant fix for the cosine output: c, -s, -c, s.  |vc|,|vs| <= 2^(DW-2)+eps, so the
@@ -438,6 +437,9 @@ struct BankShape {
   uint32_t m, pw;
   uint32_t rc, rcn;
   int32_t lsh, rsh;
+  // 64-bit tail (RTL DAT_WIDTH 31..32): b = (int32)((AAk*C2 + prnd) >> psh), S in 64 bits,
+  // out = sx(((S + fadd) >> fin), DW); A[k] are then the raw AAk and S0 the raw AA0
+  uint32_t acc64, psh, prnd, prndn, fin, fadd, flsh;
   uint32_t ntab;                        // distinct tables (1, or 2 for 3-term TAYLOR)
   uint32_t smem_words;                  // staged words in total
   uint32_t kstep[BHW_MAX_TERMS];
@@ -471,6 +473,29 @@ BHW_HD bool bank_tile_sign_uniform(const BankShape& sh, uint32_t nbase) {
   return (diff >> 31) == 0;
 }
 
+template <bool W64> struct BankAcc { typedef uint32_t type; };
+template <> struct BankAcc<true> { typedef uint64_t type; };
+
+// b_k from the 64-bit product P = A*C2; `negated`: the value v with b(-P) == -v
+template <bool W64>
+BHW_HD typename BankAcc<W64>::type bank_term(const BankShape& sh, int64_t P, bool negated) {
+  if (W64) return (typename BankAcc<W64>::type)(int64_t)(int32_t)((P + (int64_t)(negated ? sh.prndn : sh.prnd)) >> sh.psh);
+  return (typename BankAcc<W64>::type)(uint32_t)((P + (int64_t)(uint64_t)(negated ? sh.rcn : sh.rc)) >> 32);
+}
+template <bool W64>
+BHW_HD typename BankAcc<W64>::type bank_init(const BankShape& sh, int32_t S0) {
+  if (W64) return (typename BankAcc<W64>::type)((int64_t)S0 + (int64_t)sh.fadd);
+  return (typename BankAcc<W64>::type)(uint32_t)S0;
+}
+template <bool W64>
+BHW_HD int32_t bank_finish(const BankShape& sh, typename BankAcc<W64>::type S) {
+  if (W64) {
+    const int32_t t = (int32_t)((int64_t)S >> sh.fin);
+    return (int32_t)((uint32_t)t << sh.flsh) >> sh.flsh;
+  }
+  return (int32_t)((uint32_t)S << sh.lsh) >> sh.rsh;
+}
+
 // Linear tiles.  Returns true when, for every harmonic, the 128 samples starting at nbase stay
 // inside one staged domain (no wrap of the table index, no sign change); base[k] is then the
 // index of sample nbase and bit k of *neg says whether the harmonic sits in the negated half.
@@ -491,12 +516,13 @@ BHW_HD bool bank_tile_linear(const BankShape& sh, uint32_t nbase, uint32_t* base
 }
 
 // One lane's share of a linear tile: the look-ups of harmonic k are T[base + step*(lane + 32*j)].
-template <int M, int TAB, bool PAIR>
+template <int M, int TAB, bool PAIR, bool W64>
 BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
                                uint32_t lane, const uint32_t* base, uint32_t neg, int32_t* va, int32_t* vb) {
-  uint32_t Sa[kBankJ], Sb[kBankJ];
+  typedef typename BankAcc<W64>::type acc_t;
+  acc_t Sa[kBankJ], Sb[kBankJ];
 #pragma unroll
-  for (int j = 0; j < kBankJ; ++j) { Sa[j] = (uint32_t)S0; Sb[j] = (uint32_t)S0; }
+  for (int j = 0; j < kBankJ; ++j) { Sa[j] = bank_init<W64>(sh, S0); Sb[j] = Sa[j]; }
 #pragma unroll
   for (int k = 1; k < M; ++k) {
     const uint32_t step = sh.lin_step[k];
@@ -506,30 +532,31 @@ BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0
     for (int j = 0; j < kBankJ; ++j) {
       const int32_t c2 = T[(uint32_t)(32 * j) * step];
       const int64_t P = (int64_t)Ak * (int64_t)c2;
-      const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
+      const acc_t ba = bank_term<W64>(sh, P, false);
       Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
       if (PAIR) {
-        if (k & 1) Sb[j] += (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32);
+        if (k & 1) Sb[j] += bank_term<W64>(sh, P, true);
         else Sb[j] += ba;
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < kBankJ; ++j) {
-    va[j] = (int32_t)(Sa[j] << sh.lsh) >> sh.rsh;
-    if (PAIR) vb[j] = (int32_t)(Sb[j] << sh.lsh) >> sh.rsh;
+    va[j] = bank_finish<W64>(sh, Sa[j]);
+    if (PAIR) vb[j] = bank_finish<W64>(sh, Sb[j]);
   }
 }
 
 // One lane's share of a tile: samples n + 32*j (j = 0..kBankJ-1) -> va[j], and their partners half a
 // window later -> vb[j] when PAIR.  `tabs[u]` is distinct table u as the kernel sees it (staged
 // or global).  A[k] are the window's pre-shifted coefficients, S0 its initial accumulator.
-template <int M, int TAB, bool PAIR, bool LANE_SIGN>
+template <int M, int TAB, bool PAIR, bool LANE_SIGN, bool W64>
 BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
                            uint32_t n, uint32_t nbase, int32_t* va, int32_t* vb) {
-  uint32_t Sa[kBankJ], Sb[kBankJ];
+  typedef typename BankAcc<W64>::type acc_t;
+  acc_t Sa[kBankJ], Sb[kBankJ];
 #pragma unroll
-  for (int j = 0; j < kBankJ; ++j) { Sa[j] = (uint32_t)S0; Sb[j] = (uint32_t)S0; }
+  for (int j = 0; j < kBankJ; ++j) { Sa[j] = bank_init<W64>(sh, S0); Sb[j] = Sa[j]; }
 #pragma unroll
   for (int k = 1; k < M; ++k) {
     const uint32_t ks = sh.kstep[k];
@@ -545,18 +572,18 @@ BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, co
       int32_t Ae = Ak;
       if (TAB == TAB_SMEM_HALF && LANE_SIGN) Ae = ((int32_t)ph < 0) ? -Ak : Ak;
       const int64_t P = (int64_t)Ae * (int64_t)c2;
-      const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
+      const acc_t ba = bank_term<W64>(sh, P, false);
       Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
       if (PAIR) {
-        if (k & 1) Sb[j] += (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32);  // -(-1)*hi32(P+rcn)
+        if (k & 1) Sb[j] += bank_term<W64>(sh, P, true);  // b(-P) = -bank_term(P, negated)
         else Sb[j] += ba;
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < kBankJ; ++j) {
-    va[j] = (int32_t)(Sa[j] << sh.lsh) >> sh.rsh;
-    if (PAIR) vb[j] = (int32_t)(Sb[j] << sh.lsh) >> sh.rsh;
+    va[j] = bank_finish<W64>(sh, Sa[j]);
+    if (PAIR) vb[j] = bank_finish<W64>(sh, Sb[j]);
   }
 }
 

@@ -161,7 +161,7 @@ k_synth(SynthArgs a) {
 constexpr int kBankThreads = 1024;
 constexpr int kBankWarps = kBankThreads / 32;
 
-template <int M, int TAB, bool PAIR>
+template <int M, int TAB, bool PAIR, bool W64>
 __global__ void __launch_bounds__(kBankThreads, 1)
 k_synth_bank(const __grid_constant__ BankArgs a) {
   extern __shared__ __align__(16) int32_t s_tab[];
@@ -206,11 +206,11 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     int32_t va[kBankJ], vb[kBankJ];
     uint32_t lbase[M], lneg;
     if (sh.lin && bank_tile_linear<M, TAB>(sh, nbase, lbase, &lneg))   // warp-uniform
-      bank_lane_tile_lin<M, TAB, PAIR>(sh, A, S0, tabs, lane, lbase, lneg, va, vb);
+      bank_lane_tile_lin<M, TAB, PAIR, W64>(sh, A, S0, tabs, lane, lbase, lneg, va, vb);
     else if (TAB == TAB_SMEM_HALF)
-      bank_lane_tile<M, TAB, PAIR, true>(sh, A, S0, tabs, n, nbase, va, vb);
+      bank_lane_tile<M, TAB, PAIR, true, W64>(sh, A, S0, tabs, n, nbase, va, vb);
     else
-      bank_lane_tile<M, TAB, PAIR, false>(sh, A, S0, tabs, n, nbase, va, vb);
+      bank_lane_tile<M, TAB, PAIR, false, W64>(sh, A, S0, tabs, n, nbase, va, vb);
     int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
 #pragma unroll
     for (int j = 0; j < kBankJ; ++j) {
@@ -318,29 +318,29 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
 
 size_t bank_smem_limit() { return 192u * 1024u; }
 
-template <int M, int TAB, bool PAIR>
+template <int M, int TAB, bool PAIR, bool W64>
 static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_synth_bank<M, TAB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_synth_bank<M, TAB, PAIR, W64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)bank_smem_limit());
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  k_synth_bank<M, TAB, PAIR><<<grid, kBankThreads, smem, stream>>>(a);
+  k_synth_bank<M, TAB, PAIR, W64><<<grid, kBankThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
-template <int M>
+template <int M, bool W64>
 static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned grid, size_t smem,
                                  cudaStream_t stream) {
-  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, true>(a, grid, smem, stream)
-                                        : launch_bank_t<M, TAB_SMEM_FULL, false>(a, grid, smem, stream);
-  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, true>(a, grid, smem, stream);
-  return pair ? launch_bank_t<M, TAB_GLOBAL, true>(a, grid, 0, stream)
-              : launch_bank_t<M, TAB_GLOBAL, false>(a, grid, 0, stream);
+  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, true, W64>(a, grid, smem, stream)
+                                        : launch_bank_t<M, TAB_SMEM_FULL, false, W64>(a, grid, smem, stream);
+  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, true, W64>(a, grid, smem, stream);
+  return pair ? launch_bank_t<M, TAB_GLOBAL, true, W64>(a, grid, 0, stream)
+              : launch_bank_t<M, TAB_GLOBAL, false, W64>(a, grid, 0, stream);
 }
 
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream) {
@@ -351,12 +351,13 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
   const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;
   const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());
   const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);
+  const bool w64 = a.sh.acc64 != 0;
   switch (a.sh.m) {
-    case 2: return launch_bank_m<2>(a, tab, pair, grid, smem, stream);
-    case 3: return launch_bank_m<3>(a, tab, pair, grid, smem, stream);
-    case 4: return launch_bank_m<4>(a, tab, pair, grid, smem, stream);
-    case 5: return launch_bank_m<5>(a, tab, pair, grid, smem, stream);
-    case 7: return launch_bank_m<7>(a, tab, pair, grid, smem, stream);
+    case 2: return w64 ? launch_bank_m<2, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<2, false>(a, tab, pair, grid, smem, stream);
+    case 3: return w64 ? launch_bank_m<3, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<3, false>(a, tab, pair, grid, smem, stream);
+    case 4: return w64 ? launch_bank_m<4, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<4, false>(a, tab, pair, grid, smem, stream);
+    case 5: return w64 ? launch_bank_m<5, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<5, false>(a, tab, pair, grid, smem, stream);
+    case 7: return w64 ? launch_bank_m<7, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<7, false>(a, tab, pair, grid, smem, stream);
     default: return cudaErrorInvalidValue;
   }
 }

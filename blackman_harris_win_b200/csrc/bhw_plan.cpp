@@ -75,7 +75,12 @@ void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r) {
   for (int k = 0; k < m; k++) r.aa[k] = (int32_t)wp.aa[k];
   if (wp.tail == TAIL_HLS) r.flags |= WR_HLS;
   if (wp.tail == TAIL_RTL2) r.flags |= WR_RTL2;
-  if (mode == TAILMODE_ACC64) { r.flags |= WR_ACC64; return; }
+  if (mode == TAILMODE_ACC64) {   // raw coefficients; the kernels apply the 64-bit tail
+    r.flags |= WR_ACC64;
+    for (int k = 1; k < m; k++) r.A[k] = r.aa[k];
+    r.S0 = r.aa[0];
+    return;
+  }
   const int ashift = 32 - dw;
   for (int k = 1; k < m; k++) r.A[k] = (int32_t)((uint32_t)r.aa[k] << ashift);
   if (wp.tail == TAIL_HLS) {
@@ -128,12 +133,22 @@ bool source_antisymmetric(const SrcParams& sp) {
 
 bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
                 int* tab_mode, bool* pair) {
-  if (r.flags & (WR_GENERIC | WR_ACC64)) return false;
+  if (r.flags & WR_GENERIC) return false;
   if (r.pw < (uint32_t)kBankTileLog2) return false;  // a window must hold at least one tile
   memset(sh, 0, sizeof(*sh));
   sh->m = r.m; sh->pw = r.pw;
   sh->rc = r.rc; sh->rcn = 0xFFFFFFFFu - r.rc;
   sh->lsh = r.lsh; sh->rsh = r.rsh;
+  if (r.flags & WR_ACC64) {           // RTL tail in 64 bits (DAT_WIDTH 31..32)
+    sh->acc64 = 1;
+    sh->psh = r.dw - 1 + r.tshift;
+    if (sh->psh > 31) return false;
+    sh->prnd = 1u << (r.dw - 2 + r.tshift);
+    sh->prndn = ((sh->psh == 32 ? 0u : (1u << sh->psh)) - 1u) - sh->prnd;
+    sh->fin = (r.flags & WR_RTL2) ? 1 : 2;
+    sh->fadd = sh->fin;               // (pp>>2)+((pp>>1)&1) == (pp+2)>>2 ; (pp>>1)+(pp&1) == (pp+1)>>1
+    sh->flsh = 32 - r.dw;
+  }
   bool antisym = true, half_ok = true;
   for (uint32_t k = 1; k < r.m; k++) {
     if (!tk[k].ptr) return false;

@@ -115,7 +115,7 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
   WinParams wp; SrcParams src[2];
   int st = resolve_window(d, &wp, src);
   if (st) return st;
-  if (fast_tail_mode(wp, src) != TAILMODE_FAST32) return 1;
+  if (fast_tail_mode(wp, src) == TAILMODE_GENERIC) return 1;
   std::vector<I2> rom;
   if (src[0].kind == SRC_TAYLOR) build_taylor_rom(src[0].dw, src[0].lut, rom);
   HostTable tabs[2];
@@ -170,17 +170,19 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
     for (uint32_t lane = 0; lane < 32; lane++) {
       int32_t va[kBankJ], vb[kBankJ];
       const uint32_t n = nbase + lane;
-#define HC_TILE(M, TAB, PAIR)                                                                      \
+#define HC_TILE2(M, TAB, PAIR, W64)                                                                \
       do {                                                                                         \
         uint32_t lbase[M], lneg;                                                                   \
         if (sh.lin && !no_lin && bank_tile_linear<M, TAB>(sh, nbase, lbase, &lneg)) {              \
-          bank_lane_tile_lin<M, TAB, PAIR>(sh, r.A, r.S0, tp, lane, lbase, lneg, va, vb);          \
+          bank_lane_tile_lin<M, TAB, PAIR, W64>(sh, r.A, r.S0, tp, lane, lbase, lneg, va, vb);     \
           lin_tiles++;                                                                             \
         } else if (TAB == TAB_SMEM_HALF)                                                           \
-          bank_lane_tile<M, TAB, PAIR, true>(sh, r.A, r.S0, tp, n, nbase, va, vb);                 \
+          bank_lane_tile<M, TAB, PAIR, true, W64>(sh, r.A, r.S0, tp, n, nbase, va, vb);            \
         else                                                                                       \
-          bank_lane_tile<M, TAB, PAIR, false>(sh, r.A, r.S0, tp, n, nbase, va, vb);                \
+          bank_lane_tile<M, TAB, PAIR, false, W64>(sh, r.A, r.S0, tp, n, nbase, va, vb);           \
       } while (0)
+#define HC_TILE(M, TAB, PAIR)                                                                      \
+      do { if (sh.acc64) HC_TILE2(M, TAB, PAIR, true); else HC_TILE2(M, TAB, PAIR, false); } while (0)
 #define HC_MODE(M)                                                                                 \
       do {                                                                                         \
         if (mode == TAB_SMEM_FULL) { if (pair) HC_TILE(M, TAB_SMEM_FULL, true); else HC_TILE(M, TAB_SMEM_FULL, false); } \

@@ -160,7 +160,7 @@ def test_bank_body_all_modes():
     H.hostcheck().hc_lin_tiles(1)
     for v in range(1, 11):
         for pw in (8, 9, 10, 12, 14):
-            for dw in sorted({cases.VARIANT_DW[v], 12, 16, 24, 30}):
+            for dw in sorted({cases.VARIANT_DW[v], 12, 16, 24, 30, 31, 32}):
                 for st in (bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR):
                     d = bhw.variant_desc(v, pw, dw, sin_type=st)
                     if bhw.validate(d) == 0:

@@ -40,7 +40,11 @@ def main():
     torch.cuda.set_device(0)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    for name, d in cases.baseline_configs().items():
+    configs = dict(cases.baseline_configs())
+    # throughput shapes for the register-resident direct kernel (not BASELINE configs)
+    configs["x_bh4_n16m_dw17 (direct32 throughput)"] = bhw.make_desc(4, 24, 17, [47022, 64001, 18518, 1531])
+    configs["x_hamming_n16m_dw16 (direct32 throughput)"] = bhw.make_desc(2, 24, 16, [17808, 14959])
+    for name, d in configs.items():
         n = 1 << d.phi_width
         esz = bhw.elem_bytes(d)
         out = torch.empty(n, dtype=torch.int64 if esz == 8 else torch.int32, device="cuda")

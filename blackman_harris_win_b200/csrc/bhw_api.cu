@@ -357,7 +357,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     j.sp = pt.canon;
     j.tab = pt.ptr;
     j.entries = pt.entries;
-    j.fast = fast32_ok(pt.canon) ? 1u : 0u;
+    j.fast = (uint32_t)table_core32(pt.canon);
     j.tshift = (uint32_t)table_tshift(pt.canon);
     j.work_begin = work;
     j.work = pt.canon.kind == SRC_INQ ? pt.entries : pt.entries / 4;

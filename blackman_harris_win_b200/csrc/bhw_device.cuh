@@ -208,7 +208,7 @@ struct TabJob {
   SrcParams sp;         // canonical source: phase width reduced so that no phase bit is ignored
   int32_t* tab;         // the table (device memory), `entries` int32 words
   uint32_t entries;     // 2^sp.pw
-  uint32_t fast;        // 1: the 32-bit fast core is exact for this source
+  uint32_t fast;        // 1: the 32-bit core is exact for this source; 2: its biased form (W == 33)
   uint32_t work_begin;  // prefix sum of work items (threads) over the jobs of a launch
   uint32_t work;        // work items of this job: entries/4, or entries for SRC_INQ
   uint32_t rom_off;     // Taylor ROM offset (I2 units) in the rom buffer
@@ -219,22 +219,30 @@ struct TabJob {
 // SRC_DDS with 8 <= DW, DW+PRECISION <= 32 and SRC_HLS with 8 <= NW <= 30.  Amplitude is a
 // quarter of the register range, so x, y, z stay inside W-1 bits and the reference's wraps are
 // no-ops (DESIGN.md "no-wrap argument").  z0 >= 0, so stage 0 always takes the z >= 0 branch.
+//
+// BIAS: cordic_dds with DW+PRECISION == 33 (DAT_WIDTH 32).  x and y live in (-2^29, 2^31 + eps):
+// one bit too many for int32, so the registers hold X = x - 2^30, Y = y - 2^30.  For i <= 30,
+// (X + 2^30) >> i == (X >> i) + 2^(30-i) exactly, so every stage and the output shift stay exact.
+// z0 < 2^31 is formed as uint32; after stage 0, |z| <= 2^30.
+template <bool BIAS>
 BHW_HD void cordic_core_fast32(const SrcParams& p, uint32_t low, int32_t& vs, int32_t& vc) {
-  int32_t z = (int32_t)((low >> p.z_rshift) << p.z_lshift);
+  uint32_t z0 = (low >> p.z_rshift) << p.z_lshift;
   const int32_t g = (int32_t)p.gain;
-  int32_t x = g, y = g;  // stage 0: x - (0>>0), 0 + (x>>0)
-  z -= (int32_t)((c_atan[p.rom_sel][0] >> p.rom_shift) & p.rom_mask);
+  const int32_t K = BIAS ? (1 << 30) : 0;
+  int32_t x = g - K, y = g - K;  // stage 0: x - (0>>0), 0 + (x>>0)
+  int32_t z = (int32_t)(z0 - (uint32_t)((c_atan[p.rom_sel][0] >> p.rom_shift) & p.rom_mask));
   const int n_xy = p.n_xy, n_z = p.n_z;
 #pragma unroll 4
   for (int i = 1; i < n_xy; ++i) {
     const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
-    const int32_t xs = x >> i, ys = y >> i;
+    const int32_t ki = BIAS ? (K >> i) : 0;
+    const int32_t xs = (x >> i) + ki, ys = (y >> i) + ki;
     x -= d * ys;                      // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
     y += d * xs;                      // z<0: y - (x>>i)
     if (i < n_z) z -= d * (int32_t)((c_atan[p.rom_sel][i] >> p.rom_shift) & p.rom_mask);
   }
-  vs = y >> p.out_shift;
-  vc = x >> p.out_shift;
+  vs = (y >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
+  vc = (x >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
 }
 
 // Work item `e` of a table job -> table entries.
@@ -250,7 +258,8 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   const uint32_t low = e;
   int64_t vs, vc;
   if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom + job.rom_off, low, vs, vc);
-  else if (job.fast) { int32_t s32, c32; cordic_core_fast32(p, low, s32, c32); vs = s32; vc = c32; }
+  else if (job.fast == 1) { int32_t s32, c32; cordic_core_fast32<false>(p, low, s32, c32); vs = s32; vc = c32; }
+  else if (job.fast == 2) { int32_t s32, c32; cordic_core_fast32<true>(p, low, s32, c32); vs = s32; vc = c32; }
   else cordic_core_generic(p, 0, low, vs, vc);
   const uint32_t Q = job.entries >> 2;
   const int64_t t = (int64_t)1 << job.tshift;
@@ -384,7 +393,11 @@ struct Direct32Params {
 };
 
 // cos of a pw-bit phase by the unrolled CORDIC (src/cordic_dds.vhd:170-246 with the quadrant fix;
-// identical structure in hls/windows/win_function.cpp:86-154)
+// identical structure in hls/windows/win_function.cpp:86-154).  NXY = number of x/y stages, a
+// compile-time constant so that every shift is an immediate and the stages are straight-line code;
+// NXY == 0 selects the run-time loop (any stage count).  The z update of a stage past n_z uses a
+// zero atan word (HLS: the last stage reads no table entry) - z is dead after the last stage.
+template <int NXY>
 BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
   const int pw = p.pw;
   const uint32_t q = ph >> (pw - 2);
@@ -392,14 +405,26 @@ BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
   int32_t z = (int32_t)((low >> p.z_rshift) << p.z_lshift);
   int32_t x = p.gain, y = p.gain;  // stage 0 with z0 >= 0: x - (0>>0), 0 + (x>>0)
   z -= p.rom[0];
-  const int n_xy = p.n_xy, n_z = p.n_z;  // n_z == n_xy (cordic_dds) or n_xy - 1 (HLS: last atan word unused)
+  if (NXY > 0) {
+#pragma unroll
+    for (int i = 1; i < (NXY > 0 ? NXY : 1); ++i) {
+      // d = -1 when z < 0, else +1; only multiply-ADDs so that each update is one IMAD
+      const int32_t d = (z >> 31) | 1, nd = -d;
+      const int32_t xs = x >> i, ys = y >> i;
+      x = ys * nd + x;               // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
+      y = xs * d + y;                // z<0: y - (x>>i)
+      z = p.rom[i] * nd + z;
+    }
+  } else {
+    const int n_xy = p.n_xy;
 #pragma unroll 4
-  for (int i = 1; i < n_xy; ++i) {
-    const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
-    const int32_t xs = x >> i, ys = y >> i;
-    x -= d * ys;                      // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
-    y += d * xs;                      // z<0: y - (x>>i)
-    z -= d * (i < n_z ? p.rom[i] : 0);
+    for (int i = 1; i < n_xy; ++i) {
+      const int32_t d = (z >> 31) | 1;
+      const int32_t xs = x >> i, ys = y >> i;
+      x -= d * ys;
+      y += d * xs;
+      z -= d * p.rom[i];
+    }
   }
   const int32_t vc = x >> p.out_shift, vs = y >> p.out_shift;
   // quadrant fix for the cosine output: c, -s, -c, s.  |vc|,|vs| <= 2^(DW-2)+eps, so the
@@ -408,13 +433,13 @@ BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
   return ((q + 1u) & 2u) ? -v : v;
 }
 
-template <int M>
+// one output sample; the harmonics are a run-time loop (m is a kernel parameter)
+template <int NXY>
 BHW_HD int32_t direct32_sample(const Direct32Params& p, uint32_t n) {
   const uint32_t pmask = (1u << p.pw) - 1u;
   uint32_t S = (uint32_t)p.S0;
-#pragma unroll
-  for (int k = 1; k < M; ++k) {
-    const int32_t c = direct32_cos(p, (p.kmul[k] * n) & pmask);
+  for (int k = 1; k < p.m; ++k) {
+    const int32_t c = direct32_cos<NXY>(p, (p.kmul[k] * n) & pmask);
     const uint32_t b = (uint32_t)mulhi_rc(p.A[k], c << p.tshift, p.rc);
     S = (k & 1) ? S - b : S + b;
   }

@@ -242,20 +242,35 @@ k_direct_window(DirectArgs a, OutT* __restrict__ out) {
   }
 }
 
-// Register-resident 32-bit form: 4 consecutive samples per thread, one 128-bit store.
-template <int M>
+// Register-resident 32-bit form: 4 consecutive samples per thread (four independent shift-add
+// chains in flight), one 128-bit store.  NXY = compile-time stage count (0: run-time loop).
+template <int NXY>
 __global__ void __launch_bounds__(256)
 k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
   const Direct32Params& p = a.p;
   const uint64_t quads = (a.count + 3) / 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const uint32_t pmask = (1u << p.pw) - 1u;
   for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads;
        qd += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t j = qd * 4;
-    const uint32_t n = (uint32_t)(a.n0 + j) + p.n_first;  // taken modulo 2^pw inside
+    const uint32_t n = (uint32_t)(a.n0 + j) + p.n_first;  // taken modulo 2^pw below
+    uint32_t S[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) S[e] = (uint32_t)p.S0;
+    for (int k = 1; k < p.m; ++k) {
+      const uint32_t km = p.kmul[k];
+      const int32_t Ak = p.A[k];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int32_t c = direct32_cos<NXY>(p, (km * (n + e)) & pmask);
+        const uint32_t b = (uint32_t)mulhi_rc(Ak, c << p.tshift, p.rc);
+        S[e] = (k & 1) ? S[e] - b : S[e] + b;
+      }
+    }
     int32_t v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = direct32_sample<M>(p, n + e);
+    for (int e = 0; e < 4; ++e) v[e] = (int32_t)(S[e] << p.lsh) >> p.rsh;
     if (aligned && j + 4 <= a.count) {
       __stcs(reinterpret_cast<int4*>(out + j), make_int4(v[0], v[1], v[2], v[3]));
     } else {
@@ -371,16 +386,21 @@ cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t st
   return cudaGetLastError();
 }
 
+template <int NXY>
+static void launch_direct32_t(const Direct32Args& a, int32_t* out, unsigned grid, cudaStream_t stream) {
+  k_direct32<NXY><<<grid, 256, 0, stream>>>(a, out);
+}
+
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream) {
   if (!a.count) return cudaSuccess;
   const unsigned grid = grid_for(((a.count + 3) / 4 + 255) / 256, 8);
-  switch (a.p.m) {
-    case 2: k_direct32<2><<<grid, 256, 0, stream>>>(a, out); break;
-    case 3: k_direct32<3><<<grid, 256, 0, stream>>>(a, out); break;
-    case 4: k_direct32<4><<<grid, 256, 0, stream>>>(a, out); break;
-    case 5: k_direct32<5><<<grid, 256, 0, stream>>>(a, out); break;
-    case 7: k_direct32<7><<<grid, 256, 0, stream>>>(a, out); break;
-    default: return cudaErrorInvalidValue;
+  switch (a.p.n_xy) {  // DAT_WIDTH 8..31 (cordic_dds: DW-1 stages; HLS: NW stages)
+#define BHW_D32(N) case N: launch_direct32_t<N>(a, out, grid, stream); break;
+    BHW_D32(7) BHW_D32(8) BHW_D32(9) BHW_D32(10) BHW_D32(11) BHW_D32(12) BHW_D32(13) BHW_D32(14)
+    BHW_D32(15) BHW_D32(16) BHW_D32(17) BHW_D32(18) BHW_D32(19) BHW_D32(20) BHW_D32(21) BHW_D32(22)
+    BHW_D32(23) BHW_D32(24) BHW_D32(25) BHW_D32(26) BHW_D32(27) BHW_D32(28) BHW_D32(29) BHW_D32(30)
+#undef BHW_D32
+    default: launch_direct32_t<0>(a, out, grid, stream); break;
   }
   return cudaGetLastError();
 }

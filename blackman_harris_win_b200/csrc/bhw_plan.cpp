@@ -28,6 +28,14 @@ bool fast32_ok(const SrcParams& sp) {
   return false;
 }
 
+// Which 32-bit core the table builder may use: 0 none (generic 64-bit), 1 plain, 2 biased
+// (cordic_dds with DW+PRECISION == 33, i.e. DAT_WIDTH 32 in the window entities; out_shift >= 1)
+int table_core32(const SrcParams& sp) {
+  if (fast32_ok(sp)) return 1;
+  if (sp.kind == SRC_DDS && sp.dw >= 8 && sp.w == 33 && sp.out_shift >= 1 && sp.n_xy <= 31) return 2;
+  return 0;
+}
+
 // quarter-wave ROM of taylor_sincos, computed as the VHDL does with math_real
 // (src/taylor_sincos.vhd:91-111): INTEGER((2^(DW-1)-1) * cos(ii*pi/(2*depth))), round to nearest.
 void build_taylor_rom(int dw, int lut, std::vector<I2>& rom) {
@@ -111,7 +119,7 @@ bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* 
   p.S0 = r.S0; p.lsh = r.lsh; p.rsh = r.rsh; p.rc = r.rc;
   p.n_first = (uint32_t)wp.stream_offset;
   for (int k = 1; k < wp.m; k++) { p.A[k] = r.A[k]; p.kmul[k] = wp.term[k - 1].kmul; }
-  for (int i = 0; i < sp.n_z && i < 32; i++)
+  for (int i = 0; i < sp.n_z && i < 32; i++)   // entries past n_z stay 0
     p.rom[i] = (int32_t)((c_atan[sp.rom_sel][i] >> sp.rom_shift) & sp.rom_mask);
   return true;
 }

@@ -33,7 +33,7 @@ void build_table(const SrcParams& sp, const std::vector<I2>& rom, HostTable& t, 
   j.sp = t.canon;
   j.tab = t.data.data();
   j.entries = entries;
-  j.fast = (!force_generic && fast32_ok(t.canon)) ? 1u : 0u;
+  j.fast = force_generic ? 0u : (uint32_t)table_core32(t.canon);
   j.tshift = (uint32_t)table_tshift(t.canon);
   j.work = t.canon.kind == SRC_INQ ? entries : entries / 4;
   for (uint32_t e = 0; e < j.work; e++) table_build_item(j, rom.data(), e);
@@ -65,13 +65,19 @@ int hc_direct32(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
   if (wp.elem64 || !direct32_params(wp, src, &p)) return 1;
   for (uint64_t j = 0; j < count; j++) {
     const uint32_t n = (uint32_t)(n0 + j) + p.n_first;
-    switch (p.m) {
-      case 2: out[j] = direct32_sample<2>(p, n); break;
-      case 3: out[j] = direct32_sample<3>(p, n); break;
-      case 4: out[j] = direct32_sample<4>(p, n); break;
-      case 5: out[j] = direct32_sample<5>(p, n); break;
-      default: out[j] = direct32_sample<7>(p, n); break;
+    switch (p.n_xy) {   // the unrolled instantiations the launcher uses, plus the run-time loop
+      case 7: out[j] = direct32_sample<7>(p, n); break;
+      case 11: out[j] = direct32_sample<11>(p, n); break;
+      case 15: out[j] = direct32_sample<15>(p, n); break;
+      case 16: out[j] = direct32_sample<16>(p, n); break;
+      case 19: out[j] = direct32_sample<19>(p, n); break;
+      case 23: out[j] = direct32_sample<23>(p, n); break;
+      case 24: out[j] = direct32_sample<24>(p, n); break;
+      case 29: out[j] = direct32_sample<29>(p, n); break;
+      case 30: out[j] = direct32_sample<30>(p, n); break;
+      default: out[j] = direct32_sample<0>(p, n); break;
     }
+    if (direct32_sample<0>(p, n) != out[j]) return -100;   // unrolled and looped forms agree
   }
   return 0;
 }

@@ -35,6 +35,8 @@ def time_calls(fn, reps, flush=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--only", default="", help="substring filter on the config name")
+    ap.add_argument("--no-batch", action="store_true", help="skip the plan/batch line of each config")
     ap.add_argument("--sweep", action="store_true", help="also run the config-5 sweep (10 variants x PHI_WIDTH 4..26)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
@@ -45,6 +47,8 @@ def main():
     configs["x_bh4_n16m_dw17 (direct32 throughput)"] = bhw.make_desc(4, 24, 17, [47022, 64001, 18518, 1531])
     configs["x_hamming_n16m_dw16 (direct32 throughput)"] = bhw.make_desc(2, 24, 16, [17808, 14959])
     for name, d in configs.items():
+        if args.only and args.only not in name:
+            continue
         n = 1 << d.phi_width
         esz = bhw.elem_bytes(d)
         out = torch.empty(n, dtype=torch.int64 if esz == 8 else torch.int32, device="cuda")
@@ -62,7 +66,7 @@ def main():
                               "kernels_ms_per_call": {k: round(v[1] / v[0], 5) for k, v in kt.items()},
                               "launches_per_call": {k: v[0] / (reps + 3) for k, v in kt.items()}}))
         # batch of identical-shape windows through a plan (device-resident), 256 MB per step
-        if esz == 4 and n <= (1 << 22):
+        if esz == 4 and n <= (1 << 22) and not args.no_batch:
             nwin = max(1, (1 << 26) // n)
             descs = [d.copy(aa=[int(a) - (i % 7) if k == 0 else int(a) for k, a in enumerate(d.aa)]) for i in range(nwin)]
             plan = bhw.Plan(descs)

@@ -89,6 +89,7 @@ struct HostPipe {  // staging of the *_host entry points: two device chunks, two
 struct DeviceState {
   std::mutex mu;
   std::map<uint32_t, CachedRom> roms;  // key: dw << 8 | lut
+  cudaMemPool_t pool = nullptr;        // stream-ordered pool of the one-shot plans (kept warm between calls)
   std::mutex pipe_mu;                  // one host-buffer call at a time per device
   HostPipe pipe;
 };
@@ -112,6 +113,30 @@ static int get_rom(int dev, int dw, int lut, const I2** out) {
   }
   *out = it->second.ptr;
   return BHW_OK;
+}
+
+// The library's own stream-ordered pool: one-shot plans take their tables and records from it.
+// Freed blocks stay in the pool (up to kPoolKeepBytes) instead of going back to the driver at
+// the next synchronisation, so a repeated call does not pay cudaMalloc again.
+static const uint64_t kPoolKeepBytes = 1ull << 30;
+
+static cudaError_t device_pool(int dev, cudaMemPool_t* out) {
+  DeviceState& ds = g_dev[dev];
+  std::lock_guard<std::mutex> lk(ds.mu);
+  if (!ds.pool) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaError_t e = cudaMemPoolCreate(&ds.pool, &props);
+    if (e != cudaSuccess) { ds.pool = nullptr; return e; }
+    uint64_t keep = kPoolKeepBytes;
+    cudaMemPoolSetAttribute(ds.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  *out = ds.pool;
+  return cudaSuccess;
 }
 
 static int current_device(int* dev) {
@@ -192,7 +217,11 @@ static void plan_free_device(bhw_plan& plan, cudaStream_t stream) {
 }
 
 static cudaError_t plan_alloc(bhw_plan& plan, void** p, size_t bytes, cudaStream_t stream) {
-  return plan.transient ? cudaMallocAsync(p, bytes, stream) : cudaMalloc(p, bytes);
+  if (!plan.transient) return cudaMalloc(p, bytes);
+  cudaMemPool_t pool = nullptr;
+  cudaError_t e = device_pool(plan.dev, &pool);
+  if (e != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(p, bytes, pool, stream);
 }
 
 
@@ -550,7 +579,7 @@ static int run_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint6
 }
 
 // ---- host-buffer pipeline ----------------------------------------------------------------------
-static const uint64_t kHostChunkBytes = 64ull << 20;
+static const uint64_t kHostChunkBytes = 32ull << 20;
 
 static cudaError_t pipe_ensure(HostPipe& p) {
   cudaError_t e = cudaSuccess;
@@ -577,7 +606,13 @@ static void pipe_release(HostPipe& p) {
 }
 
 // Generates chunk c on the compute stream while chunk c-1 drains to the host on the copy stream.
-// The batch is planned once; the device staging buffers and streams are kept per device.
+// The request is cut at window boundaries into segments (a short first one, then >= 256 MB each);
+// every segment gets its own one-shot plan, so the host plans segment s+1 while the chunks of
+// segment s are still on their way over the link, and the first byte leaves after planning only
+// a handful of windows.  The device staging buffers and streams are kept per device.
+static const uint64_t kHostFirstSegmentBytes = 16ull << 20;
+static const uint64_t kHostSegmentBytes = 256ull << 20;
+
 static int run_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
                           void* out_host) {
   if (!descs) return BHW_E_NULL;
@@ -603,25 +638,43 @@ static int run_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin, 
   HostPipe& p = ds.pipe;
   cudaError_t e = pipe_ensure(p);
   if (e != cudaSuccess) { pipe_release(p); return cuda_fail(e, "host pipeline setup"); }
-  bhw_plan plan;
-  plan.transient = true;
-  st = plan_build(plan, descs + first, touched, local, flat_count, p.s_gen);
   const uint64_t chunk = p.buf_bytes / esz;
-  uint64_t done = 0;
-  for (int c = 0; !st && e == cudaSuccess && done < flat_count; c++) {
-    const int b = c & 1;
-    const uint64_t cnt = flat_count - done < chunk ? flat_count - done : chunk;
-    if (c >= 2 && (e = cudaStreamWaitEvent(p.s_gen, p.ev_copy[b], 0)) != cudaSuccess) break;  // buffer drained?
-    st = plan_execute(plan, local + done, cnt, p.buf[b], p.s_gen);
-    if (st) break;
-    if ((e = cudaEventRecord(p.ev_gen[b], p.s_gen)) != cudaSuccess) break;
-    if ((e = cudaStreamWaitEvent(p.s_copy, p.ev_gen[b], 0)) != cudaSuccess) break;
-    if ((e = cudaMemcpyAsync((char*)out_host + done * esz, p.buf[b], cnt * esz, cudaMemcpyDeviceToHost,
-                             p.s_copy)) != cudaSuccess) break;
-    if ((e = cudaEventRecord(p.ev_copy[b], p.s_copy)) != cudaSuccess) break;
-    done += cnt;
+  uint64_t done = 0;  // samples of the request handed to the pipeline so far
+  int c = 0;          // chunks so far (selects the staging buffer)
+  int w = first;      // first window of the next segment
+  uint64_t seg_local = local;  // where the request enters window w
+  while (!st && e == cudaSuccess && done < flat_count) {
+    // windows [w, we) of this segment and the samples of the request that fall into them
+    const uint64_t target = (done == 0 ? kHostFirstSegmentBytes : kHostSegmentBytes) / esz;
+    uint64_t seg_count = 0;
+    int we = w;
+    while (we < first + touched && seg_count < target) {
+      uint64_t n = (1ull << descs[we].phi_width) - (we == w ? seg_local : 0);
+      if (n > flat_count - done - seg_count) n = flat_count - done - seg_count;
+      seg_count += n;
+      we++;
+    }
+    bhw_plan plan;
+    plan.transient = true;
+    st = plan_build(plan, descs + w, we - w, seg_local, seg_count, p.s_gen);
+    for (uint64_t seg_done = 0; !st && seg_done < seg_count; c++) {
+      const int b = c & 1;
+      const uint64_t cnt = seg_count - seg_done < chunk ? seg_count - seg_done : chunk;
+      if (c >= 2 && (e = cudaStreamWaitEvent(p.s_gen, p.ev_copy[b], 0)) != cudaSuccess) break;  // buffer drained?
+      st = plan_execute(plan, seg_local + seg_done, cnt, p.buf[b], p.s_gen);
+      if (st) break;
+      if ((e = cudaEventRecord(p.ev_gen[b], p.s_gen)) != cudaSuccess) break;
+      if ((e = cudaStreamWaitEvent(p.s_copy, p.ev_gen[b], 0)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync((char*)out_host + (done + seg_done) * esz, p.buf[b], cnt * esz,
+                               cudaMemcpyDeviceToHost, p.s_copy)) != cudaSuccess) break;
+      if ((e = cudaEventRecord(p.ev_copy[b], p.s_copy)) != cudaSuccess) break;
+      seg_done += cnt;
+    }
+    plan_free_device(plan, p.s_gen);  // stream-ordered: after the segment's last kernel
+    done += seg_count;
+    w = we;
+    seg_local = 0;
   }
-  plan_free_device(plan, p.s_gen);
   cudaError_t e2 = cudaStreamSynchronize(p.s_gen);
   if (e == cudaSuccess) e = e2;
   e2 = cudaStreamSynchronize(p.s_copy);
@@ -841,12 +894,13 @@ int bhw_cache_clear(void) {
     DeviceState& ds = g_dev[g];
     std::lock_guard<std::mutex> pl(ds.pipe_mu);
     std::lock_guard<std::mutex> lk(ds.mu);
-    if (ds.roms.empty() && !ds.pipe.s_gen) continue;
+    if (ds.roms.empty() && !ds.pipe.s_gen && !ds.pool) continue;
     cudaSetDevice(g);
     cudaDeviceSynchronize();
     for (auto& kv : ds.roms) cudaFree(kv.second.ptr);
     ds.roms.clear();
     pipe_release(ds.pipe);
+    if (ds.pool) { cudaMemPoolDestroy(ds.pool); ds.pool = nullptr; }
   }
   cudaSetDevice(prev);
   return BHW_OK;

@@ -276,6 +276,29 @@ def test_host_entry_points():
     assert np.array_equal(bhw.generate_batch_host(descs).astype(np.int64), H.orc_batch(descs, 0, bhw.batch_total(descs)))
 
 
+def test_host_pipeline_segments():
+    """The host entry point plans the request in segments cut at window boundaries (a short first
+    one, then >= 256 MiB); a ragged range over a mixed batch that spans several segments must equal
+    the device path sample for sample."""
+    import torch
+    descs = ([bhw.variant_desc(6, 16, 17, ) for _ in range(40)]            # 10 MiB of small windows
+             + [bhw.variant_desc(1 + (i % 10), 20 + (i % 3), cases.VARIANT_DW[1 + (i % 10)]) for i in range(30)]
+             + [bhw.variant_desc(3, 26, 16)]                               # one 256 MiB window
+             + [bhw.variant_desc(9, 12, 24, stream_offset=1) for _ in range(100)])
+    for i, d in enumerate(descs):
+        d.aa[0] -= i % 5
+    total = bhw.batch_total(descs)
+    assert total * 4 > (256 << 20) + (64 << 20)
+    dev = bhw.generate_batch(descs).cpu().numpy()
+    assert np.array_equal(bhw.generate_batch_host(descs), dev)
+    b, c = 12345, total - 12345 - 777
+    assert np.array_equal(bhw.generate_batch_host(descs, b, c), dev[b:b + c])
+    b = (40 << 16) + (3 << 20) + 5                                         # starts inside a large window
+    assert np.array_equal(bhw.generate_batch_host(descs, b, 1 << 22), dev[b:b + (1 << 22)])
+    del dev
+    torch.cuda.empty_cache()
+
+
 def test_win_selector_and_errors():
     w = bhw.WinSelector(PHI_WIDTH=10, DAT_WIDTH=16, WIN_TYPE="HAMMING")
     assert np.array_equal(w.stream(AA0=17808, AA1=14959).cpu().numpy().astype(np.int64),

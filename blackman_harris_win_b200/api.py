@@ -98,6 +98,7 @@ def lib():
         "bhw_sincos": (C.c_int, [D, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
         "bhw_cache_clear": (C.c_int, []),
         "bhw_set_table_cache": (C.c_int, [C.c_int]),
+        "bhw_set_side_streams": (C.c_int, [C.c_int]),
         "bhw_launch_count": (C.c_uint64, []),
         "bhw_last_cuda_error": (C.c_char_p, []),
         "bhw_device_count": (C.c_int, []),
@@ -122,7 +123,7 @@ ABI_SYMBOLS = (
     "bhw_strerror", "bhw_version", "bhw_validate", "bhw_elem_bytes", "bhw_quantize",
     "bhw_variant_coeffs", "bhw_generate", "bhw_generate_host", "bhw_batch_total", "bhw_shard_range",
     "bhw_generate_batch", "bhw_generate_batch_host", "bhw_generate_batch_multi", "bhw_sincos",
-    "bhw_cache_clear", "bhw_set_table_cache", "bhw_launch_count", "bhw_last_cuda_error",
+    "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
     "bhw_device_count", "bhw_timing_enable", "bhw_timing_reset", "bhw_timing_read",
     "bhw_shard_windows", "bhw_plan_create", "bhw_plan_execute", "bhw_plan_total", "bhw_plan_destroy",
 )
@@ -349,6 +350,10 @@ def sincos(d: BhwDesc, n0: int = 0, count: Optional[int] = None, device=None):
 
 def cache_clear():
     _check(lib().bhw_cache_clear(), "bhw_cache_clear")
+
+
+def set_side_streams(n: int):
+    _check(lib().bhw_set_side_streams(int(n)), "bhw_set_side_streams")
 
 
 def set_table_cache(enabled: bool):

@@ -25,6 +25,7 @@ namespace bhw {
 
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_cache_enabled{1};
+static std::atomic<int> g_side_streams{4};  // bhw_set_side_streams
 static thread_local std::string t_cuda_err;
 
 static int cuda_fail(cudaError_t e, const char* where) {
@@ -80,6 +81,7 @@ struct CachedRom {
   I2* ptr = nullptr;
   uint32_t entries = 0;
 };
+static const int kMaxSideStreams = 8;
 struct HostPipe {  // staging of the *_host entry points: two device chunks, two streams
   cudaStream_t s_gen = nullptr, s_copy = nullptr;
   cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -92,6 +94,10 @@ struct DeviceState {
   cudaMemPool_t pool = nullptr;        // stream-ordered pool of the one-shot plans (kept warm between calls)
   std::mutex pipe_mu;                  // one host-buffer call at a time per device
   HostPipe pipe;
+  // fork/join of the independent launches of one execute (see LaunchFan)
+  std::mutex fan_mu;
+  cudaStream_t side[kMaxSideStreams] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSideStreams] = {nullptr};
 };
 static DeviceState g_dev[64];
 
@@ -382,14 +388,8 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     cudaError_t e = plan_alloc(plan, (void**)&pt.ptr, (size_t)pt.entries * sizeof(int32_t), stream);
     if (e != cudaSuccess) return cuda_fail(e, "alloc(trig table)");
     TabJob j;
-    memset(&j, 0, sizeof(j));
-    j.sp = pt.canon;
-    j.tab = pt.ptr;
-    j.entries = pt.entries;
-    j.fast = (uint32_t)table_core32(pt.canon);
-    j.tshift = (uint32_t)table_tshift(pt.canon);
+    init_tab_job(pt.canon, pt.ptr, &j);
     j.work_begin = work;
-    j.work = pt.canon.kind == SRC_INQ ? pt.entries : pt.entries / 4;
     if (pt.canon.kind == SRC_TAYLOR) {
       const I2* rom = nullptr;
       if ((st = get_rom(plan.dev, pt.canon.dw, pt.canon.lut, &rom))) return st;
@@ -433,6 +433,67 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   if (!need_off) { plan.flat_off.clear(); plan.flat_off.shrink_to_fit(); }
   return BHW_OK;
 }
+
+// The synthesis launches of one execute write disjoint output ranges and only read the trig
+// tables, so they are independent of each other.  A batch of many differently shaped windows
+// (the win_selector sweep: ~200 launches, most of them far too small to fill 148 SMs) is
+// therefore fanned out over a few side streams: an event recorded on the caller's stream after
+// the table build forks them, one event per side stream joins them back.  Stream-ordered as a
+// whole - the caller sees nothing but its own stream.
+struct LaunchFan {
+  DeviceState* ds = nullptr;
+  cudaStream_t main = nullptr;
+  int nside = 0;          // side streams in use for this execute (0: everything on `main`)
+  unsigned used = 0;      // side streams that received work
+  unsigned rr = 0;
+  cudaError_t err = cudaSuccess;
+  std::unique_lock<std::mutex> lock;
+
+  // `launches`: how many independent launches are coming
+  void begin(int dev, cudaStream_t stream, size_t launches) {
+    main = stream;
+    int want = g_side_streams.load();
+    if (want > kMaxSideStreams) want = kMaxSideStreams;
+    if (want <= 0 || launches < 4) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;
+    ds = &g_dev[dev];
+    lock = std::unique_lock<std::mutex>(ds->fan_mu);
+    if (!ds->ev_fork && (err = cudaEventCreateWithFlags(&ds->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return;
+    for (int i = 0; i < want; i++) {
+      if (!ds->side[i] && (err = cudaStreamCreateWithFlags(&ds->side[i], cudaStreamNonBlocking)) != cudaSuccess) return;
+      if (!ds->ev_join[i] && (err = cudaEventCreateWithFlags(&ds->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return;
+    }
+    if ((err = cudaEventRecord(ds->ev_fork, main)) != cudaSuccess) return;
+    nside = want;
+  }
+  // stream of the next launch
+  cudaStream_t next() {
+    if (!nside) return main;
+    const unsigned slot = rr++ % (unsigned)(nside + 1);
+    if (slot == 0) return main;
+    const unsigned i = slot - 1;
+    if (!(used & (1u << i))) {
+      cudaError_t e = cudaStreamWaitEvent(ds->side[i], ds->ev_fork, 0);
+      if (e != cudaSuccess) { err = e; return main; }
+      used |= 1u << i;
+    }
+    return ds->side[i];
+  }
+  // make `main` wait for everything that went to a side stream
+  cudaError_t join() {
+    for (int i = 0; i < nside; i++) {
+      if (!(used & (1u << i))) continue;
+      cudaError_t e = cudaEventRecord(ds->ev_join[i], ds->side[i]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ds->ev_join[i], 0);
+      if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+    used = 0;
+    nside = 0;
+    return err;
+  }
+  ~LaunchFan() { join(); }
+};
 
 static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
                         cudaStream_t stream) {
@@ -479,23 +540,32 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   a.rom = plan.rom;
   a.nwin = plan.nwin;
   a.uniform_pw = plan.uniform_pw;
+  // whole windows of bank runs go to the bank kernel, everything in between to the general one
+  const uint64_t flat_end = flat_begin + flat_count;
+  size_t runs_hit = 0;
+  for (const bhw_plan::BankRun& run : plan.runs) {
+    const uint64_t rb = run.flat_off, re = rb + ((uint64_t)(run.w_end - run.w_begin) << run.sh.pw);
+    if (re > flat_begin && rb < flat_end) runs_hit++;
+  }
+  LaunchFan fan;
+  fan.begin(plan.dev, stream, runs_hit);
+  if (fan.err != cudaSuccess) return cuda_fail(fan.err, "side streams");
   // any flat sub-range through the general kernel
   auto general = [&](uint64_t b, uint64_t e_) -> int {
     if (b >= e_) return BHW_OK;
     a.out = (int32_t*)out_dev + (b - flat_begin);
     a.flat_begin = b;
     a.flat_count = e_ - b;
+    cudaStream_t ls = fan.next();
     cudaError_t ce;
     {
-      LaunchTimer tm(BHW_KERNEL_SYNTH, stream);
-      ce = launch_synth(a, stream);
+      LaunchTimer tm(BHW_KERNEL_SYNTH, ls);
+      ce = launch_synth(a, ls);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "k_synth");
     g_launches++;
     return BHW_OK;
   };
-  // whole windows of bank runs go to the bank kernel, everything in between to the general one
-  const uint64_t flat_end = flat_begin + flat_count;
   uint64_t cursor = flat_begin;
   for (const bhw_plan::BankRun& run : plan.runs) {
     const uint32_t pw = run.sh.pw;
@@ -516,15 +586,20 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     ba.out = (int32_t*)out_dev + (bb - flat_begin);
     ba.w_first = (uint32_t)run.w_begin + (uint32_t)wlo;
     ba.nwin = (uint32_t)(whi - wlo);
+    cudaStream_t ls = fan.next();
     {
-      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, stream);
-      e = launch_synth_bank(ba, run.tab_mode, run.pair, stream);
+      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls);
+      e = launch_synth_bank(ba, run.tab_mode, run.pair, ls);
     }
     if (e != cudaSuccess) return cuda_fail(e, "k_synth_bank");
     g_launches++;
     cursor = be;
   }
-  return general(cursor, flat_end);
+  int st = general(cursor, flat_end);
+  if (st) return st;
+  e = fan.join();
+  if (e != cudaSuccess) return cuda_fail(e, "side streams (join)");
+  return BHW_OK;
 }
 
 // windows touched by a flat range
@@ -894,13 +969,21 @@ int bhw_cache_clear(void) {
     DeviceState& ds = g_dev[g];
     std::lock_guard<std::mutex> pl(ds.pipe_mu);
     std::lock_guard<std::mutex> lk(ds.mu);
-    if (ds.roms.empty() && !ds.pipe.s_gen && !ds.pool) continue;
+    if (ds.roms.empty() && !ds.pipe.s_gen && !ds.pool && !ds.ev_fork) continue;
     cudaSetDevice(g);
     cudaDeviceSynchronize();
     for (auto& kv : ds.roms) cudaFree(kv.second.ptr);
     ds.roms.clear();
     pipe_release(ds.pipe);
     if (ds.pool) { cudaMemPoolDestroy(ds.pool); ds.pool = nullptr; }
+    {
+      std::lock_guard<std::mutex> fl(ds.fan_mu);
+      for (int i = 0; i < kMaxSideStreams; i++) {
+        if (ds.side[i]) { cudaStreamDestroy(ds.side[i]); ds.side[i] = nullptr; }
+        if (ds.ev_join[i]) { cudaEventDestroy(ds.ev_join[i]); ds.ev_join[i] = nullptr; }
+      }
+      if (ds.ev_fork) { cudaEventDestroy(ds.ev_fork); ds.ev_fork = nullptr; }
+    }
   }
   cudaSetDevice(prev);
   return BHW_OK;
@@ -908,6 +991,12 @@ int bhw_cache_clear(void) {
 
 int bhw_set_table_cache(int enabled) {
   g_cache_enabled.store(enabled ? 1 : 0);
+  return BHW_OK;
+}
+
+int bhw_set_side_streams(int n) {
+  if (n < 0 || n > kMaxSideStreams) return BHW_E_ARG;
+  g_side_streams.store(n);
   return BHW_OK;
 }
 

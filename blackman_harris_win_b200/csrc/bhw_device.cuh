@@ -208,12 +208,15 @@ struct TabJob {
   SrcParams sp;         // canonical source: phase width reduced so that no phase bit is ignored
   int32_t* tab;         // the table (device memory), `entries` int32 words
   uint32_t entries;     // 2^sp.pw
-  uint32_t fast;        // 1: the 32-bit core is exact for this source; 2: its biased form (W == 33)
+  uint32_t fast;        // TABCORE_*: which shift-add core evaluates this source exactly
   uint32_t work_begin;  // prefix sum of work items (threads) over the jobs of a launch
   uint32_t work;        // work items of this job: entries/4, or entries for SRC_INQ
   uint32_t rom_off;     // Taylor ROM offset (I2 units) in the rom buffer
   uint32_t tshift;      // entries are stored left-shifted by this much (see WinRec)
+  int32_t rom32[32];    // TABCORE_32 / _32BIAS: atan word of stage i sliced for this register width (0 past n_z)
+  int64_t rom64[48];    // TABCORE_A64: atan word of stage i, sliced and left-aligned to bit 63 (0 past n_z)
 };
+enum : uint32_t { TABCORE_GENERIC = 0, TABCORE_32 = 1, TABCORE_32BIAS = 2, TABCORE_A64 = 3 };
 
 // 32-bit CORDIC for output-quadrant sources whose registers fit int32 and never wrap:
 // SRC_DDS with 8 <= DW, DW+PRECISION <= 32 and SRC_HLS with 8 <= NW <= 30.  Amplitude is a
@@ -225,13 +228,14 @@ struct TabJob {
 // (X + 2^30) >> i == (X >> i) + 2^(30-i) exactly, so every stage and the output shift stay exact.
 // z0 < 2^31 is formed as uint32; after stage 0, |z| <= 2^30.
 template <bool BIAS>
-BHW_HD void cordic_core_fast32(const SrcParams& p, uint32_t low, int32_t& vs, int32_t& vc) {
-  uint32_t z0 = (low >> p.z_rshift) << p.z_lshift;
+BHW_HD void cordic_core_fast32(const SrcParams& p, const int32_t* __restrict__ rom32, uint32_t low, int32_t& vs,
+                               int32_t& vc) {
+  const uint32_t z0 = (low >> p.z_rshift) << p.z_lshift;
   const int32_t g = (int32_t)p.gain;
   const int32_t K = BIAS ? (1 << 30) : 0;
   int32_t x = g - K, y = g - K;  // stage 0: x - (0>>0), 0 + (x>>0)
-  int32_t z = (int32_t)(z0 - (uint32_t)((c_atan[p.rom_sel][0] >> p.rom_shift) & p.rom_mask));
-  const int n_xy = p.n_xy, n_z = p.n_z;
+  int32_t z = (int32_t)(z0 - (uint32_t)rom32[0]);
+  const int n_xy = p.n_xy;
 #pragma unroll 4
   for (int i = 1; i < n_xy; ++i) {
     const int32_t d = (z >> 31) | 1;  // -1 when z < 0, else +1
@@ -239,10 +243,46 @@ BHW_HD void cordic_core_fast32(const SrcParams& p, uint32_t low, int32_t& vs, in
     const int32_t xs = (x >> i) + ki, ys = (y >> i) + ki;
     x -= d * ys;                      // z<0: x + (y>>i)   (src/cordic_dds.vhd:199-205)
     y += d * xs;                      // z<0: y - (x>>i)
-    if (i < n_z) z -= d * (int32_t)((c_atan[p.rom_sel][i] >> p.rom_shift) & p.rom_mask);
+    z -= d * rom32[i];                // the word is 0 for stages past n_z
   }
   vs = (y >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
   vc = (x >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
+}
+
+// 64-bit core with the registers left-aligned to bit 63: X = x << (64-w), Z = z << (64-zw).  The
+// reference's wrap of every sum to w (zw) bits is then the natural overflow of the 64-bit add, and
+// (x >> i) << (64-w) == (X >> i) with the low 64-w bits cleared.  Covers the input-quadrant
+// CORDICs (src/cordic_dds48.vhd:170-246, src/cordic_dds_scaled.vhd) and any output-quadrant one
+// too wide for the 32-bit cores; same results as cordic_core_generic.
+BHW_HD void cordic_core_aligned64(const SrcParams& p, const int64_t* __restrict__ rom64, int q, uint64_t low,
+                                  int64_t& vs, int64_t& vc) {
+  const int pw = p.pw;
+  const bool inq = p.kind == SRC_INQ;
+  const int ax = 64 - p.w, az = 64 - p.zw;
+  const int64_t mx = (int64_t)(~0ull << ax);
+  const int64_t G = (int64_t)((uint64_t)p.gain << ax);
+  int64_t X = G, Y = 0, Z;
+  if (inq) {
+    uint64_t t = low | ((uint64_t)q << (pw - 2));
+    if (q == 1) { t = low; X = 0; Y = (int64_t)(0ull - (uint64_t)G); }
+    else if (q == 2) { t = low | (3ull << (pw - 2)); X = 0; Y = G; }
+    Z = (int64_t)(t << (p.z_lshift + az));
+  } else {
+    Z = (int64_t)(((low >> p.z_rshift) << p.z_lshift) << az);
+  }
+  const int n_xy = p.n_xy;
+#pragma unroll 2
+  for (int i = 0; i < n_xy; ++i) {
+    const bool zneg = Z < 0;
+    const bool cw = inq ? !zneg : zneg;
+    const uint64_t Xs = (uint64_t)((X >> i) & mx), Ys = (uint64_t)((Y >> i) & mx);
+    const uint64_t r = (uint64_t)rom64[i];
+    X = (int64_t)(cw ? (uint64_t)X + Ys : (uint64_t)X - Ys);
+    Y = (int64_t)(cw ? (uint64_t)Y - Xs : (uint64_t)Y + Xs);
+    Z = (int64_t)(zneg ? (uint64_t)Z + r : (uint64_t)Z - r);
+  }
+  vs = Y >> (ax + p.out_shift);
+  vc = X >> (ax + p.out_shift);
 }
 
 // Work item `e` of a table job -> table entries.
@@ -251,15 +291,22 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   int32_t* T = job.tab;
   if (p.kind == SRC_INQ) {  // one phase per item, no output symmetry
     int64_t s, c;
-    eval_source_generic(p, rom, (uint64_t)e, s, c);
+    if (job.fast == TABCORE_A64) {
+      const int q = (int)(e >> (p.pw - 2));
+      cordic_core_aligned64(p, job.rom64, q, (uint64_t)(e & ((1u << (p.pw - 2)) - 1u)), s, c);
+      c = wrapb(c, p.outw);
+    } else {
+      eval_source_generic(p, rom, (uint64_t)e, s, c);
+    }
     T[e] = (int32_t)(c * ((int64_t)1 << job.tshift));
     return;
   }
   const uint32_t low = e;
   int64_t vs, vc;
   if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom + job.rom_off, low, vs, vc);
-  else if (job.fast == 1) { int32_t s32, c32; cordic_core_fast32<false>(p, low, s32, c32); vs = s32; vc = c32; }
-  else if (job.fast == 2) { int32_t s32, c32; cordic_core_fast32<true>(p, low, s32, c32); vs = s32; vc = c32; }
+  else if (job.fast == TABCORE_32) { int32_t s32, c32; cordic_core_fast32<false>(p, job.rom32, low, s32, c32); vs = s32; vc = c32; }
+  else if (job.fast == TABCORE_32BIAS) { int32_t s32, c32; cordic_core_fast32<true>(p, job.rom32, low, s32, c32); vs = s32; vc = c32; }
+  else if (job.fast == TABCORE_A64) cordic_core_aligned64(p, job.rom64, 0, low, vs, vc);
   else cordic_core_generic(p, 0, low, vs, vc);
   const uint32_t Q = job.entries >> 2;
   const int64_t t = (int64_t)1 << job.tshift;

@@ -28,12 +28,33 @@ bool fast32_ok(const SrcParams& sp) {
   return false;
 }
 
-// Which 32-bit core the table builder may use: 0 none (generic 64-bit), 1 plain, 2 biased
-// (cordic_dds with DW+PRECISION == 33, i.e. DAT_WIDTH 32 in the window entities; out_shift >= 1)
+// Which shift-add core the table builder may use (TABCORE_*): the plain 32-bit one, its biased
+// form (cordic_dds with DW+PRECISION == 33, i.e. DAT_WIDTH 32 in the window entities;
+// out_shift >= 1), the left-aligned 64-bit one, or the generic body.
 int table_core32(const SrcParams& sp) {
-  if (fast32_ok(sp)) return 1;
-  if (sp.kind == SRC_DDS && sp.dw >= 8 && sp.w == 33 && sp.out_shift >= 1 && sp.n_xy <= 31) return 2;
-  return 0;
+  if (fast32_ok(sp)) return TABCORE_32;
+  if (sp.kind == SRC_DDS && sp.dw >= 8 && sp.w == 33 && sp.out_shift >= 1 && sp.n_xy <= 31) return TABCORE_32BIAS;
+  if ((sp.kind == SRC_INQ || sp.kind == SRC_DDS || sp.kind == SRC_HLS) && sp.w >= 8 && sp.w <= 64 && sp.zw >= 8 &&
+      sp.zw <= 64 && sp.n_xy <= 48 && sp.pw >= 3 && sp.z_lshift + (64 - sp.zw) <= 63)
+    return TABCORE_A64;
+  return TABCORE_GENERIC;
+}
+
+// Everything of a table job except its place in the launch (work_begin) and the Taylor ROM offset.
+void init_tab_job(const SrcParams& canon, int32_t* tab, TabJob* j) {
+  memset(j, 0, sizeof(*j));
+  j->sp = canon;
+  j->tab = tab;
+  j->entries = 1u << canon.pw;
+  j->fast = (uint32_t)table_core32(canon);
+  j->tshift = (uint32_t)table_tshift(canon);
+  j->work = canon.kind == SRC_INQ ? j->entries : j->entries / 4;
+  if (canon.kind == SRC_TAYLOR) return;
+  for (int i = 0; i < canon.n_z && i < 48; i++) {
+    const int64_t r = (c_atan[canon.rom_sel][i] >> canon.rom_shift) & canon.rom_mask;
+    if (i < 32 && (j->fast == TABCORE_32 || j->fast == TABCORE_32BIAS)) j->rom32[i] = (int32_t)r;
+    if (j->fast == TABCORE_A64) j->rom64[i] = (int64_t)((uint64_t)r << (64 - canon.zw));
+  }
 }
 
 // quarter-wave ROM of taylor_sincos, computed as the VHDL does with math_real

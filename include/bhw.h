@@ -219,6 +219,11 @@ BHW_API int bhw_cache_clear(void);             /* free the cached sine ROMs and 
 BHW_API int bhw_set_table_cache(int enabled);  /* 1 (default): a plan builds its trig tables on its
                                           first execute and keeps them; 0: every execute
                                           rebuilds them (one-shot calls always build)        */
+BHW_API int bhw_set_side_streams(int n);        /* 0..8 (default 4): an execute with many independent
+                                          launches (a batch of differently shaped windows) fans
+                                          them out over n internal side streams, forked from and
+                                          joined back into the caller's stream; 0 keeps every
+                                          launch on the caller's stream                       */
 BHW_API uint64_t bhw_launch_count(void);       /* kernels launched by this library so far */
 BHW_API const char* bhw_last_cuda_error(void); /* text of the last CUDA failure           */
 BHW_API int bhw_device_count(void);

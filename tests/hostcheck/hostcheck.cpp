@@ -29,13 +29,8 @@ void build_table(const SrcParams& sp, const std::vector<I2>& rom, HostTable& t, 
   const uint32_t entries = 1u << t.canon.pw;
   t.data.assign(entries, 0x7FFFFFFF);
   TabJob j;
-  memset(&j, 0, sizeof(j));
-  j.sp = t.canon;
-  j.tab = t.data.data();
-  j.entries = entries;
-  j.fast = force_generic ? 0u : (uint32_t)table_core32(t.canon);
-  j.tshift = (uint32_t)table_tshift(t.canon);
-  j.work = t.canon.kind == SRC_INQ ? entries : entries / 4;
+  init_tab_job(t.canon, t.data.data(), &j);
+  if (force_generic) j.fast = TABCORE_GENERIC;
   for (uint32_t e = 0; e < j.work; e++) table_build_item(j, rom.data(), e);
 }
 

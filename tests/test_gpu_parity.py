@@ -228,6 +228,19 @@ def test_win_selector_sweep_all_variants_all_lengths():
             assert torch.equal(out[off:off + n], bhw.generate(d)), d
             assert np.array_equal(out[off + n - 4096:off + n].cpu().numpy().astype(np.int64), H.orc_window(d, n - 4096, 4096)), d
         off += n
+    # the launches of one execute are fanned out over side streams by default; everything on the
+    # caller's stream, and a ragged sub-range on a non-default stream, must give the same samples
+    bhw.set_side_streams(0)
+    try:
+        assert torch.equal(plan.execute(), out)
+    finally:
+        bhw.set_side_streams(4)
+    b, c = (1 << 20) + 12, bhw.batch_total(descs) - (1 << 22)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        part = plan.execute(b, c)
+    s.synchronize()
+    assert torch.equal(part, out[b:b + c])
     plan.destroy()
 
 

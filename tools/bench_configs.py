@@ -32,6 +32,29 @@ def time_calls(fn, reps, flush=None):
     return e0.elapsed_time(e1) / reps  # ms per call
 
 
+_SCALED_SIZE = [15, 15, 15, 18, 21, 22, 23, 26, 30, 31, 32, 33, 38, 38, 38, 42, 42, 45, 47, 47, 47, 48, 48, 48, 48]
+
+
+def alg_int_ops_per_sample(d):
+    """Algorithmic integer work of the one-thread-per-sample formulation in 32-bit-op units, with
+    the reference's own accounting of 3 additions + 2 shifts per CORDIC stage
+    (src/cordic_dds.vhd:39-43); SURVEY.md 8(d):  (M-1)*[S*5*L + 7] + (M-1)*4*L' + (M-1) + 3."""
+    m, dw = d.win_type, d.dat_width
+    if d.model == bhw.MODEL_HLS:
+        stages, width = dw, dw + 2
+    elif d.sin_type == bhw.SIN_CORDIC:
+        stages, width = dw - 1, dw + max(d.precision, 1)
+    elif d.sin_type == bhw.SIN_CORDIC48:
+        stages, width = dw, 48
+    elif d.sin_type == bhw.SIN_CORDIC_SCALED:
+        stages, width = dw, _SCALED_SIZE[dw - 8]
+    else:                       # TAYLOR: ROM look-up + 1 narrow and 2 wide multiplies + ~12 (SURVEY 8d cfg 4)
+        stages, width = 4, 32   # 4 * 5 = 20 ops per unit
+    L = 1 if width <= 32 else 2
+    Lp = 1 if 2 * dw <= 32 else (2 if dw <= 32 else 4)
+    return (m - 1) * (stages * 5 * L + 7) + (m - 1) * 4 * Lp + (m - 1) + 3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=50)
@@ -42,6 +65,11 @@ def main():
     torch.cuda.set_device(0)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    int_peak = None
+    try:
+        int_peak = json.load(open(os.path.join(ROOT, "profiles", "int_peak.json")))["int32_mix_tops"] * 1e12
+    except Exception:
+        pass
     configs = dict(cases.baseline_configs())
     # throughput shapes for the register-resident direct kernel (not BASELINE configs)
     configs["x_bh4_n16m_dw17 (direct32 throughput)"] = bhw.make_desc(4, 24, 17, [47022, 64001, 18518, 1531])
@@ -60,11 +88,21 @@ def main():
             ms = time_calls(lambda: bhw.generate(dd, out=out), reps)
             kt = {k: v for k, v in bhw.timing_read().items() if v[0]}
             bhw.timing_enable(False)
-            print(json.dumps({"config": name, "algo": algo_name, "samples": n, "ms_per_window": round(ms, 5),
-                              "gsamples_per_s": round(n / ms / 1e6, 3), "write_gbs": round(n * esz / ms / 1e6, 2),
-                              "frac_of_hbm_peak": round(n * esz / ms / 1e6 / peak, 4),
-                              "kernels_ms_per_call": {k: round(v[1] / v[0], 5) for k, v in kt.items()},
-                              "launches_per_call": {k: v[0] / (reps + 3) for k, v in kt.items()}}))
+            line = {"config": name, "algo": algo_name, "samples": n, "ms_per_window": round(ms, 5),
+                    "gsamples_per_s": round(n / ms / 1e6, 3), "write_gbs": round(n * esz / ms / 1e6, 2),
+                    "frac_of_hbm_peak": round(n * esz / ms / 1e6 / peak, 4),
+                    "kernels_ms_per_call": {k: round(v[1] / v[0], 5) for k, v in kt.items()},
+                    "launches_per_call": {k: v[0] / (reps + 3) for k, v in kt.items()}}
+            if algo == bhw.ALGO_DIRECT and "k_direct_window" in kt and int_peak:
+                # integer-ALU roofline of the direct kernel: algorithmic ops / kernel time vs the
+                # measured alu+fma issue peak of this GPU (tools/int_peak.cu -> profiles/int_peak.json)
+                ops = alg_int_ops_per_sample(d)
+                k_ms = kt["k_direct_window"][1] / kt["k_direct_window"][0]
+                line["int_roofline"] = {"alg_ops_per_sample": ops, "achieved_tops": round(ops * n / k_ms / 1e9, 3),
+                                        "peak_tops": round(int_peak / 1e12, 2),
+                                        "frac": round(ops * n / (k_ms * 1e-3) / int_peak, 4),
+                                        "peak_source": "measured, 1:1 SHF/IMAD mix on both pipes (profiles/int_peak.json)"}
+            print(json.dumps(line))
         # batch of identical-shape windows through a plan (device-resident), 256 MB per step
         if esz == 4 and n <= (1 << 22) and not args.no_batch:
             nwin = max(1, (1 << 26) // n)
@@ -89,17 +127,25 @@ def main():
         t_plan = time.perf_counter() - t0
         out = torch.empty(total, dtype=torch.int32, device="cuda")
         bhw.set_table_cache(False)
-        bhw.timing_enable(True)
-        bhw.timing_reset()
-        ms = time_calls(lambda: plan.execute(out=out), 5)
-        kt = {k: v for k, v in bhw.timing_read().items() if v[0]}
-        bhw.timing_enable(False)
+        for side in (0, 4):
+            bhw.set_side_streams(side)
+            ms_plain = time_calls(lambda: plan.execute(out=out), 10)   # without the per-launch timing events
+            bhw.timing_enable(True)
+            bhw.timing_reset()
+            ms = time_calls(lambda: plan.execute(out=out), 5)
+            kt = {k: v for k, v in bhw.timing_read().items() if v[0]}
+            bhw.timing_enable(False)
+            print(json.dumps({"config": "cfg5_sweep_10_variants_pw4_26",
+                              "algo": "auto, tables rebuilt per step, %d side streams" % side,
+                              "samples": total, "ms_per_step": round(ms_plain, 4),
+                              "gsamples_per_s": round(total / ms_plain / 1e6, 3),
+                              "frac_of_hbm_peak": round(total * 4 / ms_plain / 1e6 / peak, 4),
+                              "plan_create_ms": round(1e3 * t_plan, 2),
+                              "kernels_ms_per_step (sum of per-launch spans; they overlap with side streams)":
+                                  {k: round(v[1] / 8, 4) for k, v in kt.items()},
+                              "launches_per_step": {k: v[0] / 8 for k, v in kt.items()}}))
+        bhw.set_side_streams(4)
         bhw.set_table_cache(True)
-        print(json.dumps({"config": "cfg5_sweep_10_variants_pw4_26", "algo": "auto, tables rebuilt per step",
-                          "samples": total, "ms_per_step": round(ms, 4), "gsamples_per_s": round(total / ms / 1e6, 3),
-                          "frac_of_hbm_peak": round(total * 4 / ms / 1e6 / peak, 4), "plan_create_ms": round(1e3 * t_plan, 2),
-                          "kernels_ms_per_step": {k: round(v[1] / 8, 4) for k, v in kt.items()},
-                          "launches_per_step": {k: v[0] / 8 for k, v in kt.items()}}))
         plan.destroy()
 
 

@@ -39,6 +39,7 @@ PHI_WIDTH = 16
 DAT_WIDTH = 17
 WINDOWS_PER_GPU = 4096          # 4096 x 65536 x 4 B = 1.07 GB per GPU per step (>> 126 MB L2)
 BH4_AA = (47022, 64001, 18518, 1531)   # round(a_k * (2^17 - 1)), src/tb/tb_windows.vhd:103-111
+KERNEL_TIMING_STRIDE = 8        # steps of the timed region whose launches carry per-kernel events: 1 in 8
 METRIC = "window_gsamples_per_s"
 UNIT = "Gsamples/s"
 WORKLOAD = "bank of bh_win_4term windows, N=65536 (PHI_WIDTH 16), DAT_WIDTH 17, cordic_dds, RTL model"
@@ -71,8 +72,11 @@ def bank_descs(nwin: int, algo: int = 0):
     arr = (bhw.BhwDesc * nwin)()
     proto = bhw.make_desc(4, PHI_WIDTH, DAT_WIDTH, BH4_AA, algo=algo)
     raw = bytes(proto)
+    same = os.environ.get("BHW_BENCH_IDENTICAL_WINDOWS") == "1"   # tuning experiments only
     for i in range(nwin):
         C.memmove(C.byref(arr, i * C.sizeof(bhw.BhwDesc)), raw, len(raw))
+        if same:
+            continue
         d = arr[i]
         d.aa[0] = BH4_AA[0] - (i % 1021)
         d.aa[1] = BH4_AA[1] - (i % 509)
@@ -298,7 +302,6 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    bhw.timing_enable(True)
     bhw.timing_reset()
     clocks = ClockSampler(local)
     launches0 = bhw.launch_count()
@@ -306,7 +309,10 @@ def run_cuda(args):
     clocks.start()
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        # per-kernel CUDA events (library side, on the launching stream) bracket the launches of
+        # every KERNEL_TIMING_STRIDE-th step of the timed region; the other steps run bare
+        bhw.timing_enable(i % KERNEL_TIMING_STRIDE == 0)
         step_device()
     e1.record()
     barrier()
@@ -344,6 +350,7 @@ def run_cuda(args):
         if not torch.equal(host[: 1 << PHI_WIDTH], chk.cpu()):
             raise SystemExit("bench.py: host-path output differs from the device path")
         e2e = {"value": (total * e2e_steps) / e2e_s / 1e9, "unit": UNIT, "steps": e2e_steps,
+               "d2h_gbs_per_gpu": count * 4 * e2e_steps / e2e_s / 1e9,
                "h2d_bytes_per_step": _meta_bytes(touched), "d2h_bytes_per_step": count * 4,
                "api": "bhw_generate_batch_host (pinned host output)"}
 
@@ -368,8 +375,8 @@ def run_cuda(args):
         achieved = (count * 4) / (ms_l / n_l * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": count * 4, "avg_launch_ms": ms_l / n_l,
-                "kernel_ms_share": {k: v[1] for k, v in ktimes.items() if v[0]}}
+                "bytes_per_launch": count * 4, "avg_launch_ms": ms_l / n_l, "launches_timed": n_l,
+                "kernel_ms_timed": {k: v[1] for k, v in ktimes.items() if v[0]}}
 
     if rank == 0:
         line = {

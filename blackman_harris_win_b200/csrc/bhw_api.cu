@@ -297,6 +297,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
       DirectArgs& a = plan.wins64[(size_t)w];
       memset(&a, 0, sizeof(a));
       if ((st = resolve_window(&descs[w], &a.wp, a.src))) return st;
+      for (int u = 0; u < a.wp.nsrc; u++) init_src_core(a.src[u], &a.sc[u]);
     }
     return BHW_OK;
   }
@@ -524,13 +525,17 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   }
   std::lock_guard<std::mutex> lk(plan.mu);
   cudaError_t e = cudaSuccess;
+  bool table_ahead = false;  // k_table_build is the last thing enqueued on `stream`
+  bool tm_on = false;
   if (!plan.jobs.empty() && (!plan.tables_built || !g_cache_enabled.load())) {
     LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
+    tm_on = tm.on;
     e = launch_table_build((const TabJob*)(plan.blob_dev + plan.o_jobs), (int)plan.jobs.size(),
                            plan.table_work, plan.rom, stream);
     if (e != cudaSuccess) return cuda_fail(e, "k_table_build");
     g_launches++;
     plan.tables_built = true;
+    table_ahead = !tm_on;
   }
   SynthArgs a;
   a.recs = (const WinRec*)(plan.blob_dev + plan.o_recs);
@@ -557,6 +562,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     a.flat_begin = b;
     a.flat_count = e_ - b;
     cudaStream_t ls = fan.next();
+    table_ahead = false;
     cudaError_t ce;
     {
       LaunchTimer tm(BHW_KERNEL_SYNTH, ls);
@@ -589,7 +595,9 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     cudaStream_t ls = fan.next();
     {
       LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls);
-      e = launch_synth_bank(ba, run.tab_mode, run.pair, ls);
+      const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
+      e = launch_synth_bank(ba, run.tab_mode, run.pair, ls, pdl);
+      table_ahead = false;
     }
     if (e != cudaSuccess) return cuda_fail(e, "k_synth_bank");
     g_launches++;
@@ -769,6 +777,7 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
   DirectArgs a;
   memset(&a, 0, sizeof(a));
   if ((st = resolve_window(d, &a.wp, a.src))) return st;
+  for (int u = 0; u < a.wp.nsrc; u++) init_src_core(a.src[u], &a.sc[u]);
   const uint64_t N = 1ull << d->phi_width;
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
   if (a.src[0].kind == SRC_TAYLOR) {
@@ -946,6 +955,7 @@ int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t
   SinCosArgs a;
   memset(&a, 0, sizeof(a));
   if ((st = resolve_source(d, 0, &a.src))) return st;
+  init_src_core(a.src, &a.sc);
   if (a.src.kind == SRC_TAYLOR && (st = get_rom(dev, a.src.dw, a.src.lut, &a.rom))) return st;
   a.n_first = n0;
   a.count = count;

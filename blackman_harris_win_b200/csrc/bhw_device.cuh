@@ -317,6 +317,47 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   T[e + 3 * Q] = (int32_t)(wrapb(vs, p.outw) * t);  // quadrant 3: cos =  s
 }
 
+// ---- direct evaluation through the fast cores ------------------------------------------------
+// Which core evaluates a (non-canonical) source in the one-thread-per-sample kernels, with the
+// atan words sliced for it; lives in the kernel parameter block (constant bank).
+struct SrcCore {
+  uint32_t core;        // TABCORE_*
+  uint32_t pad;
+  int32_t rom32[32];
+  int64_t rom64[48];
+};
+
+BHW_HD void eval_source_core(const SrcParams& p, const SrcCore& sc, const I2* rom, uint64_t ph, int64_t& s,
+                             int64_t& c) {
+  const int pw = p.pw;
+  ph &= (1ull << pw) - 1;
+  const int q = (int)(ph >> (pw - 2));
+  const uint64_t low = ph & ((1ull << (pw - 2)) - 1);
+  int64_t vs, vc;
+  if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom, (uint32_t)low, vs, vc);
+  else if (sc.core == TABCORE_32) { int32_t s32, c32; cordic_core_fast32<false>(p, sc.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+  else if (sc.core == TABCORE_32BIAS) { int32_t s32, c32; cordic_core_fast32<true>(p, sc.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+  else if (sc.core == TABCORE_A64) cordic_core_aligned64(p, sc.rom64, q, low, vs, vc);
+  else cordic_core_generic(p, q, low, vs, vc);
+  if (p.kind != SRC_INQ) quadrant_fix(q, p.negw, vs, vc, vs, vc);
+  s = wrapb(vs, p.outw);
+  c = wrapb(vc, p.outw);
+}
+
+// One output sample of BHW_ALGO_DIRECT with per-source cores.
+BHW_HD int64_t direct_sample_core(const WinParams& wp, const SrcParams* src, const SrcCore* sc, const I2* rom,
+                                  uint64_t n) {
+  int64_t cosv[BHW_MAX_TERMS];
+  cosv[0] = 0;
+  for (int k = 1; k < wp.m; ++k) {
+    const TermParams& t = wp.term[k - 1];
+    const uint64_t ph = ((uint64_t)t.kmul * n) & t.ph_mask;
+    int64_t s;
+    eval_source_core(src[t.src], sc[t.src], rom, ph, s, cosv[k]);
+  }
+  return tail_generic(wp, cosv);
+}
+
 // ============================================================================================
 // Window synthesis bodies (BHW_ALGO_TABLE, stage 2)
 // ============================================================================================

@@ -13,6 +13,7 @@
 //                    in registers (also the only path for DAT_WIDTH > 32), and the sin/cos entry.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "bhw_device.cuh"
 #include "bhw_launch.h"
@@ -25,6 +26,9 @@ namespace bhw {
 __global__ void __launch_bounds__(256)
 k_table_build(const TabJob* __restrict__ jobs, int njobs, uint32_t total_work,
               const I2* __restrict__ rom) {
+  // programmatic dependent launch: the synthesis kernel queued behind this one may be scheduled
+  // now; it blocks in griddepcontrol.wait until this grid has completed and flushed its tables
+  asm volatile("griddepcontrol.launch_dependents;");
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_work;
        i += gridDim.x * blockDim.x) {
     // job of work item i: last job with work_begin <= i (few jobs; the search is noise next
@@ -168,6 +172,9 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   const BankShape& sh = a.sh;
   const int32_t* tab0 = sh.tab[0];
   const int32_t* tab1 = sh.tab[1];
+  // launched with programmatic stream serialization right behind k_table_build: wait here for
+  // its tables (a no-op for an ordinary launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (TAB != TAB_GLOBAL) {
     for (uint32_t u = 0; u < sh.ntab; ++u) {
       const uint32_t words = sh.tentries[u] >> (TAB == TAB_SMEM_HALF ? 1 : 0);
@@ -225,7 +232,7 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
 // -------------------------------------------------------------------------------------------
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-k_direct_window(DirectArgs a, OutT* __restrict__ out) {
+k_direct_window(const __grid_constant__ DirectArgs a, OutT* __restrict__ out) {
   // taylor_sincos keeps its quarter-wave ROM in shared memory when it fits
   extern __shared__ I2 s_rom[];
   const I2* rom = a.rom;
@@ -238,7 +245,7 @@ k_direct_window(DirectArgs a, OutT* __restrict__ out) {
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t n = (a.n_first + j) & nmask;
-    out[j] = (OutT)direct_sample_generic(a.wp, a.src, rom, n);
+    out[j] = (OutT)direct_sample_core(a.wp, a.src, a.sc, rom, n);
   }
 }
 
@@ -282,11 +289,11 @@ k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
 
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-k_sincos(SinCosArgs a, OutT* __restrict__ out_sin, OutT* __restrict__ out_cos) {
+k_sincos(const __grid_constant__ SinCosArgs a, OutT* __restrict__ out_sin, OutT* __restrict__ out_cos) {
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (uint64_t)gridDim.x * blockDim.x) {
     int64_t s, c;
-    eval_source_generic(a.src, a.rom, a.n_first + j, s, c);
+    eval_source_core(a.src, a.sc, a.rom, a.n_first + j, s, c);
     if (out_sin) out_sin[j] = (OutT)s;
     if (out_cos) out_cos[j] = (OutT)c;
   }
@@ -334,7 +341,7 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
 size_t bank_smem_limit() { return 192u * 1024u; }
 
 template <int M, int TAB, bool PAIR, bool W64>
-static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -344,21 +351,35 @@ static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, 
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
+  if (pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kBankThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_synth_bank<M, TAB, PAIR, W64>, a);
+  }
   k_synth_bank<M, TAB, PAIR, W64><<<grid, kBankThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 template <int M, bool W64>
 static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned grid, size_t smem,
-                                 cudaStream_t stream) {
-  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, true, W64>(a, grid, smem, stream)
-                                        : launch_bank_t<M, TAB_SMEM_FULL, false, W64>(a, grid, smem, stream);
-  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, true, W64>(a, grid, smem, stream);
-  return pair ? launch_bank_t<M, TAB_GLOBAL, true, W64>(a, grid, 0, stream)
-              : launch_bank_t<M, TAB_GLOBAL, false, W64>(a, grid, 0, stream);
+                                 cudaStream_t stream, bool pdl) {
+  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, true, W64>(a, grid, smem, stream, pdl)
+                                        : launch_bank_t<M, TAB_SMEM_FULL, false, W64>(a, grid, smem, stream, pdl);
+  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, true, W64>(a, grid, smem, stream, pdl);
+  return pair ? launch_bank_t<M, TAB_GLOBAL, true, W64>(a, grid, 0, stream, pdl)
+              : launch_bank_t<M, TAB_GLOBAL, false, W64>(a, grid, 0, stream, pdl);
 }
 
-cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream) {
+cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
   if (!a.nwin) return cudaSuccess;
   if (tab == TAB_SMEM_HALF && !pair) return cudaErrorInvalidValue;
   const uint32_t log_tpw = a.sh.pw - kBankTileLog2 - (pair ? 1 : 0);
@@ -368,11 +389,11 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
   const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);
   const bool w64 = a.sh.acc64 != 0;
   switch (a.sh.m) {
-    case 2: return w64 ? launch_bank_m<2, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<2, false>(a, tab, pair, grid, smem, stream);
-    case 3: return w64 ? launch_bank_m<3, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<3, false>(a, tab, pair, grid, smem, stream);
-    case 4: return w64 ? launch_bank_m<4, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<4, false>(a, tab, pair, grid, smem, stream);
-    case 5: return w64 ? launch_bank_m<5, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<5, false>(a, tab, pair, grid, smem, stream);
-    case 7: return w64 ? launch_bank_m<7, true>(a, tab, pair, grid, smem, stream) : launch_bank_m<7, false>(a, tab, pair, grid, smem, stream);
+    case 2: return w64 ? launch_bank_m<2, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<2, false>(a, tab, pair, grid, smem, stream, pdl);
+    case 3: return w64 ? launch_bank_m<3, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<3, false>(a, tab, pair, grid, smem, stream, pdl);
+    case 4: return w64 ? launch_bank_m<4, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<4, false>(a, tab, pair, grid, smem, stream, pdl);
+    case 5: return w64 ? launch_bank_m<5, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<5, false>(a, tab, pair, grid, smem, stream, pdl);
+    case 7: return w64 ? launch_bank_m<7, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<7, false>(a, tab, pair, grid, smem, stream, pdl);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -32,6 +32,7 @@ struct BankArgs {
 struct DirectArgs {
   WinParams wp;
   SrcParams src[2];
+  SrcCore sc[2];              // shift-add core of each source + its sliced atan words
   const I2* rom;              // Taylor ROM (global)
   uint32_t rom_smem_entries;  // > 0: copy that many ROM words to shared memory first
   uint32_t pad;
@@ -47,6 +48,7 @@ struct Direct32Args {
 
 struct SinCosArgs {
   SrcParams src;
+  SrcCore sc;
   const I2* rom;
   uint64_t n_first;
   uint64_t count;
@@ -56,7 +58,10 @@ cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total
                                cudaStream_t stream);
 cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
 // tab: TAB_SMEM_FULL / TAB_SMEM_HALF / TAB_GLOBAL; pair: lanes own (n, n + N/2) sample pairs
-cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream);
+// pdl: launch with programmatic stream serialization (the kernel directly ahead in the stream is
+// k_table_build, which releases its dependents early; k_synth_bank waits for it before its first
+// table read)
+cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl = false);
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream);

@@ -40,6 +40,18 @@ int table_core32(const SrcParams& sp) {
   return TABCORE_GENERIC;
 }
 
+// Core choice + sliced atan words for the one-thread-per-sample kernels (any source, canonical or not).
+void init_src_core(const SrcParams& sp, SrcCore* sc) {
+  memset(sc, 0, sizeof(*sc));
+  if (sp.kind == SRC_TAYLOR) return;
+  sc->core = (uint32_t)table_core32(sp);
+  for (int i = 0; i < sp.n_z && i < 48; i++) {
+    const int64_t r = (c_atan[sp.rom_sel][i] >> sp.rom_shift) & sp.rom_mask;
+    if (i < 32 && (sc->core == TABCORE_32 || sc->core == TABCORE_32BIAS)) sc->rom32[i] = (int32_t)r;
+    if (sc->core == TABCORE_A64) sc->rom64[i] = (int64_t)((uint64_t)r << (64 - sp.zw));
+  }
+}
+
 // Everything of a table job except its place in the launch (work_begin) and the Taylor ROM offset.
 void init_tab_job(const SrcParams& canon, int32_t* tab, TabJob* j) {
   memset(j, 0, sizeof(*j));

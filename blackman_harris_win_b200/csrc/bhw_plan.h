@@ -9,6 +9,7 @@ namespace bhw {
 SrcParams canonical_source(const SrcParams& sp, uint32_t* drop);
 bool fast32_ok(const SrcParams& sp);
 int table_core32(const SrcParams& sp);
+void init_src_core(const SrcParams& sp, SrcCore* sc);
 void init_tab_job(const SrcParams& canon, int32_t* tab, TabJob* j);
 void build_taylor_rom(int dw, int lut, std::vector<I2>& rom);
 enum TailMode { TAILMODE_FAST32 = 0, TAILMODE_ACC64 = 1, TAILMODE_GENERIC = 2 };

@@ -46,8 +46,13 @@ int hc_direct(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
   std::vector<I2> rom;
   if (src[0].kind == SRC_TAYLOR) build_taylor_rom(src[0].dw, src[0].lut, rom);
   const uint64_t nmask = (1ull << wp.pw) - 1;
-  for (uint64_t j = 0; j < count; j++)
-    out[j] = direct_sample_generic(wp, src, rom.data(), (n0 + j + (uint64_t)wp.stream_offset) & nmask);
+  SrcCore sc[2];
+  for (int u = 0; u < wp.nsrc; u++) init_src_core(src[u], &sc[u]);
+  for (uint64_t j = 0; j < count; j++) {
+    const uint64_t n = (n0 + j + (uint64_t)wp.stream_offset) & nmask;
+    out[j] = direct_sample_core(wp, src, sc, rom.data(), n);          // what k_direct_window runs
+    if (direct_sample_generic(wp, src, rom.data(), n) != out[j]) return -100;  // fast cores == generic body
+  }
   return 0;
 }
 
@@ -214,9 +219,13 @@ int hc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, 
   if ((st = resolve_source(d, 0, &sp))) return st;
   std::vector<I2> rom;
   if (sp.kind == SRC_TAYLOR) build_taylor_rom(sp.dw, sp.lut, rom);
+  SrcCore sc;
+  init_src_core(sp, &sc);
   for (uint64_t j = 0; j < count; j++) {
-    int64_t s, c;
-    eval_source_generic(sp, rom.data(), n0 + j, s, c);
+    int64_t s, c, s2, c2;
+    eval_source_core(sp, sc, rom.data(), n0 + j, s, c);               // what k_sincos runs
+    eval_source_generic(sp, rom.data(), n0 + j, s2, c2);
+    if (s != s2 || c != c2) return -100;
     if (out_sin) out_sin[j] = s;
     if (out_cos) out_cos[j] = c;
   }

@@ -33,8 +33,16 @@ __global__ void __launch_bounds__(256) k_peak(int outer, uint32_t seed, uint32_t
           else asm volatile("xor.b32 %0, %0, %1;" : "+r"(r[i]) : "r"(c));
         } else if (MODE == 1) { // fma pipe: integer multiply-add
           asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(r[i]) : "r"(c));
-        } else {                // both pipes, 1:1
+        } else if (MODE == 2) { // both pipes, 1:1
           if (j & 1) asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(r[i]) : "r"(c));
+          else asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(r[i]) : "r"(c));
+        } else if (MODE == 3) { // multiply-high with addend (IMAD.HI): the table path's b_k
+          asm volatile("mad.hi.s32 %0, %0, %1, %1;" : "+r"(r[i]) : "r"(c));
+        } else if (MODE == 4) { // 32x32+64 (IMAD.WIDE), result feeds the next multiplicand
+          asm volatile("{ .reg .b64 t; .reg .b32 lo, hi; mul.wide.s32 t, %0, %1; "
+                       "mov.b64 {lo, hi}, t; xor.b32 %0, lo, hi; }" : "+r"(r[i]) : "r"(c));
+        } else {                // IMAD.HI : SHF 1:1
+          if (j & 1) asm volatile("mad.hi.s32 %0, %0, %1, %1;" : "+r"(r[i]) : "r"(c));
           else asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(r[i]) : "r"(c));
         }
       }
@@ -75,13 +83,15 @@ int main() {
   uint32_t* sink = nullptr;
   cudaMalloc(&sink, 4);
   const double alu = run<0>(sms, sink), fma = run<1>(sms, sink), mix = run<2>(sms, sink);
+  const double hi = run<3>(sms, sink), wide = run<4>(sms, sink), himix = run<5>(sms, sink);
   if (cudaDeviceSynchronize() != cudaSuccess) { fprintf(stderr, "kernel failed\n"); return 1; }
   const double per_clk = 1.0 / ((double)sms * khz * 1e3);
   printf("{\"int32_alu_tops\": %.2f, \"int32_fma_tops\": %.2f, \"int32_mix_tops\": %.2f, "
          "\"alu_lanes_per_clk_sm\": %.1f, \"fma_lanes_per_clk_sm\": %.1f, \"mix_lanes_per_clk_sm\": %.1f, "
-         "\"sms\": %d, \"sm_mhz_max\": %d, \"how\": \"tools/int_peak.cu: 8 independent chains per thread, "
+         "\"imad_hi_tops\": %.2f, \"imad_wide_plus_lop_tops\": %.2f, \"imad_hi_shf_mix_tops\": %.2f, \"sms\": %d, \"sm_mhz_max\": %d, \"how\": \"tools/int_peak.cu: 8 independent chains per thread, "
          "8 CTAs x 256 threads per SM, best of 4 after warm-up, CUDA events\"}\n",
-         alu / 1e12, fma / 1e12, mix / 1e12, alu * per_clk, fma * per_clk, mix * per_clk, sms, khz / 1000);
+         alu / 1e12, fma / 1e12, mix / 1e12, alu * per_clk, fma * per_clk, mix * per_clk, hi / 1e12,
+         wide / 1e12, himix / 1e12, sms, khz / 1000);
   cudaFree(sink);
   return 0;
 }

@@ -312,6 +312,86 @@ def test_host_pipeline_segments():
     torch.cuda.empty_cache()
 
 
+def test_cuda_graph_capture_and_replay():
+    """A plan execute (table build + programmatic dependent bank launch, and a mixed batch with the
+    general kernel) captured into a CUDA graph and replayed into the same buffer."""
+    import torch
+    for descs in ([bhw.make_desc(4, 16, 17, [47022 - i, 64001, 18518, 1531 + i]) for i in range(64)],
+                  [bhw.variant_desc(v, pw, cases.VARIANT_DW[v]) for v in (1, 3, 6, 8, 10) for pw in (5, 9, 13, 17)]):
+        plan = bhw.Plan(descs)
+        want = plan.execute().clone()
+        out = torch.zeros_like(want)
+        bhw.set_table_cache(False)
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                plan.execute(out=out)                       # warm-up on the capture stream
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    plan.execute(out=out)
+            for _ in range(3):
+                out.zero_()
+                g.replay()
+                torch.cuda.synchronize()
+                assert torch.equal(out, want)
+        finally:
+            bhw.set_table_cache(True)
+        del g
+        plan.destroy()
+
+
+def test_concurrent_host_threads():
+    """The ABI is re-entrant: several host threads generate different windows at once (one-shot
+    calls on their own streams, plus the host-buffer entry point) and every result is exact."""
+    import threading
+    import torch
+    work = [bhw.variant_desc(1 + (i % 10), 9 + (i % 6), cases.VARIANT_DW[1 + (i % 10)]) for i in range(24)]
+    work += [bhw.make_desc(3, 14, 24, [7046424, 8388600, 1342176], sin_type=bhw.SIN_TAYLOR),
+             bhw.variant_desc(10, 12, 32, sin_type=bhw.SIN_CORDIC48), bhw.variant_desc(6, 18, 17)]
+    want = [H.orc_window(d, threads=4) for d in work]
+    got = [None] * len(work)
+    errs = []
+
+    def run(tid):
+        try:
+            torch.cuda.set_device(0)
+            s = torch.cuda.Stream()
+            for i in range(tid, len(work), 4):
+                with torch.cuda.stream(s):
+                    for _ in range(3):
+                        g = bhw.generate(work[i])
+                s.synchronize()
+                got[i] = g.cpu().numpy().astype(np.int64)
+                if i % 5 == 0:
+                    assert np.array_equal(bhw.generate_host(work[i]).astype(np.int64), got[i])
+        except Exception as e:   # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=run, args=(t,)) for t in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i, d in enumerate(work):
+        assert np.array_equal(got[i], want[i]), d
+
+
+def test_stream_offset_long_windows_all_kernels():
+    """DT_VLD-gated order (stream_offset = 1) is a rotation by one sample through every kernel:
+    bank (staged and global tables), general, direct."""
+    import torch
+    for d in (bhw.variant_desc(6, 16, 17), bhw.variant_desc(2, 21, 16), bhw.variant_desc(10, 18, 32),
+              bhw.variant_desc(3, 18, 24, sin_type=bhw.SIN_TAYLOR), bhw.variant_desc(9, 19, 24, sin_type=bhw.SIN_CORDIC_SCALED)):
+        base = bhw.generate(d)
+        for algo in (bhw.ALGO_AUTO, bhw.ALGO_TABLE, bhw.ALGO_DIRECT):
+            rot = bhw.generate(d.copy(stream_offset=1, algo=algo))
+            assert torch.equal(rot, torch.roll(base, -1)), (d, algo)
+        n = 1 << d.phi_width
+        part = bhw.generate(d.copy(stream_offset=1), n - 1000, 1000)        # ragged tail incl. the wrapped w[0]
+        assert torch.equal(part, torch.roll(base, -1)[n - 1000:])
+
+
 def test_win_selector_and_errors():
     w = bhw.WinSelector(PHI_WIDTH=10, DAT_WIDTH=16, WIN_TYPE="HAMMING")
     assert np.array_equal(w.stream(AA0=17808, AA1=14959).cpu().numpy().astype(np.int64),

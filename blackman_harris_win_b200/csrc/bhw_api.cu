@@ -790,9 +790,18 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
   if (!count) return BHW_OK;
   cudaError_t e;
   Direct32Args a32;
+  DirectTayArgs at;
   const bool fast32 = !a.wp.elem64 && direct32_params(a.wp, a.src, &a32.p);
-  if (only_fast32 && !fast32) return 1;
-  if (fast32) {
+  const bool tay32 = !fast32 && !a.wp.elem64 && direct_taylor_params(a.wp, a.src, &at.p);
+  if (only_fast32 && !fast32 && !tay32) return 1;
+  if (tay32) {
+    // TAYLOR in 32-bit registers, sine ROM in shared memory, 128-bit stores
+    at.rom = a.rom;
+    at.n0 = n0;
+    at.count = count;
+    LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
+    e = launch_direct_taylor(at, (int32_t*)out_dev, stream);
+  } else if (fast32) {
     // register-resident 32-bit stages, 128-bit stores
     a32.n0 = n0;
     a32.count = count;
@@ -821,9 +830,13 @@ int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, 
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
   if (!out_dev && count) return BHW_E_NULL;
   if (d->dat_width > 32 || d->algo == BHW_ALGO_DIRECT) return run_direct(d, n0, count, out_dev, (cudaStream_t)stream);
-  if (d->algo == BHW_ALGO_AUTO && count * (uint64_t)(d->win_type - 1) <= 3u * 65536u) {
+  if (d->algo == BHW_ALGO_AUTO &&
+      (count * (uint64_t)(d->win_type - 1) <= 3u * 65536u ||
+       (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR))) {
     // a short one-shot request: one launch of the register-resident kernel beats building a
-    // table first (measured: N = 65536 4-term 21 us vs 58 us per call)
+    // table first (measured: N = 65536 4-term 21 us vs 58 us per call); a TAYLOR window of any
+    // length: a Taylor evaluation (ROM look-up + two multiplies) per sample is cheaper than
+    // building, storing and re-reading tables as large as the window
     st = run_direct(d, n0, count, out_dev, (cudaStream_t)stream, true);
     if (st != 1) return st;
   }

@@ -535,6 +535,95 @@ BHW_HD int32_t direct32_sample(const Direct32Params& p, uint32_t n) {
 }
 
 // ============================================================================================
+// Register-resident 32-bit direct evaluation, TAYLOR source (k_direct_taylor)
+// ============================================================================================
+// taylor_sincos + tay1_order in int32 registers with 32x32->64 products (IMAD.WIDE): valid for every
+// legal TAYLOR window (DAT_WIDTH <= 32); same integers as taylor_core_generic.  A Taylor evaluation
+// is a ROM look-up and two multiplies, so for long windows evaluating it per sample is cheaper than
+// building, storing and re-reading a table as large as the window itself.
+struct TayUnit {
+  int32_t pw;       // phase width of the unit (PHI_WIDTH, or PHI_WIDTH-1 for the 2nd harmonic of bh_win_3term)
+  int32_t mode;     // TayMode
+  int32_t ashift;   // ROM address shift
+  int32_t cbits;    // bits of acnt
+  int32_t xs;       // XSHIFT = 19 + LUT_SIZE
+  int32_t pi;       // ramb_pi = round(pi * 2^(17-STAGE))
+};
+struct DirectTayParams {
+  int32_t m, dw;
+  int32_t tshift;                // the tail wants cos << tshift (WinRec comment)
+  int32_t S0, lsh, rsh;          // tail constants (WinRec)
+  uint32_t rc;
+  uint32_t n_first;              // sample index of output element 0 (stream offset folded in)
+  int32_t A[4];                  // A[k], k = 1..m-1
+  TayUnit unit[2];               // unit[k-1] feeds harmonic k
+  uint32_t rom_entries;          // 2^LUT_SIZE (cos, sin) words; the kernel keeps them in shared memory
+  uint32_t tmode;                // TMODE_*
+};
+
+// TMODE: the datapath both units of the window sit in (they share DAT_WIDTH, and bh_win_3term
+// rejects the one LUT_SIZE that would split them): 0 ROM only (TAY_LESS / TAY_EQ per unit),
+// 1 TAY_DSP, 2 TAY_WIDE.
+enum : int { TMODE_ROM = 0, TMODE_DSP = 1, TMODE_WIDE = 2 };
+
+template <int TMODE>
+BHW_HD void taylor_core_fast32(const TayUnit& u, int dw, const I2* __restrict__ rom, uint32_t t, int32_t& vs,
+                               int32_t& vc) {
+  if (TMODE == TMODE_ROM) {  // ROM only (src/taylor_sincos.vhd:157-167)
+    const I2 e = rom[u.mode == TAY_LESS ? (t << u.ashift) : t];
+    vc = e.x; vs = e.y;
+    return;
+  }
+  const I2 e = rom[t >> u.ashift];
+  const int32_t c0 = e.x, s0 = e.y;
+  const uint32_t acnt = t & ((1u << u.cbits) - 1u);
+  const int32_t mpi = (int32_t)(((uint32_t)u.pi * acnt) & 0xFFFFFFu);  // 24-bit ROM word (src/tay1_order.vhd:136-147)
+  const int xs = u.xs;
+  if (TMODE == TMODE_DSP) {
+    // P = C -/+ A*B, result = P[xs+dw-1 : xs] (src/tay1_order.vhd:245,316,501-502)
+    const int64_t pc = (int64_t)((uint64_t)(int64_t)c0 << xs) - (int64_t)mpi * (int64_t)s0;
+    const int64_t ps = (int64_t)((uint64_t)(int64_t)s0 << xs) + (int64_t)mpi * (int64_t)c0;
+    vc = wrapb32((int32_t)(pc >> xs), dw);
+    vs = wrapb32((int32_t)(ps >> xs), dw);
+  } else {
+    // 0 <= s0, c0 < 2^(dw-1) and 0 <= mpi < 2^20 <= 2^xs, so 0 <= m1, m2 < 2^(dw-1): the DW-bit
+    // wraps of :585-586 and of c0 - m1 are no-ops, and s0 + m2 < 2^dw goes negative in DW bits
+    // exactly when it exceeds 2^(dw-1) - 1 (unsigned compare; also right for dw = 32)
+    const int32_t m1 = (int32_t)(((int64_t)s0 * (int64_t)mpi) >> xs);               // :585
+    const int32_t m2 = (int32_t)(((int64_t)c0 * (int64_t)mpi) >> xs);               // :586
+    const int32_t cp = c0 - m1;                                                     // :595
+    const uint32_t sp = (uint32_t)s0 + (uint32_t)m2;                                // :596
+    const int32_t sat = (int32_t)((1u << (dw - 1)) - 1u);
+    vc = cp < 0 ? sat : cp;                                                         // negative -> max positive (:602-617)
+    vs = sp > (uint32_t)sat ? sat : (int32_t)sp;
+  }
+}
+
+// one output sample: every harmonic through its own taylor_sincos unit (each unit owns a +1
+// phase counter, src/bh_win_3term.vhd:221-233), output-side quadrant fix (src/taylor_sincos.vhd:237-255)
+template <int TMODE>
+BHW_HD int32_t direct_taylor_sample(const DirectTayParams& p, const I2* __restrict__ rom, uint32_t n) {
+  uint32_t S = (uint32_t)p.S0;
+#pragma unroll
+  for (int k = 1; k < 3; ++k) {
+    if (k < p.m) {
+      const TayUnit& u = p.unit[k - 1];
+      const uint32_t ph = n & ((1u << u.pw) - 1u);
+      const uint32_t q = ph >> (u.pw - 2);
+      int32_t vs, vc;
+      taylor_core_fast32<TMODE>(u, p.dw, rom, ph & ((1u << (u.pw - 2)) - 1u), vs, vc);
+      const int32_t v = (q & 1u) ? vs : vc;                                       // cos: c, -s, -c, s
+      // ROM-only and TAY_WIDE values lie in [0, 2^(dw-1)-1]: the DW-bit negation cannot wrap
+      const int32_t nv = TMODE == TMODE_DSP ? wrapb32((int32_t)(0u - (uint32_t)v), p.dw) : -v;
+      const int32_t c = ((q + 1u) & 2u) ? nv : v;
+      const uint32_t b = (uint32_t)mulhi_rc(p.A[k], (int32_t)((uint32_t)c << p.tshift), p.rc);
+      S = (k & 1) ? S - b : S + b;
+    }
+  }
+  return (int32_t)(S << p.lsh) >> p.rsh;
+}
+
+// ============================================================================================
 // Bank synthesis body (k_synth_bank): whole windows of one shape
 // ============================================================================================
 // A "bank" is a run of windows that differ only in their AAk ports (and stream offset): same

@@ -287,6 +287,33 @@ k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
   }
 }
 
+// TAYLOR windows, register-resident 32-bit form: 4 consecutive samples per thread, the quarter-wave
+// sine ROM in shared memory, one 128-bit store.  TMODE = the tay1_order datapath (compile time).
+template <int TMODE>
+__global__ void __launch_bounds__(256)
+k_direct_taylor(const __grid_constant__ DirectTayArgs a, int32_t* __restrict__ out) {
+  extern __shared__ I2 s_rom[];
+  const DirectTayParams& p = a.p;
+  for (uint32_t i = threadIdx.x; i < p.rom_entries; i += blockDim.x) s_rom[i] = a.rom[i];
+  __syncthreads();
+  const uint64_t quads = (a.count + 3) / 4;
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads;
+       qd += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t j = qd * 4;
+    const uint32_t n = (uint32_t)(a.n0 + j) + p.n_first;  // each unit masks it to its own phase width
+    int32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = direct_taylor_sample<TMODE>(p, s_rom, n + e);
+    if (aligned && j + 4 <= a.count) {
+      __stcs(reinterpret_cast<int4*>(out + j), make_int4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (j + e < a.count) out[j + e] = v[e];
+    }
+  }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_sincos(const __grid_constant__ SinCosArgs a, OutT* __restrict__ out_sin, OutT* __restrict__ out_cos) {
@@ -423,6 +450,16 @@ cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t st
 #undef BHW_D32
     default: launch_direct32_t<0>(a, out, grid, stream); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream) {
+  if (!a.count) return cudaSuccess;
+  const unsigned grid = grid_for(((a.count + 3) / 4 + 255) / 256, 8);
+  const size_t smem = (size_t)a.p.rom_entries * sizeof(I2);  // <= 32 KB (LUT_SIZE <= 12)
+  if (a.p.tmode == TMODE_ROM) k_direct_taylor<TMODE_ROM><<<grid, 256, smem, stream>>>(a, out);
+  else if (a.p.tmode == TMODE_DSP) k_direct_taylor<TMODE_DSP><<<grid, 256, smem, stream>>>(a, out);
+  else k_direct_taylor<TMODE_WIDE><<<grid, 256, smem, stream>>>(a, out);
   return cudaGetLastError();
 }
 

@@ -46,6 +46,13 @@ struct Direct32Args {
   uint64_t count;
 };
 
+struct DirectTayArgs {
+  DirectTayParams p;
+  const I2* rom;    // Taylor ROM (global)
+  uint64_t n0;      // first sample (the stream offset lives in p.n_first)
+  uint64_t count;
+};
+
 struct SinCosArgs {
   SrcParams src;
   SrcCore sc;
@@ -65,6 +72,7 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream);
+cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream);
 cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream);
 
 }  // namespace bhw

@@ -157,6 +157,42 @@ bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* 
   return true;
 }
 
+bool direct_taylor_params(const WinParams& wp, const SrcParams* src, DirectTayParams* out) {
+  if (wp.m > 3 || wp.nsrc < 1 || wp.nsrc > 2 || wp.nsrc != wp.m - 1) return false;
+  for (int u = 0; u < wp.nsrc; u++) if (src[u].kind != SRC_TAYLOR || src[u].pw < 3 || src[u].dw > 32) return false;
+  if (fast_tail_mode(wp, src) != TAILMODE_FAST32) return false;
+  WinRec r;
+  memset(&r, 0, sizeof(r));
+  fill_fast_rec(wp, src, r);
+  DirectTayParams& p = *out;
+  memset(&p, 0, sizeof(p));
+  p.m = wp.m; p.dw = wp.dw;
+  p.tshift = (int32_t)r.tshift;
+  p.S0 = r.S0; p.lsh = r.lsh; p.rsh = r.rsh; p.rc = r.rc;
+  p.n_first = (uint32_t)wp.stream_offset;
+  for (int k = 1; k < wp.m; k++) {
+    const TermParams& t = wp.term[k - 1];
+    if (t.kmul != 1 || t.src != k - 1) return false;
+    const SrcParams& sp = src[t.src];
+    p.A[k] = r.A[k];
+    TayUnit& u = p.unit[k - 1];
+    u.pw = sp.pw; u.mode = sp.tay_mode; u.ashift = sp.tay_ashift; u.cbits = sp.tay_cbits; u.xs = sp.tay_xs;
+    u.pi = (int32_t)sp.tay_pi;
+  }
+  if (src[0].lut > 12) return false;  // the kernel keeps the ROM in shared memory (32 KB at LUT_SIZE 12)
+  p.rom_entries = 1u << src[0].lut;
+  // both units share one datapath class (see TMODE_*)
+  int tm = -1;
+  for (int k = 1; k < wp.m; k++) {
+    const int md = p.unit[k - 1].mode;
+    const int cls = (md == TAY_LESS || md == TAY_EQ) ? TMODE_ROM : md == TAY_DSP ? TMODE_DSP : TMODE_WIDE;
+    if (tm >= 0 && tm != cls) return false;
+    tm = cls;
+  }
+  p.tmode = (uint32_t)tm;
+  return true;
+}
+
 bool source_antisymmetric(const SrcParams& sp) {
   switch (sp.kind) {
     case SRC_DDS:   // |value| <= 2^(DW-2) + a few LSB: far from -2^(DW-1) once DW >= 8; the quadrant

@@ -21,6 +21,10 @@ void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r);
 // generic 64-bit body (wide registers, input-quadrant CORDICs, TAYLOR, 64-bit tails).
 bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* out);
 
+// Parameters of the register-resident TAYLOR direct kernel; false when the window is not a
+// 2-/3-term TAYLOR window with a 32-bit tail.
+bool direct_taylor_params(const WinParams& wp, const SrcParams* src, DirectTayParams* out);
+
 // Trig table of one harmonic as the bank planner sees it.
 struct BankTableInfo { const int32_t* ptr; uint32_t entries; bool antisym; };
 // Is the source's cosine table provably antisymmetric over half a period, T[i + E/2] == -T[i]

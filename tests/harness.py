@@ -185,6 +185,7 @@ def hostcheck():
     L.hc_direct.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
     L.hc_table.argtypes = [D, C.c_uint64, C.c_uint64, I64P, C.c_int]
     L.hc_direct32.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
+    L.hc_direct_taylor.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
     L.hc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]
     L.hc_table_cos.argtypes = [D, I64P, C.c_int]
     L.hc_bank.argtypes = [D, I64P, C.c_uint64, C.c_int, C.c_int]

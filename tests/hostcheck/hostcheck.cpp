@@ -56,6 +56,24 @@ int hc_direct(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
   return 0;
 }
 
+// the 32-bit TAYLOR direct body (k_direct_taylor); returns 1 when the window is not eligible
+int hc_direct_taylor(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
+  WinParams wp; SrcParams src[2];
+  int st = resolve_window(d, &wp, src);
+  if (st) return st;
+  DirectTayParams p;
+  if (wp.elem64 || !direct_taylor_params(wp, src, &p)) return 1;
+  std::vector<I2> rom;
+  build_taylor_rom(src[0].dw, src[0].lut, rom);
+  for (uint64_t j = 0; j < count; j++) {
+    const uint32_t n = (uint32_t)(n0 + j) + p.n_first;
+    out[j] = p.tmode == TMODE_ROM ? direct_taylor_sample<TMODE_ROM>(p, rom.data(), n)
+           : p.tmode == TMODE_DSP ? direct_taylor_sample<TMODE_DSP>(p, rom.data(), n)
+                                  : direct_taylor_sample<TMODE_WIDE>(p, rom.data(), n);
+  }
+  return 0;
+}
+
 // the 32-bit register-resident direct body (k_direct32); returns 1 when the window is not eligible
 int hc_direct32(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
   WinParams wp; SrcParams src[2];

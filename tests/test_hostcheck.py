@@ -22,6 +22,7 @@ def hc_window(d, n0, cnt, which, force_generic_core=0):
 
 
 DIRECT32_SEEN = []
+DIRECT_TAYLOR_SEEN = []
 
 
 def check(d, cnt_cap=2048):
@@ -37,6 +38,12 @@ def check(d, cnt_cap=2048):
     if st == 0:
         DIRECT32_SEEN.append(1)
         assert np.array_equal(got32, want), ("direct32", d)
+    got_t = np.empty(cnt, np.int64)
+    st = H.hostcheck().hc_direct_taylor(C.byref(d), n0, cnt, got_t.ctypes.data_as(H.I64P))
+    assert st in (0, 1), d
+    if st == 0:
+        DIRECT_TAYLOR_SEEN.append(1)
+        assert np.array_equal(got_t, want), ("direct_taylor", d)
     if d.dat_width <= 32:
         for force in (0, 1):
             st, got = hc_window(d, n0, cnt, "table", force)
@@ -57,6 +64,7 @@ def test_rtl_sweep_all_variants_widths_sources():
     for d in descs:
         check(d)
     assert len(DIRECT32_SEEN) > 100      # the 32-bit direct body covered its share of the sweep
+    assert len(DIRECT_TAYLOR_SEEN) > 50  # and so did the TAYLOR one
 
 
 def test_validation_agrees_with_oracle():

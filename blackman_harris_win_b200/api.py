@@ -34,6 +34,12 @@ class BhwError(RuntimeError):
         super().__init__(f"{where}: {msg} [{status}]" if where else f"{msg} [{status}]")
 
 
+class BhwAtan2Desc(C.Structure):
+    """struct bhw_atan2_desc - the generics of cordic_atan2 (src/cordic_atan2.vhd:64-69)."""
+    _fields_ = [("input_width", C.c_int32), ("angle_width", C.c_int32), ("precision", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class BhwDesc(C.Structure):
     """struct bhw_desc - one field per win_selector generic/port (src/win_selector.vhd:60-87)."""
     _fields_ = [
@@ -98,6 +104,8 @@ def lib():
         "bhw_sincos": (C.c_int, [D, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
         "bhw_cache_clear": (C.c_int, []),
         "bhw_set_table_cache": (C.c_int, [C.c_int]),
+        "bhw_atan2_validate": (C.c_int, [C.POINTER(BhwAtan2Desc)]),
+        "bhw_atan2": (C.c_int, [C.POINTER(BhwAtan2Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
         "bhw_set_side_streams": (C.c_int, [C.c_int]),
         "bhw_launch_count": (C.c_uint64, []),
         "bhw_last_cuda_error": (C.c_char_p, []),
@@ -123,7 +131,7 @@ ABI_SYMBOLS = (
     "bhw_strerror", "bhw_version", "bhw_validate", "bhw_elem_bytes", "bhw_quantize",
     "bhw_variant_coeffs", "bhw_generate", "bhw_generate_host", "bhw_batch_total", "bhw_shard_range",
     "bhw_generate_batch", "bhw_generate_batch_host", "bhw_generate_batch_multi", "bhw_sincos",
-    "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
+    "bhw_atan2_validate", "bhw_atan2", "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
     "bhw_device_count", "bhw_timing_enable", "bhw_timing_reset", "bhw_timing_read",
     "bhw_shard_windows", "bhw_plan_create", "bhw_plan_execute", "bhw_plan_total", "bhw_plan_destroy",
 )
@@ -352,6 +360,21 @@ def cache_clear():
     _check(lib().bhw_cache_clear(), "bhw_cache_clear")
 
 
+def atan2(x, y, input_width: int, angle_width: int, precision: int = 1, out=None):
+    """cordic_atan2 over two int32 CUDA tensors (VEC_DX, VEC_DY) -> PHI_DT (int32 CUDA tensor)."""
+    torch = _torch()
+    assert x.is_cuda and y.is_cuda and x.dtype == torch.int32 and y.dtype == torch.int32 and x.shape == y.shape
+    x, y = x.contiguous(), y.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    d = BhwAtan2Desc(input_width, angle_width, precision, 0)
+    with torch.cuda.device(x.device):
+        st = lib().bhw_atan2(C.byref(d), x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(),
+                             torch.cuda.current_stream().cuda_stream)
+    _check(st, "bhw_atan2")
+    return out
+
+
 def set_side_streams(n: int):
     _check(lib().bhw_set_side_streams(int(n)), "bhw_set_side_streams")
 
@@ -361,7 +384,7 @@ def set_table_cache(enabled: bool):
 
 
 KERNEL_TABLE_BUILD, KERNEL_SYNTH, KERNEL_DIRECT, KERNEL_SINCOS = 0, 1, 2, 3
-KERNEL_NAMES = ("k_table_build", "k_synth", "k_direct_window", "k_sincos", "k_synth_bank")
+KERNEL_NAMES = ("k_table_build", "k_synth", "k_direct_window", "k_sincos", "k_synth_bank", "k_atan2")
 
 
 def timing_enable(on: bool):

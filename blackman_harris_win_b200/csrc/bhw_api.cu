@@ -983,6 +983,27 @@ int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t
   return BHW_OK;
 }
 
+int bhw_atan2_validate(const bhw_atan2_desc* d) { return resolve_atan2(d, nullptr); }
+
+int bhw_atan2(const bhw_atan2_desc* d, const int32_t* x_dev, const int32_t* y_dev, int32_t* phi_dev, uint64_t count,
+              void* stream) {
+  Atan2Params p;
+  int st = resolve_atan2(d, &p);
+  if (st) return st;
+  if (!count) return BHW_OK;
+  if (!x_dev || !y_dev || !phi_dev) return BHW_E_NULL;
+  int dev;
+  if ((st = current_device(&dev))) return st;
+  cudaError_t e;
+  {
+    LaunchTimer tm(BHW_KERNEL_ATAN2, (cudaStream_t)stream);
+    e = launch_atan2(p, x_dev, y_dev, phi_dev, count, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "k_atan2");
+  g_launches++;
+  return BHW_OK;
+}
+
 int bhw_cache_clear(void) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess) return BHW_E_NO_DEVICE;

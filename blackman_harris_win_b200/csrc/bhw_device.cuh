@@ -624,6 +624,79 @@ BHW_HD int32_t direct_taylor_sample(const DirectTayParams& p, const I2* __restri
 }
 
 // ============================================================================================
+// cordic_atan2 (src/cordic_atan2.vhd:80-220)
+// ============================================================================================
+// Vectoring CORDIC: W = ANGLE_WIDTH + PRECISION bit registers that DO wrap (a full-scale input
+// grows past W bits at PRECISION 1), so the registers are kept left-aligned to bit 63 like
+// cordic_core_aligned64: the wrap is the natural overflow of the 64-bit add.
+struct Atan2Params {
+  int32_t iw, aw, w;     // INPUT_WIDTH, ANGLE_WIDTH, ANGLE_WIDTH + PRECISION
+  int32_t fast32;        // 1: W <= 32, the 32-bit body applies
+  int64_t rom64[48];     // ROM_TABLE(ii) (:97-108) left-aligned to bit 63; aw-1 entries used
+  uint32_t rom32[32];    // the same words left-aligned to bit 31 (fast32)
+};
+
+// W <= 32: the same algorithm with the registers left-aligned in 32 bits.  d = +1/-1 from the sign
+// of Y turns the three conditional add/subtracts into multiply-adds (mod 2^32 = the W-bit wrap).
+BHW_HD int32_t atan2_sample32(const Atan2Params& p, int32_t xin, int32_t yin) {
+  const int aw = p.aw, ax = 32 - p.w;
+  const uint32_t sxb = ((uint32_t)xin >> (p.iw - 1)) & 1u, syb = ((uint32_t)yin >> (p.iw - 1)) & 1u;
+  const uint32_t mag_mask = (1u << (aw - 1)) - 1u;
+  const int32_t mx = (int32_t)(~0u << ax);
+  uint32_t X = (((uint32_t)xin ^ (0u - sxb)) & mag_mask) << ax;
+  uint32_t Y = (((uint32_t)yin ^ (0u - syb)) & mag_mask) << ax;
+  uint32_t Z = 0;
+#pragma unroll 4
+  for (int i = 0; i <= aw - 2; ++i) {
+    const uint32_t d = (uint32_t)(((int32_t)Y >> 31) | 1);   // -1 when y < 0, else +1
+    const uint32_t Xs = (uint32_t)(((int32_t)X >> i) & mx), Ys = (uint32_t)(((int32_t)Y >> i) & mx);
+    X += d * Ys;                                              // y >= 0: x + (y >> i)   (:169-175)
+    Y -= d * Xs;                                              //         y - (x >> i)
+    Z -= d * p.rom32[i];                                      //         z - ROM_TABLE(i)
+  }
+  const int32_t phi = (int32_t)Z >> (32 - aw);                // top ANGLE_WIDTH bits, sign-extended
+  const int32_t pi = 1 << (aw - 2);
+  int32_t o;
+  switch ((sxb << 1) | syb) {
+    case 0: o = phi; break;
+    case 1: o = (int32_t)((uint32_t)phi + (uint32_t)pi); break;
+    case 2: o = (int32_t)(0u - (uint32_t)phi); break;
+    default: o = (int32_t)((uint32_t)phi - (uint32_t)pi); break;
+  }
+  return wrapb32(o, aw);
+}
+
+BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin) {
+  if (p.fast32) return atan2_sample32(p, xin, yin);
+  const int aw = p.aw, ax = 64 - p.w;
+  const uint32_t sxb = ((uint32_t)xin >> (p.iw - 1)) & 1u, syb = ((uint32_t)yin >> (p.iw - 1)) & 1u;
+  // init_x(ii) = VEC_DX(ii) xor VEC_DX(INPUT_WIDTH-1), ii = 0..ANGLE_WIDTH-2; upper bits zero (:136-146)
+  const uint32_t mag_mask = aw - 1 >= 32 ? 0xFFFFFFFFu : ((1u << (aw - 1)) - 1u);
+  const uint64_t ix = ((uint32_t)xin ^ (0u - sxb)) & mag_mask, iy = ((uint32_t)yin ^ (0u - syb)) & mag_mask;
+  const int64_t mx = (int64_t)(~0ull << ax);
+  uint64_t X = ix << ax, Y = iy << ax, Z = 0;
+  for (int i = 0; i <= aw - 2; ++i) {                     // lpXY / lpZ (:166-184)
+    const bool yneg = (int64_t)Y < 0;
+    const uint64_t Xs = (uint64_t)(((int64_t)X >> i) & mx), Ys = (uint64_t)(((int64_t)Y >> i) & mx);
+    const uint64_t r = (uint64_t)p.rom64[i];
+    X = yneg ? X - Ys : X + Ys;
+    Y = yneg ? Y + Xs : Y - Xs;
+    Z = yneg ? Z + r : Z - r;
+  }
+  // dat_phi = sigZ(W-1 downto PRECISION): the top ANGLE_WIDTH bits (:188)
+  const int64_t phi = (int64_t)Z >> (64 - aw);
+  const int64_t pi = (int64_t)1 << (aw - 2);              // PHI_PI: only bit ANGLE_WIDTH-2 set (:121)
+  int64_t o;
+  switch ((sxb << 1) | syb) {                             // quadrant = sign(X) & sign(Y) (:129-131,203-208)
+    case 0: o = phi; break;
+    case 1: o = phi + pi; break;
+    case 2: o = -phi; break;
+    default: o = phi - pi; break;
+  }
+  return (int32_t)wrapb(o, aw);
+}
+
+// ============================================================================================
 // Bank synthesis body (k_synth_bank): whole windows of one shape
 // ============================================================================================
 // A "bank" is a run of windows that differ only in their AAk ports (and stream offset): same

@@ -326,6 +326,16 @@ k_sincos(const __grid_constant__ SinCosArgs a, OutT* __restrict__ out_sin, OutT*
   }
 }
 
+// cordic_atan2: one thread per (VEC_DX, VEC_DY) pair; 8 B read + 4 B written per sample, but
+// ~10 instructions per stage make it integer-issue-bound long before HBM.
+__global__ void __launch_bounds__(256)
+k_atan2(const __grid_constant__ Atan2Params p, const int32_t* __restrict__ x, const int32_t* __restrict__ y,
+        int32_t* __restrict__ phi, uint64_t count) {
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count;
+       j += (uint64_t)gridDim.x * blockDim.x)
+    __stcs(phi + j, atan2_sample(p, __ldcs(x + j), __ldcs(y + j)));
+}
+
 // -------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------
@@ -460,6 +470,14 @@ cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStrea
   if (a.p.tmode == TMODE_ROM) k_direct_taylor<TMODE_ROM><<<grid, 256, smem, stream>>>(a, out);
   else if (a.p.tmode == TMODE_DSP) k_direct_taylor<TMODE_DSP><<<grid, 256, smem, stream>>>(a, out);
   else k_direct_taylor<TMODE_WIDE><<<grid, 256, smem, stream>>>(a, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count,
+                         cudaStream_t stream) {
+  if (!count) return cudaSuccess;
+  const unsigned grid = grid_for((count + 255) / 256, 8);
+  k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count);
   return cudaGetLastError();
 }
 

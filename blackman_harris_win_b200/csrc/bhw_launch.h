@@ -73,6 +73,8 @@ size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for s
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream);
 cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream);
+cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count,
+                         cudaStream_t stream);
 cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream);
 
 }  // namespace bhw

@@ -193,6 +193,27 @@ bool direct_taylor_params(const WinParams& wp, const SrcParams* src, DirectTayPa
   return true;
 }
 
+// cordic_atan2 generics -> kernel parameters.  ROM_TABLE(ii) = "0" & ROM_LUT(ii)(47 downto
+// 47-(W-2)): the top W-1 bits of the 48-bit word (src/cordic_atan2.vhd:97-108).
+int resolve_atan2(const bhw_atan2_desc* d, Atan2Params* p) {
+  if (!d) return BHW_E_NULL;
+  const int prec = d->precision == 0 ? 1 : d->precision;
+  if (d->reserved != 0) return BHW_E_ARG;
+  if (d->angle_width < 4 || d->angle_width > 32) return BHW_E_DAT_WIDTH;
+  if (d->input_width > 32 || d->input_width < d->angle_width - 1) return BHW_E_PHI_WIDTH;
+  if (prec < 1 || prec > 7) return BHW_E_PRECISION;
+  if (!p) return BHW_OK;
+  memset(p, 0, sizeof(*p));
+  p->iw = d->input_width; p->aw = d->angle_width; p->w = d->angle_width + prec;
+  for (int i = 0; i <= p->aw - 2; i++) {
+    const int64_t r = c_atan[0][i] >> (48 - (p->w - 1));
+    p->rom64[i] = (int64_t)((uint64_t)r << (64 - p->w));
+    if (p->w <= 32 && i < 32) p->rom32[i] = (uint32_t)((uint64_t)r << (32 - p->w));
+  }
+  p->fast32 = p->w <= 32 ? 1 : 0;
+  return BHW_OK;
+}
+
 bool source_antisymmetric(const SrcParams& sp) {
   switch (sp.kind) {
     case SRC_DDS:   // |value| <= 2^(DW-2) + a few LSB: far from -2^(DW-1) once DW >= 8; the quadrant

@@ -25,6 +25,9 @@ bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* 
 // 2-/3-term TAYLOR window with a 32-bit tail.
 bool direct_taylor_params(const WinParams& wp, const SrcParams* src, DirectTayParams* out);
 
+// cordic_atan2: validation (+ kernel parameters when p != NULL); returns a bhw_status.
+int resolve_atan2(const bhw_atan2_desc* d, Atan2Params* p);
+
 // Trig table of one harmonic as the bank planner sees it.
 struct BankTableInfo { const int32_t* ptr; uint32_t entries; bool antisym; };
 // Is the source's cosine table provably antisymmetric over half a period, T[i + E/2] == -T[i]

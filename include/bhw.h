@@ -214,6 +214,25 @@ BHW_API int bhw_plan_destroy(bhw_plan* plan);
 BHW_API int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t n0,
                uint64_t count, void* stream);
 
+/* ---- cordic_atan2: the vectoring sibling of the DDS cores ------------------ */
+/* Replaces entity cordic_atan2 (src/cordic_atan2.vhd:64-78: generics PRECISION, INPUT_WIDTH,
+ * ANGLE_WIDTH; ports VEC_DX, VEC_DY -> PHI_DT).  No window entity instantiates it; it is here
+ * because it shares the DDS cores' ROM and stage structure.  One PHI_DT per
+ * (VEC_DX, VEC_DY) pair, in input order (the entity's ANGLE_WIDTH+1 clocks of latency and PHI_VL
+ * are timing, not data).  x_dev/y_dev: int32 per element, the low INPUT_WIDTH bits are the port
+ * bits (bit INPUT_WIDTH-1 is the sign); phi_dev: int32, PHI_DT sign-extended from ANGLE_WIDTH bits.
+ * Valid: 4 <= angle_width <= 32, angle_width - 1 <= input_width <= 32 (the entity indexes
+ * VEC_DX(ANGLE_WIDTH-2), src/cordic_atan2.vhd:140-141), 1 <= precision <= 7. */
+typedef struct bhw_atan2_desc {
+  int32_t input_width;   /* INPUT_WIDTH */
+  int32_t angle_width;   /* ANGLE_WIDTH */
+  int32_t precision;     /* PRECISION, 0 = the entity default 1 */
+  int32_t reserved;      /* must be 0 */
+} bhw_atan2_desc;
+BHW_API int bhw_atan2_validate(const bhw_atan2_desc* d);
+BHW_API int bhw_atan2(const bhw_atan2_desc* d, const int32_t* x_dev, const int32_t* y_dev, int32_t* phi_dev,
+              uint64_t count, void* stream);
+
 /* ---- cache / introspection --------------------------------------------- */
 BHW_API int bhw_cache_clear(void);             /* free the cached sine ROMs and host-pipeline staging */
 BHW_API int bhw_set_table_cache(int enabled);  /* 1 (default): a plan builds its trig tables on its
@@ -239,7 +258,8 @@ enum {
   BHW_KERNEL_DIRECT = 2,      /* k_direct*: one thread per sample, sources evaluated in registers */
   BHW_KERNEL_SINCOS = 3,      /* k_sincos                                                        */
   BHW_KERNEL_SYNTH_BANK = 4,  /* k_synth_bank: whole windows of one shape, tables in shared memory */
-  BHW_KERNEL_CLASSES = 5
+  BHW_KERNEL_ATAN2 = 5,       /* k_atan2                                                          */
+  BHW_KERNEL_CLASSES = 6
 };
 BHW_API int bhw_timing_enable(int enabled);
 BHW_API int bhw_timing_reset(void);

@@ -482,6 +482,50 @@ int orc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin,
   return BHW_OK;
 }
 
+/* ---- cordic_atan2: src/cordic_atan2.vhd:80-220 ----------------------------- */
+int orc_atan2_validate(int iw, int aw, int prec) {
+  if (prec == 0) prec = 1;
+  if (aw < 4 || aw > 32) return BHW_E_DAT_WIDTH;
+  if (iw > 32 || iw < aw - 1) return BHW_E_PHI_WIDTH;   /* VEC_DX(ii), ii <= ANGLE_WIDTH-2 (:140-141) */
+  if (prec < 1 || prec > 7) return BHW_E_PRECISION;
+  return BHW_OK;
+}
+
+int64_t orc_cordic_atan2(int iw, int aw, int prec, int64_t vx, int64_t vy) {
+  if (prec == 0) prec = 1;
+  const int w = aw + prec;                                 /* dat_array / phi_array element width :117-118 */
+  const int sxb = (int)((vx >> (iw - 1)) & 1), syb = (int)((vy >> (iw - 1)) & 1);
+  int64_t x = 0, y = 0, z = 0;                             /* init_z <= 0 :149 */
+  for (int ii = 0; ii <= aw - 2; ii++) {                   /* pr_abs :136-146 */
+    x |= (int64_t)(((vx >> ii) & 1) ^ sxb) << ii;
+    y |= (int64_t)(((vy >> ii) & 1) ^ syb) << ii;
+  }
+  for (int ii = 0; ii <= aw - 2; ii++) {                   /* lpXY, lpZ :166-184 */
+    /* ROM_TABLE(ii) = '0' & ROM_LUT(ii)(47 downto 47-(w-2))  :102-105 */
+    const int64_t rom = ROM4[ii] >> (48 - (w - 1));
+    int64_t xn, yn, zn;
+    if (y >= 0) { xn = x + (y >> ii); yn = y - (x >> ii); zn = z - rom; }   /* sigY MSB = '0' */
+    else        { xn = x - (y >> ii); yn = y + (x >> ii); zn = z + rom; }
+    x = sx(xn, w); y = sx(yn, w); z = sx(zn, w);
+  }
+  const int64_t dat_phi = sx(z >> prec, aw);               /* sigZ(AW-1)(w-1 downto PRECISION) :188 */
+  const int64_t phi_pi = (int64_t)1 << (aw - 2);           /* (ANGLE_WIDTH-2 => '1', others => '0') :121 */
+  switch ((sxb << 1) | syb) {                              /* quadrant = quadz1 & quadz2 :129-131; case :203-208 */
+    case 0: return dat_phi;
+    case 1: return sx(dat_phi + phi_pi, aw);
+    case 2: return sx(~dat_phi + 1, aw);
+    default: return sx(dat_phi - phi_pi, aw);
+  }
+}
+
+int orc_atan2(int iw, int aw, int prec, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count) {
+  int st = orc_atan2_validate(iw, aw, prec);
+  if (st) return st;
+  for (uint64_t j = 0; j < count; j++)
+    phi[j] = (int32_t)orc_cordic_atan2(iw, aw, prec, (int64_t)(uint32_t)x[j], (int64_t)(uint32_t)y[j]);
+  return BHW_OK;
+}
+
 /* ---- coefficient rules ---------------------------------------------------- */
 /* variants per README.md:30-41; values per the entity headers */
 static const double COEF[10][7] = {

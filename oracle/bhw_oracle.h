@@ -9,7 +9,8 @@
  * reference's own C++ compiled here (oracle/_ref, see oracle/Makefile).  The
  * RTL-model functions have NO executable reference in this image (no VHDL
  * simulator): they are "parity unpinned" by the reference and are anchored by
- * an independent bit-vector restatement (oracle/rtl_bitvec.py) and the
+ * an independent bit-vector restatement (oracle/rtl_bitvec.py, checked against this
+ * file by tests/test_rtl_bitvec.py) and the
  * known-answer hashes in tests/golden/.
  */
 #ifndef BHW_ORACLE_H_
@@ -35,6 +36,13 @@ int orc_validate(const bhw_desc* d);
 int orc_window(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out);
 int orc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, int64_t* out_cos);
 int orc_quantize(int variant, int rule, int dat_width, int64_t aa_out[7], int32_t* win_type);
+
+/* cordic_atan2 (src/cordic_atan2.vhd): PHI_DT of one (VEC_DX, VEC_DY) pair, sign-extended from
+ * ANGLE_WIDTH bits.  RTL-only entity: parity unpinned (see header comment). */
+int orc_atan2_validate(int input_width, int angle_width, int precision);
+int64_t orc_cordic_atan2(int input_width, int angle_width, int precision, int64_t vec_dx, int64_t vec_dy);
+int orc_atan2(int input_width, int angle_width, int precision, const int32_t* x, const int32_t* y, int32_t* phi,
+              uint64_t count);
 
 /* multi-threaded fill used by bench.py's CPU legs (pthreads, one contiguous slice per thread) */
 int orc_window_mt(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int nthreads);

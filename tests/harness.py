@@ -42,6 +42,12 @@ def oracle():
     L.orc_window_mt.argtypes = [D, C.c_uint64, C.c_uint64, I64P, C.c_int]
     L.orc_window_i32.argtypes = [D, C.c_uint64, C.c_uint64, P(C.c_int32)]
     L.orc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]
+    L.orc_atan2.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_int32), P(C.c_int32), P(C.c_int32), C.c_uint64]
+    L.orc_atan2_validate.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.orc_cordic_atan2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
+    L.orc_cordic_atan2.restype = C.c_int64
+    L.orc_cordic_dds.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, I64P, I64P]
+    L.orc_cordic_dds.restype = None
     L.orc_quantize.argtypes = [C.c_int, C.c_int, C.c_int, I64P, P(C.c_int32)]
     L.orc_taylor_rom.argtypes = [C.c_int, C.c_int, I64P, I64P]
     return L
@@ -65,6 +71,17 @@ def orc_window(d: BhwDesc, n0=0, count=None, threads=1) -> np.ndarray:
         st = oracle().orc_window(C.byref(d), n0, count, _p(out))
     if st:
         raise ValueError(f"orc_window status {st}")
+    return out
+
+
+def orc_atan2(iw: int, aw: int, prec: int, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    y = np.ascontiguousarray(y, dtype=np.int32)
+    out = np.empty(x.shape, np.int32)
+    p32 = P(C.c_int32)
+    st = oracle().orc_atan2(iw, aw, prec, x.ctypes.data_as(p32), y.ctypes.data_as(p32), out.ctypes.data_as(p32), x.size)
+    if st:
+        raise ValueError(f"orc_atan2: status {st}")
     return out
 
 
@@ -186,6 +203,8 @@ def hostcheck():
     L.hc_table.argtypes = [D, C.c_uint64, C.c_uint64, I64P, C.c_int]
     L.hc_direct32.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
     L.hc_direct_taylor.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
+    from blackman_harris_win_b200.api import BhwAtan2Desc
+    L.hc_atan2.argtypes = [P(BhwAtan2Desc), P(C.c_int32), P(C.c_int32), P(C.c_int32), C.c_uint64]
     L.hc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]
     L.hc_table_cos.argtypes = [D, I64P, C.c_int]
     L.hc_bank.argtypes = [D, I64P, C.c_uint64, C.c_int, C.c_int]

@@ -250,6 +250,15 @@ int hc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, 
   return 0;
 }
 
+// the cordic_atan2 body (k_atan2)
+int hc_atan2(const bhw_atan2_desc* d, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count) {
+  Atan2Params p;
+  int st = resolve_atan2(d, &p);
+  if (st) return st;
+  for (uint64_t j = 0; j < count; j++) phi[j] = atan2_sample(p, x[j], y[j]);
+  return 0;
+}
+
 // 1 if the planner treats the window's first source as antisymmetric over half a period
 int hc_source_antisymmetric(const bhw_desc* d) {
   WinParams wp; SrcParams src[2];

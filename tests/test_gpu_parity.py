@@ -392,6 +392,19 @@ def test_stream_offset_long_windows_all_kernels():
         assert torch.equal(part, torch.roll(base, -1)[n - 1000:])
 
 
+def test_cordic_atan2():
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(11)
+    for aw, iw, prec in [(8, 8, 1), (16, 16, 1), (16, 20, 3), (24, 24, 1), (24, 32, 2), (32, 31, 1), (32, 32, 7)]:
+        n = (1 << 20) + 77
+        x = torch.randint(-(1 << 31), 1 << 31, (n,), generator=g, dtype=torch.int64).to(torch.int32)
+        y = torch.randint(-(1 << 31), 1 << 31, (n,), generator=g, dtype=torch.int64).to(torch.int32)
+        got = bhw.atan2(x.cuda(), y.cuda(), iw, aw, prec).cpu().numpy()
+        assert np.array_equal(got, H.orc_atan2(iw, aw, prec, x.numpy(), y.numpy())), (aw, iw, prec)
+    with pytest.raises(bhw.BhwError):
+        bhw.atan2(x.cuda(), y.cuda(), 20, 24, 1)          # INPUT_WIDTH < ANGLE_WIDTH - 1
+
+
 def test_win_selector_and_errors():
     w = bhw.WinSelector(PHI_WIDTH=10, DAT_WIDTH=16, WIN_TYPE="HAMMING")
     assert np.array_equal(w.stream(AA0=17808, AA1=14959).cpu().numpy().astype(np.int64),

@@ -1,0 +1,116 @@
+"""CPU tier: the two restatements of the RTL - oracle/bhw_oracle.c (integers + explicit wraps) and
+oracle/rtl_bitvec.py (bit vectors with the VHDL's own widths, slices and std_logic_signed `+`) - must
+agree.  The RTL has no executable reference here (no VHDL simulator), so this is the anchor that
+replaces one: two texts written from the same source in two different styles."""
+import ctypes as C
+import os
+import random
+import sys
+
+import numpy as np
+
+import blackman_harris_win_b200 as bhw
+import harness as H
+
+sys.path.insert(0, os.path.join(H.ROOT, "oracle"))
+import rtl_bitvec as RB  # noqa: E402
+
+
+def test_cordic_dds_matches_oracle():
+    rng = random.Random(1234)
+    L = H.oracle()
+    s, c = C.c_int64(0), C.c_int64(0)
+    n = 0
+    for dw in (4, 8, 12, 16, 17, 24, 31, 32, 40, 47):
+        for prec in (1, 2, 7) if dw + 7 <= 49 else (1,):
+            if dw + prec > 49:
+                continue
+            for pw in (4, 7, dw - 1, dw, dw + 1, 26):
+                if pw < 4:
+                    continue
+                for _ in range(24):
+                    ph = rng.randrange(1 << pw)
+                    L.orc_cordic_dds(pw, dw, prec, ph, C.byref(s), C.byref(c))
+                    assert RB.cordic_dds(pw, dw, prec, ph) == (s.value, c.value), (pw, dw, prec, ph)
+                    n += 1
+    assert n > 2000
+
+
+def test_window_entities_match_oracle():
+    """hamming_win / bh_win_{3,4,5,7}term, CORDIC source: DT_WIN of random phases, the README variants
+    and adversarial port values (most negative / all-ones coefficients)."""
+    rng = random.Random(99)
+    n = 0
+    for m in (2, 3, 4, 5, 7):
+        for dw in (8, 13, 16, 17, 24, 31, 32):
+            for pw in (4, 9, dw, 20):
+                lo, hi = -(1 << (dw - 1)), (1 << (dw - 1)) - 1
+                sets = [[rng.randrange(lo, hi + 1) for _ in range(m)], [hi] * m, [lo] * m,
+                        [rng.randrange(0, 1 << dw) for _ in range(m)]]         # raw bits, unsigned reading
+                for aa in sets:
+                    d = bhw.make_desc(m, pw, dw, aa)
+                    if bhw.validate(d):
+                        continue
+                    N = 1 << pw
+                    idx = sorted({0, 1, N // 4, N // 2, N - 1} | {rng.randrange(N) for _ in range(6)})
+                    for i in idx:
+                        want = int(H.orc_window(d, i, 1)[0])
+                        assert RB.window(m, pw, dw, aa, i) == want, (m, pw, dw, aa, i)
+                        n += 1
+    assert n > 2500
+
+
+def test_known_answers_from_the_survey():
+    """SURVEY 8(c) [derived] anchors, PW=11 / DW=16."""
+    assert [RB.cordic_dds(11, 16, 1, i)[1] for i in range(8)] == [16385, 16384, 16384, 16384, 16384, 16380, 16380, 16379]
+    assert [RB.window(2, 11, 16, [17808, 14959], i) for i in range(8)] == [5164, 5164, 5164, 5164, 5164, 5165, 5165, 5166]
+    assert RB.window(2, 11, 16, [17808, 14959], 1024) == 12644
+    assert [RB.window(4, 11, 16, [23511, 32000, 9259, 765], i) for i in range(4)] == [2939, 2940, 2940, 2939]
+    assert RB.window(7, 11, 16, [8887, 14203, 7143, 2156, 353, 25, 0], 1024) == 5207
+
+
+def test_cordic_atan2_matches_oracle_and_converges():
+    rng = random.Random(7)
+    L = H.oracle()
+    n = 0
+    for aw, iw, prec in [(8, 8, 1), (12, 11, 2), (16, 16, 1), (16, 20, 3), (24, 24, 1), (24, 32, 1), (32, 31, 1),
+                         (32, 32, 7), (4, 3, 1), (20, 19, 4)]:
+        assert L.orc_atan2_validate(iw, aw, prec) == 0
+        for _ in range(60):
+            x, y = rng.randrange(1 << iw), rng.randrange(1 << iw)
+            want = L.orc_cordic_atan2(iw, aw, prec, x, y)
+            assert RB.cordic_atan2(iw, aw, prec, x, y) == want, (aw, iw, prec, x, y)
+            n += 1
+    assert n == 600
+    # the vectoring iterations really do measure the angle: first quadrant, magnitudes well inside the
+    # register, PHI_DT = -atan(|y|/|x|) in units of pi = 2^(ANGLE_WIDTH-1) (the entity's sign convention)
+    aw, iw, prec = 24, 24, 3
+    for _ in range(200):
+        x, y = rng.randrange(1 << 16, 1 << 20), rng.randrange(0, 1 << 20)
+        got = L.orc_cordic_atan2(iw, aw, prec, x, y)
+        want = -np.arctan2(y, x) / np.pi * (1 << (aw - 1))
+        assert abs(got - want) < 64, (x, y, got, want)
+    # invalid generics
+    assert L.orc_atan2_validate(20, 24, 1) != 0      # the entity's own defaults index VEC_DX out of range
+    assert L.orc_atan2_validate(24, 33, 1) != 0
+    assert L.orc_atan2_validate(24, 24, 8) != 0
+
+
+def test_atan2_kernel_body_matches_oracle():
+    rng = np.random.default_rng(5)
+    hc = H.hostcheck()
+    p32 = C.POINTER(C.c_int32)
+    for aw, iw, prec in [(8, 8, 1), (12, 11, 2), (16, 16, 1), (16, 20, 3), (24, 24, 1), (24, 32, 1), (32, 31, 1),
+                         (32, 32, 7), (4, 3, 1), (20, 19, 4), (24, 24, 0)]:
+        x = rng.integers(-(1 << 31), 1 << 31, 4096, dtype=np.int64).astype(np.int32)
+        y = rng.integers(-(1 << 31), 1 << 31, 4096, dtype=np.int64).astype(np.int32)
+        x[:4] = [0, -1, (1 << (iw - 1)) - 1, -(1 << (iw - 1))]
+        y[:4] = [0, -1, -(1 << (iw - 1)), (1 << (iw - 1)) - 1]
+        d = bhw.BhwAtan2Desc(iw, aw, prec, 0)
+        assert bhw.lib().bhw_atan2_validate(C.byref(d)) == 0
+        got = np.empty(4096, np.int32)
+        assert hc.hc_atan2(C.byref(d), x.ctypes.data_as(p32), y.ctypes.data_as(p32), got.ctypes.data_as(p32), 4096) == 0
+        assert np.array_equal(got, H.orc_atan2(iw, aw, prec, x, y)), (aw, iw, prec)
+    for bad in (bhw.BhwAtan2Desc(20, 24, 1, 0), bhw.BhwAtan2Desc(24, 33, 1, 0), bhw.BhwAtan2Desc(24, 24, 8, 0),
+                bhw.BhwAtan2Desc(24, 24, 1, 5)):
+        assert bhw.lib().bhw_atan2_validate(C.byref(bad)) != 0

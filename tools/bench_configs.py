@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--only", default="", help="substring filter on the config name")
     ap.add_argument("--no-batch", action="store_true", help="skip the plan/batch line of each config")
+    ap.add_argument("--atan2", action="store_true", help="also time the cordic_atan2 kernel (16M pairs)")
     ap.add_argument("--sweep", action="store_true", help="also run the config-5 sweep (10 variants x PHI_WIDTH 4..26)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
@@ -118,6 +119,27 @@ def main():
                               "frac_of_hbm_peak": round(plan.total * 4 / ms / 1e6 / peak, 4)}))
             plan.destroy()
             del big
+    if args.atan2:
+        n = 1 << 24
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.randint(-(1 << 23), 1 << 23, (n,), generator=g, dtype=torch.int32, device="cuda")
+        y = torch.randint(-(1 << 23), 1 << 23, (n,), generator=g, dtype=torch.int32, device="cuda")
+        out = torch.empty_like(x)
+        for aw, iw, prec in ((16, 16, 1), (24, 24, 1), (32, 32, 1)):
+            bhw.timing_enable(True)
+            bhw.timing_reset()
+            ms = time_calls(lambda: bhw.atan2(x, y, iw, aw, prec, out=out), 20)
+            kt = {k: v for k, v in bhw.timing_read().items() if v[0]}
+            bhw.timing_enable(False)
+            k_ms = kt["k_atan2"][1] / kt["k_atan2"][0]
+            ops = (aw - 1) * 5 * (1 if aw + prec <= 32 else 2) + 10   # 3 add + 2 shift per stage (src/cordic_atan2.vhd:24-28)
+            line = {"config": f"cordic_atan2 ANGLE_WIDTH {aw} INPUT_WIDTH {iw} PRECISION {prec}, 16M pairs", "samples": n,
+                    "ms_per_call": round(ms, 5), "kernel_ms": round(k_ms, 5), "gsamples_per_s": round(n / k_ms / 1e6, 2),
+                    "hbm_gbs (8 B read + 4 B written per pair)": round(12 * n / k_ms / 1e6, 1),
+                    "frac_of_hbm_peak": round(12 * n / k_ms / 1e6 / peak, 4)}
+            if int_peak:
+                line["int_roofline"] = {"alg_ops_per_sample": ops, "frac": round(ops * n / (k_ms * 1e-3) / int_peak, 4)}
+            print(json.dumps(line))
     if args.sweep:
         # config 5: all 10 variants x PHI_WIDTH 4..26, one batch per element size, sharded 1-way here
         descs = [bhw.variant_desc(v, pw, cases.VARIANT_DW[v]) for v in range(1, 11) for pw in range(4, 27)]

@@ -12,7 +12,9 @@ Agreement of two restatements is a regression anchor, not ground truth ("parity 
 Covered: cordic_dds (src/cordic_dds.vhd:97-249), int_multNxN_dsp48 (src/int_multNxN_dsp48.vhd:105),
 the tails of hamming_win (src/hamming_win.vhd:133-231), bh_win_3term (src/bh_win_3term.vhd:151-306),
 bh_win_4term (src/bh_win_4term.vhd:125-280), bh_win_5term (src/bh_win_5term.vhd:148-347),
-bh_win_7term (src/bh_win_7term.vhd:160-438) and cordic_atan2 (src/cordic_atan2.vhd:80-220).
+bh_win_7term (src/bh_win_7term.vhd:160-438), cordic_atan2 (src/cordic_atan2.vhd:80-220), and
+taylor_sincos + tay1_order (src/taylor_sincos.vhd:86-255, src/tay1_order.vhd:112-640) with the
+TAYLOR forms of hamming_win and bh_win_3term.
 """
 from __future__ import annotations
 
@@ -200,3 +202,106 @@ def cordic_atan2(input_width: int, angle_width: int, precision: int, vec_dx: int
     else:
         o = dat_phi - phi_pi
     return o.signed()
+
+
+# ---- taylor_sincos + tay1_order ----------------------------------------------------------------------
+# Pipeline alignment (checked on the source, not assumed): in xGEN_MORE `addr`/`acnt` are taken from
+# `cnt` combinationally, `dpo` (ROM word) and `mpi` (pi * acnt) are both one register later, and
+#   DATA_WIDTH < 19 : A (mpx, AREG=1) and B (sin_aa/cos_aa, BREG=1) meet at MREG; C (cos_cc/sin_cc,
+#                     one fabric register + CREG) meets the product at PREG          (tay1_order.vhd:180-504)
+#   DATA_WIDTH > 18 : the 35x27 multiplier has 4 clocks of latency (mults/mlt35x27_dsp48e2.vhd:23)
+#                     and the ROM word waits in the 4-deep cos_del/sin_del           (tay1_order.vhd:524-596)
+# so every sample combines its own ROM word with its own correction.
+import math
+
+
+def _taylor_rom(data_width: int, lut_size: int):
+    """ROM_ARRAY(ii) = sin & cos words, INTEGER() = round to nearest (src/taylor_sincos.vhd:91-111)."""
+    depth = 1 << lut_size
+    amp = 2.0 ** (data_width - 1) - 1.0
+    rom = []
+    for ii in range(depth):
+        pi_new = (float(ii) * math.pi) / (2.0 * float(depth))
+        re_int = int(math.floor(amp * math.cos(pi_new) + 0.5))
+        im_int = int(math.floor(amp * math.sin(pi_new) + 0.5))
+        rom.append(cat(BV(data_width, im_int), BV(data_width, re_int)))
+    return rom
+
+
+def taylor_sincos(phase_width: int, data_width: int, lut_size: int, cnt_value: int, _rom_cache={}):
+    """-> (out_sin, out_cos) for counter value cnt.  src/taylor_sincos.vhd:86-255, src/tay1_order.vhd:112-640."""
+    PW, DW, LUT = phase_width, data_width, lut_size
+    key = (DW, LUT)
+    if key not in _rom_cache:
+        _rom_cache[key] = _taylor_rom(DW, LUT)
+    ROM = _rom_cache[key]
+    cnt = BV(PW, cnt_value)
+    quadrant = (cnt[PW - 1] << 1) | cnt[PW - 2]                               # :141
+    if PW - LUT < 2:                                                          # xGEN_LESS :157-161
+        addr = cat(cnt[PW - 3:0], BV(LUT - PW + 2, 0))
+        dpo = ROM[addr.u]
+        mem_sin, mem_cos = dpo[2 * DW - 1:DW], dpo[DW - 1:0]
+    elif PW - LUT == 2:                                                       # xGEN_EQ :164-167
+        dpo = ROM[cnt[LUT - 1:0].u]
+        mem_sin, mem_cos = dpo[2 * DW - 1:DW], dpo[DW - 1:0]
+    else:                                                                     # xGEN_MORE :169-217
+        STAGE = PW - LUT - 3
+        addr = cnt[PW - 3:PW - LUT - 2]
+        acnt = cnt[PW - 3 - LUT:0]
+        assert acnt.w == STAGE + 1
+        rom_dat = ROM[addr.u]
+        XSHIFT = 19 + LUT                                                     # tay1_order.vhd:112
+        ramb_pi = int(math.floor(math.pi * 2.0 ** (17 - STAGE) + 0.5))        # :131 integer(round(...))
+        mpi = BV(24, ramb_pi * acnt.u)                                        # conv_std_logic_vector(ramb_pi*jj, 24) :136
+        mpx = cat(BV(6, 0), mpi)                                              # :168-169, 30 bits, non-negative
+        sin_w, cos_w = rom_dat[2 * DW - 1:DW], rom_dat[DW - 1:0]
+        if DW < 19:                                                           # xWIDTH18 :171-504
+            sin_aa, cos_aa = sin_w.sext(18), cos_w.sext(18)
+            # *_cc: the ROM word at bit XSHIFT, sign-extended to 48 bits, zeros below (:183-196)
+            sin_cc = BV(48, sin_w.signed() << XSHIFT)
+            cos_cc = BV(48, cos_w.signed() << XSHIFT)
+            cos_prod = BV(48, cos_cc.signed() - mpx.signed() * sin_aa.signed())   # ALUMODE "0011": C - A*B
+            sin_prod = BV(48, sin_cc.signed() + mpx.signed() * cos_aa.signed())   # ALUMODE "0000": C + A*B
+            mem_cos = cos_prod[XSHIFT + DW - 1:XSHIFT]                        # :501-502
+            mem_sin = sin_prod[XSHIFT + DW - 1:XSHIFT]
+        else:                                                                 # xWIDTH35 :506-637
+            sin_aa, cos_aa = sin_w.sext(35), cos_w.sext(35)
+            cos_pp = BV(62, cos_aa.signed() * mpx[26:0].u)                    # 35 x 27 (unsigned mpx: bits 29..24 are zero)
+            sin_pp = BV(62, sin_aa.signed() * mpx[26:0].u)
+            mlt1_bb = sin_pp[DW + XSHIFT - 1:XSHIFT]                          # :583-586
+            mlt2_bb = cos_pp[DW + XSHIFT - 1:XSHIFT]
+            cos_pdt = cos_w - mlt1_bb                                         # :595-596 (DW bits, wraps)
+            sin_pdt = sin_w + mlt2_bb
+            sat = BV(DW, (1 << (DW - 1)) - 1)                                 # ((DW-1) => '0', others => '1')
+            mem_cos = cos_pdt if cos_pdt[DW - 1] == 0 else sat                # pr_rnd :602-617
+            mem_sin = sin_pdt if sin_pdt[DW - 1] == 0 else sat
+    if quadrant == 0:                                                         # pr_quad :237-255
+        s, c = mem_sin, mem_cos
+    elif quadrant == 1:
+        s, c = mem_cos, ~mem_sin + 1
+    elif quadrant == 2:
+        s, c = ~mem_sin + 1, ~mem_cos + 1
+    else:
+        s, c = ~mem_cos + 1, mem_sin
+    return s.signed(), c.signed()
+
+
+def window_taylor(win_type: int, phi_width: int, dat_width: int, lut_size: int, aa, n: int) -> int:
+    """DT_WIN of hamming_win / bh_win_3term with SIN_TYPE = "TAYLOR": every unit has its own +1 counter,
+    the second harmonic of bh_win_3term is a PHASE_WIDTH-1 unit (src/bh_win_3term.vhd:221-233)."""
+    DW, PW, M = dat_width, phi_width, win_type
+    assert M in (2, 3)
+    AA = [BV(DW, a) for a in aa[:M]]
+    b = [AA[0]]
+    for k in range(1, M):
+        pw_k = PW - (k - 1)
+        _, ck = taylor_sincos(pw_k, DW, lut_size, n & ((1 << pw_k) - 1))
+        b.append(_round_product(AA[k], BV(DW, ck), DW))
+    if M == 2:
+        dsp_pp = cat(b[0][DW - 1], b[0]) - cat(b[1][DW - 1], b[1])
+        out = dsp_pp[DW:1]
+        return (out + 1 if dsp_pp[0] else out).signed()
+    x3 = lambda v: cat(v[DW - 1], v[DW - 1], v)                               # noqa: E731
+    dsp_pp = x3(b[2]) - x3(b[1]) + x3(b[0])
+    out = dsp_pp[DW + 1:2]
+    return (out + 1 if dsp_pp[1] else out).signed()

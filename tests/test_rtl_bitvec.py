@@ -69,6 +69,38 @@ def test_known_answers_from_the_survey():
     assert RB.window(7, 11, 16, [8887, 14203, 7143, 2156, 353, 25, 0], 1024) == 5207
 
 
+def test_taylor_units_and_windows_match_oracle():
+    """taylor_sincos + tay1_order in all four branches (ROM-only LESS / EQ, DSP48 MACC, 35x27 multiplier with
+    saturation) and the TAYLOR forms of hamming_win / bh_win_3term (BASELINE config 4 is one of them)."""
+    rng = random.Random(2024)
+    n = 0
+    for pw, lut in [(6, 6), (6, 5), (8, 6), (10, 7), (14, 9), (16, 9), (20, 9), (24, 9), (26, 10), (12, 1), (18, 16)]:
+        for dw in (8, 16, 18, 19, 24, 32):
+            d0 = bhw.make_desc(2, pw, dw, [1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=lut)
+            if bhw.validate(d0):
+                continue
+            N = 1 << pw
+            idx = sorted({0, 1, N // 4 - 1, N // 4, N // 2, 3 * N // 4 + 1, N - 1} | {rng.randrange(N) for _ in range(10)})
+            for i in idx:
+                s, c = H.orc_sincos(d0, i, 1)
+                assert RB.taylor_sincos(pw, dw, lut, i) == (int(s[0]), int(c[0])), (pw, dw, lut, i)
+                n += 1
+            amp = (1 << (dw - 1)) - 1
+            for wt, aa in ((2, [100, 77]), (3, [90, 100, 17])):
+                q = [a * amp // 128 for a in aa]
+                d = bhw.make_desc(wt, pw, dw, q, sin_type=bhw.SIN_TAYLOR, lut_size=lut)
+                if bhw.validate(d):
+                    continue
+                for i in idx[:8]:
+                    assert RB.window_taylor(wt, pw, dw, lut, q, i) == int(H.orc_window(d, i, 1)[0]), (wt, pw, dw, lut, i)
+                    n += 1
+    assert n > 800
+    # BASELINE config 4 itself: Blackman, PHI_WIDTH 24, DAT_WIDTH 24, LUT_SIZE 9
+    d = bhw.make_desc(3, 24, 24, [7046424, 8388600, 1342176], sin_type=bhw.SIN_TAYLOR, lut_size=9)
+    for i in [0, 1, 4097, (1 << 22) - 1, 1 << 22, (1 << 23) + 12345, (1 << 24) - 1] + [rng.randrange(1 << 24) for _ in range(40)]:
+        assert RB.window_taylor(3, 24, 24, 9, [7046424, 8388600, 1342176], i) == int(H.orc_window(d, i, 1)[0]), i
+
+
 def test_cordic_atan2_matches_oracle_and_converges():
     rng = random.Random(7)
     L = H.oracle()

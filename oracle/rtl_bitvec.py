@@ -9,7 +9,7 @@ with integer arithmetic + explicit wraps, this file restates them with bit vecto
 tests/test_rtl_bitvec.py requires the two to agree on randomised generics, ports and phases.
 Agreement of two restatements is a regression anchor, not ground truth ("parity unpinned").
 
-Covered: cordic_dds (src/cordic_dds.vhd:97-249), int_multNxN_dsp48 (src/int_multNxN_dsp48.vhd:105),
+Covered: cordic_dds (src/cordic_dds.vhd:97-249), cordic_dds48 (src/cordic_dds48.vhd:110-259), int_multNxN_dsp48 (src/int_multNxN_dsp48.vhd:105),
 the tails of hamming_win (src/hamming_win.vhd:133-231), bh_win_3term (src/bh_win_3term.vhd:151-306),
 bh_win_4term (src/bh_win_4term.vhd:125-280), bh_win_5term (src/bh_win_5term.vhd:148-347),
 bh_win_7term (src/bh_win_7term.vhd:160-438), cordic_atan2 (src/cordic_atan2.vhd:80-220), and
@@ -303,5 +303,60 @@ def window_taylor(win_type: int, phi_width: int, dat_width: int, lut_size: int, 
         return (out + 1 if dsp_pp[0] else out).signed()
     x3 = lambda v: cat(v[DW - 1], v[DW - 1], v)                               # noqa: E731
     dsp_pp = x3(b[2]) - x3(b[1]) + x3(b[0])
+    out = dsp_pp[DW + 1:2]
+    return (out + 1 if dsp_pp[1] else out).signed()
+
+
+# ---- cordic_dds48 --------------------------------------------------------------------------------------
+ROM_LUT48 = [  # src/cordic_dds48.vhd:115-128 (pi/4 -> 2^45; independently rounded, not ROM_LUT >> 1)
+    0x200000000000, 0x12E4051D9DF3, 0x09FB385B5EE4, 0x051111D41DDE, 0x028B0D430E59, 0x0145D7E15904,
+    0x00A2F61E5C28, 0x00517C5511D4, 0x0028BE5346D1, 0x00145F2EBB31, 0x000A2F980092, 0x000517CC14A8,
+    0x00028BE60CE0, 0x000145F306C1, 0x0000A2F9836B, 0x0000517CC1B7, 0x000028BE60DC, 0x0000145F306E,
+    0x00000A2F9837, 0x00000517CC1B, 0x0000028BE60E, 0x00000145F307, 0x000000A2F983, 0x000000517CC2,
+    0x00000028BE61, 0x000000145F30, 0x0000000A2F98, 0x0000000517CC, 0x000000028BE6, 0x0000000145F3,
+    0x00000000A2FA, 0x00000000517D, 0x0000000028BE, 0x00000000145F, 0x000000000A30, 0x000000000518,
+    0x00000000028C, 0x000000000146, 0x0000000000A3, 0x000000000051, 0x000000000029, 0x000000000014,
+    0x00000000000A, 0x000000000005, 0x000000000003, 0x000000000001, 0x000000000001, 0x000000000000]
+GAIN48_B = 0x26DD3B6A10D8  # src/cordic_dds48.vhd:110
+
+
+def cordic_dds48(phase_width: int, data_width: int, ph_in: int):
+    """-> (dt_sin, dt_cos).  src/cordic_dds48.vhd:110-259: 48-bit registers, the quadrant is folded into
+    the start vector and the phase word, DATA_WIDTH X/Y stages but only DATA_WIDTH-1 Z stages."""
+    PW, DW = phase_width, data_width
+    ph = BV(PW, ph_in)
+    quadrant = ph[PW - 1:PW - 2].u                                            # :167
+    gain = BV(48, GAIN48_B)
+    if quadrant in (0, 3):                                                    # pr_phi :170-186, pr_xy :189-216
+        init_t, init_x, init_y = ph, gain, BV(48, 0)
+    elif quadrant == 1:
+        init_t, init_x, init_y = cat(BV(2, 0), ph[PW - 3:0]), BV(48, 0), ~gain + 1
+    else:
+        init_t, init_x, init_y = cat(BV(2, 3), ph[PW - 3:0]), BV(48, 0), gain
+    init_z = cat(init_t, BV(48 - PW, 0)) if PW < 48 else init_t               # :164-165
+    x, y, z = init_x, init_y, init_z
+    for ii in range(DW):                                                      # xl :234-242
+        if z[47] == 0:
+            xn, yn = x + y[47:ii], y - x[47:ii]
+        else:
+            xn, yn = x - y[47:ii], y + x[47:ii]
+        if ii <= DW - 2:                                                      # xp :244-250
+            z = z + BV(48, ROM_LUT48[ii]) if z[47] == 1 else z - BV(48, ROM_LUT48[ii])
+        x, y = xn, yn
+    return y[47:47 - (DW - 1)].signed(), x[47:47 - (DW - 1)].signed()         # :257-258
+
+
+def window_dds48(win_type: int, phi_width: int, dat_width: int, aa, n: int) -> int:
+    """The window entities with cordic_dds48 swapped in for cordic_dds (same port list; BASELINE
+    config 3 names this composition - the reference itself never instantiates it)."""
+    DW, PW, M = dat_width, phi_width, win_type
+    AA = [BV(DW, a) for a in aa[:M]]
+    b = [AA[0]]
+    for k in range(1, M):
+        _, ck = cordic_dds48(PW, DW, (k * n) & ((1 << PW) - 1))
+        b.append(_round_product(AA[k], BV(DW, ck), DW))
+    assert M == 7
+    x3 = lambda v: cat(v[DW - 1], v[DW - 1], v)                               # noqa: E731
+    dsp_pp = ((x3(b[0]) - x3(b[1])) + (x3(b[2]) - x3(b[3]))) + ((x3(b[4]) - x3(b[5])) + x3(b[6]))
     out = dsp_pp[DW + 1:2]
     return (out + 1 if dsp_pp[1] else out).signed()

@@ -101,6 +101,27 @@ def test_taylor_units_and_windows_match_oracle():
         assert RB.window_taylor(3, 24, 24, 9, [7046424, 8388600, 1342176], i) == int(H.orc_window(d, i, 1)[0]), i
 
 
+def test_cordic_dds48_and_config3_match_oracle():
+    rng = random.Random(48)
+    n = 0
+    for dw in (4, 8, 16, 24, 32, 40, 47):
+        for pw in (4, 10, 20, 26):
+            d = bhw.make_desc(2, pw, dw, [1, 1], sin_type=bhw.SIN_CORDIC48)
+            assert bhw.validate(d) == 0
+            for i in sorted({0, 1, (1 << pw) // 4, (1 << pw) // 2 + 1, (1 << pw) - 1} | {rng.randrange(1 << pw) for _ in range(12)}):
+                s, c = H.orc_sincos(d, i, 1)
+                assert RB.cordic_dds48(pw, dw, i) == (int(s[0]), int(c[0])), (pw, dw, i)
+                n += 1
+    assert n > 400
+    # BASELINE config 3: bh_win_7term, PHI_WIDTH 20, DAT_WIDTH 32, cordic_dds48 swapped in
+    aa = [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379]
+    d = bhw.make_desc(7, 20, 32, aa, sin_type=bhw.SIN_CORDIC48)
+    for i in [0, 1, 2, 262143, 262144, 524288, 786433, (1 << 20) - 1] + [rng.randrange(1 << 20) for _ in range(40)]:
+        assert RB.window_dds48(7, 20, 32, aa, i) == int(H.orc_window(d, i, 1)[0]), i
+        # and with the entity's own cordic_dds
+        assert RB.window(7, 20, 32, aa, i) == int(H.orc_window(d.copy(sin_type=bhw.SIN_CORDIC), i, 1)[0]), i
+
+
 def test_cordic_atan2_matches_oracle_and_converges():
     rng = random.Random(7)
     L = H.oracle()

@@ -174,7 +174,8 @@ struct bhw_plan {
   std::vector<uint32_t> win_rec;
   std::vector<uint64_t> flat_off;
   std::vector<PlanTable> tables;
-  std::vector<bhw::TabJob> jobs;
+  std::vector<bhw::TabJob> jobs;       // small / other-core jobs: one combined k_table_build launch
+  std::vector<bhw::TabJob> big_jobs;   // large 32-bit-core jobs: one k_table_build_u launch each
   const bhw::I2* rom = nullptr;  // at most one Taylor (DW, LUT_SIZE) ROM per plan
   int uniform_pw = -1;
   bool all_same = false;
@@ -197,6 +198,9 @@ struct bhw_plan {
 };
 
 namespace bhw {
+
+// work items from which a table job gets its own stage-unrolled launch
+static const uint32_t kBigTableWork = 1u << 13;
 
 static int find_or_add_table(bhw_plan& plan, const SrcParams& sp, int* index) {
   uint32_t drop;
@@ -390,6 +394,11 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     if (e != cudaSuccess) return cuda_fail(e, "alloc(trig table)");
     TabJob j;
     init_tab_job(pt.canon, pt.ptr, &j);
+    if (j.work >= kBigTableWork && table_build_unrolled_ok(j)) {
+      j.work_begin = 0;
+      plan.big_jobs.push_back(j);
+      continue;
+    }
     j.work_begin = work;
     if (pt.canon.kind == SRC_TAYLOR) {
       const I2* rom = nullptr;
@@ -527,13 +536,22 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   cudaError_t e = cudaSuccess;
   bool table_ahead = false;  // k_table_build is the last thing enqueued on `stream`
   bool tm_on = false;
-  if (!plan.jobs.empty() && (!plan.tables_built || !g_cache_enabled.load())) {
-    LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
-    tm_on = tm.on;
-    e = launch_table_build((const TabJob*)(plan.blob_dev + plan.o_jobs), (int)plan.jobs.size(),
-                           plan.table_work, plan.rom, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "k_table_build");
-    g_launches++;
+  if ((!plan.jobs.empty() || !plan.big_jobs.empty()) && (!plan.tables_built || !g_cache_enabled.load())) {
+    if (!plan.jobs.empty()) {
+      LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
+      tm_on = tm.on;
+      e = launch_table_build((const TabJob*)(plan.blob_dev + plan.o_jobs), (int)plan.jobs.size(),
+                             plan.table_work, plan.rom, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "k_table_build");
+      g_launches++;
+    }
+    for (const TabJob& j : plan.big_jobs) {
+      LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
+      tm_on = tm.on;
+      e = launch_table_build_unrolled(j, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "k_table_build_u");
+      g_launches++;
+    }
     plan.tables_built = true;
     table_ahead = !tm_on;
   }

@@ -249,6 +249,30 @@ BHW_HD void cordic_core_fast32(const SrcParams& p, const int32_t* __restrict__ r
   vc = (x >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
 }
 
+// The same core with the stage count as a template parameter: every shift is an immediate, the
+// bias words are constants, the atan words come from the kernel parameter block (constant bank).
+// Uses multiply-ADD forms only (x = ys*nd + x ...) so that each update is one IMAD.
+template <int NXY, bool BIAS>
+BHW_HD void cordic_core_fast32_u(const SrcParams& p, const int32_t* __restrict__ rom32, uint32_t low, int32_t& vs,
+                                 int32_t& vc) {
+  const uint32_t z0 = (low >> p.z_rshift) << p.z_lshift;
+  const int32_t g = (int32_t)p.gain;
+  const int32_t K = BIAS ? (1 << 30) : 0;
+  int32_t x = g - K, y = g - K;
+  int32_t z = (int32_t)(z0 - (uint32_t)rom32[0]);
+#pragma unroll
+  for (int i = 1; i < NXY; ++i) {
+    const int32_t d = (z >> 31) | 1, nd = -d;
+    const int32_t ki = BIAS ? (K >> i) : 0;
+    const int32_t xs = (x >> i) + ki, ys = (y >> i) + ki;
+    x = ys * nd + x;
+    y = xs * d + y;
+    z = rom32[i] * nd + z;
+  }
+  vs = (y >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
+  vc = (x >> p.out_shift) + (BIAS ? (K >> p.out_shift) : 0);
+}
+
 // 64-bit core with the registers left-aligned to bit 63: X = x << (64-w), Z = z << (64-zw).  The
 // reference's wrap of every sum to w (zw) bits is then the natural overflow of the 64-bit add, and
 // (x >> i) << (64-w) == (X >> i) with the low 64-w bits cleared.  Covers the input-quadrant
@@ -285,6 +309,19 @@ BHW_HD void cordic_core_aligned64(const SrcParams& p, const int64_t* __restrict_
   vc = X >> (ax + p.out_shift);
 }
 
+// the four entries one core evaluation yields: cos = c, -s, -c, s in quadrants 0..3
+BHW_HD void table_store_quadrants(const TabJob& job, uint32_t e, int64_t vs, int64_t vc) {
+  const SrcParams& p = job.sp;
+  int32_t* T = job.tab;
+  const uint32_t Q = job.entries >> 2;
+  const int64_t t = (int64_t)1 << job.tshift;
+  const int64_t ns = wrapb(-vs, p.negw), nc = wrapb(-vc, p.negw);
+  T[e] = (int32_t)(wrapb(vc, p.outw) * t);          // quadrant 0: cos =  c
+  T[e + Q] = (int32_t)(wrapb(ns, p.outw) * t);      // quadrant 1: cos = -s
+  T[e + 2 * Q] = (int32_t)(wrapb(nc, p.outw) * t);  // quadrant 2: cos = -c
+  T[e + 3 * Q] = (int32_t)(wrapb(vs, p.outw) * t);  // quadrant 3: cos =  s
+}
+
 // Work item `e` of a table job -> table entries.
 BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   const SrcParams& p = job.sp;
@@ -308,13 +345,16 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   else if (job.fast == TABCORE_32BIAS) { int32_t s32, c32; cordic_core_fast32<true>(p, job.rom32, low, s32, c32); vs = s32; vc = c32; }
   else if (job.fast == TABCORE_A64) cordic_core_aligned64(p, job.rom64, 0, low, vs, vc);
   else cordic_core_generic(p, 0, low, vs, vc);
-  const uint32_t Q = job.entries >> 2;
-  const int64_t t = (int64_t)1 << job.tshift;
-  const int64_t ns = wrapb(-vs, p.negw), nc = wrapb(-vc, p.negw);
-  T[e] = (int32_t)(wrapb(vc, p.outw) * t);          // quadrant 0: cos =  c
-  T[e + Q] = (int32_t)(wrapb(ns, p.outw) * t);      // quadrant 1: cos = -s
-  T[e + 2 * Q] = (int32_t)(wrapb(nc, p.outw) * t);  // quadrant 2: cos = -c
-  T[e + 3 * Q] = (int32_t)(wrapb(vs, p.outw) * t);  // quadrant 3: cos =  s
+  table_store_quadrants(job, e, vs, vc);
+}
+
+// Work item `e` of a job whose core is the 32-bit one with NXY stages (the dedicated kernel for
+// large tables); same entries as table_build_item.
+template <int NXY, bool BIAS>
+BHW_HD void table_build_item_u(const TabJob& job, uint32_t e) {
+  int32_t s32, c32;
+  cordic_core_fast32_u<NXY, BIAS>(job.sp, job.rom32, e, s32, c32);
+  table_store_quadrants(job, e, (int64_t)s32, (int64_t)c32);
 }
 
 // ---- direct evaluation through the fast cores ------------------------------------------------

@@ -43,6 +43,16 @@ k_table_build(const TabJob* __restrict__ jobs, int njobs, uint32_t total_work,
   }
 }
 
+// One large table whose source runs on the 32-bit core: the job travels in the parameter block,
+// the stages are unrolled (NXY), one thread per quarter-wave phase.
+template <int NXY, bool BIAS>
+__global__ void __launch_bounds__(256)
+k_table_build_u(const __grid_constant__ TabJob job) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.work; i += gridDim.x * blockDim.x)
+    table_build_item_u<NXY, BIAS>(job, i);
+}
+
 // -------------------------------------------------------------------------------------------
 // stage 2: synthesis
 // -------------------------------------------------------------------------------------------
@@ -364,6 +374,17 @@ cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total
   if (!total_work) return cudaSuccess;
   const unsigned grid = grid_for(((uint64_t)total_work + 255) / 256, 8);
   k_table_build<<<grid, 256, 0, stream>>>(jobs_dev, njobs, total_work, rom_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream) {
+  if (!j.work) return cudaSuccess;
+  const unsigned grid = grid_for(((uint64_t)j.work + 255) / 256, 8);
+  if (j.fast == TABCORE_32BIAS && j.sp.n_xy == 31) k_table_build_u<31, true><<<grid, 256, 0, stream>>>(j);
+  else if (j.fast == TABCORE_32 && j.sp.n_xy == 15) k_table_build_u<15, false><<<grid, 256, 0, stream>>>(j);
+  else if (j.fast == TABCORE_32 && j.sp.n_xy == 16) k_table_build_u<16, false><<<grid, 256, 0, stream>>>(j);
+  else if (j.fast == TABCORE_32 && j.sp.n_xy == 23) k_table_build_u<23, false><<<grid, 256, 0, stream>>>(j);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -52,6 +52,13 @@ void init_src_core(const SrcParams& sp, SrcCore* sc) {
   }
 }
 
+bool table_build_unrolled_ok(const TabJob& j) {
+  if (j.sp.kind == SRC_TAYLOR || j.sp.kind == SRC_INQ) return false;
+  if (j.fast == TABCORE_32) return j.sp.n_xy == 15 || j.sp.n_xy == 16 || j.sp.n_xy == 23;
+  if (j.fast == TABCORE_32BIAS) return j.sp.n_xy == 31;
+  return false;
+}
+
 // Everything of a table job except its place in the launch (work_begin) and the Taylor ROM offset.
 void init_tab_job(const SrcParams& canon, int32_t* tab, TabJob* j) {
   memset(j, 0, sizeof(*j));

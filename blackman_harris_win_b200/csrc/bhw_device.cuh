@@ -348,6 +348,43 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   table_store_quadrants(job, e, vs, vc);
 }
 
+// cordic_core_aligned64 for the input-quadrant CORDICs with the stage count as a template
+// parameter (immediate 64-bit shifts, atan words from the constant bank).
+template <int NXY>
+BHW_HD void cordic_core_aligned64_inq_u(const SrcParams& p, const int64_t* __restrict__ rom64, int q, uint64_t low,
+                                        int64_t& vs, int64_t& vc) {
+  const int pw = p.pw;
+  const int ax = 64 - p.w, az = 64 - p.zw;
+  const int64_t mx = (int64_t)(~0ull << ax);
+  const int64_t G = (int64_t)((uint64_t)p.gain << ax);
+  int64_t X = G, Y = 0;
+  uint64_t t = low | ((uint64_t)q << (pw - 2));
+  if (q == 1) { t = low; X = 0; Y = (int64_t)(0ull - (uint64_t)G); }
+  else if (q == 2) { t = low | (3ull << (pw - 2)); X = 0; Y = G; }
+  int64_t Z = (int64_t)(t << (p.z_lshift + az));
+#pragma unroll
+  for (int i = 0; i < NXY; ++i) {
+    const bool cw = Z >= 0;  // input-quadrant sense: z >= 0 -> x + (y>>i), y - (x>>i)   (src/cordic_dds48.vhd:234-242)
+    const uint64_t Xs = (uint64_t)((X >> i) & mx), Ys = (uint64_t)((Y >> i) & mx);
+    const uint64_t r = (uint64_t)rom64[i];  // 0 for the last stage (z advances NXY-1 times)
+    X = (int64_t)(cw ? (uint64_t)X + Ys : (uint64_t)X - Ys);
+    Y = (int64_t)(cw ? (uint64_t)Y - Xs : (uint64_t)Y + Xs);
+    Z = (int64_t)(cw ? (uint64_t)Z - r : (uint64_t)Z + r);
+  }
+  vs = Y >> (ax + p.out_shift);
+  vc = X >> (ax + p.out_shift);
+}
+
+// Work item `e` (one phase) of an input-quadrant job with NXY stages: the dedicated kernel for large
+// cordic_dds48 / cordic_dds_scaled tables; same entry as table_build_item.
+template <int NXY>
+BHW_HD void table_build_item_inq_u(const TabJob& job, uint32_t e) {
+  const SrcParams& p = job.sp;
+  int64_t s, c;
+  cordic_core_aligned64_inq_u<NXY>(p, job.rom64, (int)(e >> (p.pw - 2)), (uint64_t)(e & ((1u << (p.pw - 2)) - 1u)), s, c);
+  job.tab[e] = (int32_t)(wrapb(c, p.outw) * ((int64_t)1 << job.tshift));
+}
+
 // Work item `e` of a job whose core is the 32-bit one with NXY stages (the dedicated kernel for
 // large tables); same entries as table_build_item.
 template <int NXY, bool BIAS>

@@ -53,6 +53,15 @@ k_table_build_u(const __grid_constant__ TabJob job) {
     table_build_item_u<NXY, BIAS>(job, i);
 }
 
+// the same for an input-quadrant source (one thread per phase, left-aligned 64-bit registers)
+template <int NXY>
+__global__ void __launch_bounds__(256)
+k_table_build_inq_u(const __grid_constant__ TabJob job) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.work; i += gridDim.x * blockDim.x)
+    table_build_item_inq_u<NXY>(job, i);
+}
+
 // -------------------------------------------------------------------------------------------
 // stage 2: synthesis
 // -------------------------------------------------------------------------------------------
@@ -380,7 +389,16 @@ cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total
 cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream) {
   if (!j.work) return cudaSuccess;
   const unsigned grid = grid_for(((uint64_t)j.work + 255) / 256, 8);
-  if (j.fast == TABCORE_32BIAS && j.sp.n_xy == 31) k_table_build_u<31, true><<<grid, 256, 0, stream>>>(j);
+  if (j.sp.kind == SRC_INQ) {
+    switch (j.sp.n_xy) {
+      case 16: k_table_build_inq_u<16><<<grid, 256, 0, stream>>>(j); break;
+      case 17: k_table_build_inq_u<17><<<grid, 256, 0, stream>>>(j); break;
+      case 24: k_table_build_inq_u<24><<<grid, 256, 0, stream>>>(j); break;
+      case 32: k_table_build_inq_u<32><<<grid, 256, 0, stream>>>(j); break;
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  else if (j.fast == TABCORE_32BIAS && j.sp.n_xy == 31) k_table_build_u<31, true><<<grid, 256, 0, stream>>>(j);
   else if (j.fast == TABCORE_32 && j.sp.n_xy == 15) k_table_build_u<15, false><<<grid, 256, 0, stream>>>(j);
   else if (j.fast == TABCORE_32 && j.sp.n_xy == 16) k_table_build_u<16, false><<<grid, 256, 0, stream>>>(j);
   else if (j.fast == TABCORE_32 && j.sp.n_xy == 23) k_table_build_u<23, false><<<grid, 256, 0, stream>>>(j);

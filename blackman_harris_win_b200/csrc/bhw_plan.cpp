@@ -53,7 +53,9 @@ void init_src_core(const SrcParams& sp, SrcCore* sc) {
 }
 
 bool table_build_unrolled_ok(const TabJob& j) {
-  if (j.sp.kind == SRC_TAYLOR || j.sp.kind == SRC_INQ) return false;
+  if (j.sp.kind == SRC_INQ)   // cordic_dds48 / cordic_dds_scaled at DAT_WIDTH 16, 17, 24, 32
+    return j.fast == TABCORE_A64 && (j.sp.n_xy == 16 || j.sp.n_xy == 17 || j.sp.n_xy == 24 || j.sp.n_xy == 32);
+  if (j.sp.kind == SRC_TAYLOR) return false;
   if (j.fast == TABCORE_32) return j.sp.n_xy == 15 || j.sp.n_xy == 16 || j.sp.n_xy == 23;
   if (j.fast == TABCORE_32BIAS) return j.sp.n_xy == 31;
   return false;

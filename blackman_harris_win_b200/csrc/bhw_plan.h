@@ -10,7 +10,8 @@ SrcParams canonical_source(const SrcParams& sp, uint32_t* drop);
 bool fast32_ok(const SrcParams& sp);
 int table_core32(const SrcParams& sp);
 // Does the job's source have a stage-unrolled instantiation of the 32-bit core (k_table_build_u)?
-// cordic_dds at DAT_WIDTH 16, 17, 24 (15, 16, 23 stages) and 32 (31 stages, biased).
+// cordic_dds at DAT_WIDTH 16, 17, 24 (15, 16, 23 stages) and 32 (31 stages, biased);
+// cordic_dds48 / cordic_dds_scaled at DAT_WIDTH 16, 17, 24, 32 (k_table_build_inq_u).
 bool table_build_unrolled_ok(const TabJob& j);
 void init_src_core(const SrcParams& sp, SrcCore* sc);
 void init_tab_job(const SrcParams& canon, int32_t* tab, TabJob* j);

@@ -211,37 +211,63 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   const uint32_t half = 1u << (pw - 1);
   const uint64_t U = (uint64_t)a.nwin << log_tpw;
   const uint64_t u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
-  uint32_t cur_w = 0xFFFFFFFFu, n_first = 0;
-  int32_t A[M], S0 = 0;
+  // ports of a window (warp-uniform)
+  struct Ports { int32_t A[M]; int32_t S0; uint32_t n_first; };
+  auto load_ports = [&](uint32_t w, Ports& p) {
+    const WinRec* r = a.recs + (a.win_rec ? __ldg(a.win_rec + a.w_first + w) : 0u);
+    p.A[0] = 0;
 #pragma unroll
-  for (int k = 0; k < M; ++k) A[k] = 0;
-  for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
-    const uint32_t w = (uint32_t)(u >> log_tpw);
-    const uint32_t t = (uint32_t)u & ((1u << log_tpw) - 1);
-    if (w != cur_w) {  // warp-uniform: the window's ports
-      const WinRec* r = a.recs + (a.win_rec ? __ldg(a.win_rec + a.w_first + w) : 0u);
-#pragma unroll
-      for (int k = 1; k < M; ++k) A[k] = __ldg(&r->A[k]);
-      S0 = __ldg(&r->S0);
-      n_first = __ldg(&r->n_first);
-      cur_w = w;
-    }
-    const uint32_t nbase = t * kBankTile + n_first;
+    for (int k = 1; k < M; ++k) p.A[k] = __ldg(&r->A[k]);
+    p.S0 = __ldg(&r->S0);
+    p.n_first = __ldg(&r->n_first);
+  };
+  auto do_tile = [&](const Ports& p, uint32_t w, uint32_t t) {
+    const uint32_t nbase = t * kBankTile + p.n_first;
     const uint32_t n = nbase + lane;
     const int32_t* tabs[2] = {tab0, tab1};
     int32_t va[kBankJ], vb[kBankJ];
     uint32_t lbase[M], lneg;
     if (sh.lin && bank_tile_linear<M, TAB>(sh, nbase, lbase, &lneg))   // warp-uniform
-      bank_lane_tile_lin<M, TAB, PAIR, W64>(sh, A, S0, tabs, lane, lbase, lneg, va, vb);
+      bank_lane_tile_lin<M, TAB, PAIR, W64>(sh, p.A, p.S0, tabs, lane, lbase, lneg, va, vb);
     else if (TAB == TAB_SMEM_HALF)
-      bank_lane_tile<M, TAB, PAIR, true, W64>(sh, A, S0, tabs, n, nbase, va, vb);
+      bank_lane_tile<M, TAB, PAIR, true, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
     else
-      bank_lane_tile<M, TAB, PAIR, false, W64>(sh, A, S0, tabs, n, nbase, va, vb);
+      bank_lane_tile<M, TAB, PAIR, false, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
     int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
 #pragma unroll
     for (int j = 0; j < kBankJ; ++j) {
       __stcs(o + 32 * j, va[j]);
       if (PAIR) __stcs(o + half + 32 * j, vb[j]);
+    }
+  };
+  Ports cur;
+  uint32_t cur_w = 0xFFFFFFFFu;
+  if (M <= 3) {
+    // 2- and 3-term windows have registers to spare: fetch the next window's ports one tile ahead,
+    // so that the two dependent loads (window -> record -> ports) never sit in front of a tile.
+    // Short windows start a new window with nearly every tile (N = 1024: two tile pairs per window).
+    Ports nxt;
+    if (u0 + warp < u1) {
+      cur_w = (uint32_t)((u0 + warp) >> log_tpw);
+      load_ports(cur_w, cur);
+    }
+    nxt = cur;
+    for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
+      const uint32_t w = cur_w;
+      const uint64_t u2 = u + kBankWarps;
+      const uint32_t w2 = u2 < u1 ? (uint32_t)(u2 >> log_tpw) : w;
+      if (w2 != w) load_ports(w2, nxt);  // consumed after this tile
+      do_tile(cur, w, (uint32_t)u & ((1u << log_tpw) - 1));
+      if (w2 != w) { cur = nxt; cur_w = w2; }
+    }
+  } else {
+    for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
+      const uint32_t w = (uint32_t)(u >> log_tpw);
+      if (w != cur_w) {
+        load_ports(w, cur);
+        cur_w = w;
+      }
+      do_tile(cur, w, (uint32_t)u & ((1u << log_tpw) - 1));
     }
   }
 }

@@ -246,21 +246,31 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     // 2- and 3-term windows have registers to spare: fetch the next window's ports one tile ahead,
     // so that the two dependent loads (window -> record -> ports) never sit in front of a tile.
     // Short windows start a new window with nearly every tile (N = 1024: two tile pairs per window).
+    // These light kernels are paced by the store path, not by instruction issue, and the store
+    // bandwidth an SM gets is uneven (tools/store_pattern_probe.cu): tiles are interleaved over the
+    // grid (the whole GPU sweeps the output front to back) instead of one contiguous share per CTA.
+    // (Unpaired tiles - sources without the half-period antisymmetry - measured slower interleaved
+    // and keep the contiguous share.)
     Ports nxt;
-    if (u0 + warp < u1) {
-      cur_w = (uint32_t)((u0 + warp) >> log_tpw);
+    const uint64_t first = PAIR ? (uint64_t)blockIdx.x * kBankWarps + warp : u0 + warp;
+    const uint64_t stride = PAIR ? (uint64_t)gridDim.x * kBankWarps : (uint64_t)kBankWarps;
+    const uint64_t last = PAIR ? U : u1;
+    if (first < last) {
+      cur_w = (uint32_t)(first >> log_tpw);
       load_ports(cur_w, cur);
     }
     nxt = cur;
-    for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
+    for (uint64_t u = first; u < last; u += stride) {
       const uint32_t w = cur_w;
-      const uint64_t u2 = u + kBankWarps;
-      const uint32_t w2 = u2 < u1 ? (uint32_t)(u2 >> log_tpw) : w;
+      const uint64_t u2 = u + stride;
+      const uint32_t w2 = u2 < last ? (uint32_t)(u2 >> log_tpw) : w;
       if (w2 != w) load_ports(w2, nxt);  // consumed after this tile
       do_tile(cur, w, (uint32_t)u & ((1u << log_tpw) - 1));
       if (w2 != w) { cur = nxt; cur_w = w2; }
     }
   } else {
+    // 4 and more terms: paced by instruction issue; one contiguous share per CTA measured faster
+    // than any interleaving (bh4: 171 vs 177 us, bh5: 197 vs 207 us per GiB)
     for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
       const uint32_t w = (uint32_t)(u >> log_tpw);
       if (w != cur_w) {

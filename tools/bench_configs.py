@@ -60,6 +60,8 @@ def main():
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--only", default="", help="substring filter on the config name")
     ap.add_argument("--no-batch", action="store_true", help="skip the plan/batch line of each config")
+    ap.add_argument("--entities", action="store_true",
+                    help="also time a 1 GiB bank of N = 65536 windows of every entity / sin-cos source at its BASELINE width")
     ap.add_argument("--atan2", action="store_true", help="also time the cordic_atan2 kernel (16M pairs)")
     ap.add_argument("--sweep", action="store_true", help="also run the config-5 sweep (10 variants x PHI_WIDTH 4..26)")
     args = ap.parse_args()
@@ -119,6 +121,37 @@ def main():
                               "frac_of_hbm_peak": round(plan.total * 4 / ms / 1e6 / peak, 4)}))
             plan.destroy()
             del big
+    if args.entities:
+        # one line per window entity and per sin/cos source (a7-a11): 4096 windows of
+        # N = 65536, every window with its own AA0, plan resident, tables rebuilt in every step
+        shapes = [("hamming_win DW16 cordic_dds", 1, 16, bhw.SIN_CORDIC), ("bh_win_3term DW16 cordic_dds", 3, 16, bhw.SIN_CORDIC),
+                  ("bh_win_4term DW17 cordic_dds", 6, 17, bhw.SIN_CORDIC), ("bh_win_5term DW24 cordic_dds", 8, 24, bhw.SIN_CORDIC),
+                  ("bh_win_7term DW32 cordic_dds", 10, 32, bhw.SIN_CORDIC), ("bh_win_7term DW24 cordic_dds", 10, 24, bhw.SIN_CORDIC),
+                  ("bh_win_7term DW32 cordic_dds48", 10, 32, bhw.SIN_CORDIC48), ("bh_win_4term DW17 cordic_dds_scaled", 6, 17, bhw.SIN_CORDIC_SCALED),
+                  ("hamming_win DW16 taylor", 1, 16, bhw.SIN_TAYLOR), ("bh_win_3term DW24 taylor", 3, 24, bhw.SIN_TAYLOR),
+                  ("HLS model type 4 NW17", 6, 17, None)]
+        nwin = 4096
+        big = torch.empty(nwin << 16, dtype=torch.int32, device="cuda")
+        bhw.set_table_cache(False)
+        for name, v, dw, st in shapes:
+            if st is None:
+                base = bhw.variant_desc(v, 16, dw, model=bhw.MODEL_HLS)
+            else:
+                base = bhw.variant_desc(v, 16, dw, sin_type=st)
+            descs = [base.copy(aa=[int(a) - (i % 1021) if k == 0 else int(a) for k, a in enumerate(base.aa)]) for i in range(nwin)]
+            plan = bhw.Plan(descs)
+            ms_plain = time_calls(lambda: plan.execute(out=big), 20)
+            bhw.timing_enable(True)
+            bhw.timing_reset()
+            time_calls(lambda: plan.execute(out=big), 5)
+            kt = {k: round(v_[1] / v_[0], 5) for k, v_ in bhw.timing_read().items() if v_[0]}
+            bhw.timing_enable(False)
+            print(json.dumps({"config": "bank 4096 x N=65536: " + name, "samples": plan.total, "ms_per_step": round(ms_plain, 5),
+                              "gsamples_per_s": round(plan.total / ms_plain / 1e6, 1),
+                              "frac_of_hbm_peak": round(plan.total * 4 / ms_plain / 1e6 / peak, 4), "kernel_ms": kt}))
+            plan.destroy()
+        bhw.set_table_cache(True)
+        del big
     if args.atan2:
         n = 1 << 24
         g = torch.Generator(device="cuda").manual_seed(3)

@@ -270,6 +270,8 @@ def run_cuda(args):
                          "(use --impl reference for the CPU model)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's own banner / debug lines go to stderr: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world != args.gpus and rank == 0:
         print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)

@@ -715,21 +715,34 @@ struct Atan2Params {
 
 // W <= 32: the same algorithm with the registers left-aligned in 32 bits.  d = +1/-1 from the sign
 // of Y turns the three conditional add/subtracts into multiply-adds (mod 2^32 = the W-bit wrap).
-BHW_HD int32_t atan2_sample32(const Atan2Params& p, int32_t xin, int32_t yin) {
-  const int aw = p.aw, ax = 32 - p.w;
+// AW > 0: ANGLE_WIDTH as a compile-time constant (stage count, shifts and masks become immediates);
+// AW == 0: run-time loop.
+template <int AW>
+BHW_HD int32_t atan2_sample32_t(const Atan2Params& p, int32_t xin, int32_t yin) {
+  const int aw = AW > 0 ? AW : p.aw, ax = 32 - p.w;
   const uint32_t sxb = ((uint32_t)xin >> (p.iw - 1)) & 1u, syb = ((uint32_t)yin >> (p.iw - 1)) & 1u;
   const uint32_t mag_mask = (1u << (aw - 1)) - 1u;
   const int32_t mx = (int32_t)(~0u << ax);
   uint32_t X = (((uint32_t)xin ^ (0u - sxb)) & mag_mask) << ax;
   uint32_t Y = (((uint32_t)yin ^ (0u - syb)) & mag_mask) << ax;
   uint32_t Z = 0;
-#pragma unroll 4
-  for (int i = 0; i <= aw - 2; ++i) {
-    const uint32_t d = (uint32_t)(((int32_t)Y >> 31) | 1);   // -1 when y < 0, else +1
+#pragma unroll
+  for (int i = 0; i <= (AW > 0 ? AW - 2 : -1); ++i) {
+    const uint32_t d = (uint32_t)(((int32_t)Y >> 31) | 1), nd = 0u - d;   // -1 when y < 0, else +1
     const uint32_t Xs = (uint32_t)(((int32_t)X >> i) & mx), Ys = (uint32_t)(((int32_t)Y >> i) & mx);
-    X += d * Ys;                                              // y >= 0: x + (y >> i)   (:169-175)
-    Y -= d * Xs;                                              //         y - (x >> i)
-    Z -= d * p.rom32[i];                                      //         z - ROM_TABLE(i)
+    X = Ys * d + X;                                           // y >= 0: x + (y >> i)   (:169-175)
+    Y = Xs * nd + Y;                                          //         y - (x >> i)
+    Z = p.rom32[i] * nd + Z;                                  //         z - ROM_TABLE(i)
+  }
+  if (AW == 0) {
+#pragma unroll 4
+    for (int i = 0; i <= aw - 2; ++i) {
+      const uint32_t d = (uint32_t)(((int32_t)Y >> 31) | 1);
+      const uint32_t Xs = (uint32_t)(((int32_t)X >> i) & mx), Ys = (uint32_t)(((int32_t)Y >> i) & mx);
+      X += d * Ys;
+      Y -= d * Xs;
+      Z -= d * p.rom32[i];
+    }
   }
   const int32_t phi = (int32_t)Z >> (32 - aw);                // top ANGLE_WIDTH bits, sign-extended
   const int32_t pi = 1 << (aw - 2);
@@ -742,6 +755,7 @@ BHW_HD int32_t atan2_sample32(const Atan2Params& p, int32_t xin, int32_t yin) {
   }
   return wrapb32(o, aw);
 }
+BHW_HD int32_t atan2_sample32(const Atan2Params& p, int32_t xin, int32_t yin) { return atan2_sample32_t<0>(p, xin, yin); }
 
 BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin) {
   if (p.fast32) return atan2_sample32(p, xin, yin);

@@ -391,6 +391,26 @@ k_atan2(const __grid_constant__ Atan2Params p, const int32_t* __restrict__ x, co
     __stcs(phi + j, atan2_sample(p, __ldcs(x + j), __ldcs(y + j)));
 }
 
+// ANGLE_WIDTH known at compile time (W <= 32): unrolled stages, 4 pairs per thread, 128-bit accesses
+template <int AW>
+__global__ void __launch_bounds__(256)
+k_atan2_u(const __grid_constant__ Atan2Params p, const int32_t* __restrict__ x, const int32_t* __restrict__ y,
+          int32_t* __restrict__ phi, uint64_t count) {
+  const uint64_t quads = count / 4;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (uint64_t)gridDim.x * blockDim.x) {
+    const int4 xv = __ldcs(reinterpret_cast<const int4*>(x) + q), yv = __ldcs(reinterpret_cast<const int4*>(y) + q);
+    int4 o;
+    o.x = atan2_sample32_t<AW>(p, xv.x, yv.x);
+    o.y = atan2_sample32_t<AW>(p, xv.y, yv.y);
+    o.z = atan2_sample32_t<AW>(p, xv.z, yv.z);
+    o.w = atan2_sample32_t<AW>(p, xv.w, yv.w);
+    __stcs(reinterpret_cast<int4*>(phi) + q, o);
+  }
+  // tail (count not a multiple of 4)
+  const uint64_t j = quads * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < count) phi[j] = atan2_sample32_t<AW>(p, x[j], y[j]);
+}
+
 // -------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------
@@ -551,8 +571,17 @@ cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStrea
 cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count,
                          cudaStream_t stream) {
   if (!count) return cudaSuccess;
-  const unsigned grid = grid_for((count + 255) / 256, 8);
-  k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count);
+  const bool vec = p.fast32 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                                 reinterpret_cast<uintptr_t>(phi)) & 15) == 0;
+  const unsigned gridv = grid_for((count / 4 + 255) / 256 + 1, 8);
+  if (vec && p.aw == 16) k_atan2_u<16><<<gridv, 256, 0, stream>>>(p, x, y, phi, count);
+  else if (vec && p.aw == 24) k_atan2_u<24><<<gridv, 256, 0, stream>>>(p, x, y, phi, count);
+  else if (vec && p.aw == 20) k_atan2_u<20><<<gridv, 256, 0, stream>>>(p, x, y, phi, count);
+  else if (vec && p.aw == 12) k_atan2_u<12><<<gridv, 256, 0, stream>>>(p, x, y, phi, count);
+  else {
+    const unsigned grid = grid_for((count + 255) / 256, 8);
+    k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count);
+  }
   return cudaGetLastError();
 }
 

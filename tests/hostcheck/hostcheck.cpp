@@ -273,7 +273,17 @@ int hc_atan2(const bhw_atan2_desc* d, const int32_t* x, const int32_t* y, int32_
   Atan2Params p;
   int st = resolve_atan2(d, &p);
   if (st) return st;
-  for (uint64_t j = 0; j < count; j++) phi[j] = atan2_sample(p, x[j], y[j]);
+  for (uint64_t j = 0; j < count; j++) {
+    phi[j] = atan2_sample(p, x[j], y[j]);
+    if (p.fast32) {   // the stage-unrolled instantiations k_atan2_u uses
+      int32_t u = phi[j];
+      if (p.aw == 12) u = atan2_sample32_t<12>(p, x[j], y[j]);
+      else if (p.aw == 16) u = atan2_sample32_t<16>(p, x[j], y[j]);
+      else if (p.aw == 20) u = atan2_sample32_t<20>(p, x[j], y[j]);
+      else if (p.aw == 24) u = atan2_sample32_t<24>(p, x[j], y[j]);
+      if (u != phi[j]) return -100;
+    }
+  }
   return 0;
 }
 

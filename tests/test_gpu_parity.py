@@ -123,6 +123,28 @@ def test_large_windows_properties():
         del full, parts
 
 
+def test_phi_width_beyond_the_reference_range():
+    """PHI_WIDTH 27..30 is accepted (the reference documents 64M = 2^26 points as its maximum): a
+    2^28-point window (1 GiB) through the bank kernel and a ragged range of a 2^30-point one,
+    spot-checked against the oracle and against the direct strategy."""
+    import torch
+    d = bhw.variant_desc(6, 28, 17)
+    n = 1 << 28
+    full = bhw.generate(d)
+    for n0 in (0, 4095, n // 4 - 2048, n // 2 - 2048, n - 4096):
+        assert np.array_equal(full[n0:n0 + 4096].cpu().numpy().astype(np.int64), H.orc_window(d, n0, 4096))
+    assert torch.equal(bhw.generate(d.copy(algo=bhw.ALGO_DIRECT), n - 65536, 65536), full[n - 65536:])
+    del full
+    torch.cuda.empty_cache()
+    d30 = bhw.variant_desc(2, 30, 16)
+    n0, cnt = (1 << 29) - 100003, 1 << 22
+    got = bhw.generate(d30, n0, cnt).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got[:4096], H.orc_window(d30, n0, 4096))
+    assert np.array_equal(got[-4096:], H.orc_window(d30, n0 + cnt - 4096, 4096))
+    mid = 100003 - 2048                                    # around the window's centre
+    assert np.array_equal(got[mid:mid + 4096], H.orc_window(d30, n0 + mid, 4096))
+
+
 def test_coefficient_edge_cases():
     for d in cases.edge_coeff_descs():
         want = H.orc_window(d)

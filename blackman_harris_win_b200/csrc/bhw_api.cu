@@ -867,6 +867,28 @@ int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t c
   if (st) return st;
   const uint64_t N = 1ull << d->phi_width;
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
+  if (!out_host && count) return BHW_E_NULL;
+  // a short request (one staging chunk) that bhw_generate would send to a register-resident
+  // direct kernel: one launch + one copy instead of planning, table build and two launches
+  if (count && d->dat_width <= 32 && d->algo == BHW_ALGO_AUTO && count * 4 <= kHostChunkBytes &&
+      (count * (uint64_t)(d->win_type - 1) <= 3u * 65536u ||
+       (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR))) {
+    int dev;
+    if ((st = current_device(&dev))) return st;
+    DeviceState& ds = g_dev[dev];
+    std::lock_guard<std::mutex> pipe_lock(ds.pipe_mu);
+    HostPipe& p = ds.pipe;
+    cudaError_t e = pipe_ensure(p);
+    if (e != cudaSuccess) { pipe_release(p); return cuda_fail(e, "host pipeline setup"); }
+    st = run_direct(d, n0, count, p.buf[0], p.s_gen, true);
+    if (st == BHW_OK) {
+      e = cudaMemcpyAsync(out_host, p.buf[0], count * 4, cudaMemcpyDeviceToHost, p.s_gen);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(p.s_gen);
+      if (e != cudaSuccess) return cuda_fail(e, "host copy");
+      return BHW_OK;
+    }
+    if (st != 1) return st;  // 1: not eligible for the direct kernels, take the pipeline
+  }
   return run_batch_host(d, 1, n0, count, out_host);
 }
 

@@ -24,6 +24,15 @@ static double time_calls(const bhw_desc& d, void* out, uint64_t n, int reps) {
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
 }
 
+static double time_host_calls(const bhw_desc& d, void* out_pinned, uint64_t n, int reps) {
+  for (int i = 0; i < 10; i++) bhw_generate_host(&d, out_pinned, 0, n);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; i++) {
+    if (bhw_generate_host(&d, out_pinned, 0, n) != BHW_OK) return -1.0;
+  }
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+
 static bhw_desc make(int win_type, int pw, int dw, int variant, int sin_type) {
   bhw_desc d;
   memset(&d, 0, sizeof(d));
@@ -41,6 +50,12 @@ int main() {
   const bhw_desc c3 = make(7, 20, 32, 10, BHW_SIN_CORDIC48);   // config 3: BH7 N=1M DW=32 cordic_dds48
   const bhw_desc c3b = make(7, 20, 32, 10, BHW_SIN_CORDIC);    // config 3 with the entity's own cordic_dds
   const bhw_desc c4 = make(3, 24, 24, 3, BHW_SIN_TAYLOR);      // config 4: Blackman TAYLOR N=16M DW=24
+  void* pinned = nullptr;
+  cudaMallocHost(&pinned, 64u << 20);
+  const double h1 = time_host_calls(c1, pinned, 1u << 10, 500), h2 = time_host_calls(c2, pinned, 1u << 16, 500);
+  const double h3 = time_host_calls(c3b, pinned, 1u << 20, 100), h4 = time_host_calls(c4, pinned, 1u << 24, 50);
+  printf("{\"us_per_host_call (bhw_generate_host, pinned destination, blocking)\": {\"cfg1_hamming_n1024\": %.2f, "
+         "\"cfg2_bh4_n65536\": %.2f, \"cfg3_bh7_n1m_dds\": %.2f, \"cfg4_blackman_taylor_n16m\": %.2f}}\n", h1, h2, h3, h4);
   printf("{\"us_per_call\": {\"cfg1_hamming_n1024\": %.2f, \"cfg2_bh4_n65536\": %.2f, \"cfg3_bh7_n1m_dds48\": %.2f, "
          "\"cfg3_bh7_n1m_dds\": %.2f, \"cfg4_blackman_taylor_n16m\": %.2f}, "
          "\"how\": \"bhw_generate back to back on the default stream, wall clock over 2000/200 calls incl. the final "

@@ -14,7 +14,7 @@ Reference interfaces mirrored (paths relative to the reference checkout):
 from .api import (  # noqa: F401
     ALGO_AUTO, ALGO_DIRECT, ALGO_TABLE, MODEL_CPP, MODEL_HLS, MODEL_RTL, RULE_HLS, RULE_TB,
     SIN_CORDIC, SIN_CORDIC48, SIN_CORDIC_SCALED, SIN_TAYLOR, VARIANT_NAMES, BhwAtan2Desc, BhwDesc, BhwError, Plan,
-    WinSelector, atan2, batch_total, cache_clear, desc_array, elem_bytes, generate, generate_batch,
+    WinSelector, atan2, atan2_host, batch_total, cache_clear, desc_array, elem_bytes, generate, generate_batch,
     generate_batch_host, generate_host, launch_count, lib, lib_path, make_desc, quantize,
     set_side_streams, set_table_cache, shard_range, shard_windows, sincos, strerror, timing_enable, timing_read, timing_reset,
     validate, variant_coeffs, variant_desc, win_function,

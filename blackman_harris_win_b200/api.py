@@ -106,6 +106,7 @@ def lib():
         "bhw_set_table_cache": (C.c_int, [C.c_int]),
         "bhw_atan2_validate": (C.c_int, [C.POINTER(BhwAtan2Desc)]),
         "bhw_atan2": (C.c_int, [C.POINTER(BhwAtan2Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+        "bhw_atan2_host": (C.c_int, [C.POINTER(BhwAtan2Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
         "bhw_set_side_streams": (C.c_int, [C.c_int]),
         "bhw_launch_count": (C.c_uint64, []),
         "bhw_last_cuda_error": (C.c_char_p, []),
@@ -131,7 +132,7 @@ ABI_SYMBOLS = (
     "bhw_strerror", "bhw_version", "bhw_validate", "bhw_elem_bytes", "bhw_quantize",
     "bhw_variant_coeffs", "bhw_generate", "bhw_generate_host", "bhw_batch_total", "bhw_shard_range",
     "bhw_generate_batch", "bhw_generate_batch_host", "bhw_generate_batch_multi", "bhw_sincos",
-    "bhw_atan2_validate", "bhw_atan2", "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
+    "bhw_atan2_validate", "bhw_atan2", "bhw_atan2_host", "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
     "bhw_device_count", "bhw_timing_enable", "bhw_timing_reset", "bhw_timing_read",
     "bhw_shard_windows", "bhw_plan_create", "bhw_plan_execute", "bhw_plan_total", "bhw_plan_destroy",
 )
@@ -372,6 +373,17 @@ def atan2(x, y, input_width: int, angle_width: int, precision: int = 1, out=None
         st = lib().bhw_atan2(C.byref(d), x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(),
                              torch.cuda.current_stream().cuda_stream)
     _check(st, "bhw_atan2")
+    return out
+
+
+def atan2_host(x: np.ndarray, y: np.ndarray, input_width: int, angle_width: int, precision: int = 1) -> np.ndarray:
+    """cordic_atan2 over two int32 numpy arrays (host buffers in, host buffer out)."""
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    y = np.ascontiguousarray(y, dtype=np.int32)
+    assert x.shape == y.shape
+    out = np.empty(x.shape, np.int32)
+    d = BhwAtan2Desc(input_width, angle_width, precision, 0)
+    _check(lib().bhw_atan2_host(C.byref(d), x.ctypes.data, y.ctypes.data, out.ctypes.data, x.size), "bhw_atan2_host")
     return out
 
 

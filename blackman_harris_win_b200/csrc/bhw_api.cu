@@ -1044,6 +1044,39 @@ int bhw_atan2(const bhw_atan2_desc* d, const int32_t* x_dev, const int32_t* y_de
   return BHW_OK;
 }
 
+int bhw_atan2_host(const bhw_atan2_desc* d, const int32_t* x_host, const int32_t* y_host, int32_t* phi_host,
+                   uint64_t count) {
+  Atan2Params p;
+  int st = resolve_atan2(d, &p);
+  if (st) return st;
+  if (!count) return BHW_OK;
+  if (!x_host || !y_host || !phi_host) return BHW_E_NULL;
+  int dev;
+  if ((st = current_device(&dev))) return st;
+  DeviceState& ds = g_dev[dev];
+  std::lock_guard<std::mutex> pipe_lock(ds.pipe_mu);
+  HostPipe& hp = ds.pipe;
+  cudaError_t e = pipe_ensure(hp);
+  if (e != cudaSuccess) { pipe_release(hp); return cuda_fail(e, "host pipeline setup"); }
+  // buf[0] = x | y (two halves), buf[1] = phi; one stream, chunk after chunk
+  const uint64_t chunk = hp.buf_bytes / 8;
+  int32_t* xd = (int32_t*)hp.buf[0];
+  int32_t* yd = xd + chunk;
+  int32_t* pd = (int32_t*)hp.buf[1];
+  for (uint64_t done = 0; done < count && e == cudaSuccess; done += chunk) {
+    const uint64_t cnt = count - done < chunk ? count - done : chunk;
+    if ((e = cudaMemcpyAsync(xd, x_host + done, cnt * 4, cudaMemcpyHostToDevice, hp.s_gen)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(yd, y_host + done, cnt * 4, cudaMemcpyHostToDevice, hp.s_gen)) != cudaSuccess) break;
+    if ((e = launch_atan2(p, xd, yd, pd, cnt, hp.s_gen)) != cudaSuccess) break;
+    g_launches++;
+    e = cudaMemcpyAsync(phi_host + done, pd, cnt * 4, cudaMemcpyDeviceToHost, hp.s_gen);
+  }
+  const cudaError_t e2 = cudaStreamSynchronize(hp.s_gen);
+  if (e == cudaSuccess) e = e2;
+  if (e != cudaSuccess) return cuda_fail(e, "bhw_atan2_host");
+  return BHW_OK;
+}
+
 int bhw_cache_clear(void) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess) return BHW_E_NO_DEVICE;

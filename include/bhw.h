@@ -232,6 +232,10 @@ typedef struct bhw_atan2_desc {
 BHW_API int bhw_atan2_validate(const bhw_atan2_desc* d);
 BHW_API int bhw_atan2(const bhw_atan2_desc* d, const int32_t* x_dev, const int32_t* y_dev, int32_t* phi_dev,
               uint64_t count, void* stream);
+/* The same with host buffers (pinned or pageable): chunks are staged through the library's device
+ * buffers; blocking. */
+BHW_API int bhw_atan2_host(const bhw_atan2_desc* d, const int32_t* x_host, const int32_t* y_host, int32_t* phi_host,
+                   uint64_t count);
 
 /* ---- cache / introspection --------------------------------------------- */
 BHW_API int bhw_cache_clear(void);             /* free the cached sine ROMs and host-pipeline staging */

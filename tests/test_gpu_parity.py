@@ -425,6 +425,11 @@ def test_cordic_atan2():
         assert np.array_equal(got, H.orc_atan2(iw, aw, prec, x.numpy(), y.numpy())), (aw, iw, prec)
     with pytest.raises(bhw.BhwError):
         bhw.atan2(x.cuda(), y.cuda(), 20, 24, 1)          # INPUT_WIDTH < ANGLE_WIDTH - 1
+    # host buffers, more than one staging chunk (4M pairs per chunk)
+    n = (9 << 20) + 5
+    xh = torch.randint(-(1 << 23), 1 << 23, (n,), generator=g, dtype=torch.int32).numpy()
+    yh = torch.randint(-(1 << 23), 1 << 23, (n,), generator=g, dtype=torch.int32).numpy()
+    assert np.array_equal(bhw.atan2_host(xh, yh, 24, 24, 2), H.orc_atan2(24, 24, 2, xh, yh))
 
 
 def test_win_selector_and_errors():

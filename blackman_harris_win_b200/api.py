@@ -104,6 +104,8 @@ def lib():
         "bhw_sincos": (C.c_int, [D, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
         "bhw_cache_clear": (C.c_int, []),
         "bhw_set_table_cache": (C.c_int, [C.c_int]),
+        "bhw_shard_range_cost": (C.c_int, [C.POINTER(BhwDesc), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_uint64)]),
         "bhw_atan2_validate": (C.c_int, [C.POINTER(BhwAtan2Desc)]),
         "bhw_atan2": (C.c_int, [C.POINTER(BhwAtan2Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
         "bhw_atan2_host": (C.c_int, [C.POINTER(BhwAtan2Desc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -130,7 +132,7 @@ def lib():
 
 ABI_SYMBOLS = (
     "bhw_strerror", "bhw_version", "bhw_validate", "bhw_elem_bytes", "bhw_quantize",
-    "bhw_variant_coeffs", "bhw_generate", "bhw_generate_host", "bhw_batch_total", "bhw_shard_range",
+    "bhw_variant_coeffs", "bhw_generate", "bhw_generate_host", "bhw_batch_total", "bhw_shard_range", "bhw_shard_range_cost",
     "bhw_generate_batch", "bhw_generate_batch_host", "bhw_generate_batch_multi", "bhw_sincos",
     "bhw_atan2_validate", "bhw_atan2", "bhw_atan2_host", "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
     "bhw_device_count", "bhw_timing_enable", "bhw_timing_reset", "bhw_timing_read",
@@ -212,6 +214,14 @@ def batch_total(descs) -> int:
 def shard_range(total: int, rank: int, nranks: int):
     b, c = C.c_uint64(0), C.c_uint64(0)
     _check(lib().bhw_shard_range(total, rank, nranks, C.byref(b), C.byref(c)), "bhw_shard_range")
+    return b.value, c.value
+
+
+def shard_range_cost(descs, rank: int, nranks: int):
+    """Cost-balanced contiguous flat slice of rank `rank` (bhw_shard_range_cost)."""
+    arr = descs if isinstance(descs, C.Array) else desc_array(descs)
+    b, c = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().bhw_shard_range_cost(arr, len(arr), rank, nranks, C.byref(b), C.byref(c)), "bhw_shard_range_cost")
     return b.value, c.value
 
 

@@ -190,6 +190,9 @@ struct bhw_plan {
     bhw::BankShape sh;
     int tab_mode;
     bool pair;
+    // shape for a tile range inside one window of the run (unpaired, table read from global memory)
+    bhw::BankShape sh_part;
+    bool part_ok;
   };
   std::vector<BankRun> runs;
   // DAT_WIDTH > 32: one direct launch per window
@@ -263,6 +266,9 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
       }
       bhw_plan::BankRun run;
       run.w_begin = w; run.w_end = w + 1; run.flat_off = off; run.sh = sh; run.tab_mode = mode; run.pair = pair;
+      int mode_p = 0;
+      bool pair_p = false;
+      run.part_ok = bank_shape(r, ti, 0, &run.sh_part, &mode_p, &pair_p, false) && mode_p == TAB_GLOBAL && !pair_p;
       plan.runs.push_back(run);
     }
     off += N;
@@ -591,35 +597,65 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     return BHW_OK;
   };
   uint64_t cursor = flat_begin;
+  // one bank launch: whole windows [wa, wb) of the run, or (ntiles > 0) tiles [tile_off, +ntiles) of window wa
+  auto bank = [&](const bhw_plan::BankRun& run, uint64_t out_flat, uint32_t wa, uint32_t wb, uint32_t tile_off,
+                  uint32_t ntiles) -> int {
+    BankArgs ba;
+    ba.sh = ntiles ? run.sh_part : run.sh;
+    ba.recs = a.recs;
+    ba.win_rec = a.win_rec;
+    ba.out = (int32_t*)out_dev + (out_flat - flat_begin);
+    ba.w_first = (uint32_t)run.w_begin + wa;
+    ba.nwin = wb - wa;
+    ba.tile_off = tile_off;
+    ba.ntiles = ntiles;
+    cudaStream_t ls = fan.next();
+    cudaError_t ce;
+    {
+      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls);
+      const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
+      ce = ntiles ? launch_synth_bank(ba, TAB_GLOBAL, false, ls, pdl) : launch_synth_bank(ba, run.tab_mode, run.pair, ls, pdl);
+      table_ahead = false;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "k_synth_bank");
+    g_launches++;
+    return BHW_OK;
+  };
+  // samples [pa, pb) inside window widx of the run: whole tiles through the bank kernel (unpaired
+  // shape), the ragged ends through the general kernel
+  auto partial = [&](const bhw_plan::BankRun& run, uint32_t widx, uint64_t pa, uint64_t pb) -> int {
+    const uint64_t ws = run.flat_off + ((uint64_t)widx << run.sh.pw);
+    const uint64_t ta = (pa - ws + kBankTile - 1) / kBankTile, tb = (pb - ws) / kBankTile;
+    if (!run.part_ok || tb < ta + 32) return general(pa, pb);       // short: not worth a launch of its own
+    int st = general(pa, ws + ta * kBankTile);
+    if (!st) st = bank(run, ws + ta * kBankTile, widx, widx + 1, (uint32_t)ta, (uint32_t)(tb - ta));
+    if (!st) st = general(ws + tb * kBankTile, pb);
+    return st;
+  };
   for (const bhw_plan::BankRun& run : plan.runs) {
     const uint32_t pw = run.sh.pw;
     const uint64_t N = 1ull << pw;
     const uint64_t rb = run.flat_off, re = rb + ((uint64_t)(run.w_end - run.w_begin) << pw);
     if (re <= cursor) continue;
     if (rb >= flat_end) break;
-    const uint64_t lo = rb > cursor ? rb : cursor, hi = re < flat_end ? re : flat_end;
-    const uint64_t wlo = (lo - rb + N - 1) >> pw, whi = (hi - rb) >> pw;  // whole windows [wlo, whi) of the run
-    if (whi <= wlo) continue;
-    const uint64_t bb = rb + (wlo << pw), be = rb + (whi << pw);
-    int st = general(cursor, bb);
+    uint64_t lo = rb > cursor ? rb : cursor;
+    const uint64_t hi = re < flat_end ? re : flat_end;
+    int st = general(cursor, lo);                                     // windows between the runs
     if (st) return st;
-    BankArgs ba;
-    ba.sh = run.sh;
-    ba.recs = a.recs;
-    ba.win_rec = a.win_rec;
-    ba.out = (int32_t*)out_dev + (bb - flat_begin);
-    ba.w_first = (uint32_t)run.w_begin + (uint32_t)wlo;
-    ba.nwin = (uint32_t)(whi - wlo);
-    cudaStream_t ls = fan.next();
-    {
-      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls);
-      const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
-      e = launch_synth_bank(ba, run.tab_mode, run.pair, ls, pdl);
-      table_ahead = false;
+    if ((lo - rb) & (N - 1)) {                                        // the range enters the run inside a window
+      const uint32_t widx = (uint32_t)((lo - rb) >> pw);
+      const uint64_t wend = rb + ((uint64_t)(widx + 1) << pw);
+      const uint64_t pe = wend < hi ? wend : hi;
+      if ((st = partial(run, widx, lo, pe))) return st;
+      lo = pe;
     }
-    if (e != cudaSuccess) return cuda_fail(e, "k_synth_bank");
-    g_launches++;
-    cursor = be;
+    const uint64_t wlo = (lo - rb) >> pw, whi = (hi - rb) >> pw;      // whole windows [wlo, whi) of the run
+    if (whi > wlo) {
+      if ((st = bank(run, rb + (wlo << pw), (uint32_t)wlo, (uint32_t)whi, 0, 0))) return st;
+      lo = rb + (whi << pw);
+    }
+    if (lo < hi && (st = partial(run, (uint32_t)whi, lo, hi))) return st;   // ... and leaves it inside one
+    cursor = hi;
   }
   int st = general(cursor, flat_end);
   if (st) return st;

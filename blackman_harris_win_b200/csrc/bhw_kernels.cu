@@ -209,7 +209,10 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   const uint32_t pw = sh.pw;
   const uint32_t log_tpw = pw - kBankTileLog2 - (PAIR ? 1 : 0);  // log2(tiles per window)
   const uint32_t half = 1u << (pw - 1);
-  const uint64_t U = (uint64_t)a.nwin << log_tpw;
+  // whole windows, or a tile range inside one window (a shard or a requested range that cuts a long
+  // window): unit u is tile (u + tile_off) of the launch's windows
+  const uint64_t U = a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
+  const uint64_t toff = a.ntiles ? (uint64_t)a.tile_off : 0;
   const uint64_t u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
   // ports of a window (warp-uniform)
   struct Ports { int32_t A[M]; int32_t S0; uint32_t n_first; };
@@ -233,7 +236,7 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
       bank_lane_tile<M, TAB, PAIR, true, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
     else
       bank_lane_tile<M, TAB, PAIR, false, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
-    int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
+    int32_t* o = a.out + ((uint64_t)w << pw) + (uint64_t)t * kBankTile - toff * kBankTile + lane;
 #pragma unroll
     for (int j = 0; j < kBankJ; ++j) {
       __stcs(o + 32 * j, va[j]);
@@ -256,28 +259,28 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     const uint64_t stride = PAIR ? (uint64_t)gridDim.x * kBankWarps : (uint64_t)kBankWarps;
     const uint64_t last = PAIR ? U : u1;
     if (first < last) {
-      cur_w = (uint32_t)(first >> log_tpw);
+      cur_w = (uint32_t)((first + toff) >> log_tpw);
       load_ports(cur_w, cur);
     }
     nxt = cur;
     for (uint64_t u = first; u < last; u += stride) {
       const uint32_t w = cur_w;
       const uint64_t u2 = u + stride;
-      const uint32_t w2 = u2 < last ? (uint32_t)(u2 >> log_tpw) : w;
+      const uint32_t w2 = u2 < last ? (uint32_t)((u2 + toff) >> log_tpw) : w;
       if (w2 != w) load_ports(w2, nxt);  // consumed after this tile
-      do_tile(cur, w, (uint32_t)u & ((1u << log_tpw) - 1));
+      do_tile(cur, w, (uint32_t)(u + toff) & ((1u << log_tpw) - 1));
       if (w2 != w) { cur = nxt; cur_w = w2; }
     }
   } else {
     // 4 and more terms: paced by instruction issue; one contiguous share per CTA measured faster
     // than any interleaving (bh4: 171 vs 177 us, bh5: 197 vs 207 us per GiB)
     for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
-      const uint32_t w = (uint32_t)(u >> log_tpw);
+      const uint32_t w = (uint32_t)((u + toff) >> log_tpw);
       if (w != cur_w) {
         load_ports(w, cur);
         cur_w = w;
       }
-      do_tile(cur, w, (uint32_t)u & ((1u << log_tpw) - 1));
+      do_tile(cur, w, (uint32_t)(u + toff) & ((1u << log_tpw) - 1));
     }
   }
 }
@@ -514,8 +517,9 @@ static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
   if (!a.nwin) return cudaSuccess;
   if (tab == TAB_SMEM_HALF && !pair) return cudaErrorInvalidValue;
+  if (a.ntiles && (pair || a.nwin != 1)) return cudaErrorInvalidValue;
   const uint32_t log_tpw = a.sh.pw - kBankTileLog2 - (pair ? 1 : 0);
-  const uint64_t units = (uint64_t)a.nwin << log_tpw;
+  const uint64_t units = a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
   const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;
   const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());
   const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);

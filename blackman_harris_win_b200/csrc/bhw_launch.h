@@ -27,6 +27,8 @@ struct BankArgs {
   int32_t* out;              // sample 0 of window w_first
   uint32_t w_first;          // first window of the launch (index into win_rec)
   uint32_t nwin;             // whole windows to generate
+  uint32_t tile_off;         // ntiles > 0: tiles [tile_off, tile_off + ntiles) of window w_first only
+  uint32_t ntiles;           //             (unpaired shape); `out` is then the first of those tiles
 };
 
 struct DirectArgs {

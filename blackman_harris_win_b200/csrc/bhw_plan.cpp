@@ -239,7 +239,7 @@ bool source_antisymmetric(const SrcParams& sp) {
 }
 
 bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
-                int* tab_mode, bool* pair) {
+                int* tab_mode, bool* pair, bool allow_pair) {
   if (r.flags & WR_GENERIC) return false;
   if (r.pw < (uint32_t)kBankTileLog2) return false;  // a window must hold at least one tile
   memset(sh, 0, sizeof(*sh));
@@ -277,7 +277,7 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
   for (uint32_t u = 0; u < sh->ntab; u++) words += sh->tentries[u];
   if (sh->ntab == 1) { sh->tab[1] = sh->tab[0]; sh->tentries[1] = sh->tentries[0]; }
   const size_t limit = smem_limit_bytes / sizeof(int32_t);
-  const bool can_pair = antisym && r.pw >= (uint32_t)kBankTileLog2 + 1;
+  const bool can_pair = allow_pair && antisym && r.pw >= (uint32_t)kBankTileLog2 + 1;
   if (words <= limit) { *tab_mode = TAB_SMEM_FULL; *pair = can_pair; }
   else if (can_pair && half_ok && words / 2 <= limit) { *tab_mode = TAB_SMEM_HALF; *pair = true; }
   else { *tab_mode = TAB_GLOBAL; *pair = can_pair; }

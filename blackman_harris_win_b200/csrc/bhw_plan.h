@@ -40,7 +40,9 @@ struct BankTableInfo { const int32_t* ptr; uint32_t entries; bool antisym; };
 bool source_antisymmetric(const SrcParams& sp);
 // Shape of a record for the bank kernel (tables_k[k] = table of harmonic k), the table placement
 // (TAB_*) and whether lanes take (n, n + N/2) pairs; false when the record cannot go there.
+// allow_pair = false: lanes own single samples even where pairing would be valid (tile ranges inside
+// one window, where the partner half is somebody else's).
 bool bank_shape(const WinRec& r, const BankTableInfo* tables_k, size_t smem_limit_bytes, BankShape* sh,
-                int* tab_mode, bool* pair);
+                int* tab_mode, bool* pair, bool allow_pair = true);
 
 }  // namespace bhw

@@ -365,4 +365,70 @@ int bhw_shard_range(uint64_t total, int rank, int nranks, uint64_t* begin, uint6
   return BHW_OK;
 }
 
+// Relative generation time of one sample of window d (1.0 = a paired 2-term window with its table in
+// shared memory, about 0.6 ps on B200), fitted to round-1 measurements (tools/window_costs.py,
+// DESIGN.md): an issue-bound estimate from the per-entity banks (terms, 64-bit tail, sources without
+// sample pairing) and, for tables that do not fit shared memory, a gather-bound estimate from the
+// big windows of the sweep - stride-k gathers when no phase bit is dropped (from L2, or from HBM
+// above ~100 MB), broadcast-friendly gathers otherwise.
+static double window_cost_per_sample(const bhw_desc& d) {
+  const int m = d.win_type, pw = d.phi_width, dw = d.dat_width;
+  if (dw > 32) return 60.0 * (m - 1);                        // one-thread-per-sample int64 kernel
+  double a = m <= 3 ? 1.0 : m == 4 ? 1.05 : m == 5 ? 1.2 : 1.75;
+  if (d.model == BHW_MODEL_RTL && dw >= 31) a *= 1.55;       // 64-bit tail
+  const bool taylor = d.model == BHW_MODEL_RTL && d.sin_type == BHW_SIN_TAYLOR;
+  const bool inq = d.model == BHW_MODEL_RTL && (d.sin_type == BHW_SIN_CORDIC48 || d.sin_type == BHW_SIN_CORDIC_SCALED);
+  const bool pair = !inq && !(taylor && dw < 19);
+  if (!pair) a *= 1.7;
+  if (pw < 8) return a * 4.0;                                // general kernel, tiles straddle windows
+  const int idx_bits = (inq || taylor) ? pw : (pw < dw ? pw : dw);   // log2(table entries)
+  const double table_bytes = 4.0 * (double)(1ull << idx_bits);
+  if (table_bytes / (pair ? 2.0 : 1.0) <= 192.0 * 1024.0) return a;
+  const bool dropped = !(inq || taylor) && pw > dw;
+  double g;
+  if (dropped) g = 1.0 + (m - 1) * (table_bytes > 8e6 ? 0.29 : 0.13);
+  else g = (double)(m * (m - 1) / 2) * (table_bytes > 100e6 ? 0.42 : 0.2) * (pair ? 1.0 : 2.0);
+  return a > g ? a : g;
+}
+// launch + ramp of one more window in a mixed batch, in the same unit (samples of the cheapest kind)
+static const double kWindowFixedCost = 5.0e6;
+
+int bhw_shard_range_cost(const bhw_desc* descs, int nwin, int rank, int nranks, uint64_t* begin,
+                                    uint64_t* count) {
+  if (!descs || !begin || !count) return BHW_E_NULL;
+  if (nwin <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return BHW_E_ARG;
+  double total_cost = 0.0;
+  uint64_t total = 0;
+  for (int w = 0; w < nwin; w++) {
+    if (descs[w].phi_width < 4 || descs[w].phi_width > 30) return BHW_E_PHI_WIDTH;
+    const uint64_t N = 1ull << descs[w].phi_width;
+    total_cost += window_cost_per_sample(descs[w]) * (double)N + kWindowFixedCost;
+    total += N;
+  }
+  // flat index at which the cumulative cost reaches fraction r/nranks, rounded down to 4 samples
+  auto cut = [&](int r) -> uint64_t {
+    if (r <= 0) return 0;
+    if (r >= nranks) return total;
+    const double target = total_cost * (double)r / (double)nranks;
+    double acc = 0.0;
+    uint64_t off = 0;
+    for (int w = 0; w < nwin; w++) {
+      const uint64_t N = 1ull << descs[w].phi_width;
+      const double cw = window_cost_per_sample(descs[w]) + kWindowFixedCost / (double)N;   // per sample, fixed part spread
+      if (acc + cw * (double)N >= target) {
+        uint64_t in = (uint64_t)((target - acc) / cw);
+        if (in > N) in = N;
+        return (off + in) & ~(uint64_t)3;
+      }
+      acc += cw * (double)N;
+      off += N;
+    }
+    return total;
+  };
+  const uint64_t b = cut(rank), e = cut(rank + 1);
+  *begin = b;
+  *count = e > b ? e - b : 0;
+  return BHW_OK;
+}
+
 }  // extern "C"

@@ -173,6 +173,14 @@ BHW_API int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, ui
 BHW_API int bhw_batch_total(const bhw_desc* descs, int nwin, uint64_t* total_samples);
 BHW_API int bhw_shard_range(uint64_t total_samples, int rank, int nranks, uint64_t* begin,
                     uint64_t* count);
+/* Cost-balanced variant for batches of unlike windows (the win_selector sweep): still one contiguous
+ * flat slice per rank, but the cuts equalise an estimate of the generation time instead of the
+ * sample count - a sample of a 7-term 32-bit window whose table lives in L2 costs several times a
+ * sample of a Hann window.  Cuts fall on multiples of 4 samples; the slices of ranks 0..nranks-1
+ * tile [0, total) in order.  The estimate is a heuristic of this implementation, not of the
+ * reference (which has no notion of sharding). */
+BHW_API int bhw_shard_range_cost(const bhw_desc* descs, int nwin, int rank, int nranks, uint64_t* begin,
+                         uint64_t* count);
 BHW_API int bhw_generate_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin,
                        uint64_t flat_count, void* out_dev, void* stream);
 BHW_API int bhw_generate_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin,

@@ -129,3 +129,30 @@ def test_win_selector_mirror():
         bhw.WinSelector(WIN_TYPE="BH6TERM")
     with pytest.raises(bhw.BhwError):
         bhw.WinSelector(WIN_TYPE="BH4TERM", SIN_TYPE="TAYLOR").desc(AA0=1)
+
+
+def test_cost_balanced_shards_tile_the_batch():
+    """bhw_shard_range_cost: contiguous slices in rank order that tile [0, total), cut at multiples of
+    4 samples; equal windows -> (nearly) equal slices; costly windows get shorter slices."""
+    import cases
+    sweep = [bhw.variant_desc(v, pw, cases.VARIANT_DW[v]) for v in range(1, 11) for pw in range(4, 27)]
+    same = [bhw.variant_desc(6, 16, 17) for _ in range(64)]
+    for descs in (sweep, same, [bhw.variant_desc(10, 20, 32)]):
+        total = bhw.batch_total(descs)
+        for world in (1, 2, 3, 8):
+            cursor = 0
+            for r in range(world):
+                b, c = bhw.shard_range_cost(descs, r, world)
+                assert b == cursor and b % 4 == 0
+                cursor = b + c
+            assert cursor == total
+    total = bhw.batch_total(same)
+    for r in range(8):
+        b, c = bhw.shard_range_cost(same, r, 8)
+        assert abs(c - total // 8) <= 4
+    # the sweep ends with the 7-term 32-bit windows: the last of 8 ranks must get far fewer samples
+    total = bhw.batch_total(sweep)
+    _, c_last = bhw.shard_range_cost(sweep, 7, 8)
+    assert c_last < total // 16
+    with pytest.raises(bhw.BhwError):
+        bhw.shard_range_cost(sweep, 8, 8)

@@ -295,6 +295,39 @@ def test_shards_reassemble():
         assert torch.equal(torch.cat(parts), full)
 
 
+def test_cost_balanced_shards_reassemble_and_cut_long_windows():
+    """bhw_shard_range_cost on a mixed batch: the cuts fall inside long windows, so each shard runs
+    whole tiles of a cut window through the bank kernel (tile range of one window, unpaired shape)
+    and the ragged ends through the general kernel; the shards must reassemble to the unsharded
+    batch, which is checked against the oracle on its short windows."""
+    import torch
+    descs = [bhw.variant_desc(v, pw, cases.VARIANT_DW[v]) for v in range(1, 11) for pw in (6, 13, 19, 21)]
+    arr = bhw.desc_array(descs)
+    total = bhw.batch_total(descs)
+    full = bhw.generate_batch(descs)
+    off = 0
+    for d in descs:
+        n = 1 << d.phi_width
+        if n <= 1 << 13:
+            assert np.array_equal(full[off:off + n].cpu().numpy().astype(np.int64), H.orc_window(d)), d
+        off += n
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            b, c = bhw.shard_range_cost(arr, r, world)
+            first, touched, local = bhw.shard_windows(arr, b, c)
+            parts.append(bhw.generate_batch(descs[first:first + touched], local, c))
+        assert torch.equal(torch.cat(parts), full), world
+    # ranges that cut one long window of every entity at odd places (plan route)
+    for v in (1, 3, 6, 8, 10):
+        d = bhw.variant_desc(v, 22, cases.VARIANT_DW[v])
+        whole = bhw.generate(d)
+        plan = bhw.Plan([d])
+        for b, c in ((100, (1 << 19) - 200), ((1 << 21) - 12345, (1 << 20) + 777), ((1 << 22) - 70000, 70000)):
+            assert torch.equal(plan.execute(b, c), whole[b:b + c]), (v, b, c)
+        plan.destroy()
+
+
 def test_host_entry_points():
     d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
     want = H.orc_window(d)

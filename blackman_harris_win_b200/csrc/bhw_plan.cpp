@@ -102,6 +102,32 @@ int table_tshift(const SrcParams& sp) {
   }
 }
 
+// DAT_WIDTH 31..32: dsp_pp has DW+2 (DW+1) bits, more than a 32-bit register - unless the ports
+// keep it small.  |b_k| <= (|AAk|*cmax + 2^(DW-2)) >> (DW-1), cmax = largest |cos| the source can
+// emit, so when |AA0| + sum_k |b_k| + rounding stays below 2^31 the true sum fits an int32: the
+// entity's wraps of dsp_pp (DW+2 bits) and DT_WIN (DW bits) are then no-ops and the 32-bit tail
+// applies with lsh = 0 (intermediate wraps of the 32-bit accumulator are harmless, the arithmetic is
+// modular).  Every real coefficient set qualifies (a0 + (a1+..)/2 < 1 at the CORDIC amplitude
+// 2^(DW-2)); full-scale synthetic ports fall back to the 64-bit tail.  With DW = 32 the table holds
+// the unshifted cosine (tshift 0) and the coefficient carries the factor 2: A_k = 2*AAk must fit.
+static bool narrow_sum_ok(const WinParams& wp, const SrcParams* src) {
+  const int dw = wp.dw;
+  if (dw < 31 || dw > 32) return false;
+  const int t = table_tshift(src[0]);
+  for (int u = 1; u < wp.nsrc; u++) if (table_tshift(src[u]) != t) return false;
+  if (t != 33 - dw && t != 32 - dw) return false;           // A_k = AAk << (33 - DW - t), shift 0 or 1
+  const int ash = 33 - dw - t;
+  int64_t bound = (wp.aa[0] < 0 ? -wp.aa[0] : wp.aa[0]) + 4;
+  for (int k = 1; k < wp.m; k++) {
+    const int64_t a = wp.aa[k] < 0 ? -wp.aa[k] : wp.aa[k];
+    if (ash && a >= ((int64_t)1 << 30)) return false;       // 2*AAk and its negative must fit an int32
+    const SrcParams& sp = src[wp.term[k - 1].src];
+    const int64_t cmax = sp.kind == SRC_TAYLOR ? ((int64_t)1 << (dw - 1)) : ((int64_t)1 << (dw - 2)) + 64;
+    bound += ((a * cmax) >> (dw - 1)) + 2;
+  }
+  return bound < ((int64_t)1 << 31);
+}
+
 // Which synthesis tail reproduces the entity for this window.
 TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src) {
   if (wp.dw > 32) return TAILMODE_GENERIC;
@@ -112,7 +138,8 @@ TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src) {
   const int64_t lo = -((int64_t)1 << (wp.dw - 1));
   for (int k = 1; k < wp.m; k++) if (wp.aa[k] == lo) return TAILMODE_GENERIC;
   const int dmax = wp.tail == TAIL_RTL2 ? 31 : 30;  // dsp_pp (DW+1 / DW+2 bits) must fit 32 bits
-  return (t == 1 && wp.dw <= dmax) ? TAILMODE_FAST32 : TAILMODE_ACC64;
+  if (t == 1 && wp.dw <= dmax) return TAILMODE_FAST32;
+  return narrow_sum_ok(wp, src) ? TAILMODE_FAST32 : TAILMODE_ACC64;
 }
 
 // Fill the tail record of a window (see the derivation above WinRec).
@@ -131,15 +158,20 @@ void fill_fast_rec(const WinParams& wp, const SrcParams* src, WinRec& r) {
     r.S0 = r.aa[0];
     return;
   }
-  const int ashift = 32 - dw;
-  for (int k = 1; k < m; k++) r.A[k] = (int32_t)((uint32_t)r.aa[k] << ashift);
   if (wp.tail == TAIL_HLS) {
+    const int ashift = 32 - dw;
+    for (int k = 1; k < m; k++) r.A[k] = (int32_t)((uint32_t)r.aa[k] << ashift);
     r.rc = 0; r.S0 = r.aa[0]; r.lsh = 32 - dw; r.rsh = 32 - dw;
-  } else if (wp.tail == TAIL_RTL2) {
-    r.rc = 0x80000000u; r.S0 = (int32_t)((uint32_t)r.aa[0] + 1u); r.lsh = 31 - dw; r.rsh = 32 - dw;
-  } else {
-    r.rc = 0x80000000u; r.S0 = (int32_t)((uint32_t)r.aa[0] + 2u); r.lsh = 30 - dw; r.rsh = 32 - dw;
+    return;
   }
+  // b_k = hi32(A_k * (cos << tshift) + 2^31) needs A_k * 2^tshift == AAk * 2^(33-DW)
+  const int ashift = 33 - dw - (int)r.tshift;
+  for (int k = 1; k < m; k++) r.A[k] = (int32_t)((uint32_t)r.aa[k] << ashift);
+  const int fin = wp.tail == TAIL_RTL2 ? 1 : 2;             // dsp_pp carries DW+fin bits
+  r.rc = 0x80000000u;
+  r.S0 = (int32_t)((uint32_t)r.aa[0] + (uint32_t)fin);
+  if (dw + fin <= 32) { r.lsh = 32 - fin - dw; r.rsh = 32 - dw; }
+  else { r.lsh = 0; r.rsh = fin; }                          // narrow_sum_ok(): the sum fits as it is
 }
 
 bool direct32_params(const WinParams& wp, const SrcParams* src, Direct32Params* out) {

@@ -57,4 +57,14 @@ def edge_coeff_descs():
             out.append(bhw.make_desc(m, 9, dw, [(1 << dw) - 1] * m))   # raw bits, unsigned reading
             out.append(bhw.make_desc(m, 9, dw, [0] * m))
             out.append(bhw.make_desc(m, 9, dw, [-3, 5, -7, 11, -13, 17, -19][:m]))
+    # DAT_WIDTH 31..32: ports around the limits of the 32-bit tail (|AAk| < 2^30 at DW 32, and the
+    # bound on the sum that keeps dsp_pp inside an int32) - both sides of each limit
+    q = 1 << 30
+    for dw in (31, 32):
+        for m in (2, 3, 4, 5, 7):
+            for a0 in (0, q - 1, -q, (1 << (dw - 1)) - 1):
+                for ak in (q - 1, q, -q + 1, -q, q // 2, q // 3, -(q // 5)):
+                    if -(1 << (dw - 1)) <= ak < (1 << (dw - 1)):
+                        out.append(bhw.make_desc(m, 9, dw, [a0] + [ak] * (m - 1)))
+            out.append(bhw.make_desc(m, 9, dw, [q + q // 2] + [q - 1] + [q // 8] * (m - 2)))
     return out

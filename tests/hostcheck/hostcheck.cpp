@@ -296,6 +296,14 @@ int hc_source_antisymmetric(const bhw_desc* d) {
   return source_antisymmetric(canonical_source(src[0], &drop)) ? 1 : 0;
 }
 
+// which synthesis tail the planner picks: 0 = 32-bit, 1 = 64-bit, 2 = generic body
+int hc_tail_mode(const bhw_desc* d) {
+  WinParams wp; SrcParams src[2];
+  int st = resolve_window(d, &wp, src);
+  if (st) return st;
+  return (int)fast_tail_mode(wp, src);
+}
+
 // the cosine table of the window's first source, expanded to one value per phase
 int hc_table_cos(const bhw_desc* d, int64_t* out_cos, int force_generic_core) {
   WinParams wp; SrcParams src[2];

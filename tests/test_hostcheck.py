@@ -103,6 +103,35 @@ def test_coefficient_edge_cases():
                 check(d2, 512)
 
 
+def test_wide_windows_take_the_32_bit_tail_when_the_sum_provably_fits():
+    """DAT_WIDTH 31..32: dsp_pp has more bits than a register, but with real coefficient sets the sum
+    stays inside an int32 and the planner keeps the 32-bit tail; full-scale ports, |AAk| >= 2^30 at
+    DAT_WIDTH 32 and AAk = -2^(DW-1) do not qualify.  (Bit-exactness of both routes: the sweeps.)"""
+    hc = H.hostcheck()
+    T32, T64, GEN = 0, 1, 2
+    for v in range(1, 11):
+        for dw in (31, 32):
+            for st in (bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED):
+                d = bhw.variant_desc(v, 12, dw, sin_type=st)
+                if bhw.validate(d) == 0:
+                    # 32 bits: the 3-/4-term rules scale to 2^W (AA1 ~ 2^31), Hann has AA1 = 2^30 exactly and
+                    # the flat-top coefficients sum to 4.6 * 2^(W-2); 31 bits: 2*AAk always fits, sums are small
+                    want = T32 if dw == 31 or v in (1, 9, 10) else T64
+                    assert hc.hc_tail_mode(C.byref(d)) == want, (v, dw, st)
+    q = 1 << 30
+    hi = (1 << 31) - 1
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [hi] * 4))) == T64
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [0, q, 0, 0]))) == T64
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [0, q - 1, 0, 0]))) == T32
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [0, -q, 0, 0]))) == T64
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [0, -q + 1, 0, 0]))) == T32
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [hi, q - 1, q - 1, q - 1]))) == T64   # sum too large
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 32, [0, -(1 << 31), 0, 0]))) == GEN
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(2, 12, 31, [q - 1, q - 1]))) == T32
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 30, [(1 << 29) - 1] * 4))) == T32          # always, DW <= 30
+    assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 40, [1, 2, 3, 4]))) == GEN
+
+
 def test_stream_offset_is_a_rotation():
     for d in (bhw.make_desc(2, 8, 16, [17808, 14959]), bhw.make_desc(3, 14, 24, [7046424, 8388600, 1342176],
                                                                   sin_type=bhw.SIN_TAYLOR)):

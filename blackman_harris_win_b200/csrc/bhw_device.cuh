@@ -213,7 +213,8 @@ struct TabJob {
   uint32_t work;        // work items of this job: entries/4, or entries for SRC_INQ
   uint32_t rom_off;     // Taylor ROM offset (I2 units) in the rom buffer
   uint32_t tshift;      // entries are stored left-shifted by this much (see WinRec)
-  int32_t rom32[32];    // TABCORE_32 / _32BIAS: atan word of stage i sliced for this register width (0 past n_z)
+  int32_t rom32[32];    // TABCORE_32 / _32BIAS: atan word of stage i sliced for this register width (0 past n_z);
+                        // TABCORE_A64: high half of rom64[i] plus 1 when its low half reads negative as an int32
   int64_t rom64[48];    // TABCORE_A64: atan word of stage i, sliced and left-aligned to bit 63 (0 past n_z)
 };
 enum : uint32_t { TABCORE_GENERIC = 0, TABCORE_32 = 1, TABCORE_32BIAS = 2, TABCORE_A64 = 3 };
@@ -348,31 +349,78 @@ BHW_HD void table_build_item(const TabJob& job, const I2* rom, uint32_t e) {
   table_store_quadrants(job, e, vs, vc);
 }
 
-// cordic_core_aligned64 for the input-quadrant CORDICs with the stage count as a template
-// parameter (immediate 64-bit shifts, atan words from the constant bank).
+// acc += a*b, signed 32x32 -> 64 with a 64-bit addend: one IMAD.WIDE
+BHW_HD void madw(int64_t& acc, int32_t a, int32_t b) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+#else
+  acc = (int64_t)((uint64_t)acc + (uint64_t)((int64_t)a * (int64_t)b));
+#endif
+}
+// high word of acc += a*b (mod 2^32): one IMAD
+BHW_HD void madhi(int64_t& acc, int32_t a, int32_t b) {
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .u32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmad.lo.s32 hi, %1, %2, hi;\n\tmov.b64 %0, {lo, hi};\n\t}"
+      : "+l"(acc) : "r"(a), "r"(b));
+#else
+  acc = (int64_t)((uint64_t)acc + ((uint64_t)((uint32_t)a * (uint32_t)b) << 32));
+#endif
+}
+// 32x32 multiply-add kept as one IMAD
+BHW_HD int32_t mad32(int32_t a, int32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+  int32_t d;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return (int32_t)((uint32_t)a * (uint32_t)b + (uint32_t)c);
+#endif
+}
+// acc += s * v for a 64-bit v and s = +-1: v = vt*2^32 + (int32)vl with vt = vh + (vl >> 31), so the
+// product is one signed IMAD.WIDE on the low half plus one IMAD into the high word - no sign-
+// dependent select and no carry chain on the alu pipe
+BHW_HD void mad64_pm1(int64_t& acc, int64_t v, int32_t s) {
+  const uint32_t vl = (uint32_t)(uint64_t)v;
+  const int32_t vt = (int32_t)(uint32_t)((uint64_t)v >> 32) + (int32_t)(vl >> 31);
+  madw(acc, (int32_t)vl, s);
+  madhi(acc, vt, s);
+}
+
+// The input-quadrant core with the stage count as a template parameter (cordic_dds48,
+// cordic_dds_scaled at DAT_WIDTH 16, 17, 24, 32; src/cordic_dds48.vhd:170-258,
+// src/cordic_dds_scaled.vhd:196-283).  X and Y are held as plain (right-aligned) 64-bit integers:
+// the gain puts the rotating vector at a quarter of the w-bit register range (|x|, |y| <=
+// 2^(w-2) * (1 + eps) at every stage, the CORDIC magnitude only grows towards its final value), so
+// the reference's wrap of x and y to w bits never acts and (x >> i) is the arithmetic shift of the
+// value itself.  Z stays left-aligned to bit 63 (its wrap is then the natural overflow).  With
+// m = z >> 63 and s = 2m + 1 (+1: z >= 0, -1: z < 0; src/cordic_dds48.vhd:234-250):
+//   x += s * (y >> i)      y -= s * (x >> i)      z -= s * atan_i
+// each as IMAD.WIDE + IMAD (mad64_pm1; the atan word arrives split the same way, `romh`).  Per
+// stage: 8 alu instructions (sign mask, s, 2 x (funnel shift, high shift, LEA.HI)) and 7 fma ones,
+// against 22 + 6 for the select-based form.
 template <int NXY>
-BHW_HD void cordic_core_aligned64_inq_u(const SrcParams& p, const int64_t* __restrict__ rom64, int q, uint64_t low,
-                                        int64_t& vs, int64_t& vc) {
+BHW_HD void cordic_core_inq_u(const SrcParams& p, const int64_t* __restrict__ rom64, const int32_t* __restrict__ romh,
+                              int q, uint64_t low, int64_t& vs, int64_t& vc) {
   const int pw = p.pw;
-  const int ax = 64 - p.w, az = 64 - p.zw;
-  const int64_t mx = (int64_t)(~0ull << ax);
-  const int64_t G = (int64_t)((uint64_t)p.gain << ax);
+  const int az = 64 - p.zw;
+  const int64_t G = (int64_t)p.gain;
   int64_t X = G, Y = 0;
   uint64_t t = low | ((uint64_t)q << (pw - 2));
-  if (q == 1) { t = low; X = 0; Y = (int64_t)(0ull - (uint64_t)G); }
+  if (q == 1) { t = low; X = 0; Y = -G; }
   else if (q == 2) { t = low | (3ull << (pw - 2)); X = 0; Y = G; }
   int64_t Z = (int64_t)(t << (p.z_lshift + az));
 #pragma unroll
   for (int i = 0; i < NXY; ++i) {
-    const bool cw = Z >= 0;  // input-quadrant sense: z >= 0 -> x + (y>>i), y - (x>>i)   (src/cordic_dds48.vhd:234-242)
-    const uint64_t Xs = (uint64_t)((X >> i) & mx), Ys = (uint64_t)((Y >> i) & mx);
-    const uint64_t r = (uint64_t)rom64[i];  // 0 for the last stage (z advances NXY-1 times)
-    X = (int64_t)(cw ? (uint64_t)X + Ys : (uint64_t)X - Ys);
-    Y = (int64_t)(cw ? (uint64_t)Y - Xs : (uint64_t)Y + Xs);
-    Z = (int64_t)(cw ? (uint64_t)Z - r : (uint64_t)Z + r);
+    const int32_t m = (int32_t)(Z >> 63);
+    const int32_t s = 2 * m + 1, ns = mad32(m, -2, -1);
+    const int64_t Xs = X >> i, Ys = Y >> i;   // old values on both sides
+    mad64_pm1(X, Ys, s);
+    mad64_pm1(Y, Xs, ns);
+    madw(Z, (int32_t)(uint32_t)(uint64_t)rom64[i], ns);   // rom64[i] = 0 for the last stage (z advances NXY-1 times)
+    madhi(Z, romh[i], ns);
   }
-  vs = Y >> (ax + p.out_shift);
-  vc = X >> (ax + p.out_shift);
+  vs = Y >> p.out_shift;
+  vc = X >> p.out_shift;
 }
 
 // Work item `e` (one phase) of an input-quadrant job with NXY stages: the dedicated kernel for large
@@ -381,7 +429,9 @@ template <int NXY>
 BHW_HD void table_build_item_inq_u(const TabJob& job, uint32_t e) {
   const SrcParams& p = job.sp;
   int64_t s, c;
-  cordic_core_aligned64_inq_u<NXY>(p, job.rom64, (int)(e >> (p.pw - 2)), (uint64_t)(e & ((1u << (p.pw - 2)) - 1u)), s, c);
+  const int q = (int)(e >> (p.pw - 2));
+  const uint64_t low = (uint64_t)(e & ((1u << (p.pw - 2)) - 1u));
+  cordic_core_inq_u<NXY>(p, job.rom64, job.rom32, q, low, s, c);
   job.tab[e] = (int32_t)(wrapb(c, p.outw) * ((int64_t)1 << job.tshift));
 }
 

@@ -211,8 +211,11 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   const uint32_t half = 1u << (pw - 1);
   // whole windows, or a tile range inside one window (a shard or a requested range that cuts a long
   // window): unit u is tile (u + tile_off) of the launch's windows
-  const uint64_t U = a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
-  const uint64_t toff = a.ntiles ? (uint64_t)a.tile_off : 0;
+  // (only the unpaired global-table instantiations take tile ranges - launch_synth_bank() - so the
+  // staged, paired kernels of whole-window banks carry none of this)
+  constexpr bool kRange = TAB == TAB_GLOBAL && !PAIR;
+  const uint64_t U = kRange && a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
+  const uint64_t toff = kRange && a.ntiles ? (uint64_t)a.tile_off : 0;
   const uint64_t u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
   // ports of a window (warp-uniform)
   struct Ports { int32_t A[M]; int32_t S0; uint32_t n_first; };
@@ -236,7 +239,8 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
       bank_lane_tile<M, TAB, PAIR, true, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
     else
       bank_lane_tile<M, TAB, PAIR, false, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
-    int32_t* o = a.out + ((uint64_t)w << pw) + (uint64_t)t * kBankTile - toff * kBankTile + lane;
+    int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
+    if (kRange) o -= toff * kBankTile;
 #pragma unroll
     for (int j = 0; j < kBankJ; ++j) {
       __stcs(o + 32 * j, va[j]);
@@ -517,7 +521,7 @@ static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
   if (!a.nwin) return cudaSuccess;
   if (tab == TAB_SMEM_HALF && !pair) return cudaErrorInvalidValue;
-  if (a.ntiles && (pair || a.nwin != 1)) return cudaErrorInvalidValue;
+  if (a.ntiles && (pair || tab != TAB_GLOBAL || a.nwin != 1)) return cudaErrorInvalidValue;
   const uint32_t log_tpw = a.sh.pw - kBankTileLog2 - (pair ? 1 : 0);
   const uint64_t units = a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
   const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;

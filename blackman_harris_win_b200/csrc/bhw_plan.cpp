@@ -74,7 +74,11 @@ void init_tab_job(const SrcParams& canon, int32_t* tab, TabJob* j) {
   for (int i = 0; i < canon.n_z && i < 48; i++) {
     const int64_t r = (c_atan[canon.rom_sel][i] >> canon.rom_shift) & canon.rom_mask;
     if (i < 32 && (j->fast == TABCORE_32 || j->fast == TABCORE_32BIAS)) j->rom32[i] = (int32_t)r;
-    if (j->fast == TABCORE_A64) j->rom64[i] = (int64_t)((uint64_t)r << (64 - canon.zw));
+    if (j->fast == TABCORE_A64) {
+      const uint64_t a = (uint64_t)r << (64 - canon.zw);
+      j->rom64[i] = (int64_t)a;
+      if (i < 32) j->rom32[i] = (int32_t)(uint32_t)((a + ((a & 0x80000000ull) << 1)) >> 32);
+    }
   }
 }
 

@@ -609,6 +609,14 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     ba.nwin = wb - wa;
     ba.tile_off = tile_off;
     ba.ntiles = ntiles;
+    {
+      // window-minor walk (BankArgs::win_minor): pays where the stride-k gathers dominate - no phase
+      // bit dropped and 5 or more terms (measured on 256 MB banks: 7-term DAT_WIDTH 32 N=2^20 123 -> 99 us,
+      // cordic_dds48 239 -> 145 us, 5-term DAT_WIDTH 24 79 -> 71 us; 2-term 48 -> 54 us, so not there)
+      const uint32_t log_tpw = run.sh.pw - kBankTileLog2 - (run.pair ? 1 : 0);
+      ba.win_minor = (!ntiles && run.tab_mode == TAB_GLOBAL && ba.nwin > 1 && run.sh.lin && run.sh.m >= 5 &&
+                      !(((uint64_t)ba.nwin << log_tpw) >> 32)) ? 1u : 0u;
+    }
     cudaStream_t ls = fan.next();
     cudaError_t ce;
     {

@@ -249,6 +249,20 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   };
   Ports cur;
   uint32_t cur_w = 0xFFFFFFFFu;
+  if (TAB == TAB_GLOBAL && a.win_minor) {
+    // Tables read from L2: a bank of windows over one table walks it window-minor - unit u is tile
+    // u / nwin of window u % nwin - so that the warps of a CTA work on the same tile of consecutive
+    // windows at the same time and all but the first find the table sectors in L1 (a stride-k
+    // gather pulls 4k sectors per warp instruction; window-major, every tile pulled them from L2
+    // again: 2.7 GB per 256 MB of 7-term output, L2 82 % busy).
+    const uint32_t nwin = a.nwin;
+    for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
+      const uint32_t t = (uint32_t)u / nwin, w = (uint32_t)u - t * nwin;
+      load_ports(w, cur);
+      do_tile(cur, w, t);
+    }
+    return;
+  }
   if (M <= 3) {
     // 2- and 3-term windows have registers to spare: fetch the next window's ports one tile ahead,
     // so that the two dependent loads (window -> record -> ports) never sit in front of a tile.
@@ -524,6 +538,7 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
   if (a.ntiles && (pair || tab != TAB_GLOBAL || a.nwin != 1)) return cudaErrorInvalidValue;
   const uint32_t log_tpw = a.sh.pw - kBankTileLog2 - (pair ? 1 : 0);
   const uint64_t units = a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
+  if (a.win_minor && (tab != TAB_GLOBAL || a.ntiles || units >> 32)) return cudaErrorInvalidValue;
   const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;
   const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());
   const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);

@@ -29,6 +29,7 @@ struct BankArgs {
   uint32_t nwin;             // whole windows to generate
   uint32_t tile_off;         // ntiles > 0: tiles [tile_off, tile_off + ntiles) of window w_first only
   uint32_t ntiles;           //             (unpaired shape); `out` is then the first of those tiles
+  uint32_t win_minor;        // TAB_GLOBAL, whole windows: walk the bank tile by tile across its windows
 };
 
 struct DirectArgs {

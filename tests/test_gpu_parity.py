@@ -328,6 +328,31 @@ def test_cost_balanced_shards_reassemble_and_cut_long_windows():
         plan.destroy()
 
 
+def test_banks_over_a_table_too_large_for_shared_memory():
+    """Runs of same-shape windows whose trig table stays in L2 (TAB_GLOBAL): the bank kernel walks
+    them window-minor (same tile of consecutive windows side by side).  Every window must equal its
+    one-shot generation, and the oracle on a slice."""
+    import torch
+    for v, pw, dw, st, nwin in ((10, 18, 32, bhw.SIN_CORDIC, 5), (10, 17, 32, bhw.SIN_CORDIC48, 3),
+                                (8, 19, 24, bhw.SIN_CORDIC, 4), (6, 18, 17, bhw.SIN_CORDIC_SCALED, 33),
+                                (1, 19, 24, bhw.SIN_CORDIC, 7)):
+        base = bhw.variant_desc(v, pw, dw, sin_type=st)
+        descs = [base.copy(aa=[int(a) - 3 * i if k == 0 else int(a) + (i if k == 1 else 0) for k, a in enumerate(base.aa)],
+                           stream_offset=i & 1) for i in range(nwin)]
+        plan = bhw.Plan(descs)
+        out = plan.execute()
+        n = 1 << pw
+        for i, d in enumerate(descs):
+            assert torch.equal(out[i * n:(i + 1) * n], bhw.generate(d)), (v, pw, dw, st, i)
+        i = nwin - 1
+        assert np.array_equal(out[i * n + n // 2 - 1000:i * n + n // 2 + 1000].cpu().numpy().astype(np.int64),
+                              H.orc_window(descs[i], n // 2 - 1000, 2000))
+        # a sub-range that starts and ends inside windows of the run
+        b, c = n // 3 + 5, (nwin - 1) * n
+        assert torch.equal(plan.execute(b, c), out[b:b + c])
+        plan.destroy()
+
+
 def test_host_entry_points():
     d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
     want = H.orc_window(d)

@@ -616,6 +616,11 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       const uint32_t log_tpw = run.sh.pw - kBankTileLog2 - (run.pair ? 1 : 0);
       ba.win_minor = (!ntiles && run.tab_mode == TAB_GLOBAL && ba.nwin > 1 && run.sh.lin && run.sh.m >= 5 &&
                       !(((uint64_t)ba.nwin << log_tpw) >> 32)) ? 1u : 0u;
+      // one long 7-term window: spread the warps of a CTA over the window (BankArgs::spread); 5 and
+      // fewer terms measured no different (they are not bound by the L2 -> L1 gather traffic)
+      const uint32_t G = 30u;
+      ba.spread = (!ntiles && run.tab_mode == TAB_GLOBAL && ba.nwin == 1 && run.sh.lin && run.sh.m >= 7 &&
+                   log_tpw < 32 && (1ull << log_tpw) >= (uint64_t)G * 148u) ? G : 0u;
     }
     cudaStream_t ls = fan.next();
     cudaError_t ce;

@@ -263,6 +263,28 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     }
     return;
   }
+  if (TAB == TAB_GLOBAL && a.spread) {
+    // One long window over an L2-resident (or larger) table.  Harmonic k of tile n reads the table
+    // around k*n at stride k: 4k sectors per warp instruction of which it uses every k-th word; the
+    // other words belong to the tiles a k-th of a period away.  So warp j of G takes the j-th G-th
+    // of the window (tiles U*j/G + i, all warps at the same i): harmonic k then reads G/gcd(k,G)
+    // distinct regions instead of G, their sectors shared through L1 by the warps whose offsets
+    // differ by a multiple of period/k.  G = 30 for 7 terms: 7 sector fetches per tile row instead of
+    // 21 at best (measured, 7-term DAT_WIDTH 32: N=2^25 135 -> 92 us, N=2^26 340 -> 226 us, cordic_dds48
+    // N=2^24 80 -> 48 us; a CTA barrier per step to keep the warps together measured slower).
+    const uint32_t G = a.spread;
+    if (warp < G) {
+      const uint32_t Ut = (uint32_t)U;
+      const uint32_t b0 = (uint32_t)((uint64_t)Ut * warp / G), b1 = (uint32_t)((uint64_t)Ut * (warp + 1) / G);
+      const uint32_t L = (Ut + G - 1) / G;
+      const uint32_t i0 = (uint32_t)((uint64_t)L * blockIdx.x / gridDim.x);
+      const uint32_t i1 = (uint32_t)((uint64_t)L * (blockIdx.x + 1) / gridDim.x);
+      load_ports(0, cur);
+      for (uint32_t i = i0; i < i1; ++i)
+        if (b0 + i < b1) do_tile(cur, 0, b0 + i);
+    }
+    return;
+  }
   if (M <= 3) {
     // 2- and 3-term windows have registers to spare: fetch the next window's ports one tile ahead,
     // so that the two dependent loads (window -> record -> ports) never sit in front of a tile.
@@ -539,7 +561,9 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
   const uint32_t log_tpw = a.sh.pw - kBankTileLog2 - (pair ? 1 : 0);
   const uint64_t units = a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
   if (a.win_minor && (tab != TAB_GLOBAL || a.ntiles || units >> 32)) return cudaErrorInvalidValue;
-  const uint64_t ctas = (units + kBankWarps - 1) / kBankWarps;
+  if (a.spread && (tab != TAB_GLOBAL || a.ntiles || a.win_minor || a.nwin != 1 || a.spread > (uint32_t)kBankWarps || units >> 32))
+    return cudaErrorInvalidValue;
+  const uint64_t ctas = a.spread ? (units + a.spread - 1) / a.spread : (units + kBankWarps - 1) / kBankWarps;
   const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());
   const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);
   const bool w64 = a.sh.acc64 != 0;

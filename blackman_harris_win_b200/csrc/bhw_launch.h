@@ -30,6 +30,7 @@ struct BankArgs {
   uint32_t tile_off;         // ntiles > 0: tiles [tile_off, tile_off + ntiles) of window w_first only
   uint32_t ntiles;           //             (unpaired shape); `out` is then the first of those tiles
   uint32_t win_minor;        // TAB_GLOBAL, whole windows: walk the bank tile by tile across its windows
+  uint32_t spread;           // TAB_GLOBAL, one whole window: G > 0 = warp j of G takes the j-th G-th of the window
 };
 
 struct DirectArgs {

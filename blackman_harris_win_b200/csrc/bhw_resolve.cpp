@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "bhw_internal.h"
+#include "bhw_plan.h"
 
 namespace bhw {
 
@@ -375,7 +376,10 @@ static double window_cost_per_sample(const bhw_desc& d) {
   const int m = d.win_type, pw = d.phi_width, dw = d.dat_width;
   if (dw > 32) return 60.0 * (m - 1);                        // one-thread-per-sample int64 kernel
   double a = m <= 3 ? 1.0 : m == 4 ? 1.05 : m == 5 ? 1.2 : 1.75;
-  if (d.model == BHW_MODEL_RTL && dw >= 31) a *= 1.55;       // 64-bit tail
+  if (d.model == BHW_MODEL_RTL && dw >= 31) {                // 64-bit tail, unless the ports keep dsp_pp in 32 bits
+    WinParams wp; SrcParams src[2];
+    if (resolve_window(&d, &wp, src) != BHW_OK || fast_tail_mode(wp, src) != TAILMODE_FAST32) a *= 1.55;
+  }
   const bool taylor = d.model == BHW_MODEL_RTL && d.sin_type == BHW_SIN_TAYLOR;
   const bool inq = d.model == BHW_MODEL_RTL && (d.sin_type == BHW_SIN_CORDIC48 || d.sin_type == BHW_SIN_CORDIC_SCALED);
   const bool pair = !inq && !(taylor && dw < 19);
@@ -387,7 +391,11 @@ static double window_cost_per_sample(const bhw_desc& d) {
   const bool dropped = !(inq || taylor) && pw > dw;
   double g;
   if (dropped) g = 1.0 + (m - 1) * (table_bytes > 8e6 ? 0.29 : 0.13);
-  else g = (double)(m * (m - 1) / 2) * (table_bytes > 100e6 ? 0.42 : 0.2) * (pair ? 1.0 : 2.0);
+  else {
+    double per = table_bytes > 100e6 ? 0.42 : 0.2;
+    if (m >= 7 && pw >= 23) per = table_bytes > 200e6 ? 0.27 : 0.215;   // warps spread over the window (BankArgs::spread)
+    g = (double)(m * (m - 1) / 2) * per * (pair ? 1.0 : 2.0);
+  }
   return a > g ? a : g;
 }
 // launch + ramp of one more window in a mixed batch, in the same unit (samples of the cheapest kind)

@@ -103,12 +103,19 @@ def test_baseline_configs_full_size(name):
 def test_large_windows_properties():
     """N = 2^24 .. 2^26: strategies agree, splits reproduce the whole, spot ranges match the oracle."""
     import torch
-    for v, pw, dw in ((1, 26, 16), (6, 25, 17), (9, 24, 24), (10, 24, 32)):
-        d = bhw.variant_desc(v, pw, dw)
+    for v, pw, dw, st in ((1, 26, 16, bhw.SIN_CORDIC), (6, 25, 17, bhw.SIN_CORDIC), (9, 24, 24, bhw.SIN_CORDIC),
+                          (10, 24, 32, bhw.SIN_CORDIC), (10, 23, 32, bhw.SIN_CORDIC48)):
+        d = bhw.variant_desc(v, pw, dw, sin_type=st)
         n = 1 << pw
         full = bhw.generate(d)
-        # spot ranges against the oracle
-        for n0 in (0, 12345, n // 2 - 2048, n - 4096):
+        # spot ranges against the oracle; for the 7-term windows also around the seams between the
+        # shares of the 30 warps a CTA spreads over the window (tile U*j/30 of U tiles of 256 samples,
+        # or of U tile pairs (n, n + N/2) for the paired sources)
+        spots = [0, 12345, n // 2 - 2048, n - 4096]
+        if d.win_type == 7:
+            for tiles in (n // 256, n // 512):
+                spots += [max(0, (tiles * j // 30) * 256 - 2048) for j in (1, 7, 16, 29)]
+        for n0 in spots:
             assert np.array_equal(full[n0:n0 + 4096].cpu().numpy().astype(np.int64), H.orc_window(d, n0, 4096))
         # ragged 3-way split equals the whole
         cuts = [0, n // 3 + 1, n // 3 + 1 + 777, n]

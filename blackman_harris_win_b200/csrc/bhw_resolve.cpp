@@ -393,7 +393,8 @@ static double window_cost_per_sample(const bhw_desc& d) {
   if (dropped) g = 1.0 + (m - 1) * (table_bytes > 8e6 ? 0.29 : 0.13);
   else {
     double per = table_bytes > 100e6 ? 0.42 : 0.2;
-    if (m >= 7 && pw >= 23) per = table_bytes > 200e6 ? 0.27 : 0.215;   // warps spread over the window (BankArgs::spread)
+    if (m >= 7 && pw >= 23)                                             // warps spread over the window (BankArgs::spread)
+      per = table_bytes > 200e6 ? 0.255 : table_bytes > 100e6 ? 0.19 : 0.135;
     g = (double)(m * (m - 1) / 2) * per * (pair ? 1.0 : 2.0);
   }
   return a > g ? a : g;

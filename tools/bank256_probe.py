@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""256 MB banks of same-shape windows whose trig table stays in L2 (TAB_GLOBAL): BASELINE config 3 as a bank
+of 64, and neighbours.  One JSON line per shape (device time per execute, plan resident, tables kept)."""
 import sys, os, json
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import torch, blackman_harris_win_b200 as bhw, cases
@@ -19,6 +22,6 @@ for name, d, nwin in shapes:
     plan = bhw.Plan(descs)
     out = torch.empty(plan.total, dtype=torch.int32, device="cuda")
     us = t(lambda: plan.execute(out=out))
-    print(json.dumps({"shape": name, "win_minor": os.environ.get("BHW_WIN_MINOR", "1"), "us": round(us, 1), "gsamples_per_s": round(plan.total / us / 1e3, 1),
+    print(json.dumps({"shape": name, "us": round(us, 1), "gsamples_per_s": round(plan.total / us / 1e3, 1),
                       "frac_hbm": round(plan.total * 4 / us / 1e3 / 6554.6, 3)}))
     plan.destroy()

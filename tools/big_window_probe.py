@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Single long windows (2^22 .. 2^26 points) over tables too large for shared memory, through a resident
+plan; includes ~15 us of Python/ctypes call overhead per execute.  One JSON object."""
 import sys, os, json
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import torch, blackman_harris_win_b200 as bhw, cases
@@ -21,4 +24,4 @@ for v, pw, dw, st in shapes:
     chk = int(out[: 1 << pw].to(torch.int64).sum().item())
     res.append({"v": v, "m": d.win_type, "pw": pw, "dw": dw, "st": st, "us": round(us, 1), "frac_hbm": round((4 << pw) / us / 1e3 / 6554.6, 3), "sum": chk})
     plan.destroy()
-print(json.dumps({"env": {k: os.environ.get(k) for k in ("BHW_SPREAD_MINM", "BHW_SPREAD_G", "BHW_SPREAD_SYNC")}, "res": res}))
+print(json.dumps({"res": res}))

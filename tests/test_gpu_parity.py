@@ -360,6 +360,24 @@ def test_banks_over_a_table_too_large_for_shared_memory():
         plan.destroy()
 
 
+def test_reference_selfcheck_criteria_on_the_gpu():
+    """The reference's own pass/fail criteria (hls/cordic/cordic_test.cpp:66-93,
+    hls/windows/window_test.cpp:93-216) applied to what the CUDA path generates at the reference's
+    widths - on top of, not instead of, the bit-exact comparisons above."""
+    import test_reference_selfchecks as R
+    s, c = bhw.sincos(bhw.variant_desc(1, 10, 16, model=bhw.MODEL_HLS))
+    es, ec = R.cordic_selfcheck_errors(s.cpu().numpy().astype(np.int64), c.cpu().numpy().astype(np.int64), 10, 16)
+    assert es < 10 and ec < 10
+    for win_type in sorted(R.SELFCHECK):
+        for algo in (bhw.ALGO_AUTO, bhw.ALGO_DIRECT, bhw.ALGO_TABLE):
+            d = bhw.variant_desc(cases.HLS_TYPES[win_type], 10, 24, model=bhw.MODEL_HLS, algo=algo)
+            out = bhw.generate(d).cpu().numpy().astype(np.int64)
+            if win_type == 2:        # the Hann centre sample wraps in the reference model itself
+                assert out[512] == -(1 << 23)
+                out[512] = (1 << 23) - 1
+            assert R.window_selfcheck_error(win_type, out, 10, 24) < 10, (win_type, algo)
+
+
 def test_host_entry_points():
     d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
     want = H.orc_window(d)

@@ -866,6 +866,9 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
     at.rom = a.rom;
     at.n0 = n0;
     at.count = count;
+    // whole window: evaluate the units once per sample pair (n, n + N/2)
+    at.pair = (n0 == 0 && count == N && N >= 8 && at.p.unit[0].pw == d->phi_width &&
+               (at.p.m == 2 || at.p.unit[1].pw == d->phi_width - 1)) ? 1u : 0u;
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct_taylor(at, (int32_t*)out_dev, stream);
   } else if (fast32) {

@@ -750,6 +750,44 @@ BHW_HD int32_t direct_taylor_sample(const DirectTayParams& p, const I2* __restri
   return (int32_t)(S << p.lsh) >> p.rsh;
 }
 
+// Samples n and n + N/2 from one evaluation of the units.  Half a window later the first unit's
+// phase has its quadrant advanced by two and the same low bits: the entity's quadrant mux then picks
+// the other one of (v, -v) (src/taylor_sincos.vhd:237-255) - nothing is assumed about v, so this holds
+// for the wrapping DSP48 branch too.  The second unit of bh_win_3term counts PHI_WIDTH-1 bits
+// (src/bh_win_3term.vhd:221-233): its phase, and with it b_2, is the same for both samples.
+template <int TMODE>
+BHW_HD void direct_taylor_pair(const DirectTayParams& p, const I2* __restrict__ rom, uint32_t n, int32_t& wa, int32_t& wb) {
+  uint32_t Sa = (uint32_t)p.S0, Sb = Sa;
+  {
+    const TayUnit& u = p.unit[0];
+    const uint32_t ph = n & ((1u << u.pw) - 1u);
+    const uint32_t q = ph >> (u.pw - 2);
+    int32_t vs, vc;
+    taylor_core_fast32<TMODE>(u, p.dw, rom, ph & ((1u << (u.pw - 2)) - 1u), vs, vc);
+    const int32_t v = (q & 1u) ? vs : vc;
+    const int32_t nv = TMODE == TMODE_DSP ? wrapb32((int32_t)(0u - (uint32_t)v), p.dw) : -v;
+    const bool neg = ((q + 1u) & 2u) != 0;
+    const int32_t ca = neg ? nv : v, cb = neg ? v : nv;
+    Sa -= (uint32_t)mulhi_rc(p.A[1], (int32_t)((uint32_t)ca << p.tshift), p.rc);
+    Sb -= (uint32_t)mulhi_rc(p.A[1], (int32_t)((uint32_t)cb << p.tshift), p.rc);
+  }
+  if (p.m > 2) {
+    const TayUnit& u = p.unit[1];
+    const uint32_t ph = n & ((1u << u.pw) - 1u);
+    const uint32_t q = ph >> (u.pw - 2);
+    int32_t vs, vc;
+    taylor_core_fast32<TMODE>(u, p.dw, rom, ph & ((1u << (u.pw - 2)) - 1u), vs, vc);
+    const int32_t v = (q & 1u) ? vs : vc;
+    const int32_t nv = TMODE == TMODE_DSP ? wrapb32((int32_t)(0u - (uint32_t)v), p.dw) : -v;
+    const int32_t c = ((q + 1u) & 2u) ? nv : v;
+    const uint32_t b = (uint32_t)mulhi_rc(p.A[2], (int32_t)((uint32_t)c << p.tshift), p.rc);
+    Sa += b;
+    Sb += b;
+  }
+  wa = (int32_t)(Sa << p.lsh) >> p.rsh;
+  wb = (int32_t)(Sb << p.lsh) >> p.rsh;
+}
+
 // ============================================================================================
 // cordic_atan2 (src/cordic_atan2.vhd:80-220)
 // ============================================================================================

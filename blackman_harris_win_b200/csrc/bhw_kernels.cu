@@ -394,8 +394,28 @@ k_direct_taylor(const __grid_constant__ DirectTayArgs a, int32_t* __restrict__ o
   const DirectTayParams& p = a.p;
   for (uint32_t i = threadIdx.x; i < p.rom_entries; i += blockDim.x) s_rom[i] = a.rom[i];
   __syncthreads();
-  const uint64_t quads = (a.count + 3) / 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (a.pair) {
+    // whole window: 4 consecutive samples of the first half and their partners half a window later
+    const uint64_t half = a.count / 2;
+    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < half / 4;
+         qd += (uint64_t)gridDim.x * blockDim.x) {
+      const uint64_t j = qd * 4;
+      const uint32_t n = (uint32_t)j + p.n_first;
+      int32_t va[4], vb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) direct_taylor_pair<TMODE>(p, s_rom, n + e, va[e], vb[e]);
+      if (aligned) {
+        __stcs(reinterpret_cast<int4*>(out + j), make_int4(va[0], va[1], va[2], va[3]));
+        __stcs(reinterpret_cast<int4*>(out + half + j), make_int4(vb[0], vb[1], vb[2], vb[3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { out[j + e] = va[e]; out[half + j + e] = vb[e]; }
+      }
+    }
+    return;
+  }
+  const uint64_t quads = (a.count + 3) / 4;
   for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads;
        qd += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t j = qd * 4;
@@ -607,7 +627,7 @@ cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t st
 
 cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream) {
   if (!a.count) return cudaSuccess;
-  const unsigned grid = grid_for(((a.count + 3) / 4 + 255) / 256, 8);
+  const unsigned grid = grid_for(((a.count / (a.pair ? 2 : 1) + 3) / 4 + 255) / 256, 8);
   const size_t smem = (size_t)a.p.rom_entries * sizeof(I2);  // <= 32 KB (LUT_SIZE <= 12)
   if (a.p.tmode == TMODE_ROM) k_direct_taylor<TMODE_ROM><<<grid, 256, smem, stream>>>(a, out);
   else if (a.p.tmode == TMODE_DSP) k_direct_taylor<TMODE_DSP><<<grid, 256, smem, stream>>>(a, out);

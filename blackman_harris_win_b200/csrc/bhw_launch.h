@@ -55,6 +55,8 @@ struct DirectTayArgs {
   const I2* rom;    // Taylor ROM (global)
   uint64_t n0;      // first sample (the stream offset lives in p.n_first)
   uint64_t count;
+  uint32_t pair;    // whole window (n0 = 0, count = N >= 8, bh_win_3term's second unit one bit narrower): one
+                    // evaluation serves samples n and n + N/2 (direct_taylor_pair)
 };
 
 struct SinCosArgs {

@@ -89,6 +89,20 @@ int hc_direct_taylor(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* ou
            : p.tmode == TMODE_DSP ? direct_taylor_sample<TMODE_DSP>(p, rom.data(), n)
                                   : direct_taylor_sample<TMODE_WIDE>(p, rom.data(), n);
   }
+  // the paired body (whole windows in the kernel) must give the same two samples
+  const uint64_t N = 1ull << d->phi_width;
+  if (p.unit[0].pw == d->phi_width && (p.m == 2 || p.unit[1].pw == d->phi_width - 1)) {
+    for (uint64_t j = 0; j < count; j++) {
+      const uint64_t pos = n0 + j, partner = (pos + N / 2) & (N - 1);
+      if (partner < n0 || partner >= n0 + count) continue;
+      const uint32_t n = (uint32_t)pos + p.n_first;
+      int32_t wa, wb;
+      if (p.tmode == TMODE_ROM) direct_taylor_pair<TMODE_ROM>(p, rom.data(), n, wa, wb);
+      else if (p.tmode == TMODE_DSP) direct_taylor_pair<TMODE_DSP>(p, rom.data(), n, wa, wb);
+      else direct_taylor_pair<TMODE_WIDE>(p, rom.data(), n, wa, wb);
+      if (wa != out[j] || wb != out[partner - n0]) return -101;
+    }
+  }
   return 0;
 }
 

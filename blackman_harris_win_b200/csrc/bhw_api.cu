@@ -875,6 +875,7 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
     // register-resident 32-bit stages, 128-bit stores
     a32.n0 = n0;
     a32.count = count;
+    a32.pair = (n0 == 0 && count == N && N >= 8 && a32.p.pw == d->phi_width) ? 1u : 0u;   // whole window: sample pairs
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct32(a32, (int32_t*)out_dev, stream);
   } else {

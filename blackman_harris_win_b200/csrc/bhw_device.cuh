@@ -661,6 +661,25 @@ BHW_HD int32_t direct32_sample(const Direct32Params& p, uint32_t n) {
   return (int32_t)(S << p.lsh) >> p.rsh;
 }
 
+// Samples n and n + N/2 from one set of CORDIC evaluations: half a window later the phase of an
+// odd harmonic has its quadrant advanced by two on the same low bits, so the output mux above picks
+// the negated value (direct32_cos: -v instead of v); the phase of an even harmonic is unchanged.
+template <int NXY>
+BHW_HD void direct32_pair(const Direct32Params& p, uint32_t n, int32_t& wa, int32_t& wb) {
+  const uint32_t pmask = (1u << p.pw) - 1u;
+  uint32_t Sa = (uint32_t)p.S0, Sb = Sa;
+  for (int k = 1; k < p.m; ++k) {
+    const uint32_t km = p.kmul[k];
+    const int32_t c = direct32_cos<NXY>(p, (km * n) & pmask);
+    const uint32_t ba = (uint32_t)mulhi_rc(p.A[k], c << p.tshift, p.rc);
+    const uint32_t bb = (km & 1u) ? (uint32_t)mulhi_rc(p.A[k], (-c) << p.tshift, p.rc) : ba;
+    Sa = (k & 1) ? Sa - ba : Sa + ba;
+    Sb = (k & 1) ? Sb - bb : Sb + bb;
+  }
+  wa = (int32_t)(Sa << p.lsh) >> p.rsh;
+  wb = (int32_t)(Sb << p.lsh) >> p.rsh;
+}
+
 // ============================================================================================
 // Register-resident 32-bit direct evaluation, TAYLOR source (k_direct_taylor)
 // ============================================================================================

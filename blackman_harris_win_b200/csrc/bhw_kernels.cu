@@ -353,9 +353,48 @@ template <int NXY>
 __global__ void __launch_bounds__(256)
 k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
   const Direct32Params& p = a.p;
-  const uint64_t quads = (a.count + 3) / 4;
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const uint32_t pmask = (1u << p.pw) - 1u;
+  if (a.pair) {
+    // whole window: 4 consecutive samples of the first half and their partners half a window later
+    const uint64_t half = a.count / 2;
+    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < half / 4;
+         qd += (uint64_t)gridDim.x * blockDim.x) {
+      const uint64_t j = qd * 4;
+      const uint32_t n = (uint32_t)j + p.n_first;
+      uint32_t Sa[4], Sb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { Sa[e] = (uint32_t)p.S0; Sb[e] = Sa[e]; }
+      for (int k = 1; k < p.m; ++k) {
+        const uint32_t km = p.kmul[k];
+        const int32_t Ak = p.A[k];
+        const bool odd = (km & 1u) != 0;      // odd harmonic: the partner sees the negated cosine
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int32_t c = direct32_cos<NXY>(p, (km * (n + e)) & pmask);
+          const uint32_t ba = (uint32_t)mulhi_rc(Ak, c << p.tshift, p.rc);
+          const uint32_t bb = odd ? (uint32_t)mulhi_rc(Ak, (-c) << p.tshift, p.rc) : ba;
+          Sa[e] = (k & 1) ? Sa[e] - ba : Sa[e] + ba;
+          Sb[e] = (k & 1) ? Sb[e] - bb : Sb[e] + bb;
+        }
+      }
+      int32_t va[4], vb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        va[e] = (int32_t)(Sa[e] << p.lsh) >> p.rsh;
+        vb[e] = (int32_t)(Sb[e] << p.lsh) >> p.rsh;
+      }
+      if (aligned) {
+        __stcs(reinterpret_cast<int4*>(out + j), make_int4(va[0], va[1], va[2], va[3]));
+        __stcs(reinterpret_cast<int4*>(out + half + j), make_int4(vb[0], vb[1], vb[2], vb[3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { out[j + e] = va[e]; out[half + j + e] = vb[e]; }
+      }
+    }
+    return;
+  }
+  const uint64_t quads = (a.count + 3) / 4;
   for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads;
        qd += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t j = qd * 4;
@@ -613,7 +652,7 @@ static void launch_direct32_t(const Direct32Args& a, int32_t* out, unsigned grid
 
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream) {
   if (!a.count) return cudaSuccess;
-  const unsigned grid = grid_for(((a.count + 3) / 4 + 255) / 256, 8);
+  const unsigned grid = grid_for(((a.count / (a.pair ? 2 : 1) + 3) / 4 + 255) / 256, 8);
   switch (a.p.n_xy) {  // DAT_WIDTH 8..31 (cordic_dds: DW-1 stages; HLS: NW stages)
 #define BHW_D32(N) case N: launch_direct32_t<N>(a, out, grid, stream); break;
     BHW_D32(7) BHW_D32(8) BHW_D32(9) BHW_D32(10) BHW_D32(11) BHW_D32(12) BHW_D32(13) BHW_D32(14)

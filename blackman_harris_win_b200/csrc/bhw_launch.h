@@ -48,6 +48,8 @@ struct Direct32Args {
   Direct32Params p;
   uint64_t n0;      // first sample (the stream offset lives in p.n_first)
   uint64_t count;
+  uint32_t pair;    // whole window (n0 = 0, count = N >= 8): one set of CORDIC evaluations serves samples n and
+                    // n + N/2 (direct32_pair)
 };
 
 struct DirectTayArgs {

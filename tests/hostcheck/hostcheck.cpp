@@ -129,6 +129,20 @@ int hc_direct32(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
     }
     if (direct32_sample<0>(p, n) != out[j]) return -100;   // unrolled and looped forms agree
   }
+  // the paired body (whole windows in the kernel) must give the same two samples
+  const uint64_t N = 1ull << d->phi_width;
+  if (p.pw == d->phi_width) {
+    for (uint64_t j = 0; j < count; j++) {
+      const uint64_t pos = n0 + j, partner = (pos + N / 2) & (N - 1);
+      if (partner < n0 || partner >= n0 + count) continue;
+      int32_t wa, wb;
+      const uint32_t n = (uint32_t)pos + p.n_first;
+      if (p.n_xy == 15) direct32_pair<15>(p, n, wa, wb);
+      else if (p.n_xy == 16) direct32_pair<16>(p, n, wa, wb);
+      else direct32_pair<0>(p, n, wa, wb);
+      if (wa != out[j] || wb != out[partner - n0]) return -102;
+    }
+  }
   return 0;
 }
 

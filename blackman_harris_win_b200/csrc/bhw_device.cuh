@@ -398,41 +398,49 @@ BHW_HD void mad64_pm1(int64_t& acc, int64_t v, int32_t s) {
 // each as IMAD.WIDE + IMAD (mad64_pm1; the atan word arrives split the same way, `romh`).  Per
 // stage: 8 alu instructions (sign mask, s, 2 x (funnel shift, high shift, LEA.HI)) and 7 fma ones,
 // against 22 + 6 for the select-based form.
+// Two phases per evaluation of z: quadrants 0 and 1 run on t = "00" & low, quadrants 3 and 2 on
+// t = "11" & low (src/cordic_dds48.vhd:170-216) - the same z, hence the same rotation directions,
+// for two different start vectors.  `hi` = 0: entries of quadrants 0 (a) and 1 (b); 1: quadrants 3
+// (a) and 2 (b).  Saves the z update (a third of the fma work of a stage) for every second entry.
 template <int NXY>
-BHW_HD void cordic_core_inq_u(const SrcParams& p, const int64_t* __restrict__ rom64, const int32_t* __restrict__ romh,
-                              int q, uint64_t low, int64_t& vs, int64_t& vc) {
+BHW_HD void cordic_core_inq_u2(const SrcParams& p, const int64_t* __restrict__ rom64, const int32_t* __restrict__ romh,
+                               int hi, uint64_t low, int64_t& ca, int64_t& cb) {
   const int pw = p.pw;
   const int az = 64 - p.zw;
   const int64_t G = (int64_t)p.gain;
-  int64_t X = G, Y = 0;
-  uint64_t t = low | ((uint64_t)q << (pw - 2));
-  if (q == 1) { t = low; X = 0; Y = -G; }
-  else if (q == 2) { t = low | (3ull << (pw - 2)); X = 0; Y = G; }
+  int64_t Xa = G, Ya = 0;                    // quadrants 0 / 3
+  int64_t Xb = 0, Yb = hi ? G : -G;          // quadrant 2: (0, +G); quadrant 1: (0, -G)
+  const uint64_t t = low | (hi ? (3ull << (pw - 2)) : 0ull);
   int64_t Z = (int64_t)(t << (p.z_lshift + az));
 #pragma unroll
   for (int i = 0; i < NXY; ++i) {
     const int32_t m = (int32_t)(Z >> 63);
     const int32_t s = 2 * m + 1, ns = mad32(m, -2, -1);
-    const int64_t Xs = X >> i, Ys = Y >> i;   // old values on both sides
-    mad64_pm1(X, Ys, s);
-    mad64_pm1(Y, Xs, ns);
-    madw(Z, (int32_t)(uint32_t)(uint64_t)rom64[i], ns);   // rom64[i] = 0 for the last stage (z advances NXY-1 times)
+    const int64_t Xsa = Xa >> i, Ysa = Ya >> i, Xsb = Xb >> i, Ysb = Yb >> i;
+    mad64_pm1(Xa, Ysa, s);
+    mad64_pm1(Ya, Xsa, ns);
+    mad64_pm1(Xb, Ysb, s);
+    mad64_pm1(Yb, Xsb, ns);
+    madw(Z, (int32_t)(uint32_t)(uint64_t)rom64[i], ns);
     madhi(Z, romh[i], ns);
   }
-  vs = Y >> p.out_shift;
-  vc = X >> p.out_shift;
+  ca = Xa >> p.out_shift;
+  cb = Xb >> p.out_shift;
 }
 
-// Work item `e` (one phase) of an input-quadrant job with NXY stages: the dedicated kernel for large
-// cordic_dds48 / cordic_dds_scaled tables; same entry as table_build_item.
+// Work item `e` of the dedicated input-quadrant kernel when it takes two entries per item
+// (e < entries / 2): see cordic_core_inq_u2.
 template <int NXY>
-BHW_HD void table_build_item_inq_u(const TabJob& job, uint32_t e) {
+BHW_HD void table_build_item_inq_u2(const TabJob& job, uint32_t e) {
   const SrcParams& p = job.sp;
-  int64_t s, c;
-  const int q = (int)(e >> (p.pw - 2));
-  const uint64_t low = (uint64_t)(e & ((1u << (p.pw - 2)) - 1u));
-  cordic_core_inq_u<NXY>(p, job.rom64, job.rom32, q, low, s, c);
-  job.tab[e] = (int32_t)(wrapb(c, p.outw) * ((int64_t)1 << job.tshift));
+  const uint32_t Q = 1u << (p.pw - 2);
+  const int hi = (int)(e >> (p.pw - 2));
+  const uint32_t low = e & (Q - 1u);
+  int64_t ca, cb;
+  cordic_core_inq_u2<NXY>(p, job.rom64, job.rom32, hi, (uint64_t)low, ca, cb);
+  const int64_t t = (int64_t)1 << job.tshift;
+  job.tab[(hi ? 3u * Q : 0u) + low] = (int32_t)(wrapb(ca, p.outw) * t);
+  job.tab[(hi ? 2u * Q : Q) + low] = (int32_t)(wrapb(cb, p.outw) * t);
 }
 
 // Work item `e` of a job whose core is the 32-bit one with NXY stages (the dedicated kernel for

@@ -58,8 +58,9 @@ template <int NXY>
 __global__ void __launch_bounds__(256)
 k_table_build_inq_u(const __grid_constant__ TabJob job) {
   asm volatile("griddepcontrol.launch_dependents;");
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.work; i += gridDim.x * blockDim.x)
-    table_build_item_inq_u<NXY>(job, i);
+  // two entries per thread: quadrants 0/1 and 3/2 share their z (cordic_core_inq_u2)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.work / 2; i += gridDim.x * blockDim.x)
+    table_build_item_inq_u2<NXY>(job, i);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -546,7 +547,7 @@ cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total
 
 cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream) {
   if (!j.work) return cudaSuccess;
-  const unsigned grid = grid_for(((uint64_t)j.work + 255) / 256, 8);
+  const unsigned grid = grid_for(((uint64_t)j.work / (j.sp.kind == SRC_INQ ? 2 : 1) + 255) / 256, 8);
   if (j.sp.kind == SRC_INQ) {
     switch (j.sp.n_xy) {
       case 16: k_table_build_inq_u<16><<<grid, 256, 0, stream>>>(j); break;

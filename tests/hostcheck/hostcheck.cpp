@@ -37,11 +37,12 @@ void build_table(const SrcParams& sp, const std::vector<I2>& rom, HostTable& t, 
     TabJob ju = j;
     ju.tab = again.data();
     for (uint32_t e = 0; e < ju.work; e++) {
-      if (ju.sp.kind == SRC_INQ) {
-        if (ju.sp.n_xy == 16) table_build_item_inq_u<16>(ju, e);
-        else if (ju.sp.n_xy == 17) table_build_item_inq_u<17>(ju, e);
-        else if (ju.sp.n_xy == 24) table_build_item_inq_u<24>(ju, e);
-        else table_build_item_inq_u<32>(ju, e);
+      if (ju.sp.kind == SRC_INQ) {   // the kernel takes two entries per item (quadrants sharing their z)
+        if (e >= ju.work / 2) break;
+        if (ju.sp.n_xy == 16) table_build_item_inq_u2<16>(ju, e);
+        else if (ju.sp.n_xy == 17) table_build_item_inq_u2<17>(ju, e);
+        else if (ju.sp.n_xy == 24) table_build_item_inq_u2<24>(ju, e);
+        else table_build_item_inq_u2<32>(ju, e);
       }
       else if (ju.fast == TABCORE_32BIAS) table_build_item_u<31, true>(ju, e);
       else if (ju.sp.n_xy == 15) table_build_item_u<15, false>(ju, e);

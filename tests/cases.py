@@ -68,3 +68,42 @@ def edge_coeff_descs():
                         out.append(bhw.make_desc(m, 9, dw, [a0] + [ak] * (m - 1)))
             out.append(bhw.make_desc(m, 9, dw, [q + q // 2] + [q - 1] + [q // 8] * (m - 2)))
     return out
+
+
+def random_descs(count, seed, max_pw=12, models=("rtl", "hls")):
+    """Seeded random descriptors over everything the library accepts: entity, widths, source, model,
+    stream offset, strategy, and ports drawn from {full-range random, small, real-window-like,
+    extremes} so that every tail route (32-bit, bounded 32-bit at DAT_WIDTH 31..32, 64-bit, generic)
+    is hit."""
+    import random
+    rng = random.Random(seed)
+    out = []
+    while len(out) < count:
+        m = rng.choice((2, 3, 4, 5, 7))
+        pw = rng.randint(4, max_pw)
+        model = rng.choice(models)
+        if model == "hls":
+            dw = rng.choice((8, 12, 16, 17, 24, 30, 31, 32))
+            st, mdl = bhw.SIN_CORDIC, bhw.MODEL_HLS
+        else:
+            dw = rng.choice((8, 9, 12, 16, 17, 18, 19, 24, 30, 31, 32, 33, 40, 47))
+            st, mdl = rng.choice((bhw.SIN_CORDIC, bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR)), bhw.MODEL_RTL
+        lo, hi = -(1 << (dw - 1)), (1 << (dw - 1)) - 1
+        kind = rng.choice(("full", "small", "window", "extreme", "quarter"))
+        if kind == "full":
+            aa = [rng.randint(lo, hi) for _ in range(m)]
+        elif kind == "small":
+            aa = [rng.randint(-1000, 1000) for _ in range(m)]
+        elif kind == "window":       # positive, decaying, summing to about the CORDIC full scale
+            aa = [int(hi * 0.45 / (k + 1) ** 1.5) + rng.randint(-3, 3) for k in range(m)]
+        elif kind == "quarter":      # around the 2^(DW-2) limit of the bounded 32-bit tail
+            q = 1 << (dw - 2)
+            aa = [rng.choice((q - 1, q, -q, -q + 1, q // 2, 0)) for _ in range(m)]
+        else:
+            aa = [rng.choice((lo, hi, 0, -1, 1, lo + 1)) for _ in range(m)]
+        d = bhw.make_desc(m, pw, dw, aa, sin_type=st, model=mdl, stream_offset=rng.randint(0, 1),
+                          lut_size=rng.choice((0, 0, 4, 7, 9)) if st == bhw.SIN_TAYLOR else 0,
+                          algo=rng.choice((bhw.ALGO_AUTO, bhw.ALGO_AUTO, bhw.ALGO_TABLE, bhw.ALGO_DIRECT)))
+        if bhw.validate(d) == 0:
+            out.append(d)
+    return out

@@ -378,6 +378,29 @@ def test_reference_selfcheck_criteria_on_the_gpu():
             assert R.window_selfcheck_error(win_type, out, 10, 24) < 10, (win_type, algo)
 
 
+def test_random_descriptors_one_shot_and_in_one_plan():
+    """Seeded fuzz (cases.random_descs): every descriptor through the one-shot entry point, and all
+    32-bit ones of one seed together in a single plan, against the oracle."""
+    descs = cases.random_descs(300, seed=20260102)
+    for d in descs:
+        assert np.array_equal(gpu_window(d), H.orc_window(d)), d
+    batch, tay = [], None
+    for d in descs:
+        if d.dat_width > 32 or len(batch) == 120:
+            continue
+        if d.sin_type == bhw.SIN_TAYLOR and d.model == bhw.MODEL_RTL:   # one Taylor ROM (DAT_WIDTH, LUT_SIZE) per plan
+            tay = tay or (d.dat_width, d.lut_size)
+            if (d.dat_width, d.lut_size) != tay:
+                continue
+        batch.append(d.copy(algo=bhw.ALGO_AUTO))
+    want = H.orc_batch(batch, 0, bhw.batch_total(batch))
+    assert np.array_equal(bhw.generate_batch(batch).cpu().numpy().astype(np.int64), want)
+    plan = bhw.Plan(batch)
+    b, c = 1234, bhw.batch_total(batch) - 5000
+    assert np.array_equal(plan.execute(b, c).cpu().numpy().astype(np.int64), want[b:b + c])
+    plan.destroy()
+
+
 def test_host_entry_points():
     d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
     want = H.orc_window(d)

@@ -132,6 +132,13 @@ def test_wide_windows_take_the_32_bit_tail_when_the_sum_provably_fits():
     assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 40, [1, 2, 3, 4]))) == GEN
 
 
+def test_random_descriptors():
+    """Seeded fuzz over entity x widths x source x model x ports (cases.random_descs): every kernel
+    body that accepts the descriptor must reproduce the oracle."""
+    for d in cases.random_descs(400, seed=20260101):
+        check(d, 1024)
+
+
 def test_stream_offset_is_a_rotation():
     for d in (bhw.make_desc(2, 8, 16, [17808, 14959]), bhw.make_desc(3, 14, 24, [7046424, 8388600, 1342176],
                                                                   sin_type=bhw.SIN_TAYLOR)):

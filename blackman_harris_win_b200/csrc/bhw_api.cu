@@ -898,6 +898,21 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
   return BHW_OK;
 }
 
+// BHW_ALGO_AUTO, one-shot request: does one launch of a register-resident direct kernel beat the
+// table path (table build + synthesis, two launches and a plan: ~11 us per call however short)?
+// A TAYLOR window of any length: a Taylor evaluation (ROM look-up + two multiplies) per sample is
+// cheaper than building, storing and re-reading tables as large as the window.  CORDIC: the direct
+// kernel's work is count x (M-1) evaluations of ~DAT_WIDTH stages, halved for a whole window (sample
+// pairs); measured crossover (tools/call_latency --route, us per call direct / table): 4-term DW 17
+// N=2^19 7.3 / 10.9, 2^20 12.3 / 10.9; 2-term DW 16 2^21 8.2 / 11.3, 2^22 14.4 / 12.8; 7-term DW 24
+// 2^18 10.1 / 12.9, 2^19 14.4 / 13.4; 5-term DW 24 2^19 10.3 / 11.5, 2^20 18.5 / 13.4.
+static bool auto_prefers_direct(const bhw_desc* d, uint64_t n0, uint64_t count) {
+  if (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR) return true;
+  const bool whole = n0 == 0 && count == (1ull << d->phi_width);
+  const uint64_t work = count * (uint64_t)(d->win_type - 1) * (uint64_t)d->dat_width * (whole ? 1u : 2u);
+  return work <= 52000000ull;
+}
+
 }  // namespace bhw
 
 using namespace bhw;
@@ -912,13 +927,7 @@ int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, 
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
   if (!out_dev && count) return BHW_E_NULL;
   if (d->dat_width > 32 || d->algo == BHW_ALGO_DIRECT) return run_direct(d, n0, count, out_dev, (cudaStream_t)stream);
-  if (d->algo == BHW_ALGO_AUTO &&
-      (count * (uint64_t)(d->win_type - 1) <= 3u * 65536u ||
-       (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR))) {
-    // a short one-shot request: one launch of the register-resident kernel beats building a
-    // table first (measured: N = 65536 4-term 21 us vs 58 us per call); a TAYLOR window of any
-    // length: a Taylor evaluation (ROM look-up + two multiplies) per sample is cheaper than
-    // building, storing and re-reading tables as large as the window
+  if (d->algo == BHW_ALGO_AUTO && auto_prefers_direct(d, n0, count)) {
     st = run_direct(d, n0, count, out_dev, (cudaStream_t)stream, true);
     if (st != 1) return st;
   }
@@ -935,8 +944,7 @@ int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t c
   // a short request (one staging chunk) that bhw_generate would send to a register-resident
   // direct kernel: one launch + one copy instead of planning, table build and two launches
   if (count && d->dat_width <= 32 && d->algo == BHW_ALGO_AUTO && count * 4 <= kHostChunkBytes &&
-      (count * (uint64_t)(d->win_type - 1) <= 3u * 65536u ||
-       (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR))) {
+      auto_prefers_direct(d, n0, count)) {
     int dev;
     if ((st = current_device(&dev))) return st;
     DeviceState& ds = g_dev[dev];

@@ -50,6 +50,7 @@ struct Direct32Args {
   uint64_t count;
   uint32_t pair;    // whole window (n0 = 0, count = N >= 8): one set of CORDIC evaluations serves samples n and
                     // n + N/2 (direct32_pair)
+  uint32_t narrow;  // short request: one sample (pair) per thread instead of four
 };
 
 struct DirectTayArgs {

@@ -42,9 +42,28 @@ static bhw_desc make(int win_type, int pw, int dw, int variant, int sin_type) {
   return d;
 }
 
-int main() {
+int main(int argc, char** argv) {
   void* out = nullptr;
   if (cudaMalloc(&out, 64u << 20) != cudaSuccess) { fprintf(stderr, "no CUDA device\n"); return 1; }
+  if (argc > 1 && !strcmp(argv[1], "--route")) {
+    // where BHW_ALGO_AUTO should switch from the direct kernel to the table path: whole windows of
+    // PHI_WIDTH 14..22 through each strategy, one JSON line per entity
+    const struct { const char* name; int m, dw, variant; } ent[] = {{"hamming_dw16", 2, 16, 1}, {"bh3_dw16", 3, 16, 4},
+      {"bh4_dw17", 4, 17, 6}, {"bh5_dw24", 5, 24, 9}, {"bh7_dw24", 7, 24, 10}};
+    for (const auto& e : ent) {
+      printf("{\"entity\": \"%s\", \"us_per_call [auto, table, direct]\": {", e.name);
+      for (int pw = 14; pw <= 22; pw++) {
+        bhw_desc d = make(e.m, pw, e.dw, e.variant, BHW_SIN_CORDIC);
+        double t[3];
+        const int algos[3] = {BHW_ALGO_AUTO, BHW_ALGO_TABLE, BHW_ALGO_DIRECT};
+        for (int a = 0; a < 3; a++) { d.algo = algos[a]; t[a] = time_calls(d, out, 1ull << pw, 300); }
+        printf("%s\"%d\": [%.2f, %.2f, %.2f]", pw > 14 ? ", " : "", pw, t[0], t[1], t[2]);
+      }
+      printf("}}\n");
+    }
+    cudaFree(out);
+    return 0;
+  }
   const bhw_desc c1 = make(2, 10, 16, 1, BHW_SIN_CORDIC);      // config 1: Hamming N=1024 DW=16
   const bhw_desc c2 = make(4, 16, 17, 6, BHW_SIN_CORDIC);      // config 2: BH4 N=65536 DW=17
   const bhw_desc c3 = make(7, 20, 32, 10, BHW_SIN_CORDIC48);   // config 3: BH7 N=1M DW=32 cordic_dds48

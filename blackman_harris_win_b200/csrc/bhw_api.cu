@@ -631,7 +631,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       // fewer terms measured no different (they are not bound by the L2 -> L1 gather traffic)
       const uint32_t G = 30u;
       ba.spread = (!ntiles && run.tab_mode == TAB_GLOBAL && ba.nwin == 1 && run.sh.lin && run.sh.m >= 7 &&
-                   log_tpw < 32 && (1ull << log_tpw) >= (uint64_t)G * 148u) ? G : 0u;
+                   log_tpw < 32 && (1ull << log_tpw) >= (uint64_t)G * (uint64_t)device_sm_count()) ? G : 0u;
     }
     cudaStream_t ls = fan.next();
     cudaError_t ce;

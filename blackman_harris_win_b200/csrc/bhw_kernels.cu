@@ -549,6 +549,8 @@ static int sm_count() {
   return g_sm_count[dev];
 }
 
+int device_sm_count() { return sm_count(); }
+
 // grid sized as a multiple of the SM count, capped at `per_sm` resident CTAs per SM
 static unsigned grid_for(uint64_t ctas_needed, int per_sm) {
   const uint64_t cap = (uint64_t)sm_count() * (uint64_t)per_sm;

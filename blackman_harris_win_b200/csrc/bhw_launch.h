@@ -82,6 +82,7 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
 // table read)
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl = false);
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
+int device_sm_count();     // SMs of the current device (148 on B200)
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream);
 cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream);

@@ -941,6 +941,21 @@ constexpr int kBankJ = 8;               // samples per lane and tile (per half w
 constexpr int kBankTile = 32 * kBankJ;  // samples per warp tile (per half when paired)
 constexpr int kBankTileLog2 = 8;
 
+// Tile walks of the bank kernel over tables that stay in L2 (bhw_kernels.cu, k_synth_bank).
+// Spread walk of one window of U tiles: warp j of G owns tiles [U*j/G, U*(j+1)/G) and takes the i-th
+// of them at step i; the steps 0 .. spread_steps()-1 are split over the CTAs of the grid.
+BHW_HD uint32_t spread_steps(uint32_t U, uint32_t G) { return (U + G - 1) / G; }
+BHW_HD bool spread_tile(uint32_t U, uint32_t G, uint32_t warp, uint32_t step, uint32_t* tile) {
+  const uint32_t b0 = (uint32_t)((uint64_t)U * warp / G), b1 = (uint32_t)((uint64_t)U * (warp + 1) / G);
+  *tile = b0 + step;
+  return warp < G && b0 + step < b1;
+}
+// Window-minor walk of a bank of nwin windows: unit u is tile u / nwin of window u % nwin.
+BHW_HD void win_minor_unit(uint32_t u, uint32_t nwin, uint32_t* w, uint32_t* tile) {
+  *tile = u / nwin;
+  *w = u - *tile * nwin;
+}
+
 // Do all samples of the tile starting at sample nbase see, for every harmonic, a phase in one
 // and the same half-period?  (TAB_SMEM_HALF only; needs 127*kstep < 2^31, guaranteed by the host.)
 template <int M>

@@ -258,7 +258,8 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     // again: 2.7 GB per 256 MB of 7-term output, L2 82 % busy).
     const uint32_t nwin = a.nwin;
     for (uint64_t u = u0 + warp; u < u1; u += kBankWarps) {
-      const uint32_t t = (uint32_t)u / nwin, w = (uint32_t)u - t * nwin;
+      uint32_t t, w;
+      win_minor_unit((uint32_t)u, nwin, &w, &t);
       load_ports(w, cur);
       do_tile(cur, w, t);
     }
@@ -276,13 +277,14 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
     const uint32_t G = a.spread;
     if (warp < G) {
       const uint32_t Ut = (uint32_t)U;
-      const uint32_t b0 = (uint32_t)((uint64_t)Ut * warp / G), b1 = (uint32_t)((uint64_t)Ut * (warp + 1) / G);
-      const uint32_t L = (Ut + G - 1) / G;
+      const uint32_t L = spread_steps(Ut, G);
       const uint32_t i0 = (uint32_t)((uint64_t)L * blockIdx.x / gridDim.x);
       const uint32_t i1 = (uint32_t)((uint64_t)L * (blockIdx.x + 1) / gridDim.x);
       load_ports(0, cur);
-      for (uint32_t i = i0; i < i1; ++i)
-        if (b0 + i < b1) do_tile(cur, 0, b0 + i);
+      for (uint32_t i = i0; i < i1; ++i) {
+        uint32_t t;
+        if (spread_tile(Ut, G, warp, i, &t)) do_tile(cur, 0, t);
+      }
     }
     return;
   }

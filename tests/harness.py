@@ -210,6 +210,7 @@ def hostcheck():
     L.hc_bank.argtypes = [D, I64P, C.c_uint64, C.c_int, C.c_int]
     L.hc_source_antisymmetric.argtypes = [D]
     L.hc_tail_mode.argtypes = [D]
+    L.hc_walk.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     L.hc_lin_tiles.argtypes = [C.c_int]
     L.hc_lin_tiles.restype = C.c_uint64
     return L

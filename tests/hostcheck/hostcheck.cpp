@@ -325,6 +325,45 @@ int hc_source_antisymmetric(const bhw_desc* d) {
   return source_antisymmetric(canonical_source(src[0], &drop)) ? 1 : 0;
 }
 
+// The bank kernel's tile walks, replayed with the kernel's own index helpers: every (window, tile) of
+// the launch must be visited exactly once.  mode 0: spread walk of one window of U tiles over G warps
+// and `grid` CTAs; mode 1: window-minor walk of nwin = G windows of U tiles each over `grid` CTAs of
+// 32 warps.  Returns 0, or the number of units visited a wrong number of times.
+int hc_walk(int mode, uint32_t U, uint32_t G, uint32_t grid) {
+  const uint32_t warps = 32;
+  if (mode == 0) {
+    std::vector<uint8_t> seen(U, 0);
+    const uint32_t L = spread_steps(U, G);
+    for (uint32_t cta = 0; cta < grid; cta++) {
+      const uint32_t i0 = (uint32_t)((uint64_t)L * cta / grid), i1 = (uint32_t)((uint64_t)L * (cta + 1) / grid);
+      for (uint32_t warp = 0; warp < warps; warp++)
+        for (uint32_t i = i0; i < i1; i++) {
+          uint32_t t;
+          if (spread_tile(U, G, warp, i, &t)) { if (t >= U) return -1; seen[t]++; }
+        }
+    }
+    int bad = 0;
+    for (uint32_t t = 0; t < U; t++) bad += seen[t] != 1;
+    return bad;
+  }
+  const uint32_t nwin = G;
+  const uint64_t units = (uint64_t)nwin * U;
+  std::vector<uint8_t> seen(units, 0);
+  for (uint32_t cta = 0; cta < grid; cta++) {
+    const uint64_t u0 = units * cta / grid, u1 = units * (cta + 1) / grid;
+    for (uint32_t warp = 0; warp < warps; warp++)
+      for (uint64_t u = u0 + warp; u < u1; u += warps) {
+        uint32_t w, t;
+        win_minor_unit((uint32_t)u, nwin, &w, &t);
+        if (w >= nwin || t >= U) return -1;
+        seen[(uint64_t)w * U + t]++;
+      }
+  }
+  int bad = 0;
+  for (uint64_t i = 0; i < units; i++) bad += seen[i] != 1;
+  return bad;
+}
+
 // which synthesis tail the planner picks: 0 = 32-bit, 1 = 64-bit, 2 = generic body
 int hc_tail_mode(const bhw_desc* d) {
   WinParams wp; SrcParams src[2];

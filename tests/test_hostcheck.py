@@ -132,6 +132,21 @@ def test_wide_windows_take_the_32_bit_tail_when_the_sum_provably_fits():
     assert hc.hc_tail_mode(C.byref(bhw.make_desc(4, 12, 40, [1, 2, 3, 4]))) == GEN
 
 
+def test_bank_kernel_tile_walks_visit_every_tile_once():
+    """The spread walk (one long window, warps of a CTA spread over the window) and the window-minor walk
+    (a bank over one L2-resident table) are index permutations: replayed on the CPU with the kernel's own
+    helpers, every tile of every window must come up exactly once, for grids that do and do not divide the work."""
+    hc = H.hostcheck()
+    for U in (4440, 4441, 8192, 16384, 32768, 100003):
+        for G in (30, 24, 15, 32, 7):
+            for grid in (148, 132, 1, 37):
+                assert hc.hc_walk(0, U, G, grid) == 0, (U, G, grid)
+    for U in (1, 2, 64, 1000):
+        for nwin in (2, 3, 5, 33, 64, 257):
+            for grid in (148, 1, 37, 7):
+                assert hc.hc_walk(1, U, nwin, grid) == 0, (U, nwin, grid)
+
+
 def test_random_descriptors():
     """Seeded fuzz over entity x widths x source x model x ports (cases.random_descs): every kernel
     body that accepts the descriptor must reproduce the oracle."""

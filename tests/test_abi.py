@@ -154,5 +154,9 @@ def test_cost_balanced_shards_tile_the_batch():
     total = bhw.batch_total(sweep)
     _, c_last = bhw.shard_range_cost(sweep, 7, 8)
     assert c_last < total // 16
+    # a cut that would land just inside a long window is moved onto its boundary: with 8 ranks the last rank
+    # gets exactly the 2^26-point 7-term window (whole windows run through the paired / spread walks)
+    b_last, c_last = bhw.shard_range_cost(sweep, 7, 8)
+    assert c_last == 1 << 26 and b_last == total - (1 << 26)
     with pytest.raises(bhw.BhwError):
         bhw.shard_range_cost(sweep, 8, 8)

@@ -890,6 +890,8 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct32(a32, (int32_t*)out_dev, stream);
   } else {
+    uint32_t flip = 0;
+    a.pair_flip = (n0 == 0 && count == N && N >= 8 && direct_pair_flip(a.wp, a.src, &flip)) ? (0x80000000u | flip) : 0u;
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct_window(a, out_dev, stream);
   }

@@ -493,6 +493,45 @@ BHW_HD int64_t direct_sample_core(const WinParams& wp, const SrcParams* src, con
   return tail_generic(wp, cosv);
 }
 
+// Samples n and n + N/2 of a window from one evaluation per harmonic (whole-window requests of
+// k_direct_window).  Half a window later a harmonic's phase has either not moved (even harmonics; the
+// second, PHI_WIDTH-1 bit unit of bh_win_3term) or advanced by half the source's period - then the
+// quadrant has advanced by two on the same low phase bits and the output mux picks the other value
+// of each (v, negated v) pair, which quadrant_fix gives without a second shift-add evaluation.  Bit k
+// of `flip` marks the harmonics of the second kind (direct_pair_flip() decides, and excludes the
+// input-quadrant CORDICs, which have no such mux).
+BHW_HD void direct_sample_core_pair(const WinParams& wp, const SrcParams* src, const SrcCore* sc, const I2* rom,
+                                    uint64_t n, uint32_t flip, int64_t& wa, int64_t& wb) {
+  int64_t ca[BHW_MAX_TERMS], cb[BHW_MAX_TERMS];
+  ca[0] = cb[0] = 0;
+  for (int k = 1; k < wp.m; ++k) {
+    const TermParams& t = wp.term[k - 1];
+    const SrcParams& p = src[t.src];
+    const SrcCore& c = sc[t.src];
+    const uint64_t ph = ((uint64_t)t.kmul * n) & t.ph_mask;
+    const int pw = p.pw;
+    const int q = (int)(ph >> (pw - 2));
+    const uint64_t low = ph & ((1ull << (pw - 2)) - 1);
+    int64_t vs, vc;
+    if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom, (uint32_t)low, vs, vc);
+    else if (c.core == TABCORE_32) { int32_t s32, c32; cordic_core_fast32<false>(p, c.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+    else if (c.core == TABCORE_32BIAS) { int32_t s32, c32; cordic_core_fast32<true>(p, c.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+    else if (c.core == TABCORE_A64) cordic_core_aligned64(p, c.rom64, q, low, vs, vc);
+    else cordic_core_generic(p, q, low, vs, vc);
+    int64_t s0, c0, s1, c1;
+    if (p.kind != SRC_INQ) {
+      quadrant_fix(q, p.negw, vs, vc, s0, c0);
+      quadrant_fix((q + 2) & 3, p.negw, vs, vc, s1, c1);
+    } else {
+      c0 = c1 = vc;            // flip is never set for these
+    }
+    ca[k] = wrapb(c0, p.outw);
+    cb[k] = ((flip >> k) & 1u) ? wrapb(c1, p.outw) : ca[k];
+  }
+  wa = tail_generic(wp, ca);
+  wb = tail_generic(wp, cb);
+}
+
 // ============================================================================================
 // Window synthesis bodies (BHW_ALGO_TABLE, stage 2)
 // ============================================================================================

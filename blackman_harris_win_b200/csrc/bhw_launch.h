@@ -39,7 +39,8 @@ struct DirectArgs {
   SrcCore sc[2];              // shift-add core of each source + its sliced atan words
   const I2* rom;              // Taylor ROM (global)
   uint32_t rom_smem_entries;  // > 0: copy that many ROM words to shared memory first
-  uint32_t pad;
+  uint32_t pair_flip;         // bit 31: whole window, samples (n, n + N/2) from one evaluation per harmonic;
+                              // bits 1..6: the harmonics whose quadrant is flipped half a window later
   uint64_t n_first;           // n of output element 0 (stream offset folded in)
   uint64_t count;
 };

@@ -259,6 +259,23 @@ int resolve_atan2(const bhw_atan2_desc* d, Atan2Params* p) {
   return BHW_OK;
 }
 
+// Which harmonics see the flipped quadrant half a window later (bit k), or false when some harmonic
+// does neither "same phase" nor "half a source period further" (then there is no pairing).
+bool direct_pair_flip(const WinParams& wp, const SrcParams* src, uint32_t* flip) {
+  if (wp.pw < 3) return false;
+  const uint64_t half = 1ull << (wp.pw - 1);
+  uint32_t f = 0;
+  for (int k = 1; k < wp.m; ++k) {
+    const TermParams& t = wp.term[k - 1];
+    const uint64_t delta = ((uint64_t)t.kmul * half) & t.ph_mask;
+    if (delta == 0) continue;
+    if (delta != ((uint64_t)t.ph_mask + 1) >> 1 || src[t.src].kind == SRC_INQ) return false;
+    f |= 1u << k;
+  }
+  *flip = f;
+  return true;
+}
+
 bool source_antisymmetric(const SrcParams& sp) {
   switch (sp.kind) {
     case SRC_DDS:   // |value| <= 2^(DW-2) + a few LSB: far from -2^(DW-1) once DW >= 8; the quadrant

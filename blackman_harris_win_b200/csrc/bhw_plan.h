@@ -38,6 +38,9 @@ struct BankTableInfo { const int32_t* ptr; uint32_t entries; bool antisym; };
 // as plain integers?  (It is whenever no entry can be the most negative DW-bit number, whose
 // negation wraps onto itself.)
 bool source_antisymmetric(const SrcParams& sp);
+// k_direct_window on a whole window: can samples (n, n + N/2) share one evaluation per harmonic, and
+// which harmonics (bit k) see the flipped quadrant half a window later (direct_sample_core_pair)?
+bool direct_pair_flip(const WinParams& wp, const SrcParams* src, uint32_t* flip);
 // Shape of a record for the bank kernel (tables_k[k] = table of harmonic k), the table placement
 // (TAB_*) and whether lanes take (n, n + N/2) pairs; false when the record cannot go there.
 // allow_pair = false: lanes own single samples even where pairing would be valid (tile ranges inside

@@ -72,6 +72,18 @@ int hc_direct(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
     out[j] = direct_sample_core(wp, src, sc, rom.data(), n);          // what k_direct_window runs
     if (direct_sample_generic(wp, src, rom.data(), n) != out[j]) return -100;  // fast cores == generic body
   }
+  // the paired body (whole windows in the kernel) must give the same two samples
+  uint32_t flip = 0;
+  const uint64_t N = 1ull << wp.pw;
+  if (N >= 8 && direct_pair_flip(wp, src, &flip)) {
+    for (uint64_t j = 0; j < count; j++) {
+      const uint64_t pos = n0 + j, partner = (pos + N / 2) & (N - 1);
+      if (partner < n0 || partner >= n0 + count) continue;
+      int64_t wa, wb;
+      direct_sample_core_pair(wp, src, sc, rom.data(), (pos + (uint64_t)wp.stream_offset) & nmask, flip, wa, wb);
+      if (wa != out[j] || wb != out[partner - n0]) return -103;
+    }
+  }
   return 0;
 }
 

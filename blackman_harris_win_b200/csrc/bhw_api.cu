@@ -537,6 +537,8 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       if (lo < hi) {
         a.n_first = (lo - off) + (uint64_t)a.wp.stream_offset;
         a.count = hi - lo;
+        uint32_t flip = 0;   // a whole window: sample pairs (n, n + N/2) from one evaluation per harmonic
+        a.pair_flip = (lo == off && hi == off + N && N >= 8 && direct_pair_flip(a.wp, a.src, &flip)) ? (0x80000000u | flip) : 0u;
         cudaError_t e;
         {
           LaunchTimer tm(BHW_KERNEL_DIRECT, stream);

@@ -1088,6 +1088,8 @@ int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t
   if (a.src.kind == SRC_TAYLOR && (st = get_rom(dev, a.src.dw, a.src.lut, &a.rom))) return st;
   a.n_first = n0;
   a.count = count;
+  // the whole table of a source with an output quadrant mux: four phases per evaluation
+  a.quad = (n0 == 0 && a.src.pw >= 3 && count == (1ull << a.src.pw) && a.src.kind != SRC_INQ) ? 1u : 0u;
   if (!count || (!out_sin_dev && !out_cos_dev)) return BHW_OK;
   cudaError_t e;
   {

@@ -479,6 +479,31 @@ BHW_HD void eval_source_core(const SrcParams& p, const SrcCore& sc, const I2* ro
   c = wrapb(vc, p.outw);
 }
 
+// The four phases low, low + N/4, low + N/2, low + 3N/4 of an output-quadrant source from one
+// shift-add evaluation: they share the quarter-wave phase `low`, and the entity's quadrant mux
+// (quadrant_fix) turns the one (sin, cos) pair into the four outputs (src/cordic_dds.vhd:232-246,
+// src/taylor_sincos.vhd:237-255).  s[r], c[r] belong to phase ph + r*N/4.  Not for SRC_INQ.
+BHW_HD void eval_source_core_quad(const SrcParams& p, const SrcCore& sc, const I2* rom, uint64_t ph, int64_t* s,
+                                  int64_t* c) {
+  const int pw = p.pw;
+  ph &= (1ull << pw) - 1;
+  const int q = (int)(ph >> (pw - 2));
+  const uint64_t low = ph & ((1ull << (pw - 2)) - 1);
+  int64_t vs, vc;
+  if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom, (uint32_t)low, vs, vc);
+  else if (sc.core == TABCORE_32) { int32_t s32, c32; cordic_core_fast32<false>(p, sc.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+  else if (sc.core == TABCORE_32BIAS) { int32_t s32, c32; cordic_core_fast32<true>(p, sc.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+  else if (sc.core == TABCORE_A64) cordic_core_aligned64(p, sc.rom64, q, low, vs, vc);
+  else cordic_core_generic(p, q, low, vs, vc);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int64_t so, co;
+    quadrant_fix((q + r) & 3, p.negw, vs, vc, so, co);
+    s[r] = wrapb(so, p.outw);
+    c[r] = wrapb(co, p.outw);
+  }
+}
+
 // One output sample of BHW_ALGO_DIRECT with per-source cores.
 BHW_HD int64_t direct_sample_core(const WinParams& wp, const SrcParams* src, const SrcCore* sc, const I2* rom,
                                   uint64_t n) {

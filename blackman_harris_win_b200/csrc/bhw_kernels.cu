@@ -507,6 +507,19 @@ k_direct_taylor(const __grid_constant__ DirectTayArgs a, int32_t* __restrict__ o
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_sincos(const __grid_constant__ SinCosArgs a, OutT* __restrict__ out_sin, OutT* __restrict__ out_cos) {
+  if (a.quad) {
+    const uint64_t Q = a.count / 4;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < Q; j += (uint64_t)gridDim.x * blockDim.x) {
+      int64_t s[4], c[4];
+      eval_source_core_quad(a.src, a.sc, a.rom, a.n_first + j, s, c);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (out_sin) out_sin[j + r * Q] = (OutT)s[r];
+        if (out_cos) out_cos[j + r * Q] = (OutT)c[r];
+      }
+    }
+    return;
+  }
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.count;
        j += (uint64_t)gridDim.x * blockDim.x) {
     int64_t s, c;
@@ -731,7 +744,7 @@ cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* 
 
 cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream) {
   if (!a.count) return cudaSuccess;
-  const unsigned grid = grid_for((a.count + 255) / 256, 8);
+  const unsigned grid = grid_for((a.count / (a.quad ? 4 : 1) + 255) / 256, 8);
   if (elem64) k_sincos<int64_t><<<grid, 256, 0, stream>>>(a, (int64_t*)out_sin, (int64_t*)out_cos);
   else k_sincos<int32_t><<<grid, 256, 0, stream>>>(a, (int32_t*)out_sin, (int32_t*)out_cos);
   return cudaGetLastError();

@@ -69,6 +69,7 @@ struct SinCosArgs {
   const I2* rom;
   uint64_t n_first;
   uint64_t count;
+  uint32_t quad;   // whole table of an output-quadrant source: phases j, j + N/4, j + N/2, j + 3N/4 from one evaluation
 };
 
 cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total_work, const I2* rom_dev,

@@ -305,6 +305,14 @@ int hc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, 
     if (s != s2 || c != c2) return -100;
     if (out_sin) out_sin[j] = s;
     if (out_cos) out_cos[j] = c;
+    if (sp.kind != SRC_INQ && sp.pw >= 3) {   // the four-phases-per-evaluation body of whole-table requests
+      int64_t s4[4], c4[4];
+      eval_source_core_quad(sp, sc, rom.data(), n0 + j, s4, c4);
+      for (int r = 0; r < 4; r++) {
+        eval_source_generic(sp, rom.data(), n0 + j + ((uint64_t)r << (sp.pw - 2)), s2, c2);
+        if (s4[r] != s2 || c4[r] != c2) return -104;
+      }
+    }
   }
   return 0;
 }

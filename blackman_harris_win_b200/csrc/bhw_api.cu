@@ -888,7 +888,8 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
     // register-resident 32-bit stages, 128-bit stores
     a32.n0 = n0;
     a32.count = count;
-    a32.pair = (n0 == 0 && count == N && N >= 8 && a32.p.pw == d->phi_width) ? 1u : 0u;   // whole window: sample pairs
+    // whole window: sample pairs, or all four quarter-window partners, from one set of evaluations
+    a32.pair = (n0 == 0 && count == N && N >= 8 && a32.p.pw == d->phi_width) ? (N >= 32 ? 2u : 1u) : 0u;
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct32(a32, (int32_t*)out_dev, stream);
   } else {
@@ -906,15 +907,15 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
 // table path (table build + synthesis, two launches and a plan: ~11 us per call however short)?
 // A TAYLOR window of any length: a Taylor evaluation (ROM look-up + two multiplies) per sample is
 // cheaper than building, storing and re-reading tables as large as the window.  CORDIC: the direct
-// kernel's work is count x (M-1) evaluations of ~DAT_WIDTH stages, halved for a whole window (sample
-// pairs); measured crossover (tools/call_latency --route, us per call direct / table): 4-term DW 17
-// N=2^19 7.3 / 10.9, 2^20 12.3 / 10.9; 2-term DW 16 2^21 8.2 / 11.3, 2^22 14.4 / 12.8; 7-term DW 24
-// 2^18 10.1 / 12.9, 2^19 14.4 / 13.4; 5-term DW 24 2^19 10.3 / 11.5, 2^20 18.5 / 13.4.
+// kernel's work is count x (M-1) evaluations of ~DAT_WIDTH stages, quartered for a whole window (four
+// samples per evaluation); measured crossover (tools/call_latency --route, us per call direct /
+// table): 4-term DW 17 N=2^20 8.2 / 11.0, 2^21 14.4 / 11.3; 2-term DW 16 2^22 10.3 / 12.9; 3-term
+// DW 16 2^21 10.3 / 11.3, 2^22 16.4 / 13.4.
 static bool auto_prefers_direct(const bhw_desc* d, uint64_t n0, uint64_t count) {
   if (d->model == BHW_MODEL_RTL && d->sin_type == BHW_SIN_TAYLOR) return true;
   const bool whole = n0 == 0 && count == (1ull << d->phi_width);
-  const uint64_t work = count * (uint64_t)(d->win_type - 1) * (uint64_t)d->dat_width * (whole ? 1u : 2u);
-  return work <= 52000000ull;
+  const uint64_t work = count * (uint64_t)(d->win_type - 1) * (uint64_t)d->dat_width * (whole ? 1u : 4u);
+  return work <= 80000000ull;
 }
 
 }  // namespace bhw

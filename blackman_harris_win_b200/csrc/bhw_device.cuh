@@ -685,9 +685,8 @@ struct Direct32Params {
 // NXY == 0 selects the run-time loop (any stage count).  The z update of a stage past n_z uses a
 // zero atan word (HLS: the last stage reads no table entry) - z is dead after the last stage.
 template <int NXY>
-BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
+BHW_HD void direct32_sc(const Direct32Params& p, uint32_t ph, int32_t& vs, int32_t& vc) {
   const int pw = p.pw;
-  const uint32_t q = ph >> (pw - 2);
   const uint32_t low = ph & ((1u << (pw - 2)) - 1u);
   int32_t z = (int32_t)((low >> p.z_rshift) << p.z_lshift);
   int32_t x = p.gain, y = p.gain;  // stage 0 with z0 >= 0: x - (0>>0), 0 + (x>>0)
@@ -713,11 +712,20 @@ BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
       z -= d * p.rom[i];
     }
   }
-  const int32_t vc = x >> p.out_shift, vs = y >> p.out_shift;
-  // quadrant fix for the cosine output: c, -s, -c, s.  |vc|,|vs| <= 2^(DW-2)+eps, so the
-  // reference's wrapped negation is the plain one
+  vc = x >> p.out_shift;
+  vs = y >> p.out_shift;
+}
+// quadrant fix for the cosine output: c, -s, -c, s.  |vc|,|vs| <= 2^(DW-2)+eps, so the
+// reference's wrapped negation is the plain one
+BHW_HD int32_t direct32_fix(uint32_t q, int32_t vs, int32_t vc) {
   const int32_t v = (q & 1u) ? vs : vc;
   return ((q + 1u) & 2u) ? -v : v;
+}
+template <int NXY>
+BHW_HD int32_t direct32_cos(const Direct32Params& p, uint32_t ph) {
+  int32_t vs, vc;
+  direct32_sc<NXY>(p, ph, vs, vc);
+  return direct32_fix(ph >> (p.pw - 2), vs, vc);
 }
 
 // one output sample; the harmonics are a run-time loop (m is a kernel parameter)
@@ -750,6 +758,32 @@ BHW_HD void direct32_pair(const Direct32Params& p, uint32_t n, int32_t& wa, int3
   }
   wa = (int32_t)(Sa << p.lsh) >> p.rsh;
   wb = (int32_t)(Sb << p.lsh) >> p.rsh;
+}
+
+// Samples n + r*N/4, r = 0..3, from one set of CORDIC evaluations: a quarter window later the phase
+// of harmonic k has advanced by k quarter periods on the same low bits, so its cosine is the
+// quadrant fix of the same (sin, cos) pair at quadrant q + k*r.
+template <int NXY>
+BHW_HD void direct32_quad(const Direct32Params& p, uint32_t n, int32_t* w) {
+  const uint32_t pmask = (1u << p.pw) - 1u;
+  uint32_t S[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) S[r] = (uint32_t)p.S0;
+  for (int k = 1; k < p.m; ++k) {
+    const uint32_t km = p.kmul[k];
+    const uint32_t ph = (km * n) & pmask;
+    const uint32_t q = ph >> (p.pw - 2);
+    int32_t vs, vc;
+    direct32_sc<NXY>(p, ph, vs, vc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int32_t c = direct32_fix((q + km * (uint32_t)r) & 3u, vs, vc);
+      const uint32_t b = (uint32_t)mulhi_rc(p.A[k], c << p.tshift, p.rc);
+      S[r] = (k & 1) ? S[r] - b : S[r] + b;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) w[r] = (int32_t)(S[r] << p.lsh) >> p.rsh;
 }
 
 // ============================================================================================

@@ -372,10 +372,15 @@ k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
     // are a dependent chain, so a thread that owns 4 samples x (M-1) harmonics runs ~4 x (M-1) x NXY
     // stages back to back while most of the GPU idles; spreading them shortens the kernel 4-fold
     // (N = 65536 4-term: 6.2 -> 4.x us per call).
-    const uint64_t items = a.pair ? a.count / 2 : a.count;
+    const uint64_t items = a.pair == 2 ? a.count / 4 : a.pair ? a.count / 2 : a.count;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < items; j += (uint64_t)gridDim.x * blockDim.x) {
       const uint32_t n = (uint32_t)(a.n0 + j) + p.n_first;
-      if (a.pair) {
+      if (a.pair == 2) {
+        int32_t w[4];
+        direct32_quad<NXY>(p, n, w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) out[r * items + j] = w[r];
+      } else if (a.pair) {
         int32_t wa, wb;
         direct32_pair<NXY>(p, n, wa, wb);
         out[j] = wa;
@@ -388,6 +393,29 @@ k_direct32(const __grid_constant__ Direct32Args a, int32_t* __restrict__ out) {
   }
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const uint32_t pmask = (1u << p.pw) - 1u;
+  if (a.pair == 2) {
+    // whole window: 4 consecutive samples of the first quarter and their partners a quarter, half and
+    // three quarters of a window later - one set of CORDIC evaluations for the sixteen of them
+    const uint64_t quarter = a.count / 4;
+    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quarter / 4;
+         qd += (uint64_t)gridDim.x * blockDim.x) {
+      const uint64_t j = qd * 4;
+      const uint32_t n = (uint32_t)j + p.n_first;
+      int32_t v[4][4];   // [sample e][quarter r]
+#pragma unroll
+      for (int e = 0; e < 4; ++e) direct32_quad<NXY>(p, n + e, v[e]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (aligned) {
+          __stcs(reinterpret_cast<int4*>(out + r * quarter + j), make_int4(v[0][r], v[1][r], v[2][r], v[3][r]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) out[r * quarter + j + e] = v[e][r];
+        }
+      }
+    }
+    return;
+  }
   if (a.pair) {
     // whole window: 4 consecutive samples of the first half and their partners half a window later
     const uint64_t half = a.count / 2;
@@ -701,7 +729,7 @@ static void launch_direct32_t(const Direct32Args& a, int32_t* out, unsigned grid
 cudaError_t launch_direct32(const Direct32Args& a_in, int32_t* out, cudaStream_t stream) {
   if (!a_in.count) return cudaSuccess;
   Direct32Args a = a_in;
-  const uint64_t items = a.count / (a.pair ? 2 : 1);
+  const uint64_t items = a.count / (a.pair == 2 ? 4 : a.pair ? 2 : 1);
   a.narrow = items <= (uint64_t)sm_count() * 8u * 256u ? 1u : 0u;   // fewer items than thread slots: one per thread
   const unsigned grid = grid_for(((a.narrow ? items : (items + 3) / 4) + 255) / 256, 8);
   switch (a.p.n_xy) {  // DAT_WIDTH 8..31 (cordic_dds: DW-1 stages; HLS: NW stages)

@@ -155,6 +155,23 @@ int hc_direct32(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
       else direct32_pair<0>(p, n, wa, wb);
       if (wa != out[j] || wb != out[partner - n0]) return -102;
     }
+    // ... and the four-samples-per-evaluation body
+    for (uint64_t j = 0; j < count && N >= 16; j++) {
+      const uint64_t pos = n0 + j;
+      bool all_in = true;
+      for (int r = 1; r < 4; r++) {
+        const uint64_t pr = (pos + r * (N / 4)) & (N - 1);
+        if (pr < n0 || pr >= n0 + count) all_in = false;
+      }
+      if (!all_in) continue;
+      int32_t w4[4];
+      const uint32_t n = (uint32_t)pos + p.n_first;
+      if (p.n_xy == 15) direct32_quad<15>(p, n, w4);
+      else if (p.n_xy == 16) direct32_quad<16>(p, n, w4);
+      else direct32_quad<0>(p, n, w4);
+      for (int r = 0; r < 4; r++)
+        if (w4[r] != out[((pos + r * (N / 4)) & (N - 1)) - n0]) return -106;
+    }
   }
   return 0;
 }

@@ -729,6 +729,10 @@ static void launch_direct32_t(const Direct32Args& a, int32_t* out, unsigned grid
 cudaError_t launch_direct32(const Direct32Args& a_in, int32_t* out, cudaStream_t stream) {
   if (!a_in.count) return cudaSuccess;
   Direct32Args a = a_in;
+  // four samples per evaluation set only from about one 256-thread CTA of pairs per SM up: below that
+  // the kernel is a latency chain and more, lighter threads finish sooner (7-term DW 24, us per call
+  // pairs / fours: N = 2^14 5.1 / 6.2, 2^16 6.2 / 6.2, 2^18 10.1 / 6.7)
+  if (a.pair == 2 && a.count / 2 <= (uint64_t)sm_count() * 256u) a.pair = 1;
   const uint64_t items = a.count / (a.pair == 2 ? 4 : a.pair ? 2 : 1);
   a.narrow = items <= (uint64_t)sm_count() * 8u * 256u ? 1u : 0u;   // fewer items than thread slots: one per thread
   const unsigned grid = grid_for(((a.narrow ? items : (items + 3) / 4) + 255) / 256, 8);

@@ -539,6 +539,9 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
         a.count = hi - lo;
         uint32_t flip = 0;   // a whole window: sample pairs (n, n + N/2) from one evaluation per harmonic
         a.pair_flip = (lo == off && hi == off + N && N >= 8 && direct_pair_flip(a.wp, a.src, &flip)) ? (0x80000000u | flip) : 0u;
+        uint32_t adv = 0;
+        a.quad_adv = (a.pair_flip && N / 2 > (uint64_t)device_sm_count() * 256u && direct_quad_adv(a.wp, a.src, &adv))
+                         ? (0x80000000u | adv) : 0u;
         cudaError_t e;
         {
           LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
@@ -893,8 +896,11 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct32(a32, (int32_t*)out_dev, stream);
   } else {
-    uint32_t flip = 0;
+    uint32_t flip = 0, adv = 0;
     a.pair_flip = (n0 == 0 && count == N && N >= 8 && direct_pair_flip(a.wp, a.src, &flip)) ? (0x80000000u | flip) : 0u;
+    // from about one CTA of pairs per SM up: all four quarter-window partners from one evaluation
+    a.quad_adv = (a.pair_flip && N / 2 > (uint64_t)device_sm_count() * 256u && direct_quad_adv(a.wp, a.src, &adv))
+                     ? (0x80000000u | adv) : 0u;
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct_window(a, out_dev, stream);
   }

@@ -557,6 +557,41 @@ BHW_HD void direct_sample_core_pair(const WinParams& wp, const SrcParams* src, c
   wb = tail_generic(wp, cb);
 }
 
+// The four samples n + r*N/4 (r = 0..3) of a window from one evaluation per harmonic: a quarter
+// window later harmonic k's phase has advanced by adv_k of its source's own quarter periods on the
+// same low phase bits (adv_k = 2 bits at position 2k of `adv`; direct_quad_adv() decides), so
+// quadrant_fix at quadrant q + adv_k*r gives its cosine.  Sources with an output quadrant mux only.
+BHW_HD void direct_sample_core_quad(const WinParams& wp, const SrcParams* src, const SrcCore* sc, const I2* rom,
+                                    uint64_t n, uint32_t adv, int64_t* w) {
+  int64_t cq[4][BHW_MAX_TERMS];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) cq[r][0] = 0;
+  for (int k = 1; k < wp.m; ++k) {
+    const TermParams& t = wp.term[k - 1];
+    const SrcParams& p = src[t.src];
+    const SrcCore& c = sc[t.src];
+    const uint64_t ph = ((uint64_t)t.kmul * n) & t.ph_mask;
+    const int pw = p.pw;
+    const int q = (int)(ph >> (pw - 2));
+    const uint64_t low = ph & ((1ull << (pw - 2)) - 1);
+    int64_t vs, vc;
+    if (p.kind == SRC_TAYLOR) taylor_core_generic(p, rom, (uint32_t)low, vs, vc);
+    else if (c.core == TABCORE_32) { int32_t s32, c32; cordic_core_fast32<false>(p, c.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+    else if (c.core == TABCORE_32BIAS) { int32_t s32, c32; cordic_core_fast32<true>(p, c.rom32, (uint32_t)low, s32, c32); vs = s32; vc = c32; }
+    else if (c.core == TABCORE_A64) cordic_core_aligned64(p, c.rom64, q, low, vs, vc);
+    else cordic_core_generic(p, q, low, vs, vc);
+    const int a = (int)((adv >> (2 * k)) & 3u);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int64_t so, co;
+      quadrant_fix((q + a * r) & 3, p.negw, vs, vc, so, co);
+      cq[r][k] = wrapb(co, p.outw);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) w[r] = tail_generic(wp, cq[r]);
+}
+
 // ============================================================================================
 // Window synthesis bodies (BHW_ALGO_TABLE, stage 2)
 // ============================================================================================

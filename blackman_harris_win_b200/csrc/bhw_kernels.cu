@@ -343,6 +343,17 @@ k_direct_window(const __grid_constant__ DirectArgs a, OutT* __restrict__ out) {
     rom = s_rom;
   }
   const uint64_t nmask = (1ull << a.wp.pw) - 1;
+  if (a.quad_adv >> 31) {    // whole window: one shift-add evaluation per harmonic and four samples
+    const uint64_t quarter = a.count / 4;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < quarter;
+         j += (uint64_t)gridDim.x * blockDim.x) {
+      int64_t w[4];
+      direct_sample_core_quad(a.wp, a.src, a.sc, rom, (a.n_first + j) & nmask, a.quad_adv & 0x7FFFFFFFu, w);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) out[r * quarter + j] = (OutT)w[r];
+    }
+    return;
+  }
   if (a.pair_flip >> 31) {   // whole window: one shift-add evaluation per harmonic and sample pair
     const uint64_t half = a.count / 2;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half;
@@ -714,7 +725,7 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
 
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream) {
   if (!a.count) return cudaSuccess;
-  const unsigned grid = grid_for((a.count / ((a.pair_flip >> 31) ? 2 : 1) + 255) / 256, 8);
+  const unsigned grid = grid_for((a.count / ((a.quad_adv >> 31) ? 4 : (a.pair_flip >> 31) ? 2 : 1) + 255) / 256, 8);
   const size_t smem = (size_t)a.rom_smem_entries * sizeof(I2);
   if (a.wp.elem64) k_direct_window<int64_t><<<grid, 256, smem, stream>>>(a, (int64_t*)out);
   else k_direct_window<int32_t><<<grid, 256, smem, stream>>>(a, (int32_t*)out);

@@ -41,6 +41,10 @@ struct DirectArgs {
   uint32_t rom_smem_entries;  // > 0: copy that many ROM words to shared memory first
   uint32_t pair_flip;         // bit 31: whole window, samples (n, n + N/2) from one evaluation per harmonic;
                               // bits 1..6: the harmonics whose quadrant is flipped half a window later
+  uint32_t quad_adv;          // bit 31: whole window, the four samples n + r*N/4 from one evaluation per
+                              // harmonic (wins over pair_flip); bits 2k, 2k+1: quadrants harmonic k advances
+                              // per quarter window
+  uint32_t pad2;
   uint64_t n_first;           // n of output element 0 (stream offset folded in)
   uint64_t count;
 };

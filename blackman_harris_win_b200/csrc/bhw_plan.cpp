@@ -276,6 +276,25 @@ bool direct_pair_flip(const WinParams& wp, const SrcParams* src, uint32_t* flip)
   return true;
 }
 
+// Quadrants harmonic k's source advances per quarter window (2 bits at position 2k), or false when
+// some harmonic does not advance by whole quadrants or its source has no output quadrant mux.
+bool direct_quad_adv(const WinParams& wp, const SrcParams* src, uint32_t* adv) {
+  if (wp.pw < 5) return false;                       // N >= 32
+  const uint64_t quarter = 1ull << (wp.pw - 2);
+  uint32_t a = 0;
+  for (int k = 1; k < wp.m; ++k) {
+    const TermParams& t = wp.term[k - 1];
+    if (src[t.src].kind == SRC_INQ) return false;
+    const uint64_t period = (uint64_t)t.ph_mask + 1;
+    if (period < 4) return false;
+    const uint64_t delta = ((uint64_t)t.kmul * quarter) & t.ph_mask;
+    if (delta % (period / 4)) return false;
+    a |= (uint32_t)(delta / (period / 4)) << (2 * k);
+  }
+  *adv = a;
+  return true;
+}
+
 bool source_antisymmetric(const SrcParams& sp) {
   switch (sp.kind) {
     case SRC_DDS:   // |value| <= 2^(DW-2) + a few LSB: far from -2^(DW-1) once DW >= 8; the quadrant

@@ -41,6 +41,8 @@ bool source_antisymmetric(const SrcParams& sp);
 // k_direct_window on a whole window: can samples (n, n + N/2) share one evaluation per harmonic, and
 // which harmonics (bit k) see the flipped quadrant half a window later (direct_sample_core_pair)?
 bool direct_pair_flip(const WinParams& wp, const SrcParams* src, uint32_t* flip);
+// ... and the four samples n + r*N/4 (direct_sample_core_quad)?  adv: 2 bits per harmonic.
+bool direct_quad_adv(const WinParams& wp, const SrcParams* src, uint32_t* adv);
 // Shape of a record for the bank kernel (tables_k[k] = table of harmonic k), the table placement
 // (TAB_*) and whether lanes take (n, n + N/2) pairs; false when the record cannot go there.
 // allow_pair = false: lanes own single samples even where pairing would be valid (tile ranges inside

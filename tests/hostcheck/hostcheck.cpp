@@ -84,6 +84,23 @@ int hc_direct(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out) {
       if (wa != out[j] || wb != out[partner - n0]) return -103;
     }
   }
+  // ... and the four-samples-per-evaluation body
+  uint32_t adv = 0;
+  if (direct_quad_adv(wp, src, &adv)) {
+    for (uint64_t j = 0; j < count; j++) {
+      const uint64_t pos = n0 + j;
+      bool all_in = true;
+      for (int r = 1; r < 4; r++) {
+        const uint64_t pr = (pos + r * (N / 4)) & (N - 1);
+        if (pr < n0 || pr >= n0 + count) all_in = false;
+      }
+      if (!all_in) continue;
+      int64_t w4[4];
+      direct_sample_core_quad(wp, src, sc, rom.data(), (pos + (uint64_t)wp.stream_offset) & nmask, adv, w4);
+      for (int r = 0; r < 4; r++)
+        if (w4[r] != out[((pos + r * (N / 4)) & (N - 1)) - n0]) return -107;
+    }
+  }
   return 0;
 }
 

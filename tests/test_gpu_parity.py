@@ -284,6 +284,28 @@ def test_batch_int64_windows():
         bhw.generate_batch(descs + [bhw.variant_desc(1, 8, 16)])       # mixed element sizes
 
 
+def test_long_int64_windows_whole_and_in_pieces():
+    """DAT_WIDTH > 32 windows long enough for the whole-window route of k_direct_window (four samples
+    n + r*N/4 per evaluation): whole window == the same window in unpaired pieces == the oracle on slices,
+    one-shot and through a plan, with and without the stream offset."""
+    import torch
+    for v, pw, dw, st, off in ((10, 18, 40, bhw.SIN_CORDIC, 0), (6, 17, 47, bhw.SIN_CORDIC, 1), (3, 18, 33, bhw.SIN_CORDIC, 1),
+                               (10, 17, 36, bhw.SIN_CORDIC48, 0)):
+        d = bhw.variant_desc(v, pw, dw, sin_type=st, stream_offset=off)
+        n = 1 << pw
+        whole = bhw.generate(d)
+        assert whole.dtype.itemsize == 8
+        pieces = torch.cat([bhw.generate(d, 0, n // 3), bhw.generate(d, n // 3, n - n // 3)])
+        assert torch.equal(whole, pieces), (v, pw, dw, st)
+        for n0 in (0, n // 4 - 500, n // 2 - 500, 3 * n // 4 - 500, n - 1000):
+            assert np.array_equal(whole[n0:n0 + 1000].cpu().numpy(), H.orc_window(d, n0, 1000)), (v, pw, dw, st, n0)
+        plan = bhw.Plan([d, d.copy(stream_offset=1 - off)])
+        out = plan.execute()
+        assert torch.equal(out[:n], whole)
+        assert torch.equal(out[n:], torch.roll(whole, -1 if off == 0 else 1))
+        plan.destroy()
+
+
 def test_shards_reassemble():
     """1/2/4/8-way sharding by flat sample range (what each rank of bench.py does) reproduces the
     unsharded batch; shards are planned from their own windows only."""

@@ -176,13 +176,21 @@ struct bhw_plan {
   std::vector<PlanTable> tables;
   std::vector<bhw::TabJob> jobs;       // small / other-core jobs: one combined k_table_build launch
   std::vector<bhw::TabJob> big_jobs;   // large 32-bit-core jobs: one k_table_build_u launch each
-  const bhw::I2* rom = nullptr;  // at most one Taylor (DW, LUT_SIZE) ROM per plan
+  // Taylor sine ROMs of the plan, one per distinct (DAT_WIDTH, LUT_SIZE), concatenated; they live in
+  // the plan's own metadata blob (the per-device ROM cache only serves the one-shot direct kernels)
+  std::vector<bhw::I2> rom_host;
+  std::map<uint32_t, uint32_t> rom_offs;   // (dw << 8 | lut) -> offset in rom_host (I2 units)
+  const bhw::I2* rom = nullptr;            // device copy (inside blob_dev)
   int uniform_pw = -1;
   bool all_same = false;
   char* blob_dev = nullptr;      // [recs][gens][jobs][flat_off][win_rec]
-  size_t o_recs = 0, o_gens = 0, o_jobs = 0, o_off = 0, o_wr = 0;
+  size_t o_recs = 0, o_gens = 0, o_jobs = 0, o_off = 0, o_wr = 0, o_rom = 0;
   uint32_t table_work = 0;
+  // Tables kept by the plan (table cache on): built by the first eager execute; `ev_built` is recorded
+  // behind that build so that executes on other streams can order themselves after it.
   bool tables_built = false;
+  cudaEvent_t ev_built = nullptr;
+  cudaStream_t built_stream = nullptr;
   // runs of consecutive same-shape windows that the bank kernel can take whole
   struct BankRun {
     int w_begin, w_end;      // windows [w_begin, w_end)
@@ -220,7 +228,21 @@ static int find_or_add_table(bhw_plan& plan, const SrcParams& sp, int* index) {
   return BHW_OK;
 }
 
+// offset (I2 units) of the (dw, lut) sine ROM inside the plan's ROM block, appending it on first use
+static uint32_t plan_rom_off(bhw_plan& plan, int dw, int lut) {
+  const uint32_t key = ((uint32_t)dw << 8) | (uint32_t)lut;
+  auto it = plan.rom_offs.find(key);
+  if (it != plan.rom_offs.end()) return it->second;
+  std::vector<I2> rom;
+  build_taylor_rom(dw, lut, rom);
+  const uint32_t off = (uint32_t)plan.rom_host.size();
+  plan.rom_host.insert(plan.rom_host.end(), rom.begin(), rom.end());
+  plan.rom_offs.emplace(key, off);
+  return off;
+}
+
 static void plan_free_device(bhw_plan& plan, cudaStream_t stream) {
+  if (plan.ev_built) { cudaEventDestroy(plan.ev_built); plan.ev_built = nullptr; }
   for (auto& pt : plan.tables)
     if (pt.ptr) { if (plan.transient) cudaFreeAsync(pt.ptr, stream); else cudaFree(pt.ptr); pt.ptr = nullptr; }
   if (plan.blob_dev) {
@@ -302,7 +324,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   plan.flat_off.resize((size_t)nwin + 1);
   uint64_t off = 0;
   for (int w = 0; w < nwin; w++) {
-    if (descs[w].phi_width < 4 || descs[w].phi_width > 30) return BHW_E_PHI_WIDTH;
+    if (descs[w].phi_width < BHW_MIN_PHI_WIDTH || descs[w].phi_width > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
     plan.flat_off[w] = off;
     off += 1ull << descs[w].phi_width;
   }
@@ -378,13 +400,8 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
       r.flags = WR_GENERIC;
       r.m = (uint32_t)wp.m; r.dw = (uint32_t)wp.dw; r.pw = (uint32_t)wp.pw;
       r.gen_idx = (uint32_t)plan.gens.size();
+      if (src[0].kind == SRC_TAYLOR && rec_used[i]) g.rom_off = plan_rom_off(plan, src[0].dw, src[0].lut);
       plan.gens.push_back(g);
-      if (src[0].kind == SRC_TAYLOR && rec_used[i]) {
-        const I2* rom = nullptr;
-        if ((st = get_rom(plan.dev, src[0].dw, src[0].lut, &rom))) return st;
-        if (plan.rom && plan.rom != rom) return BHW_E_ARG;  // one Taylor (DW, LUT_SIZE) per batch
-        plan.rom = rom;
-      }
     } else {
       fill_fast_rec(wp, src, r);
       if (rec_used[i]) {
@@ -417,12 +434,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
       continue;
     }
     j.work_begin = work;
-    if (pt.canon.kind == SRC_TAYLOR) {
-      const I2* rom = nullptr;
-      if ((st = get_rom(plan.dev, pt.canon.dw, pt.canon.lut, &rom))) return st;
-      if (plan.rom && plan.rom != rom) return BHW_E_ARG;  // one Taylor (DW, LUT_SIZE) per batch
-      plan.rom = rom;
-    }
+    if (pt.canon.kind == SRC_TAYLOR) j.rom_off = plan_rom_off(plan, pt.canon.dw, pt.canon.lut);
     work += j.work;
     plan.jobs.push_back(j);
   }
@@ -441,8 +453,10 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   plan.o_jobs = align16(plan.o_gens + plan.gens.size() * sizeof(GenRec));
   plan.o_off = align16(plan.o_jobs + plan.jobs.size() * sizeof(TabJob));
   plan.o_wr = align16(plan.o_off + (need_off ? plan.flat_off.size() * sizeof(uint64_t) : 0));
-  const size_t total = align16(plan.o_wr + (need_wr ? plan.win_rec.size() * sizeof(uint32_t) : 0));
+  plan.o_rom = align16(plan.o_wr + (need_wr ? plan.win_rec.size() * sizeof(uint32_t) : 0));
+  const size_t total = align16(plan.o_rom + plan.rom_host.size() * sizeof(I2));
   std::vector<char> blob(total);
+  if (!plan.rom_host.empty()) memcpy(blob.data() + plan.o_rom, plan.rom_host.data(), plan.rom_host.size() * sizeof(I2));
   memcpy(blob.data() + plan.o_recs, plan.recs.data(), plan.recs.size() * sizeof(WinRec));
   if (!plan.gens.empty()) memcpy(blob.data() + plan.o_gens, plan.gens.data(), plan.gens.size() * sizeof(GenRec));
   if (!plan.jobs.empty()) memcpy(blob.data() + plan.o_jobs, plan.jobs.data(), plan.jobs.size() * sizeof(TabJob));
@@ -457,6 +471,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize(plan)");
   }
+  if (!plan.rom_host.empty()) plan.rom = (const I2*)(plan.blob_dev + plan.o_rom);
   if (!need_off) { plan.flat_off.clear(); plan.flat_off.shrink_to_fit(); }
   return BHW_OK;
 }
@@ -558,7 +573,19 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   cudaError_t e = cudaSuccess;
   bool table_ahead = false;  // k_table_build is the last thing enqueued on `stream`
   bool tm_on = false;
-  if ((!plan.jobs.empty() || !plan.big_jobs.empty()) && (!plan.tables_built || !g_cache_enabled.load())) {
+  const bool have_jobs = !plan.jobs.empty() || !plan.big_jobs.empty();
+  const bool keep = g_cache_enabled.load() != 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  if (have_jobs && keep && plan.tables_built) {
+    // kept tables: an execute on another stream than the one that built them orders itself behind the
+    // build (inside a capture the event lies outside the graph, so the host waits for it instead)
+    if (plan.ev_built && stream != plan.built_stream) {
+      e = capturing ? cudaEventSynchronize(plan.ev_built) : cudaStreamWaitEvent(stream, plan.ev_built, 0);
+      if (e != cudaSuccess) return cuda_fail(e, "wait(table build)");
+    }
+  } else if (have_jobs) {
     if (!plan.jobs.empty()) {
       LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
       tm_on = tm.on;
@@ -574,8 +601,16 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       if (e != cudaSuccess) return cuda_fail(e, "k_table_build_u");
       g_launches++;
     }
-    plan.tables_built = true;
-    table_ahead = !tm_on;
+    // A build that is only captured has not happened: the flag stays clear, so an eager execute (or
+    // the next capture) builds again; replays of the graph rebuild the tables every time.
+    if (keep && !capturing) {
+      if (!plan.ev_built && (e = cudaEventCreateWithFlags(&plan.ev_built, cudaEventDisableTiming)) != cudaSuccess)
+        return cuda_fail(e, "cudaEventCreate(table build)");
+      if ((e = cudaEventRecord(plan.ev_built, stream)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(table build)");
+      plan.built_stream = stream;
+      plan.tables_built = true;
+    }
+    table_ahead = !tm_on && !(keep && !capturing);   // an event record sits between the two kernels otherwise
   }
   SynthArgs a;
   a.recs = (const WinRec*)(plan.blob_dev + plan.o_recs);
@@ -701,7 +736,7 @@ static int shard_windows(const bhw_desc* descs, int nwin, uint64_t flat_begin, u
   uint64_t first_off = 0;
   const uint64_t end = flat_begin + flat_count;
   for (int w = 0; w < nwin; w++) {
-    if (descs[w].phi_width < 4 || descs[w].phi_width > 30) return BHW_E_PHI_WIDTH;
+    if (descs[w].phi_width < BHW_MIN_PHI_WIDTH || descs[w].phi_width > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
     const uint64_t N = 1ull << descs[w].phi_width;
     if (flat_count && off < end && off + N > flat_begin) {
       if (first < 0) { first = w; first_off = off; }
@@ -736,6 +771,10 @@ static int run_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint6
   int st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
   if (st) return st;
   if (!touched) return BHW_OK;
+  // a one-shot call uploads its records from a stack-lifetime buffer: it cannot be recorded into a
+  // CUDA graph (capture a bhw_plan_execute instead)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return BHW_E_CAPTURE;
   bhw_plan plan;
   plan.transient = true;
   st = plan_build(plan, descs + first, touched, local, flat_count, stream);

@@ -136,11 +136,12 @@ static bool narrow_sum_ok(const WinParams& wp, const SrcParams* src) {
 TailMode fast_tail_mode(const WinParams& wp, const SrcParams* src) {
   if (wp.dw > 32) return TAILMODE_GENERIC;
   const int t = table_tshift(src[0]);
-  if (wp.tail == TAIL_HLS) return t == 2 ? TAILMODE_FAST32 : TAILMODE_GENERIC;
-  // AAk = -2^(DW-1) (k >= 1) is left to the generic body (b_k is computed there with the
-  // entity's own DW-bit wrap)
+  // AAk = -2^(DW-1) (k >= 1) is left to the generic body: the RTL tail computes b_k there with the
+  // entity's own DW-bit wrap, and for both models the pre-shifted coefficient is then INT32_MIN,
+  // which the half-period table placement cannot negate (it folds the table's sign into -A_k)
   const int64_t lo = -((int64_t)1 << (wp.dw - 1));
   for (int k = 1; k < wp.m; k++) if (wp.aa[k] == lo) return TAILMODE_GENERIC;
+  if (wp.tail == TAIL_HLS) return t == 2 ? TAILMODE_FAST32 : TAILMODE_GENERIC;
   const int dmax = wp.tail == TAIL_RTL2 ? 31 : 30;  // dsp_pp (DW+1 / DW+2 bits) must fit 32 bits
   if (t == 1 && wp.dw <= dmax) return TAILMODE_FAST32;
   return narrow_sum_ok(wp, src) ? TAILMODE_FAST32 : TAILMODE_ACC64;

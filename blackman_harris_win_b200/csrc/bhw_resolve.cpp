@@ -36,7 +36,7 @@ int validate_desc(const bhw_desc* d, bool for_window) {
     const int m = d->win_type;
     if (m != 2 && m != 3 && m != 4 && m != 5 && m != 7) return BHW_E_WIN_TYPE;
   }
-  if (pw < 4 || pw > 30) return BHW_E_PHI_WIDTH;
+  if (pw < BHW_MIN_PHI_WIDTH || pw > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
   switch (d->model) {
     case BHW_MODEL_RTL:
       switch (d->sin_type) {
@@ -300,6 +300,7 @@ const char* bhw_strerror(int s) {
     case BHW_E_ALLOC: return "allocation failed";
     case BHW_E_VARIANT: return "unknown window variant or quantisation rule";
     case BHW_E_ARG: return "invalid argument";
+    case BHW_E_CAPTURE: return "one-shot batch call on a capturing stream (capture bhw_plan_execute instead)";
     default: return "unknown status";
   }
 }
@@ -346,7 +347,7 @@ int bhw_batch_total(const bhw_desc* descs, int nwin, uint64_t* total) {
   if (nwin < 0) return BHW_E_ARG;
   uint64_t t = 0;
   for (int i = 0; i < nwin; i++) {
-    if (descs[i].phi_width < 4 || descs[i].phi_width > 30) return BHW_E_PHI_WIDTH;
+    if (descs[i].phi_width < BHW_MIN_PHI_WIDTH || descs[i].phi_width > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
     t += 1ull << descs[i].phi_width;
   }
   *total = t;
@@ -410,7 +411,7 @@ int bhw_shard_range_cost(const bhw_desc* descs, int nwin, int rank, int nranks, 
   double total_cost = 0.0;
   uint64_t total = 0;
   for (int w = 0; w < nwin; w++) {
-    if (descs[w].phi_width < 4 || descs[w].phi_width > 30) return BHW_E_PHI_WIDTH;
+    if (descs[w].phi_width < BHW_MIN_PHI_WIDTH || descs[w].phi_width > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
     const uint64_t N = 1ull << descs[w].phi_width;
     total_cost += window_cost_per_sample(descs[w]) * (double)N + window_fixed_cost(descs[w]);
     total += N;

@@ -41,6 +41,8 @@ extern "C" {
 
 #define BHW_VERSION 0x000100 /* 0.1.0 */
 #define BHW_MAX_TERMS 7
+#define BHW_MIN_PHI_WIDTH 4   /* 16 points ...                                  */
+#define BHW_MAX_PHI_WIDTH 26  /* ... 64M points, the reference's range (README.md:2) */
 
 /* ---- status codes ------------------------------------------------------ */
 typedef enum bhw_status {
@@ -63,7 +65,10 @@ typedef enum bhw_status {
   BHW_E_NO_DEVICE = -13,  /* no CUDA device / device index out of range       */
   BHW_E_ALLOC = -14,      /* workspace allocation failed                      */
   BHW_E_VARIANT = -15,    /* bhw_quantize: unknown variant or rule            */
-  BHW_E_ARG = -16         /* any other invalid argument                       */
+  BHW_E_ARG = -16,        /* any other invalid argument                       */
+  BHW_E_CAPTURE = -17     /* a one-shot batch call on a stream that is being
+                             captured into a CUDA graph (capture
+                             bhw_plan_execute instead)                        */
 } bhw_status;
 
 /* ---- enumerations mirroring the generics ------------------------------- */
@@ -198,13 +203,16 @@ BHW_API int bhw_shard_windows(const bhw_desc* descs, int nwin, uint64_t flat_beg
 
 /* ---- plans: resolve once, execute many times ------------------------------ */
 /* A plan is a batch resolved and resident on the current device: per-window records, trig-table
- * storage and (for TAYLOR) the sine ROM.  It corresponds to the elaborated entity instances of
- * the reference (generics fixed at elaboration, src/win_selector.vhd:61-70); executing it is the
- * ENABLE burst.  bhw_plan_execute writes flat samples [flat_begin, flat_begin+flat_count) of the
- * batch to out_dev, stream-ordered, without host-side planning work.  Trig tables are built by
- * the first execute and kept, unless the table cache is off (bhw_set_table_cache(0)), in which
- * case every execute rebuilds them.  A plan must be executed and destroyed on the device it was
- * created on; concurrent executes of one plan must use one stream. */
+ * storage and (for TAYLOR) its own copy of every sine ROM the batch needs (any mix of DAT_WIDTH /
+ * LUT_SIZE).  It corresponds to the elaborated entity instances of the reference (generics fixed at
+ * elaboration, src/win_selector.vhd:61-70); executing it is the ENABLE burst.  bhw_plan_execute
+ * writes flat samples [flat_begin, flat_begin+flat_count) of the batch to out_dev, stream-ordered,
+ * without host-side planning work.  Trig tables are built by the first eager execute and kept
+ * (an execute on another stream waits for that build through an event), unless the table cache is
+ * off (bhw_set_table_cache(0)), in which case every execute rebuilds them and concurrent executes
+ * of one plan must share one stream.  bhw_plan_execute may be captured into a CUDA graph: a build
+ * that is only captured does not count as done, the graph then rebuilds the tables on every
+ * replay.  A plan must be executed and destroyed on the device it was created on. */
 typedef struct bhw_plan bhw_plan;
 BHW_API int bhw_plan_create(const bhw_desc* descs, int nwin, bhw_plan** plan_out);
 BHW_API int bhw_plan_execute(bhw_plan* plan, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
@@ -246,7 +254,11 @@ BHW_API int bhw_atan2_host(const bhw_atan2_desc* d, const int32_t* x_host, const
                    uint64_t count);
 
 /* ---- cache / introspection --------------------------------------------- */
-BHW_API int bhw_cache_clear(void);             /* free the cached sine ROMs and host-pipeline staging */
+BHW_API int bhw_cache_clear(void);             /* free the per-device sine ROMs of the one-shot direct
+                                          kernels, the host-pipeline staging, the one-shot memory
+                                          pool and the side streams.  Synchronises every device
+                                          first; no other library call may be in flight.  Plans
+                                          own their ROMs and tables and are not affected.     */
 BHW_API int bhw_set_table_cache(int enabled);  /* 1 (default): a plan builds its trig tables on its
                                           first execute and keeps them; 0: every execute
                                           rebuilds them (one-shot calls always build)        */

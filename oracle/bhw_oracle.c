@@ -257,7 +257,7 @@ static int eff_lut(const bhw_desc* d) { return d->lut_size == 0 ? 9 : d->lut_siz
 
 static int validate_source(const bhw_desc* d, int for_window) {
   const int pw = d->phi_width, dw = d->dat_width;
-  if (pw < 4 || pw > 30) return BHW_E_PHI_WIDTH;
+  if (pw < BHW_MIN_PHI_WIDTH || pw > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;   /* 16 .. 64M points (README.md:2) */
   switch (d->model) {
     case BHW_MODEL_RTL:
       switch (d->sin_type) {

@@ -76,7 +76,8 @@ def test_validate_rejections():
     t3 = bhw.make_desc(3, 12, 16, [1, 1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=9)
     assert bhw.validate(t3) == -8                                         # PHI_WIDTH - LUT_SIZE == 3
     assert bhw.validate(t3.copy(phi_width=13)) == 0
-    assert bhw.validate(bhw.make_desc(2, 30, 16, [1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=9)) == -8  # STAGE > 15
+    assert bhw.validate(bhw.make_desc(2, 26, 16, [1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=7)) == -8  # STAGE > 15
+    assert bhw.validate(ok.copy(phi_width=27)) == -5                      # 64M points is the reference's maximum
     assert bhw.validate(bhw.make_desc(2, 10, 33, [1, 1], sin_type=bhw.SIN_TAYLOR)) == -6
     assert bhw.validate(bhw.make_desc(2, 20, 16, [1, 1], model=bhw.MODEL_HLS)) == -5  # NP > NW+2
     assert bhw.lib().bhw_validate(None) == -1

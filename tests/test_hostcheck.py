@@ -257,6 +257,34 @@ def test_bank_body_half_table_sign_boundaries():
     assert st == 0 and np.array_equal(got, H.orc_window(d))
 
 
+def test_bank_body_most_negative_coefficients_every_placement():
+    """a_k = -2^(DW-1) pre-shifts to INT32_MIN, which the half-period placement cannot negate: such
+    windows (RTL and HLS alike) must take the generic body, whatever placement is asked for."""
+    cases_ = [bhw.make_desc(4, 16, 17, [47022, 64001, -65536, 1531], model=bhw.MODEL_HLS),
+              bhw.make_desc(4, 12, 17, [47022, -65536, 18518, -65536], model=bhw.MODEL_HLS),
+              bhw.make_desc(3, 14, 16, [27518, -32768, 5242], model=bhw.MODEL_HLS),
+              bhw.make_desc(4, 16, 17, [47022, 64001, -65536, 1531]),
+              bhw.make_desc(7, 12, 24, [1, -(1 << 23), 3, -(1 << 23), 5, 6, -(1 << 23)], model=bhw.MODEL_HLS)]
+    for d in cases_:
+        assert bhw.validate(d) == 0
+        want = H.orc_window(d)
+        ran = 0
+        for mode in (-1, 0, 1, 2):
+            for pair in (-1, 0, 1):
+                st, got = hc_bank(d, mode=mode, pair=pair)
+                assert st in (0, 1)
+                if st == 0:
+                    ran += 1
+                    assert np.array_equal(got, want), (mode, pair, d.model, list(d.aa))
+        # the bank body refuses them (generic record) ...
+        assert ran == 0
+        # ... and the generic body, which is where they go, matches the oracle
+        n = 1 << d.phi_width
+        st, got = hc_window(d, 0, min(n, 4096), "direct")
+        assert st == 0 and np.array_equal(got, want[:min(n, 4096)])
+        assert hc_window(d, 0, 16, "table")[0] == 1      # not eligible for the fast tail
+
+
 def test_antisymmetry_claim_holds_wherever_the_planner_relies_on_it():
     """Pairing and the half-period table assume T[i + E/2] == -T[i]; check the claim against the
     oracle's cosine sequence for every source the planner declares antisymmetric - and that the

@@ -406,7 +406,7 @@ def set_table_cache(enabled: bool):
 
 
 KERNEL_TABLE_BUILD, KERNEL_SYNTH, KERNEL_DIRECT, KERNEL_SINCOS = 0, 1, 2, 3
-KERNEL_NAMES = ("k_table_build", "k_synth", "k_direct_window", "k_sincos", "k_synth_bank", "k_atan2")
+KERNEL_NAMES = ("k_table_build", "k_synth", "k_direct_window", "k_sincos", "k_synth_bank", "k_atan2", "k_synth_group")
 
 
 def timing_enable(on: bool):

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <new>
@@ -203,6 +204,32 @@ struct bhw_plan {
     bool part_ok;
   };
   std::vector<BankRun> runs;
+  // families (one half-period pyramid each) and groups (bhw_group.cuh): windows that k_synth_group takes
+  struct Family {
+    bhw::SrcParams key;          // canonical source at the maximum PHI_WIDTH: the family's identity
+    bhw::SrcParams canon;        // canonical source at PHI_WIDTH = top: what the pyramid job evaluates
+    bhw_desc proto;              // a descriptor of the family
+    uint32_t top = 0, lmin = 0;  // pyramid levels
+    uint32_t max_pw = 0, min_pw = 99;
+    int tab_mode = 0;            // G_*
+    int32_t* pyr = nullptr;      // 2^top words
+    uint16_t* q16 = nullptr;     // G_Q16: 2^(top-1) uint16
+  };
+  struct Group {
+    int family = 0;
+    bhw::GroupShape sh;
+    std::vector<uint32_t> wins;          // member windows, ascending
+    std::vector<bhw::GroupWin> list;     // whole-window (paired) launch list, one entry per member + sentinel
+    size_t o_list = 0;                   // its place in blob_dev
+    // long windows over a pyramid in L2 / HBM get a launch of their own (spread walk, k_synth_group):
+    // entry + sentinel per window
+    std::vector<bhw::GroupWin> singles;
+    size_t o_singles = 0;
+  };
+  std::vector<Family> families;
+  std::vector<Group> groups;
+  std::vector<int32_t> win_group;        // [nwin] group of each window, -1: none
+  std::vector<uint32_t> win_gidx;        // [nwin] index of the window in its group's list (or in `singles`, bit 31 set)
   // DAT_WIDTH > 32: one direct launch per window
   std::vector<bhw::DirectArgs> wins64;
   std::mutex mu;
@@ -245,6 +272,10 @@ static void plan_free_device(bhw_plan& plan, cudaStream_t stream) {
   if (plan.ev_built) { cudaEventDestroy(plan.ev_built); plan.ev_built = nullptr; }
   for (auto& pt : plan.tables)
     if (pt.ptr) { if (plan.transient) cudaFreeAsync(pt.ptr, stream); else cudaFree(pt.ptr); pt.ptr = nullptr; }
+  for (auto& f : plan.families) {
+    if (f.pyr) { if (plan.transient) cudaFreeAsync(f.pyr, stream); else cudaFree(f.pyr); f.pyr = nullptr; }
+    if (f.q16) { if (plan.transient) cudaFreeAsync(f.q16, stream); else cudaFree(f.q16); f.q16 = nullptr; }
+  }
   if (plan.blob_dev) {
     if (plan.transient) cudaFreeAsync(plan.blob_dev, stream); else cudaFree(plan.blob_dev);
     plan.blob_dev = nullptr;
@@ -345,7 +376,21 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     return BHW_OK;
   }
 
-  // pass 1: windows with a byte-identical descriptor share one record
+  // pass 1: windows with a byte-identical descriptor share one record.  Runs of two or more consecutive
+  // windows of one shape (a bank: everything but the ports equal) of at least 2^17 samples keep the uniform
+  // bank kernel and its per-shape tables (`banked`); everything else may join a group (bhw_group.cuh).
+  auto same_shape = [](const bhw_desc& a, const bhw_desc& b) {
+    return a.win_type == b.win_type && a.sin_type == b.sin_type && a.model == b.model && a.phi_width == b.phi_width &&
+           a.dat_width == b.dat_width && a.precision == b.precision && a.lut_size == b.lut_size && a.algo == b.algo;
+  };
+  std::vector<uint8_t> banked((size_t)nwin, 0);
+  for (int w = 0; w < nwin;) {
+    int e = w + 1;
+    while (e < nwin && same_shape(descs[w], descs[e])) e++;
+    if (e - w >= 2 && ((uint64_t)(e - w) << descs[w].phi_width) >= (1ull << 17))
+      for (int i = w; i < e; i++) banked[(size_t)i] = 1;
+    w = e;
+  }
   plan.win_rec.resize((size_t)nwin);
   std::vector<int> rec_desc;       // descriptor index that defines record i
   std::vector<uint64_t> rec_used;  // hinted samples that fall into windows of record i
@@ -360,9 +405,11 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     const uint64_t hi = e < hint_end ? e : hint_end;
     const uint64_t used = lo < hi ? hi - lo : 0;
     int ri;
-    if (w > 0 && !memcmp(&d, &descs[w - 1], sizeof(d))) ri = (int)plan.win_rec[w - 1];
+    if (w > 0 && banked[(size_t)w] == banked[(size_t)w - 1] && !memcmp(&d, &descs[w - 1], sizeof(d))) ri = (int)plan.win_rec[w - 1];
     else {
-      auto ins = seen.emplace(std::string((const char*)&d, sizeof(d)), (int)rec_desc.size());
+      std::string key((const char*)&d, sizeof(d));
+      key.push_back((char)banked[(size_t)w]);
+      auto ins = seen.emplace(std::move(key), (int)rec_desc.size());
       ri = ins.first->second;
       if (ins.second) { rec_desc.push_back(w); rec_used.push_back(0); }
     }
@@ -375,6 +422,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   // pass 2: validate + resolve every distinct descriptor, give the used ones their trig tables
   struct TabRef { int rec, k, tab; };
   std::vector<TabRef> refs;
+  std::vector<int> rec_family(rec_desc.size(), -1);
   plan.recs.reserve(rec_desc.size());
   for (size_t i = 0; i < rec_desc.size(); i++) {
     const bhw_desc& d = descs[rec_desc[i]];
@@ -402,6 +450,25 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
       r.gen_idx = (uint32_t)plan.gens.size();
       if (src[0].kind == SRC_TAYLOR && rec_used[i]) g.rom_off = plan_rom_off(plan, src[0].dw, src[0].lut);
       plan.gens.push_back(g);
+    } else if (!banked[(size_t)rec_desc[i]] && rec_used[i] && group_eligible(d, wp, src)) {
+      // member of a family: no table of its own, it reads the family's pyramid (pointers set below)
+      fill_fast_rec(wp, src, r);
+      SrcParams key;
+      if ((st = family_source(d, BHW_MAX_PHI_WIDTH, &key))) return st;
+      int f = -1;
+      for (size_t j = 0; j < plan.families.size(); j++)
+        if (!memcmp(&plan.families[j].key, &key, sizeof(key))) { f = (int)j; break; }
+      if (f < 0) {
+        bhw_plan::Family fam;
+        fam.key = key;
+        fam.proto = d;
+        plan.families.push_back(fam);
+        f = (int)plan.families.size() - 1;
+      }
+      bhw_plan::Family& fam = plan.families[(size_t)f];
+      if ((uint32_t)wp.pw > fam.max_pw) fam.max_pw = (uint32_t)wp.pw;
+      if ((uint32_t)wp.pw < fam.min_pw) fam.min_pw = (uint32_t)wp.pw;
+      rec_family[i] = f;
     } else {
       fill_fast_rec(wp, src, r);
       if (rec_used[i]) {
@@ -438,6 +505,101 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     work += j.work;
     plan.jobs.push_back(j);
   }
+  // families: one half-period pyramid each, built by one more table job
+  for (auto& fam : plan.families) {
+    const uint32_t res = (uint32_t)fam.key.pw;                   // phase bits the source looks at
+    fam.top = fam.max_pw < res ? fam.max_pw : res;
+    const uint32_t low = fam.min_pw < fam.top ? fam.min_pw : fam.top;
+    fam.lmin = low > 4 ? low - 2 : 2;                            // even harmonics read up to two levels down
+    if ((st = family_source(fam.proto, (int)fam.top, &fam.canon))) return st;
+    fam.tab_mode = group_tab_mode(fam.canon, fam.top, group_smem_limit());
+    cudaError_t e = plan_alloc(plan, (void**)&fam.pyr, sizeof(int32_t) << fam.top, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "alloc(table pyramid)");
+    if (fam.tab_mode == G_Q16) {
+      e = plan_alloc(plan, (void**)&fam.q16, sizeof(uint16_t) << (fam.top - 1), stream);
+      if (e != cudaSuccess) return cuda_fail(e, "alloc(quarter-wave image)");
+    }
+    TabJob j;
+    init_pyramid_job(fam.canon, fam.lmin, fam.pyr, fam.q16, &j);
+    if (j.work >= kBigTableWork && table_build_unrolled_ok(j)) {
+      j.work_begin = 0;
+      plan.big_jobs.push_back(j);
+    } else {
+      j.work_begin = work;
+      work += j.work;
+      plan.jobs.push_back(j);
+    }
+  }
+  // records of family members read the pyramid level of their own PHI_WIDTH (general kernel)
+  for (size_t i = 0; i < plan.recs.size(); i++) {
+    if (rec_family[i] < 0) continue;
+    const bhw_plan::Family& fam = plan.families[(size_t)rec_family[i]];
+    WinRec& r = plan.recs[i];
+    const uint32_t L = r.pw < fam.top ? r.pw : fam.top;
+    r.flags |= WR_HALFTAB;
+    for (uint32_t k = 1; k < r.m; k++) {
+      r.kstep[k] = k << (32 - r.pw);
+      r.idx_rsh[k] = 32 - L;
+      r.tabp[k] = fam.pyr + ((size_t)1 << (L - 1));
+    }
+  }
+  // groups: the windows of a family with one entity (number of terms) and tail, in window order
+  plan.win_group.assign((size_t)nwin, -1);
+  plan.win_gidx.assign((size_t)nwin, 0);
+  for (int w = 0; w < nwin && !plan.families.empty(); w++) {
+    const uint32_t ri = plan.win_rec[(size_t)w];
+    const int f = rec_family[ri];
+    if (f < 0) continue;
+    const WinRec& r = plan.recs[ri];
+    int g = -1;
+    for (size_t j = 0; j < plan.groups.size(); j++) {
+      const bhw_plan::Group& gr = plan.groups[j];
+      if (gr.family == f && gr.sh.m == r.m && gr.sh.rc == r.rc && gr.sh.lsh == r.lsh && gr.sh.rsh == r.rsh) { g = (int)j; break; }
+    }
+    if (g < 0) {
+      bhw_plan::Group gr;
+      gr.family = f;
+      const bhw_plan::Family& fam = plan.families[(size_t)f];
+      group_shape(r, fam.top, fam.lmin, &gr.sh);
+      gr.sh.pyr = fam.pyr;
+      gr.sh.q16 = fam.q16;
+      plan.groups.push_back(gr);
+      g = (int)plan.groups.size() - 1;
+    }
+    bhw_plan::Group& gr = plan.groups[(size_t)g];
+    plan.win_group[(size_t)w] = g;
+    gr.wins.push_back((uint32_t)w);
+  }
+  const uint32_t kSpreadG = 30;
+  for (auto& gr : plan.groups) {
+    const bool can_spread = plan.families[(size_t)gr.family].tab_mode == G_GLOBAL && gr.sh.m >= 5;
+    uint32_t units = 0;
+    for (uint32_t w : gr.wins) {
+      GroupWin gw;
+      memset(&gw, 0, sizeof(gw));
+      gw.pw = (uint32_t)descs[w].phi_width;
+      gw.rec = plan.win_rec[w];
+      gw.out_off = (int64_t)plan.flat_off[w];
+      const uint32_t wu = 1u << (gw.pw - kBankTileLog2 - 1);   // tiles of 256 sample pairs
+      if (can_spread && wu >= kSpreadG * (uint32_t)device_sm_count() * 2u) {
+        plan.win_gidx[w] = 0x80000000u | (uint32_t)(gr.singles.size() / 2);
+        gr.singles.push_back(gw);                              // unit_begin 0
+        GroupWin end;
+        memset(&end, 0, sizeof(end));
+        end.unit_begin = wu;
+        gr.singles.push_back(end);
+        continue;
+      }
+      plan.win_gidx[w] = (uint32_t)gr.list.size();
+      gw.unit_begin = units;
+      gr.list.push_back(gw);
+      units += wu;
+    }
+    GroupWin end;
+    memset(&end, 0, sizeof(end));
+    end.unit_begin = units;
+    gr.list.push_back(end);
+  }
   plan.table_work = work;
   std::vector<int> rec_tab(plan.recs.size() * BHW_MAX_TERMS, -1);
   for (const TabRef& tr : refs) {
@@ -454,8 +616,16 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   plan.o_off = align16(plan.o_jobs + plan.jobs.size() * sizeof(TabJob));
   plan.o_wr = align16(plan.o_off + (need_off ? plan.flat_off.size() * sizeof(uint64_t) : 0));
   plan.o_rom = align16(plan.o_wr + (need_wr ? plan.win_rec.size() * sizeof(uint32_t) : 0));
-  const size_t total = align16(plan.o_rom + plan.rom_host.size() * sizeof(I2));
+  size_t total = align16(plan.o_rom + plan.rom_host.size() * sizeof(I2));
+  for (auto& gr : plan.groups) {
+    gr.o_list = total; total = align16(total + gr.list.size() * sizeof(GroupWin));
+    gr.o_singles = total; total = align16(total + gr.singles.size() * sizeof(GroupWin));
+  }
   std::vector<char> blob(total);
+  for (auto& gr : plan.groups) {
+    memcpy(blob.data() + gr.o_list, gr.list.data(), gr.list.size() * sizeof(GroupWin));
+    if (!gr.singles.empty()) memcpy(blob.data() + gr.o_singles, gr.singles.data(), gr.singles.size() * sizeof(GroupWin));
+  }
   if (!plan.rom_host.empty()) memcpy(blob.data() + plan.o_rom, plan.rom_host.data(), plan.rom_host.size() * sizeof(I2));
   memcpy(blob.data() + plan.o_recs, plan.recs.data(), plan.recs.size() * sizeof(WinRec));
   if (!plan.gens.empty()) memcpy(blob.data() + plan.o_gens, plan.gens.data(), plan.gens.size() * sizeof(GenRec));
@@ -472,7 +642,6 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize(plan)");
   }
   if (!plan.rom_host.empty()) plan.rom = (const I2*)(plan.blob_dev + plan.o_rom);
-  if (!need_off) { plan.flat_off.clear(); plan.flat_off.shrink_to_fit(); }
   return BHW_OK;
 }
 
@@ -627,11 +796,53 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     const uint64_t rb = run.flat_off, re = rb + ((uint64_t)(run.w_end - run.w_begin) << run.sh.pw);
     if (re > flat_begin && rb < flat_end) runs_hit++;
   }
+  // Groups (bhw_group.cuh): the member windows that lie wholly inside the range form one contiguous piece of
+  // their group's launch list -> one paired launch per group; a member window the range cuts contributes its
+  // whole 256-sample tiles to an unpaired launch (inline list); `covered` collects what these launches write.
+  struct Covered { uint64_t b, e; };
+  const uint32_t kSpreadG_ = 30;
+  std::vector<Covered> covered;
+  struct GroupWork { uint32_t i0 = 0, i1 = 0; GroupWin part[2]; uint32_t nparts = 0; std::vector<uint32_t> singles; };
+  std::vector<GroupWork> gwork(plan.groups.size());
+  size_t group_launches = 0;
+  if (!plan.groups.empty()) {
+    size_t w = (size_t)(std::upper_bound(plan.flat_off.begin(), plan.flat_off.end(), flat_begin) - plan.flat_off.begin());
+    w = w ? w - 1 : 0;
+    for (; w < (size_t)plan.nwin && plan.flat_off[w] < flat_end; w++) {
+      const int g = plan.win_group[w];
+      if (g < 0) continue;
+      GroupWork& gk = gwork[(size_t)g];
+      const uint64_t wb = plan.flat_off[w], we = plan.flat_off[w + 1];
+      const uint64_t lo = wb > flat_begin ? wb : flat_begin, hi = we < flat_end ? we : flat_end;
+      if (lo >= hi) continue;
+      if (lo == wb && hi == we) {
+        const uint32_t gi = plan.win_gidx[w];
+        if (gi & 0x80000000u) { gk.singles.push_back(gi & 0x7FFFFFFFu); group_launches++; }
+        else {
+          if (gk.i1 == gk.i0) { gk.i0 = gi; group_launches++; }
+          gk.i1 = gi + 1;
+        }
+        covered.push_back({wb, we});
+      } else {
+        const uint64_t ta = (lo - wb + kBankTile - 1) / kBankTile, tb = (hi - wb) / kBankTile;
+        if (tb <= ta || gk.nparts >= 2) continue;
+        GroupWin& pw_ = gk.part[gk.nparts];
+        memset(&pw_, 0, sizeof(pw_));
+        pw_.pw = plan.recs[plan.win_rec[w]].pw;
+        pw_.rec = plan.win_rec[w];
+        pw_.tile_first = (uint32_t)ta;
+        pw_.out_off = (int64_t)wb;
+        pw_.unit_begin = (uint32_t)(tb - ta);                   // tile count for now; prefix-summed at launch
+        if (!gk.nparts++) group_launches++;
+        covered.push_back({wb + ta * kBankTile, wb + tb * kBankTile});
+      }
+    }
+  }
   LaunchFan fan;
-  fan.begin(plan.dev, stream, runs_hit);
+  fan.begin(plan.dev, stream, runs_hit + group_launches);
   if (fan.err != cudaSuccess) return cuda_fail(fan.err, "side streams");
-  // any flat sub-range through the general kernel
-  auto general = [&](uint64_t b, uint64_t e_) -> int {
+  // one flat sub-range through the general kernel
+  auto general_raw = [&](uint64_t b, uint64_t e_) -> int {
     if (b >= e_) return BHW_OK;
     a.out = (int32_t*)out_dev + (b - flat_begin);
     a.flat_begin = b;
@@ -646,6 +857,17 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     if (ce != cudaSuccess) return cuda_fail(ce, "k_synth");
     g_launches++;
     return BHW_OK;
+  };
+  // ... minus what the group launches cover
+  auto general = [&](uint64_t b, uint64_t e_) -> int {
+    if (b >= e_) return BHW_OK;
+    auto it = std::lower_bound(covered.begin(), covered.end(), b, [](const Covered& c, uint64_t v) { return c.e <= v; });
+    uint64_t cur = b;
+    for (; it != covered.end() && it->b < e_; ++it) {
+      if (it->b > cur) { int st_ = general_raw(cur, it->b); if (st_) return st_; }
+      if (it->e > cur) cur = it->e;
+    }
+    return cur < e_ ? general_raw(cur, e_) : BHW_OK;
   };
   uint64_t cursor = flat_begin;
   // one bank launch: whole windows [wa, wb) of the run, or (ntiles > 0) tiles [tile_off, +ntiles) of window wa
@@ -723,6 +945,57 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   }
   int st = general(cursor, flat_end);
   if (st) return st;
+  // the group launches (after the small general pieces: these kernels fill the GPU)
+  for (size_t g = 0; g < plan.groups.size(); g++) {
+    const bhw_plan::Group& gr = plan.groups[g];
+    GroupWork& gk = gwork[g];
+    const int tabm = plan.families[(size_t)gr.family].tab_mode;
+    const int npass = 2 + (int)gk.singles.size();
+    for (int pass = 0; pass < npass; pass++) {
+      GroupArgs ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.sh = gr.sh;
+      ga.recs = a.recs;
+      ga.out = (int32_t*)out_dev - flat_begin;                  // GroupWin::out_off is a flat index of the batch
+      if (pass == 0) {
+        if (gk.i1 == gk.i0) continue;
+        ga.wins = (const GroupWin*)(plan.blob_dev + gr.o_list) + gk.i0;
+        ga.nwin = gk.i1 - gk.i0;
+        ga.unit_base = gr.list[gk.i0].unit_begin;
+        ga.nunits = gr.list[gk.i1].unit_begin - ga.unit_base;
+      } else if (pass >= 2) {
+        const uint32_t si = gk.singles[(size_t)pass - 2];
+        ga.wins = (const GroupWin*)(plan.blob_dev + gr.o_singles) + 2 * si;
+        ga.nwin = 1;
+        ga.nunits = gr.singles[2 * (size_t)si + 1].unit_begin;
+        ga.spread = kSpreadG_;
+      } else {
+        if (!gk.nparts) continue;
+        uint32_t units = 0;
+        for (uint32_t i = 0; i < gk.nparts; i++) {
+          ga.iw[i] = gk.part[i];
+          const uint32_t cnt = gk.part[i].unit_begin;
+          ga.iw[i].unit_begin = units;
+          units += cnt;
+        }
+        ga.iw[gk.nparts].unit_begin = units;
+        ga.wins = nullptr;
+        ga.nwin = gk.nparts;
+        ga.nunits = units;
+        ga.sh.interleave = 0;
+      }
+      cudaStream_t ls = fan.next();
+      cudaError_t ce;
+      {
+        LaunchTimer tm(BHW_KERNEL_SYNTH_GROUP, ls);
+        const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
+        ce = launch_synth_group(ga, tabm, pass != 1, ls, pdl);
+        table_ahead = false;
+      }
+      if (ce != cudaSuccess) return cuda_fail(ce, "k_synth_group");
+      g_launches++;
+    }
+  }
   e = fan.join();
   if (e != cudaSuccess) return cuda_fail(e, "side streams (join)");
   return BHW_OK;

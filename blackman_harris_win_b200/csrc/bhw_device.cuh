@@ -213,6 +213,10 @@ struct TabJob {
   uint32_t work;        // work items of this job: entries/4, or entries for SRC_INQ
   uint32_t rom_off;     // Taylor ROM offset (I2 units) in the rom buffer
   uint32_t tshift;      // entries are stored left-shifted by this much (see WinRec)
+  uint32_t pyr_lmin;    // > 0: `tab` is a half-period pyramid (bhw_group.cuh) with top level sp.pw and lowest
+                        // level pyr_lmin instead of a plain full-period table (output-quadrant sources only)
+  uint32_t pad0;
+  uint16_t* q16;        // pyramid jobs: also write the uint16 quarter-wave image (cos16[Q], sin16[Q]) here, or NULL
   int32_t rom32[32];    // TABCORE_32 / _32BIAS: atan word of stage i sliced for this register width (0 past n_z);
                         // TABCORE_A64: high half of rom64[i] plus 1 when its low half reads negative as an int32
   int64_t rom64[48];    // TABCORE_A64: atan word of stage i, sliced and left-aligned to bit 63 (0 past n_z)
@@ -310,6 +314,27 @@ BHW_HD void cordic_core_aligned64(const SrcParams& p, const int64_t* __restrict_
   vc = X >> (ax + p.out_shift);
 }
 
+// Half-period pyramid: see bhw_group.cuh.  Work item e (a quarter-wave phase of the top level) writes
+// `c` = cos of quadrant 0 and `ns` = cos of quadrant 1 (= -sin), already wrapped and shifted as table
+// entries, into every level that contains phase e: level L starts at word 2^(L-1) and holds the first half
+// period at L-bit phase resolution.  (vs, vc): the raw pair, for the uint16 quarter-wave image.
+constexpr uint32_t kQ16Bias = 1024;   // uint16 image: stored value = cos + bias (the CORDIC's error is << bias)
+BHW_HD void pyramid_store(int32_t* H, uint32_t top, uint32_t lmin, uint16_t* q16, uint32_t e, int32_t c, int32_t ns,
+                          int32_t vs, int32_t vc) {
+  for (uint32_t L = top; L >= lmin; --L) {
+    const uint32_t d = top - L;
+    if (e & ((1u << d) - 1u)) break;
+    const uint32_t i = e >> d;
+    H[(1u << (L - 1)) + i] = c;
+    H[(1u << (L - 1)) + (1u << (L - 2)) + i] = ns;
+  }
+  if (q16) {
+    const uint32_t Q = 1u << (top - 2);
+    q16[e] = (uint16_t)((uint32_t)vc + kQ16Bias);
+    q16[Q + e] = (uint16_t)((uint32_t)vs + kQ16Bias);
+  }
+}
+
 // the four entries one core evaluation yields: cos = c, -s, -c, s in quadrants 0..3
 BHW_HD void table_store_quadrants(const TabJob& job, uint32_t e, int64_t vs, int64_t vc) {
   const SrcParams& p = job.sp;
@@ -317,6 +342,11 @@ BHW_HD void table_store_quadrants(const TabJob& job, uint32_t e, int64_t vs, int
   const uint32_t Q = job.entries >> 2;
   const int64_t t = (int64_t)1 << job.tshift;
   const int64_t ns = wrapb(-vs, p.negw), nc = wrapb(-vc, p.negw);
+  if (job.pyr_lmin) {
+    pyramid_store(T, (uint32_t)p.pw, job.pyr_lmin, job.q16, e, (int32_t)(wrapb(vc, p.outw) * t),
+                  (int32_t)(wrapb(ns, p.outw) * t), (int32_t)vs, (int32_t)vc);
+    return;
+  }
   T[e] = (int32_t)(wrapb(vc, p.outw) * t);          // quadrant 0: cos =  c
   T[e + Q] = (int32_t)(wrapb(ns, p.outw) * t);      // quadrant 1: cos = -s
   T[e + 2 * Q] = (int32_t)(wrapb(nc, p.outw) * t);  // quadrant 2: cos = -c
@@ -633,7 +663,9 @@ enum : uint32_t {
   WR_ACC64 = 2u,    // accumulator / shifts need more than 32 bits: 64-bit tail on table values
   WR_HLS = 4u,      // HLS tail
   WR_RTL2 = 8u,     // 2-term entity
-  WR_GENERIC = 16u  // fall back to the generic 64-bit body (direct evaluation)
+  WR_GENERIC = 16u, // fall back to the generic 64-bit body (direct evaluation)
+  WR_HALFTAB = 32u  // tabp[k] is one level of a half-period pyramid (bhw_group.cuh): it holds the first half
+                    // period only, the second half is its negation; idx_rsh[k] = 32 - level
 };
 
 // hi32(a*b + rc): one IMAD.WIDE with a 64-bit addend, high word taken
@@ -645,10 +677,17 @@ BHW_HD int32_t mulhi_rc(int32_t a, int32_t b, uint32_t rc) {
 template <int M>
 BHW_HD int32_t synth_sample32(const WinRec& r, uint32_t n) {
   uint32_t S = (uint32_t)r.S0;
+  const bool halftab = (r.flags & WR_HALFTAB) != 0;
 #pragma unroll
   for (int k = 1; k < M; ++k) {
     const uint32_t ph = n * r.kstep[k];
-    const int32_t c2 = r.tabp[k][ph >> r.idx_rsh[k]];
+    int32_t c2;
+    if (halftab) {
+      const int32_t t = r.tabp[k][(ph & 0x7FFFFFFFu) >> r.idx_rsh[k]];
+      c2 = (ph >> 31) ? -t : t;     // exact: the table is antisymmetric over half a period
+    } else {
+      c2 = r.tabp[k][ph >> r.idx_rsh[k]];
+    }
     const uint32_t b = (uint32_t)mulhi_rc(r.A[k], c2, r.rc);
     S = (k & 1) ? S - b : S + b;
   }

@@ -1,0 +1,182 @@
+// bhw_group.cu - k_synth_group: one launch generates every window of a group (bhw_group.cuh): windows of one
+// family (sin/cos source + DAT_WIDTH) and one entity (number of terms), of ANY mix of PHI_WIDTHs and ports.
+// Persistent, one CTA of 1024 threads per SM; the family's table is staged in shared memory once per CTA
+// (G_HALF32 / G_Q16) or gathered from the half-period pyramid through L1/L2 (G_GLOBAL); every warp takes
+// tiles of 256 samples (sample pairs (n, n + N/2) in the paired instantiations: one look-up serves both),
+// lane-interleaved so that every store instruction writes 128 contiguous bytes, streaming.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "bhw_group.cuh"
+#include "bhw_launch.h"
+
+namespace bhw {
+
+constexpr int kGroupThreads = 1024;
+constexpr int kGroupWarps = kGroupThreads / 32;
+
+template <int M, int TAB, bool PAIR>
+__global__ void __launch_bounds__(kGroupThreads, 1)
+k_synth_group(const __grid_constant__ GroupArgs a) {
+  extern __shared__ __align__(16) int32_t s_img[];
+  const GroupShape& sh = a.sh;
+  // launched with programmatic stream serialization behind the table build (a no-op otherwise)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const void* tab = sh.pyr;
+  if (TAB != G_GLOBAL) {
+    // G_HALF32: level `top` of the pyramid (2^(top-1) words from word 2^(top-1)); G_Q16: 2 * 2^(top-2) uint16
+    const uint32_t words = TAB == G_HALF32 ? (1u << (sh.top - 1)) : (1u << (sh.top - 2));
+    const int4* src = TAB == G_HALF32 ? reinterpret_cast<const int4*>(sh.pyr + (1u << (sh.top - 1)))
+                                      : reinterpret_cast<const int4*>(sh.q16);
+    int4* dst = reinterpret_cast<int4*>(s_img);
+    for (uint32_t i = threadIdx.x; i < words / 4; i += kGroupThreads) dst[i] = __ldg(src + i);
+    __syncthreads();
+    tab = s_img;
+  }
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t U = a.nunits;
+  if (TAB == G_GLOBAL && a.spread) {
+    // One long window over a pyramid that lives in L2 / HBM.  Odd harmonic k of tile n reads its level around
+    // k*n at stride k: k sectors per 8 look-ups, of which it uses every k-th word; the other words belong to
+    // the tiles a k-th of a period away.  So warp j of G takes the j-th G-th of the window (tiles U*j/G + i,
+    // all warps at the same i): with G = 30 the warps j, j + 10, j + 20 read the same sectors for k = 3 (and
+    // j + 6m for k = 5) at the same time, through L1 - every sector crosses L2 -> SM once and every level is
+    // swept once per harmonic (r1: N = 2^26 7-term 340 -> 226 us; with the pyramid's even-harmonic levels less).
+    const uint32_t G = a.spread;
+    if (warp >= G) return;
+    const GroupWin* gw = a.wins ? a.wins : a.iw;
+    const uint32_t pw = gw->pw;
+    const WinRec* r = a.recs + gw->rec;
+    int32_t A[M];
+    A[0] = 0;
+#pragma unroll
+    for (int k = 1; k < M; ++k) A[k] = __ldg(&r->A[k]);
+    const int32_t S0 = __ldg(&r->S0);
+    const uint32_t n_first = __ldg(&r->n_first);
+    int32_t* o = a.out + gw->out_off;
+    const size_t half = (size_t)1 << (pw - 1);
+    const uint32_t L = spread_steps(U, G);
+    const uint32_t i0 = (uint32_t)((uint64_t)L * blockIdx.x / gridDim.x);
+    const uint32_t i1 = (uint32_t)((uint64_t)L * (blockIdx.x + 1) / gridDim.x);
+    for (uint32_t i = i0; i < i1; ++i) {
+      uint32_t t;
+      if (!spread_tile(U, G, warp, i, &t)) continue;
+      int32_t va[kBankJ], vb[kBankJ];
+      group_lane_tile<M, TAB, PAIR>(sh, pw, A, S0, tab, t * kBankTile + n_first, lane, va, vb);
+      int32_t* ot = o + (size_t)t * kBankTile + lane;
+#pragma unroll
+      for (int j = 0; j < kBankJ; ++j) {
+        __stcs(ot + 32 * j, va[j]);
+        if (PAIR) __stcs(ot + half + 32 * j, vb[j]);
+      }
+    }
+    return;
+  }
+  uint32_t u, u_end, u_step;
+  if (sh.interleave) {
+    u = blockIdx.x * kGroupWarps + warp; u_end = U; u_step = gridDim.x * kGroupWarps;
+  } else {
+    const uint32_t u0 = (uint32_t)((uint64_t)U * blockIdx.x / gridDim.x);
+    u_end = (uint32_t)((uint64_t)U * (blockIdx.x + 1) / gridDim.x);
+    u = u0 + warp; u_step = kGroupWarps;
+  }
+  if (u >= u_end) return;
+  const GroupWin* wins = a.wins ? a.wins : a.iw;
+  u += a.unit_base;
+  u_end += a.unit_base;
+  uint32_t w = group_find_window(wins, a.nwin, u);
+  uint32_t w_begin = 0, w_next = 0, pw = 0, n_first = 0, tile_first = 0;
+  int32_t A[M], S0 = 0;
+  int32_t* o = nullptr;
+  bool loaded = false;
+  for (; u < u_end; u += u_step) {
+    if (!loaded || u >= w_next) {
+      if (loaded) { do { ++w; } while (u >= wins[w + 1].unit_begin); }
+      const GroupWin* gw = wins + w;
+      w_begin = gw->unit_begin;
+      w_next = gw[1].unit_begin;
+      pw = gw->pw;
+      tile_first = gw->tile_first;
+      o = a.out + gw->out_off;
+      const WinRec* r = a.recs + gw->rec;
+      A[0] = 0;
+#pragma unroll
+      for (int k = 1; k < M; ++k) A[k] = __ldg(&r->A[k]);
+      S0 = __ldg(&r->S0);
+      n_first = __ldg(&r->n_first);
+      loaded = true;
+    }
+    const uint32_t t = u - w_begin + tile_first;
+    int32_t va[kBankJ], vb[kBankJ];
+    group_lane_tile<M, TAB, PAIR>(sh, pw, A, S0, tab, t * kBankTile + n_first, lane, va, vb);
+    int32_t* ot = o + (size_t)t * kBankTile + lane;
+    const size_t half = (size_t)1 << (pw - 1);
+#pragma unroll
+    for (int j = 0; j < kBankJ; ++j) {
+      __stcs(ot + 32 * j, va[j]);
+      if (PAIR) __stcs(ot + half + 32 * j, vb[j]);
+    }
+  }
+}
+
+size_t group_smem_limit() { return 192u * 1024u; }
+
+template <int M, int TAB, bool PAIR>
+static cudaError_t launch_group_t(const GroupArgs& a, unsigned grid, size_t smem, cudaStream_t stream, bool pdl) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_synth_group<M, TAB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)group_smem_limit());
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGroupThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_synth_group<M, TAB, PAIR>, a);
+}
+
+template <int M>
+static cudaError_t launch_group_m(const GroupArgs& a, int tab, bool pair, unsigned grid, size_t smem,
+                                  cudaStream_t stream, bool pdl) {
+  if (tab == G_HALF32) return pair ? launch_group_t<M, G_HALF32, true>(a, grid, smem, stream, pdl)
+                                   : launch_group_t<M, G_HALF32, false>(a, grid, smem, stream, pdl);
+  if (tab == G_Q16) return pair ? launch_group_t<M, G_Q16, true>(a, grid, smem, stream, pdl)
+                                : launch_group_t<M, G_Q16, false>(a, grid, smem, stream, pdl);
+  return pair ? launch_group_t<M, G_GLOBAL, true>(a, grid, 0, stream, pdl)
+              : launch_group_t<M, G_GLOBAL, false>(a, grid, 0, stream, pdl);
+}
+
+cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
+  if (!a.nunits || !a.nwin) return cudaSuccess;
+  if (a.spread && (tab != G_GLOBAL || a.nwin != 1 || a.unit_base || a.spread > (uint32_t)kGroupWarps)) return cudaErrorInvalidValue;
+  const uint64_t ctas = a.spread ? ((uint64_t)a.nunits + a.spread - 1) / a.spread
+                                 : ((uint64_t)a.nunits + kGroupWarps - 1) / kGroupWarps;
+  const unsigned sms = (unsigned)device_sm_count();
+  const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
+  size_t smem = 0;
+  if (tab == G_HALF32) smem = (size_t)4 << (a.sh.top - 1);
+  else if (tab == G_Q16) smem = (size_t)4 << (a.sh.top - 2);
+  if (smem > group_smem_limit()) return cudaErrorInvalidValue;
+  switch (a.sh.m) {
+    case 2: return launch_group_m<2>(a, tab, pair, grid, smem, stream, pdl);
+    case 3: return launch_group_m<3>(a, tab, pair, grid, smem, stream, pdl);
+    case 4: return launch_group_m<4>(a, tab, pair, grid, smem, stream, pdl);
+    case 5: return launch_group_m<5>(a, tab, pair, grid, smem, stream, pdl);
+    case 7: return launch_group_m<7>(a, tab, pair, grid, smem, stream, pdl);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace bhw

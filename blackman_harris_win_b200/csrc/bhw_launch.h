@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "bhw_device.cuh"
+#include "bhw_group.cuh"
 
 namespace bhw {
 
@@ -31,6 +32,19 @@ struct BankArgs {
   uint32_t ntiles;           //             (unpaired shape); `out` is then the first of those tiles
   uint32_t win_minor;        // TAB_GLOBAL, whole windows: walk the bank tile by tile across its windows
   uint32_t spread;           // TAB_GLOBAL, one whole window: G > 0 = warp j of G takes the j-th G-th of the window
+};
+
+struct GroupArgs {
+  GroupShape sh;
+  const WinRec* recs;        // per-window records (A[k], S0, n_first are read)
+  const GroupWin* wins;      // [nwin + 1] windows of the launch in unit order (the last one is a sentinel whose
+                             // unit_begin closes the unit range); NULL: the list is `iw` below
+  GroupWin iw[3];            // inline list for the one or two windows a requested range cuts
+  int32_t* out;              // GroupWin::out_off is relative to this
+  uint32_t nwin;
+  uint32_t unit_base;        // the launch covers units [unit_base, unit_base + nunits) of the list's numbering
+  uint32_t nunits;           // tiles of 256 samples (sample pairs) in the launch
+  uint32_t spread;           // G_GLOBAL, one whole window: G > 0 = warp j of G takes the j-th G-th of the window
 };
 
 struct DirectArgs {
@@ -88,6 +102,9 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
 // k_table_build, which releases its dependents early; k_synth_bank waits for it before its first
 // table read)
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl = false);
+// tab: G_HALF32 / G_Q16 / G_GLOBAL; pair: units are tiles of sample pairs (whole windows only)
+cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl = false);
+size_t group_smem_limit();  // bytes of shared memory a group launch may use for the staged table image
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 int device_sm_count();     // SMs of the current device (148 on B200)
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);

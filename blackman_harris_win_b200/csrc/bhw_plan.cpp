@@ -373,4 +373,60 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
   return true;
 }
 
+
+// ---- families and groups --------------------------------------------------------------------------
+bool group_eligible(const bhw_desc& d, const WinParams& wp, const SrcParams* src) {
+  if (d.algo == BHW_ALGO_DIRECT || wp.nsrc != 1 || wp.pw < kBankTileLog2 + 1 || wp.elem64) return false;
+  const SrcParams& sp = src[0];
+  if (sp.kind != SRC_DDS && sp.kind != SRC_HLS) return false;
+  if (!source_antisymmetric(sp) || sp.pw != wp.pw) return false;
+  if (fast_tail_mode(wp, src) != TAILMODE_FAST32) return false;
+  for (int k = 1; k < wp.m; k++) {
+    const TermParams& t = wp.term[k - 1];
+    if (t.kmul != (uint32_t)k || t.src != 0 || t.ph_mask != (uint32_t)((1ull << wp.pw) - 1)) return false;
+  }
+  return true;
+}
+
+int family_source(const bhw_desc& d, int pw, SrcParams* canon) {
+  bhw_desc d2 = d;
+  d2.phi_width = pw;
+  SrcParams sp;
+  int st = resolve_source(&d2, 0, &sp);
+  if (st) return st;
+  uint32_t drop;
+  *canon = canonical_source(sp, &drop);
+  return BHW_OK;
+}
+
+int group_tab_mode(const SrcParams& canon, uint32_t top, size_t smem_limit_bytes) {
+  if (((size_t)4 << (top - 1)) <= smem_limit_bytes) return G_HALF32;
+  // uint16 quarter waves: |cos|, |sin| <= 2^(DW-2) + (a few LSB of CORDIC error) must fit 16 bits with the
+  // bias on both sides: DAT_WIDTH <= 17 (amplitude 2^15; the error is below DAT_WIDTH LSB, the bias is 1024)
+  if (canon.dw <= 17 && ((size_t)4 << (top - 2)) <= smem_limit_bytes) return G_Q16;
+  return G_GLOBAL;
+}
+
+void group_shape(const WinRec& r, uint32_t top, uint32_t lmin, GroupShape* sh) {
+  memset(sh, 0, sizeof(*sh));
+  sh->m = r.m;
+  sh->top = top;
+  sh->lmin = lmin;
+  sh->rc = r.rc;
+  sh->rcn = 0xFFFFFFFFu - r.rc;
+  sh->lsh = r.lsh;
+  sh->rsh = r.rsh;
+  // light kernels are paced by the store path: the whole GPU sweeps the output front to back; from 4
+  // terms up a contiguous share per CTA measured faster (k_synth_bank)
+  sh->interleave = r.m <= 3 ? 1u : 0u;
+  sh->tmul = 1u << r.tshift;
+  sh->tbias = kQ16Bias << r.tshift;
+}
+
+void init_pyramid_job(const SrcParams& canon, uint32_t lmin, int32_t* pyr, uint16_t* q16, TabJob* j) {
+  init_tab_job(canon, pyr, j);
+  j->pyr_lmin = lmin;
+  j->q16 = q16;
+}
+
 }  // namespace bhw

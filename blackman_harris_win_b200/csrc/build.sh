@@ -1,9 +1,18 @@
 #!/usr/bin/env bash
 # Build blackman_harris_win_b200/libbhw.so for sm_100a (cross-compiles without a GPU).
+# The translation units are compiled in parallel, then linked.
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libbhw.so"
+OBJ="$HERE/../build"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -shared"
-"$NVCC" $FLAGS ${BHW_NVCC_EXTRA:-} "$HERE/bhw_kernels.cu" "$HERE/bhw_api.cu" "$HERE/bhw_resolve.cpp" "$HERE/bhw_plan.cpp" -o "$OUT"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden"
+mkdir -p "$OBJ"
+pids=()
+for f in bhw_kernels.cu bhw_group.cu bhw_api.cu bhw_resolve.cpp bhw_plan.cpp; do
+  "$NVCC" $FLAGS ${BHW_NVCC_EXTRA:-} -c "$HERE/$f" -o "$OBJ/${f%.*}.o" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared "$OBJ"/bhw_kernels.o "$OBJ"/bhw_group.o "$OBJ"/bhw_api.o "$OBJ"/bhw_resolve.o "$OBJ"/bhw_plan.o -o "$OUT"
 echo "built $OUT"

@@ -283,7 +283,8 @@ enum {
   BHW_KERNEL_SINCOS = 3,      /* k_sincos                                                        */
   BHW_KERNEL_SYNTH_BANK = 4,  /* k_synth_bank: whole windows of one shape, tables in shared memory */
   BHW_KERNEL_ATAN2 = 5,       /* k_atan2                                                          */
-  BHW_KERNEL_CLASSES = 6
+  BHW_KERNEL_SYNTH_GROUP = 6, /* k_synth_group: all windows of one family and entity, any PHI_WIDTHs  */
+  BHW_KERNEL_CLASSES = 7
 };
 BHW_API int bhw_timing_enable(int enabled);
 BHW_API int bhw_timing_reset(void);

@@ -192,7 +192,7 @@ def hostcheck():
     path = os.path.join(HOSTCHECK_DIR, "libbhw_hostcheck.so")
     srcs = [os.path.join(HOSTCHECK_DIR, "hostcheck.cpp")] + [
         os.path.join(ROOT, "blackman_harris_win_b200", "csrc", f)
-        for f in ("bhw_resolve.cpp", "bhw_plan.cpp", "bhw_device.cuh", "bhw_internal.h", "bhw_plan.h")]
+        for f in ("bhw_resolve.cpp", "bhw_plan.cpp", "bhw_device.cuh", "bhw_group.cuh", "bhw_internal.h", "bhw_plan.h")]
     stale = not os.path.exists(path) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(path) for s in srcs)
     if stale:
@@ -209,6 +209,7 @@ def hostcheck():
     L.hc_table_cos.argtypes = [D, I64P, C.c_int]
     L.hc_bank.argtypes = [D, I64P, C.c_uint64, C.c_int, C.c_int]
     L.hc_source_antisymmetric.argtypes = [D]
+    L.hc_group.argtypes = [D, C.c_int, I64P, C.c_int, C.c_int]
     L.hc_tail_mode.argtypes = [D]
     L.hc_walk.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     L.hc_lin_tiles.argtypes = [C.c_int]

@@ -12,6 +12,7 @@
 
 #include "../../blackman_harris_win_b200/csrc/bhw_device.cuh"
 #include "../../blackman_harris_win_b200/csrc/bhw_plan.h"
+#include "../../blackman_harris_win_b200/csrc/bhw_group.cuh"
 
 using namespace bhw;
 
@@ -318,6 +319,119 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
         if (pair) out[half + t * kBankTile + lane + 32 * j] = vb[j];
       }
     }
+  }
+  return 0;
+}
+
+
+// Group kernel body (k_synth_group) for a list of windows of ONE family and entity, any PHI_WIDTHs: builds the
+// family's half-period pyramid with the table-builder bodies (as bhw_api.cu plans it), then runs every
+// window through group_lane_tile with the kernel's tile/lane mapping.  out = the windows' samples concatenated.
+// force_tab: -1 = the planner's choice for 192 KB, else G_*; unpaired: 1 = the unpaired instantiation
+// (what a window cut by the requested range gets).  Also checks the pyramid against the level rule
+// and runs the general-kernel body (WR_HALFTAB records) on the first samples of every window.
+// Returns 1 when the windows are not group material (or the forced placement does not fit).
+int hc_group(const bhw_desc* descs, int nwin, int64_t* out, int force_tab, int unpaired) {
+  if (nwin <= 0) return -1;
+  SrcParams key0;
+  uint32_t max_pw = 0, min_pw = 99;
+  std::vector<WinRec> recs((size_t)nwin);
+  for (int w = 0; w < nwin; w++) {
+    WinParams wp; SrcParams src[2];
+    int st = resolve_window(&descs[w], &wp, src);
+    if (st) return st;
+    if (!group_eligible(descs[w], wp, src)) return 1;
+    SrcParams key;
+    if ((st = family_source(descs[w], BHW_MAX_PHI_WIDTH, &key))) return st;
+    if (w == 0) key0 = key;
+    else if (memcmp(&key, &key0, sizeof(key))) return 1;
+    memset(&recs[w], 0, sizeof(WinRec));
+    fill_fast_rec(wp, src, recs[w]);
+    recs[w].n_first = (uint32_t)wp.stream_offset;
+    if (recs[w].m != recs[0].m || recs[w].rc != recs[0].rc || recs[w].lsh != recs[0].lsh || recs[w].rsh != recs[0].rsh) return 1;
+    if ((uint32_t)wp.pw > max_pw) max_pw = (uint32_t)wp.pw;
+    if ((uint32_t)wp.pw < min_pw) min_pw = (uint32_t)wp.pw;
+  }
+  const uint32_t res = (uint32_t)key0.pw;
+  const uint32_t top = max_pw < res ? max_pw : res;
+  const uint32_t low = min_pw < top ? min_pw : top;
+  const uint32_t lmin = low > 4 ? low - 2 : 2;
+  SrcParams canon;
+  int st = family_source(descs[0], (int)top, &canon);
+  if (st) return st;
+  int tab = group_tab_mode(canon, top, 192 * 1024);
+  if (force_tab >= 0) {
+    if (force_tab == G_HALF32 && top > 22) return 1;
+    if (force_tab == G_Q16 && (canon.dw > 17 || top > 22)) return 1;
+    tab = force_tab;
+  }
+  std::vector<int32_t> pyr((size_t)1 << top, 0x7FFFFFFF);
+  std::vector<uint16_t> q16((size_t)1 << (top - 1), 0xFFFF);
+  TabJob j;
+  init_pyramid_job(canon, lmin, pyr.data(), tab == G_Q16 ? q16.data() : nullptr, &j);
+  std::vector<I2> norom;
+  for (uint32_t e = 0; e < j.work; e++) table_build_item(j, norom.data(), e);
+  if (table_build_unrolled_ok(j)) {      // the stage-unrolled kernel body must give the same pyramid
+    std::vector<int32_t> again((size_t)1 << top, 0x7FFFFFFF);
+    TabJob ju = j;
+    ju.tab = again.data();
+    ju.q16 = nullptr;
+    for (uint32_t e = 0; e < ju.work; e++) {
+      if (ju.fast == TABCORE_32BIAS) table_build_item_u<31, true>(ju, e);
+      else if (ju.sp.n_xy == 15) table_build_item_u<15, false>(ju, e);
+      else if (ju.sp.n_xy == 16) table_build_item_u<16, false>(ju, e);
+      else table_build_item_u<23, false>(ju, e);
+    }
+    if (again != pyr) return -201;
+  }
+  // level rule: level L-1 is every second entry of level L
+  for (uint32_t L = top; L > lmin; L--)
+    for (uint32_t i = 0; i < (1u << (L - 2)); i++)
+      if (pyr[(1u << (L - 2)) + i] != pyr[(1u << (L - 1)) + 2 * i]) return -202;
+  GroupShape sh;
+  group_shape(recs[0], top, lmin, &sh);
+  sh.pyr = pyr.data();
+  sh.q16 = q16.data();
+  const void* img = tab == G_HALF32 ? (const void*)(pyr.data() + ((size_t)1 << (top - 1)))
+                  : tab == G_Q16 ? (const void*)q16.data() : (const void*)pyr.data();
+  uint64_t off = 0;
+  for (int w = 0; w < nwin; w++) {
+    const WinRec& r = recs[w];
+    const uint32_t pw = r.pw;
+    const uint64_t N = 1ull << pw;
+    const uint32_t tiles = unpaired ? (uint32_t)(N >> kBankTileLog2) : (uint32_t)(N >> (kBankTileLog2 + 1));
+    for (uint32_t t = 0; t < tiles; t++) {
+      for (uint32_t lane = 0; lane < 32; lane++) {
+        int32_t va[kBankJ], vb[kBankJ];
+        const uint32_t nbase = t * kBankTile + r.n_first;
+#define HC_G3(M, TAB) do { if (unpaired) group_lane_tile<M, TAB, false>(sh, pw, r.A, r.S0, img, nbase, lane, va, vb); \
+                           else group_lane_tile<M, TAB, true>(sh, pw, r.A, r.S0, img, nbase, lane, va, vb); } while (0)
+#define HC_G2(M) do { if (tab == G_HALF32) HC_G3(M, G_HALF32); else if (tab == G_Q16) HC_G3(M, G_Q16); else HC_G3(M, G_GLOBAL); } while (0)
+        switch (r.m) {
+          case 2: HC_G2(2); break;
+          case 3: HC_G2(3); break;
+          case 4: HC_G2(4); break;
+          case 5: HC_G2(5); break;
+          default: HC_G2(7); break;
+        }
+        for (int jj = 0; jj < kBankJ; jj++) {
+          out[off + (uint64_t)t * kBankTile + lane + 32 * jj] = va[jj];
+          if (!unpaired) out[off + N / 2 + (uint64_t)t * kBankTile + lane + 32 * jj] = vb[jj];
+        }
+      }
+    }
+    // the general kernel's body on a record that reads the pyramid (WR_HALFTAB), a few samples
+    WinRec rr = r;
+    const uint32_t L = pw < top ? pw : top;
+    rr.flags |= WR_HALFTAB;
+    for (uint32_t k = 1; k < rr.m; k++) {
+      rr.kstep[k] = k << (32 - pw);
+      rr.idx_rsh[k] = 32 - L;
+      rr.tabp[k] = pyr.data() + ((size_t)1 << (L - 1));
+    }
+    for (uint64_t n = 0; n < N; n += (N > 4096 ? 61 : 1))
+      if ((int64_t)synth_sample(rr, (uint32_t)n + rr.n_first) != out[off + n]) return -203;
+    off += N;
   }
   return 0;
 }

@@ -130,26 +130,143 @@ def test_large_windows_properties():
         del full, parts
 
 
-def test_phi_width_beyond_the_reference_range():
-    """PHI_WIDTH 27..30 is accepted (the reference documents 64M = 2^26 points as its maximum): a
-    2^28-point window (1 GiB) through the bank kernel and a ragged range of a 2^30-point one,
-    spot-checked against the oracle and against the direct strategy."""
+def test_phi_width_beyond_the_reference_range_is_rejected():
+    """The reference documents 16 .. 64M points (README.md:2): PHI_WIDTH 27 and up is an argument error on
+    every entry point, not an untested code path."""
+    d = bhw.variant_desc(6, 26, 17)
+    d27 = d.copy(phi_width=27)
+    assert bhw.validate(d) == 0 and bhw.validate(d27) == -5
+    with pytest.raises(bhw.BhwError):
+        bhw.generate(d27, 0, 16)
+    with pytest.raises(bhw.BhwError):
+        bhw.Plan([d, d27])
+    with pytest.raises(bhw.BhwError):
+        bhw.sincos(d27, 0, 16)
+
+
+def test_bench_bank_shape_against_the_oracle():
+    """The instantiation bench.py times for BASELINE config 2 - k_synth_bank<4, staged half period, paired> on
+    bh_win_4term, PHI_WIDTH 16, DAT_WIDTH 17, every window with its own AA0..AA3 - sample by sample against
+    the oracle (src/bh_win_4term.vhd:225-280), whole bank and a ragged sub-range of it."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    nwin = 256
+    arr = bench.bank_descs(nwin)
+    descs = [bhw.BhwDesc.from_buffer_copy(bytes(arr[i])) for i in range(nwin)]
+    assert len({tuple(d.aa) for d in descs}) == nwin
+    want = H.orc_batch(descs, 0, nwin << 16)
+    n0 = bhw.launch_count()
+    plan = bhw.Plan(descs)
+    bhw.timing_enable(True)
+    bhw.timing_reset()
+    got = plan.execute().cpu().numpy().astype(np.int64)
+    kt = bhw.timing_read()
+    bhw.timing_enable(False)
+    assert kt["k_synth_bank"][0] == 1 and kt["k_synth"][0] == 0 and kt["k_synth_group"][0] == 0   # the bench kernel ran
+    assert np.array_equal(got, want)
+    b, c = 3 * 65536 + 1001, 200 * 65536 + 4444
+    assert np.array_equal(plan.execute(b, c).cpu().numpy().astype(np.int64), want[b:b + c])
+    plan.destroy()
+    assert bhw.launch_count() > n0
+
+
+@pytest.mark.parametrize("m", [2, 3, 4, 5, 7])
+def test_bank_kernel_every_placement_against_the_oracle(m):
+    """k_synth_bank on uniform banks, one instantiation per table placement and tail per entity: table staged
+    whole (short windows), staged half period (N = 65536 at DAT_WIDTH 16), read from L2 (DAT_WIDTH 24), the
+    64-bit tail (DAT_WIDTH 32 with full-scale ports), an unpaired source (cordic_dds48) and TAYLOR."""
+    v = {2: 1, 3: 4, 4: 6, 5: 9, 7: 10}[m]
+    hi = (1 << 31) - 1
+    shapes = [("staged full", bhw.variant_desc(v, 12, 16), 64),
+              ("staged half", bhw.variant_desc(v, 16, 16), 4),
+              ("global", bhw.variant_desc(v, 17, 24), 2),
+              ("64-bit tail", bhw.make_desc(m, 13, 32, [hi - 3 * k for k in range(m)]), 32),
+              ("unpaired", bhw.variant_desc(v, 13, 24, sin_type=bhw.SIN_CORDIC48), 32)]
+    if m <= 3:
+        shapes.append(("taylor", bhw.variant_desc(v, 14, 24, sin_type=bhw.SIN_TAYLOR), 16))
+    for name, d, nwin in shapes:
+        descs = [d.copy(aa=[int(a) - (5 * i + k) % 97 if k < m else 0 for k, a in enumerate(d.aa)], stream_offset=i & 1)
+                 for i in range(nwin)]
+        want = H.orc_batch(descs, 0, nwin << d.phi_width)
+        plan = bhw.Plan(descs)
+        bhw.timing_enable(True)
+        bhw.timing_reset()
+        got = plan.execute().cpu().numpy().astype(np.int64)
+        kt = bhw.timing_read()
+        bhw.timing_enable(False)
+        plan.destroy()
+        assert kt["k_synth_bank"][0] >= 1, (name, kt)
+        assert np.array_equal(got, want), (m, name)
+
+
+def group_descs(variants, dw, pws, model=0):
+    out = []
+    for i, pw in enumerate(pws):
+        for v in variants:
+            d = bhw.variant_desc(v, pw, dw, model=model)
+            out.append(d.copy(stream_offset=(i + v) & 1, aa=[int(a) - (i if k == 0 else 0) for k, a in enumerate(d.aa)]))
+    return out
+
+
+@pytest.mark.parametrize("variants,dw,pws", [((1, 2), 16, (4, 9, 12, 15, 16, 17, 19)), ((3, 4), 16, (10, 16, 18, 20)),
+                                             ((5, 6, 7), 17, (8, 9, 13, 17, 18, 20)), ((8, 9), 24, (9, 14, 18, 19, 20)),
+                                             ((10,), 32, (9, 12, 17, 19, 20)), ((10,), 24, (11, 18))])
+def test_group_kernel_mixed_phi_widths_against_the_oracle(variants, dw, pws):
+    """k_synth_group: windows of one family with different PHI_WIDTHs, entities' ports and stream offsets in one
+    plan - every sample against the oracle; then ragged sub-ranges that cut windows (unpaired tile ranges,
+    general-kernel ends reading the pyramid), on a side stream, and the same batch one-shot."""
     import torch
-    d = bhw.variant_desc(6, 28, 17)
-    n = 1 << 28
-    full = bhw.generate(d)
-    for n0 in (0, 4095, n // 4 - 2048, n // 2 - 2048, n - 4096):
-        assert np.array_equal(full[n0:n0 + 4096].cpu().numpy().astype(np.int64), H.orc_window(d, n0, 4096))
-    assert torch.equal(bhw.generate(d.copy(algo=bhw.ALGO_DIRECT), n - 65536, 65536), full[n - 65536:])
-    del full
-    torch.cuda.empty_cache()
-    d30 = bhw.variant_desc(2, 30, 16)
-    n0, cnt = (1 << 29) - 100003, 1 << 22
-    got = bhw.generate(d30, n0, cnt).cpu().numpy().astype(np.int64)
-    assert np.array_equal(got[:4096], H.orc_window(d30, n0, 4096))
-    assert np.array_equal(got[-4096:], H.orc_window(d30, n0 + cnt - 4096, 4096))
-    mid = 100003 - 2048                                    # around the window's centre
-    assert np.array_equal(got[mid:mid + 4096], H.orc_window(d30, n0 + mid, 4096))
+    descs = group_descs(variants, dw, pws)
+    total = bhw.batch_total(descs)
+    want = H.orc_batch(descs, 0, total)
+    plan = bhw.Plan(descs)
+    bhw.timing_enable(True)
+    bhw.timing_reset()
+    got = plan.execute().cpu().numpy().astype(np.int64)
+    kt = bhw.timing_read()
+    bhw.timing_enable(False)
+    assert kt["k_synth_group"][0] >= 1, kt
+    assert np.array_equal(got, want), int(np.argmax(got != want))
+    rng = np.random.default_rng(dw * 100 + len(pws))
+    s = torch.cuda.Stream()
+    for _ in range(6):
+        b = int(rng.integers(0, total - 1))
+        c = int(rng.integers(1, total - b + 1))
+        with torch.cuda.stream(s):
+            part = plan.execute(b, c)
+        s.synchronize()
+        assert np.array_equal(part.cpu().numpy().astype(np.int64), want[b:b + c]), (b, c)
+    plan.destroy()
+    assert np.array_equal(bhw.generate_batch(descs).cpu().numpy().astype(np.int64), want)
+    b, c = total // 3 + 5, total // 2
+    assert np.array_equal(bhw.generate_batch(descs, b, c).cpu().numpy().astype(np.int64), want[b:b + c])
+
+
+def test_group_kernel_hls_family_and_mixed_families_in_one_plan():
+    """HLS-model families (tshift 2, floor products) through the group kernel, and a plan that mixes several
+    families, entities, a TAYLOR window, a cordic_dds48 window and a uniform bank: every launch kind at once."""
+    hls = [bhw.variant_desc(v, pw, 17, model=bhw.MODEL_HLS) for v in (1, 3, 6) for pw in (9, 14, 17, 19)]
+    want = H.orc_batch(hls, 0, bhw.batch_total(hls))
+    assert np.array_equal(bhw.generate_batch(hls).cpu().numpy().astype(np.int64), want)
+    mix = (group_descs((1, 3, 6), 16, (10, 14)) + [bhw.variant_desc(4, 14, 24, sin_type=bhw.SIN_TAYLOR, lut_size=9)]
+           + group_descs((9, 10), 24, (12, 18)) + [bhw.variant_desc(10, 13, 32, sin_type=bhw.SIN_CORDIC48)]
+           + [bhw.variant_desc(6, 16, 17).copy(aa=[47022 - i, 64001, 18518, 1531]) for i in range(4)]
+           + [bhw.variant_desc(1, 14, 16, sin_type=bhw.SIN_TAYLOR, lut_size=9), bhw.variant_desc(2, 6, 16)]
+           + group_descs((5,), 17, (9, 19)))
+    total = bhw.batch_total(mix)
+    want = H.orc_batch(mix, 0, total)
+    plan = bhw.Plan(mix)
+    bhw.timing_enable(True)
+    bhw.timing_reset()
+    got = plan.execute().cpu().numpy().astype(np.int64)
+    kt = bhw.timing_read()
+    bhw.timing_enable(False)
+    assert kt["k_synth_group"][0] >= 4 and kt["k_synth_bank"][0] >= 1 and kt["k_synth"][0] >= 1, kt
+    assert np.array_equal(got, want)
+    for b, c in ((12345, total - 99999), (total // 2 + 77, 4096), (0, 1 << 14)):
+        assert np.array_equal(plan.execute(b, c).cpu().numpy().astype(np.int64), want[b:b + c])
+    plan.destroy()
 
 
 def test_coefficient_edge_cases():
@@ -406,15 +523,12 @@ def test_random_descriptors_one_shot_and_in_one_plan():
     descs = cases.random_descs(300, seed=20260102)
     for d in descs:
         assert np.array_equal(gpu_window(d), H.orc_window(d)), d
-    batch, tay = [], None
+    batch = []
     for d in descs:
-        if d.dat_width > 32 or len(batch) == 120:
+        if d.dat_width > 32 or len(batch) == 140:
             continue
-        if d.sin_type == bhw.SIN_TAYLOR and d.model == bhw.MODEL_RTL:   # one Taylor ROM (DAT_WIDTH, LUT_SIZE) per plan
-            tay = tay or (d.dat_width, d.lut_size)
-            if (d.dat_width, d.lut_size) != tay:
-                continue
-        batch.append(d.copy(algo=bhw.ALGO_AUTO))
+        batch.append(d.copy(algo=bhw.ALGO_AUTO))      # TAYLOR windows of any (DAT_WIDTH, LUT_SIZE) mix: a plan owns its ROMs
+    assert len({(d.dat_width, d.lut_size) for d in batch if d.sin_type == bhw.SIN_TAYLOR and d.model == bhw.MODEL_RTL}) > 2
     want = H.orc_batch(batch, 0, bhw.batch_total(batch))
     assert np.array_equal(bhw.generate_batch(batch).cpu().numpy().astype(np.int64), want)
     plan = bhw.Plan(batch)

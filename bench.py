@@ -2,23 +2,29 @@
 """bench.py - window-generation throughput on B200 (and the reference's CPU model beside it).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's own C++ model, host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the same workload on the host cores
 
-Workload (BASELINE.json configs[1]): a bank of bh_win_4term windows, PHI_WIDTH 16 (N = 65536),
-DAT_WIDTH 17, cordic_dds.  One *step* generates the whole bank once: WINDOWS_PER_GPU windows per
-GPU (weak scaling; the global bank is the concatenation over ranks, rank r owns flat slice r of it
-- bhw_shard_range - and no data-path collective exists).  Every window of the bank has its own
-AA0..AA3 port values (the BH4 set with a per-window perturbation), so no two windows are equal.
-Trig tables are rebuilt inside every step (bhw_set_table_cache(0)): nothing computed in one step
-is reused by the next.
+Headline workload = BASELINE.json configs[4], the largest single-GPU configuration: the win_selector
+sweep (src/win_selector.vhd:93-199) - all 10 window variants x PHI_WIDTH 4..26 (230 windows, 1.342 G
+samples, 5.37 GB as int32; DAT_WIDTH per variant as SURVEY.md 8d: 16 / 17 / 24 / 32), RTL model,
+cordic_dds.  One *step* generates the whole sweep once; every step rebuilds every trig table
+(bhw_set_table_cache(0)): nothing computed in one step is reused by the next.  With N GPUs the sweep is
+cut into N contiguous flat slices of equal estimated cost (bhw_shard_range_cost) - strong scaling, no
+data-path collective.
 
-Prints ONE JSON line (rank 0).  `value` = Gsamples/s of bhw_plan_execute with the plan (the resolved
-per-window records) and the output resident in HBM (CUDA events on the launching stream, max over
-ranks); `e2e` = the same bank through the host-buffer entry point
-(bhw_generate_batch_host: descriptors in host memory, result in pinned host memory, all copies in
-the timed region); `roofline` = k_synth's algorithmic store bytes / its device time (library-side
-CUDA events) against the measured HBM copy bandwidth; `cpu_baseline` = the reference HLS model
-timed on the host cores on a bounded sample.
+Prints ONE JSON line (rank 0):
+  value        Gsamples/s of bhw_plan_execute, plan (resolved records) and output resident in HBM, CUDA
+               events on the launching stream, max over ranks
+  e2e          the same sweep through bhw_generate_batch_host: descriptors in host memory, result in
+               pinned host memory, planning + all copies inside the timed region
+  roofline     the dominant kernel class (k_synth_group): algorithmic bytes written / device time of its
+               launches, from the library's per-launch CUDA events in a SEPARATE pass with the launches
+               serialised (side streams off), against the measured HBM copy bandwidth
+  configs      BASELINE configs 1-4: us per single C-ABI call and a bank of same-shape windows each, as
+               fractions of the HBM roof and of the measured integer issue peak
+  cpu_baseline the CPU restatement of the same RTL entities (oracle/, plain C) on all host cores on a
+               bounded sample of the sweep; cpu_baseline_hls: the reference's own HLS C++ model
+               (oracle/_ref, unmodified hls/windows/win_function.cpp) on the shapes it can express
 """
 from __future__ import annotations
 
@@ -35,17 +41,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PHI_WIDTH = 16
-DAT_WIDTH = 17
-WINDOWS_PER_GPU = 4096          # 4096 x 65536 x 4 B = 1.07 GB per GPU per step (>> 126 MB L2)
-BH4_AA = (47022, 64001, 18518, 1531)   # round(a_k * (2^17 - 1)), src/tb/tb_windows.vhd:103-111
-KERNEL_TIMING_STRIDE = 8        # steps of the timed region whose launches carry per-kernel events: 1 in 8
 METRIC = "window_gsamples_per_s"
 UNIT = "Gsamples/s"
-WORKLOAD = "bank of bh_win_4term windows, N=65536 (PHI_WIDTH 16), DAT_WIDTH 17, cordic_dds, RTL model"
+VARIANT_DW = {1: 16, 2: 16, 3: 16, 4: 16, 5: 17, 6: 17, 7: 17, 8: 24, 9: 24, 10: 32}
+PW_MIN, PW_MAX = 4, 26
+WORKLOAD = ("config 5: win_selector sweep, all 10 window variants x PHI_WIDTH 4..26 (230 windows, 1.342 G samples), "
+            "RTL model, cordic_dds, DAT_WIDTH 16/17/24/32 per variant")
+CPU_SAMPLE_PW_MAX = 16          # the CPU legs run the sweep's variants at PHI_WIDTH 4..16 (cost per sample does not depend on it)
+
+# config 2 bank (the round-1 bench shape, kept as a sub-line and used by the parity tests)
+PHI_WIDTH = 16
+DAT_WIDTH = 17
+WINDOWS_PER_GPU = 4096
+BH4_AA = (47022, 64001, 18518, 1531)   # round(a_k * (2^17 - 1)), src/tb/tb_windows.vhd:103-111
 
 
-# ---- helpers shared with tests/test_shard_gloo.py ------------------------------------------------
+# ---- helpers shared with the tests ----------------------------------------------------------------
 def max_over_ranks(x: float) -> float:
     import torch
     import torch.distributed as dist
@@ -57,8 +68,20 @@ def max_over_ranks(x: float) -> float:
     return float(t.item())
 
 
+def gather_ranks(x: float):
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(x)]
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
 def rank_workload(rank: int, world: int, nwin_per_gpu: int = WINDOWS_PER_GPU):
-    """-> (flat_begin, flat_count, total): rank's contiguous slice of the global bank."""
+    """-> (flat_begin, flat_count, total): rank's contiguous slice of a global bank of config-2 windows."""
     import blackman_harris_win_b200 as bhw
     total = (world * nwin_per_gpu) << PHI_WIDTH
     b, c = bhw.shard_range(total, rank, world)
@@ -66,23 +89,35 @@ def rank_workload(rank: int, world: int, nwin_per_gpu: int = WINDOWS_PER_GPU):
 
 
 def bank_descs(nwin: int, algo: int = 0):
-    """The global bank: window i = BH4 with AA_k nudged by a per-window amount (distinct port
-    values per window, all inside DAT_WIDTH bits)."""
+    """Config-2 bank: window i = BH4 with AA_k nudged by a per-window amount (distinct port values per
+    window, all inside DAT_WIDTH bits)."""
     import blackman_harris_win_b200 as bhw
     arr = (bhw.BhwDesc * nwin)()
     proto = bhw.make_desc(4, PHI_WIDTH, DAT_WIDTH, BH4_AA, algo=algo)
     raw = bytes(proto)
-    same = os.environ.get("BHW_BENCH_IDENTICAL_WINDOWS") == "1"   # tuning experiments only
     for i in range(nwin):
         C.memmove(C.byref(arr, i * C.sizeof(bhw.BhwDesc)), raw, len(raw))
-        if same:
-            continue
         d = arr[i]
         d.aa[0] = BH4_AA[0] - (i % 1021)
         d.aa[1] = BH4_AA[1] - (i % 509)
         d.aa[2] = BH4_AA[2] + (i % 251)
         d.aa[3] = BH4_AA[3] + (i % 127)
     return arr
+
+
+def sweep_descs(pw_max: int = PW_MAX, algo: int = 0):
+    """BASELINE config 5: variant-major, PHI_WIDTH ascending; coefficients by the testbench rules."""
+    import blackman_harris_win_b200 as bhw
+    return bhw.desc_array([bhw.variant_desc(v, pw, VARIANT_DW[v], algo=algo)
+                           for v in range(1, 11) for pw in range(PW_MIN, pw_max + 1)])
+
+
+def rank_sweep(descs, rank: int, world: int):
+    """-> (flat_begin, flat_count, first_window, windows_touched, local_begin) of rank's cost-balanced slice."""
+    import blackman_harris_win_b200 as bhw
+    b, c = bhw.shard_range_cost(descs, rank, world)
+    first, touched, local = bhw.shard_windows(descs, b, c) if c else (0, 0, 0)
+    return b, c, first, touched, local
 
 
 # ---- clocks during the timed region ---------------------------------------------------------------
@@ -150,75 +185,115 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ---- the reference's CPU model -----------------------------------------------------------------------
-def _ref_worker(args):
-    """One process = one core = independent windows (the HLS cordic() rewrites a static table on
-    every call, hls/windows/win_function.cpp:74-80, so it is run in processes, not threads)."""
-    so, kind, nwin, desc_bytes = args
+# ---- the CPU legs (checker / baseline only: the one place bench.py executes oracle/) ------------------
+_W = {}
+
+
+def _cpu_init(kind: str, so_map: dict):
+    """Pool initializer: every worker process loads its libraries ONCE."""
+    _W["kind"] = kind
+    if kind == "port":
+        from blackman_harris_win_b200.api import BhwDesc
+        L = C.CDLL(so_map["port"])
+        L.orc_window_i32.argtypes = [C.POINTER(BhwDesc), C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]
+        L.orc_window_i32.restype = C.c_int
+        _W["lib"] = L
+    else:
+        libs = {}
+        for key, so in so_map.items():
+            L = C.CDLL(so)
+            L.ref_hls_window_i32.argtypes = [C.c_int, C.c_longlong, C.c_longlong, C.POINTER(C.c_int)]
+            libs[key] = L
+        _W["libs"] = libs
+
+
+def _cpu_work(job):
+    """One worker = one core.  job = (items, reps): generate every item `reps` times; the time is taken
+    INSIDE the worker, around the generate loop only.  -> (seconds, samples)"""
     import numpy as np
-    n = 1 << PHI_WIDTH
-    out = np.empty(n, dtype=np.int32)
-    if kind == "reference":
-        L = C.CDLL(so)
-        L.ref_hls_window_i32.argtypes = [C.c_int, C.c_longlong, C.c_longlong, C.POINTER(C.c_int)]
+    items, reps = job
+    out = np.empty(1 << max(pw for _, pw in items), dtype=np.int32)
+    p = out.ctypes.data_as(C.POINTER(C.c_int32))
+    samples = 0
+    if _W["kind"] == "port":
+        from blackman_harris_win_b200.api import BhwDesc
+        L = _W["lib"]
+        descs = [(BhwDesc.from_buffer_copy(raw), pw) for raw, pw in items]
         t0 = time.perf_counter()
-        for _ in range(nwin):
-            L.ref_hls_window_i32(4, 0, n, out.ctypes.data_as(C.POINTER(C.c_int)))   # type 4 = BH4
-        return time.perf_counter() - t0
-    from blackman_harris_win_b200.api import BhwDesc
-    L = C.CDLL(so)
-    d = BhwDesc.from_buffer_copy(desc_bytes)
-    L.orc_window_i32.argtypes = [C.POINTER(BhwDesc), C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]
+        for _ in range(reps):
+            for d, pw in descs:
+                st = L.orc_window_i32(C.byref(d), 0, 1 << pw, p)
+                assert st == 0, st
+                samples += 1 << pw
+        return time.perf_counter() - t0, samples
+    libs = _W["libs"]
     t0 = time.perf_counter()
-    for _ in range(nwin):
-        L.orc_window_i32(C.byref(d), 0, n, out.ctypes.data_as(C.POINTER(C.c_int32)))
-    return time.perf_counter() - t0
+    for _ in range(reps):
+        for (key, wtype), pw in items:
+            libs[key].ref_hls_window_i32(wtype, 0, 1 << pw, p)
+            samples += 1 << pw
+    return time.perf_counter() - t0, samples
 
 
 class CpuModel:
-    """The reference's own CPU implementation of the path: oracle/_ref (unmodified
-    hls/windows/win_function.cpp compiled for NPHASE 16 / NWIDTH 17) when present, else the
-    oracle port of the RTL.  Executing oracle/ here is the checker/baseline leg only."""
+    """The CPU implementation of the path on all host cores, one process per core (the HLS cordic()
+    rewrites a static table on every call, hls/windows/win_function.cpp:74-80, so processes, not threads).
+      kind "port"      : oracle/bhw_oracle.c - the plain-C restatement of the RTL entities the GPU arm
+                         generates (the VHDL itself cannot run on a CPU); items = the sweep's 10 variants at
+                         PHI_WIDTH 4..CPU_SAMPLE_PW_MAX
+      kind "reference" : oracle/_ref - the unmodified hls/windows/win_function.cpp (ap_int stand-in), the
+                         reference's own software model: its window types at the (NPHASE, NWIDTH) pairs
+                         compiled by oracle/build_ref.sh that match the sweep's DAT_WIDTHs"""
 
-    def __init__(self):
+    HLS_SHAPES = ((16, 16, (1, 2, 3)), (16, 17, (4,)), (20, 32, (7,)), (22, 24, (5,)))   # (NPHASE, NWIDTH, win types)
+
+    def __init__(self, kind: str):
         import multiprocessing as mp
-        ref = os.path.join(ROOT, "oracle", "_ref", f"hls_win_np{PHI_WIDTH}_nw{DAT_WIDTH}.so")
-        port = os.path.join(ROOT, "oracle", "libbhw_oracle.so")
-        if os.path.exists(ref):
-            self.kind, self.so = "reference", ref
-            self.what = ("unmodified hls/windows/win_function.cpp type 4 (BH4), NPHASE 16 / NWIDTH 17, "
-                         "g++ -O2, ap_int stand-in")
-        elif os.path.exists(port):
-            self.kind, self.so = "port", port
-            self.what = "oracle/bhw_oracle.c restatement of bh_win_4term + cordic_dds"
-        else:
-            raise RuntimeError("neither oracle/_ref nor oracle/libbhw_oracle.so is built")
         import blackman_harris_win_b200 as bhw
-        self.desc_bytes = bytes(bhw.make_desc(4, PHI_WIDTH, DAT_WIDTH, BH4_AA))
+        self.kind = kind
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        self.pool = mp.get_context("spawn").Pool(self.cores)
-        self.pool.map(_ref_worker, [(self.so, self.kind, 0, self.desc_bytes)] * self.cores)   # spin up
+        if kind == "port":
+            so = os.path.join(ROOT, "oracle", "libbhw_oracle.so")
+            if not os.path.exists(so):
+                raise RuntimeError("oracle/libbhw_oracle.so is not built (make -C oracle oracle)")
+            so_map = {"port": so}
+            self.items = [(bytes(bhw.variant_desc(v, pw, VARIANT_DW[v])), pw)
+                          for v in range(1, 11) for pw in range(PW_MIN, CPU_SAMPLE_PW_MAX + 1)]
+            self.what = (f"oracle/bhw_oracle.c (plain C restatement of the RTL entities, gcc -O2), the sweep's 10 variants "
+                         f"x PHI_WIDTH {PW_MIN}..{CPU_SAMPLE_PW_MAX} per pass")
+        else:
+            so_map, self.items = {}, []
+            for np_, nw, types in self.HLS_SHAPES:
+                so = os.path.join(ROOT, "oracle", "_ref", f"hls_win_np{np_}_nw{nw}.so")
+                if os.path.exists(so):
+                    so_map[(np_, nw)] = so
+                    self.items += [(((np_, nw), t), min(np_, CPU_SAMPLE_PW_MAX)) for t in types]
+            if not so_map:
+                raise RuntimeError("oracle/_ref is not built")
+            self.what = ("unmodified hls/windows/win_function.cpp (g++ -O2, ap_int stand-in): types 1,2,3 NWIDTH 16, type 4 "
+                         "NWIDTH 17, type 5 NWIDTH 24, type 7 NWIDTH 32, 65536 samples each per pass")
+        self.samples_per_pass = sum(1 << pw for _, pw in self.items)
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(kind, so_map))
+        self.pool.map(_cpu_work, [(self.items[:1], 1)] * self.cores)     # spin up + load
 
-    def run(self, windows_per_core: int) -> float:
-        """All cores generate `windows_per_core` windows each; -> wall seconds."""
-        t0 = time.perf_counter()
-        self.pool.map(_ref_worker, [(self.so, self.kind, windows_per_core, self.desc_bytes)] * self.cores)
-        return time.perf_counter() - t0
+    def run(self, reps: int):
+        """Every core generates all items `reps` times -> (slowest worker's in-loop seconds, total samples)."""
+        res = self.pool.map(_cpu_work, [(self.items, reps)] * self.cores)
+        return max(r[0] for r in res), sum(r[1] for r in res)
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-def cpu_baseline(budget_s: float = 12.0):
-    m = CpuModel()
+def cpu_baseline(kind: str, budget_s: float):
+    m = CpuModel(kind)
     try:
-        t1 = m.run(1)
-        reps = max(1, min(4096, int(budget_s / max(t1, 1e-3))))
-        t = m.run(reps)
-        samples = reps * m.cores << PHI_WIDTH
-        return {"value": samples / t / 1e9, "unit": UNIT, "cores": m.cores, "kind": m.kind,
-                "sample": f"{reps} window(s) of 65536 samples per core, one process per core, {m.what}; "
+        t1, _ = m.run(1)
+        reps = max(1, min(64, int(budget_s / max(t1, 1e-3))))
+        t, samples = m.run(reps)
+        return {"value": samples / t / 1e9, "unit": UNIT, "cores": m.cores, "kind": kind,
+                "sample": f"{reps} pass(es) per core, one process per core, timed inside the workers: {m.what}; "
                           f"{samples} samples in {t:.2f} s"}
     finally:
         m.close()
@@ -228,35 +303,156 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    m = CpuModel()
+    m = CpuModel("port")
     try:
         for _ in range(min(args.warmup, 2)):
             m.run(1)
-        per_step = []
+        tot_t, tot_s = 0.0, 0
         for _ in range(args.steps):
-            per_step.append(m.run(1))
-        t = sum(per_step)
-        samples_per_step = m.cores << PHI_WIDTH
-        v = samples_per_step * args.steps / t / 1e9
+            t, s = m.run(1)
+            tot_t += t
+            tot_s += s
+        v = tot_s / tot_t / 1e9
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic (the descriptor is the input; no RNG)",
-            "config": {"workload": WORKLOAD, "step": f"{m.cores} windows of 65536 samples, one per host core "
-                                                      "(bounded sample of the GPU arm's bank)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": m.cores, "kind": m.kind,
-                             "sample": f"{args.steps} steps x {m.cores} windows x 65536 samples; {m.what}"},
+            "config": {"workload": WORKLOAD,
+                       "step": f"every host core generates the sweep's 10 variants at PHI_WIDTH {PW_MIN}..{CPU_SAMPLE_PW_MAX} once "
+                               f"({m.samples_per_pass} samples per core: a bounded sample of the GPU arm's sweep - the CPU cost "
+                               "per sample does not depend on PHI_WIDTH)",
+                       "model": "RTL entities as restated in oracle/bhw_oracle.c - the model the GPU arm generates; the VHDL "
+                                "cannot execute on a CPU and the reference's HLS C++ model is a different (not bit-identical) "
+                                "model: it is timed beside this one as cpu_baseline_hls"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": m.cores, "kind": "port",
+                             "sample": f"{args.steps} steps x {m.cores} cores x {m.samples_per_pass} samples, timed inside the workers; {m.what}"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
     finally:
         m.close()
+    try:
+        line["cpu_baseline_hls"] = cpu_baseline("reference", min(args.cpu_budget, 8.0))
+    except Exception as ex:      # oracle/_ref absent: say so, the port figure stands
+        line["cpu_baseline_hls"] = {"unavailable": str(ex)}
+    print(json.dumps(line))
     return 0
 
 
+# ---- integer-issue roofline of a configuration --------------------------------------------
+_SCALED_SIZE = [15, 15, 15, 18, 21, 22, 23, 26, 30, 31, 32, 33, 38, 38, 38, 42, 42, 45, 47, 47, 47, 48, 48, 48, 48]
+
+
+def alg_int_ops_per_sample(d):
+    """Algorithmic integer work of the one-thread-per-sample formulation in 32-bit-op units, with the
+    reference's own accounting of 3 additions + 2 shifts per CORDIC stage (src/cordic_dds.vhd:39-43);
+    SURVEY.md 8(d):  (M-1)*[S*5*L + 7] + (M-1)*4*L' + (M-1) + 3."""
+    import blackman_harris_win_b200 as bhw
+    m, dw = d.win_type, d.dat_width
+    if d.model == bhw.MODEL_HLS:
+        stages, width = dw, dw + 2
+    elif d.sin_type == bhw.SIN_CORDIC:
+        stages, width = dw - 1, dw + max(d.precision, 1)
+    elif d.sin_type == bhw.SIN_CORDIC48:
+        stages, width = dw, 48
+    elif d.sin_type == bhw.SIN_CORDIC_SCALED:
+        stages, width = dw, _SCALED_SIZE[dw - 8]
+    else:                       # TAYLOR: ROM look-up + 1 narrow and 2 wide multiplies + ~12 (SURVEY 8d cfg 4)
+        stages, width = 4, 32
+    L = 1 if width <= 32 else 2
+    Lp = 1 if 2 * dw <= 32 else (2 if dw <= 32 else 4)
+    return (m - 1) * (stages * 5 * L + 7) + (m - 1) * 4 * Lp + (m - 1) + 3
+
+
 # ---- the CUDA arm ---------------------------------------------------------------------------------------
+def _events():
+    import torch
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _time_loop(fn, reps, warm=3):
+    """-> ms per call of fn(), CUDA events on the current stream."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = _events()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _dominant(kt):
+    kt = {k: v for k, v in kt.items() if v[0]}
+    return max(kt, key=lambda k: kt[k][1]) if kt else None
+
+
+def config_lines(bhw, peak_gbs, int_peak, scratch):
+    """BASELINE configs 1-4 on one GPU: (a) one whole window per bhw_generate call, `reps` calls issued from C
+    (bhw_generate_repeat) into rotating output slots spanning more than L2, us per call; (b) a bank of
+    same-shape windows with distinct AA0 through a resident plan, tables rebuilt every step."""
+    import torch
+    L2_BYTES = 126 << 20
+    cfgs = [
+        ("cfg1 hamming_win N=1024 DW16 cordic_dds", bhw.make_desc(2, 10, 16, [17808, 14959]), 65536),
+        ("cfg2 bh_win_4term N=65536 DW17 cordic_dds", bhw.make_desc(4, 16, 17, list(BH4_AA)), 4096),
+        ("cfg3 bh_win_7term N=1M DW32 cordic_dds48", bhw.variant_desc(10, 20, 32, sin_type=bhw.SIN_CORDIC48), 64),
+        ("cfg3 bh_win_7term N=1M DW32 cordic_dds", bhw.variant_desc(10, 20, 32), 64),
+        ("cfg4 bh_win_3term N=16M DW24 taylor_sincos LUT 9",
+         bhw.make_desc(3, 24, 24, [7046424, 8388600, 1342176], sin_type=bhw.SIN_TAYLOR, lut_size=9), 0),
+    ]
+    out = []
+    for name, d, nbank in cfgs:
+        n = 1 << d.phi_width
+        ops = alg_int_ops_per_sample(d)
+        slots = max(1, min(len(scratch) // n, (2 * L2_BYTES) // (4 * n) + 1))
+        reps = 200 if n <= (1 << 20) else 40
+
+        def call():
+            bhw.generate_repeat(d, scratch, reps, out_stride=n, out_slots=slots)
+        bhw.set_table_cache(True)
+        ms = _time_loop(call, 3, warm=1) / reps
+        bhw.timing_enable(True)
+        bhw.timing_reset()
+        bhw.generate_repeat(d, scratch, 8, out_stride=n, out_slots=slots)
+        torch.cuda.synchronize()
+        kt = bhw.timing_read()
+        bhw.timing_enable(False)
+        dom = _dominant(kt)
+        k_ms = sum(v[1] for v in kt.values()) / 8
+        line = {"config": name, "single_call": {
+            "us_per_call": round(ms * 1e3, 3), "kernel_us_per_call": round(k_ms * 1e3, 3), "kernel": dom,
+            "gsamples_per_s": round(n / ms / 1e6, 2), "frac_hbm": round(4 * n / ms / 1e6 / peak_gbs, 4),
+            "frac_int_issue": round(ops * n / (ms * 1e-3) / int_peak, 4) if int_peak else None,
+            "alg_int_ops_per_sample": ops,
+            "l2": f"{slots} rotating output slot(s) of {4 * n} B (more than L2 in total where the window is smaller than L2)"}}
+        if nbank:
+            descs = [d.copy(aa=[int(a) - (i % 1021) if k == 0 else int(a) for k, a in enumerate(d.aa)]) for i in range(nbank)]
+            plan = bhw.Plan(descs)
+            total = plan.total
+            bhw.set_table_cache(False)
+            bms = _time_loop(lambda: plan.execute(out=scratch[:total]), 20)
+            bhw.timing_enable(True)
+            bhw.timing_reset()
+            for _ in range(4):
+                plan.execute(out=scratch[:total])
+            torch.cuda.synchronize()
+            kt = bhw.timing_read()
+            bhw.timing_enable(False)
+            bhw.set_table_cache(True)
+            plan.destroy()
+            line["bank"] = {"windows": nbank, "bytes": 4 * total, "ms_per_step": round(bms, 5), "kernel": _dominant(kt),
+                            "gsamples_per_s": round(total / bms / 1e6, 1), "frac_hbm": round(4 * total / bms / 1e6 / peak_gbs, 4),
+                            "frac_int_issue": round(ops * total / (bms * 1e-3) / int_peak, 4) if int_peak else None,
+                            "tables": "rebuilt every step", "kernel_ms": {k: round(v[1] / 4, 5) for k, v in kt.items() if v[0]}}
+        out.append(line)
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -264,15 +460,14 @@ def run_cuda(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the window generator has no CPU path "
                          "(use --impl reference for the CPU model)")
-    torch.cuda.set_device(local)
+    torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's own banner / debug lines go to stderr: stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus and rank == 0:
         print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
 
@@ -282,81 +477,134 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     algo = {"auto": bhw.ALGO_AUTO, "direct": bhw.ALGO_DIRECT, "table": bhw.ALGO_TABLE}[args.algo]
-    nwin = world * args.windows_per_gpu
-    descs = bank_descs(nwin, algo)                       # the global bank (host memory)
-    begin, count, total = rank_workload(rank, world, args.windows_per_gpu)
-    first, touched, local = bhw.shard_windows(descs, begin, count)   # this rank's windows
-    mine = (bhw.BhwDesc * touched).from_address(C.addressof(descs) + first * C.sizeof(bhw.BhwDesc))
-    out = torch.empty(count, dtype=torch.int32, device="cuda")
+    descs = sweep_descs(args.pw_max, algo)                      # the whole sweep (host memory)
+    nwin = len(descs)
+    total = bhw.batch_total(descs)
+    begin, count, first, touched, local = rank_sweep(descs, rank, world)
+    mine = (bhw.BhwDesc * max(touched, 1)).from_address(C.addressof(descs) + first * C.sizeof(bhw.BhwDesc))
+    out = torch.empty(max(count, 1), dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     L = bhw.lib()
-    bhw.set_table_cache(False)          # every step rebuilds its trig tables
+    bhw.set_table_cache(False)                                  # every step rebuilds its trig tables
     t_plan = time.perf_counter()
-    plan = bhw.Plan(mine)               # per-window records resident in HBM before the timed region
+    plan = bhw.Plan(mine) if count else None                    # per-window records resident in HBM before the timed region
     t_plan = time.perf_counter() - t_plan
 
     def step_device():
+        if plan is None:
+            return
         st = L.bhw_plan_execute(plan._h, local, count, out.data_ptr(), stream)
         if st:
             raise bhw.BhwError(st, "bhw_plan_execute")
 
-    # ---- device-resident timing -------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    # ---- pass 1: device-resident timing, no per-kernel events ------------------------------------
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
     barrier()
-    bhw.timing_reset()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local_rank)
     launches0 = bhw.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = _events()
     clocks.start()
     barrier()
     e0.record()
-    for i in range(args.steps):
-        # per-kernel CUDA events (library side, on the launching stream) bracket the launches of
-        # every KERNEL_TIMING_STRIDE-th step of the timed region; the other steps run bare
-        bhw.timing_enable(i % KERNEL_TIMING_STRIDE == 0)
+    for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
     clocks.stop()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = bhw.launch_count() - launches0
+    my_ms = e0.elapsed_time(e1) / args.steps
+    per_rank_ms = gather_ranks(my_ms)
+    dev_ms = max(per_rank_ms)
+    launches = (bhw.launch_count() - launches0) // args.steps
+    value = total / (dev_ms * 1e-3) / 1e9
+
+    # ---- pass 2 (separate): per-launch CUDA events on every step, launches serialised -----------
+    ksteps = max(1, min(args.steps, 8))
+    bhw.set_side_streams(0)
+    for _ in range(2):
+        step_device()
+    barrier()
+    e0, e1 = _events()
+    e0.record()
+    for _ in range(ksteps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    serial_ms = e0.elapsed_time(e1) / ksteps                    # bare, side streams off
+    bhw.timing_enable(True)
+    bhw.timing_reset()
+    e0, e1 = _events()
+    e0.record()
+    for _ in range(ksteps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    timed_pass_ms = e0.elapsed_time(e1) / ksteps
     ktimes = bhw.timing_read()
+    recs = bhw.timing_launches()
     bhw.timing_enable(False)
-    value = (total * args.steps) / (dev_ms * 1e-3) / 1e9
+    bhw.set_side_streams(4)
+    barrier()
 
-    # sanity: the bank really was written (first and last window of this rank vs a second, single-window call)
-    chk = bhw.generate(bhw.BhwDesc.from_buffer_copy(bytes(descs[begin >> PHI_WIDTH])))
-    if not torch.equal(chk, out[: 1 << PHI_WIDTH]):
-        raise SystemExit("bench.py: bank output differs from the single-window call")
+    # ---- sanity against the oracle: first, middle and last window of this rank's slice -----------
+    checked = []
+    if plan is not None and rank == 0 or (plan is not None and args.check_all_ranks):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import harness as H
+        import numpy as np
+        offs = [0]
+        for i in range(touched):
+            offs.append(offs[-1] + (1 << mine[i].phi_width))
+        for wi in sorted({0, touched // 2, touched - 1}):
+            wb, we = offs[wi], offs[wi + 1]
+            lo, hi = max(wb, local), min(we, local + count)
+            if lo >= hi:
+                continue
+            for a, b in ((lo, min(hi, lo + 4096)), (max(lo, hi - 4096), hi)):
+                got = out[a - local:b - local].cpu().numpy().astype(np.int64)
+                d = bhw.BhwDesc.from_buffer_copy(bytes(mine[wi]))
+                want = H.orc_window(d, a - wb, b - a)
+                if not np.array_equal(got, want):
+                    raise SystemExit(f"bench.py: window {first + wi} samples [{a - wb}, {b - wb}) differ from the oracle")
+            checked.append(first + wi)
 
-    # ---- end to end through the host-buffer entry point ----------------------------------------
-    host = torch.empty(count, dtype=torch.int32, pin_memory=True)
-
-    def step_host():
-        st = L.bhw_generate_batch_host(mine, touched, local, count, host.data_ptr())
-        if st:
-            raise bhw.BhwError(st, "bhw_generate_batch_host")
-
+    # ---- end to end through the host-buffer entry point ----------------------------------------------
     e2e = None
     if args.e2e_steps > 0:
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        for _ in range(2):
-            step_host()
+        host = torch.empty(max(count, 1), dtype=torch.int32, pin_memory=True)
+
+        def step_host():
+            if not count:
+                return
+            st = L.bhw_generate_batch_host(mine, touched, local, count, host.data_ptr())
+            if st:
+                raise bhw.BhwError(st, "bhw_generate_batch_host")
+
+        step_host()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        for _ in range(args.e2e_steps):
             step_host()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        if not torch.equal(host[: 1 << PHI_WIDTH], chk.cpu()):
+        if count and not torch.equal(host[:4096], out[:4096].cpu()):
             raise SystemExit("bench.py: host-path output differs from the device path")
-        e2e = {"value": (total * e2e_steps) / e2e_s / 1e9, "unit": UNIT, "steps": e2e_steps,
-               "d2h_gbs_per_gpu": count * 4 * e2e_steps / e2e_s / 1e9,
+        # the link ceiling of this box, measured here: a plain pinned device -> host copy of the same slice
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+        link_s = time.perf_counter() - t0
+        e2e = {"value": total * args.e2e_steps / e2e_s / 1e9, "unit": UNIT, "steps": args.e2e_steps,
+               "d2h_gbs_per_gpu": count * 4 * args.e2e_steps / e2e_s / 1e9,
+               "d2h_box_gbs": max_over_ranks(count * 4 / link_s / 1e9) if count else None,
+               "d2h_box_gbs_note": "plain pinned cudaMemcpy of this rank's slice, all ranks at once: the link ceiling of this box",
                "h2d_bytes_per_step": _meta_bytes(touched), "d2h_bytes_per_step": count * 4,
-               "api": "bhw_generate_batch_host (pinned host output)"}
+               "api": "bhw_generate_batch_host (descriptors in host memory, pinned host output, planning inside the timed region)"}
+        del host
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    # ---- roofline of the dominant kernel class -------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -364,65 +612,110 @@ def run_cuda(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    dom = max(ktimes, key=lambda k: ktimes[k][1])
-    n_l, ms_l = ktimes[dom]
-    traffic = None
+    int_peak = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        traffic = prof.get(dom, {}).get("dram_bytes_per_launch")
+        int_peak = json.load(open(os.path.join(ROOT, "profiles", "int_peak.json")))["int32_mix_tops"] * 1e12
     except Exception:
         pass
     roof = None
-    if n_l:
-        achieved = (count * 4) / (ms_l / n_l * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": count * 4, "avg_launch_ms": ms_l / n_l, "launches_timed": n_l,
-                "kernel_ms_timed": {k: v[1] for k, v in ktimes.items() if v[0]}}
+    dom = _dominant(ktimes)
+    if dom:
+        mine_recs = [r for r in recs if r["kernel"] == dom]
+        n_l = len(mine_recs)
+        bytes_l = sum(r["bytes"] for r in mine_recs)
+        ms_l = sum(r["ms"] for r in mine_recs)
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = prof.get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        achieved = bytes_l / (ms_l * 1e-3) / 1e9
+        # per instantiation (terms, table placement): share of the class's time and its own fraction of the roof
+        by = {}
+        names = {0: "staged half period (int32)", 1: "staged quarter waves (uint16)", 2: "pyramid through L1/L2"}
+        for r in mine_recs:
+            key = (r["terms"], r["table"], r["spread"])
+            b = by.setdefault(key, {"terms": r["terms"], "table": names.get(r["table"], str(r["table"])), "spread_walk": r["spread"],
+                                    "launches_per_step": 0, "bytes_per_step": 0, "ms_per_step": 0.0})
+            b["launches_per_step"] += 1 / ksteps
+            b["bytes_per_step"] += r["bytes"] / ksteps
+            b["ms_per_step"] += r["ms"] / ksteps
+        for b in by.values():
+            b["frac"] = round(b["bytes_per_step"] / (b["ms_per_step"] * 1e-3) / 1e9 / peak, 4)
+            b["ms_per_step"] = round(b["ms_per_step"], 5)
+            b["launches_per_step"] = round(b["launches_per_step"], 2)
+            b["bytes_per_step"] = int(b["bytes_per_step"])
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": bytes_l / n_l, "avg_launch_ms": ms_l / n_l, "launches_timed": n_l,
+                "launches_per_step": n_l / ksteps,
+                "kernel_ms_per_step": {k: round(v[1] / ksteps, 5) for k, v in ktimes.items() if v[0]},
+                "ms_per_step_of_this_pass": timed_pass_ms, "ms_per_step_serialised_bare": serial_ms,
+                "pass": f"separate pass of {ksteps} steps after the timed region, per-launch CUDA events on every launch, "
+                        "side streams off so that launches do not overlap (sum of launch times <= step time of the pass)",
+                "by_instantiation": sorted(by.values(), key=lambda b: -b["ms_per_step"]),
+                "whole_step_frac": 4 * count / (my_ms * 1e-3) / 1e9 / peak if count else None}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "warmup": warm, "ms_per_step": dev_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic (the descriptor is the input; no RNG)",
-            "config": {"workload": WORKLOAD, "windows_per_gpu": args.windows_per_gpu,
-                       "samples_per_step": total, "bytes_per_step_per_gpu": count * 4, "algo": args.algo,
-                       "l2": "output per step (1.07 GB/GPU) is larger than the 126 MB L2; no flush needed",
+            "config": {"workload": WORKLOAD if args.pw_max == PW_MAX else WORKLOAD + f" [PHI_WIDTH capped at {args.pw_max}]",
+                       "windows": nwin, "samples_per_step": total, "bytes_per_step": 4 * total, "algo": args.algo,
+                       "l2": "output per step (5.37 GB over the ranks) is larger than the 126 MB L2; no flush needed",
                        "tables": "rebuilt every step (table cache off)",
                        "plan_create_ms": round(1e3 * t_plan, 3),
-                       "sharding": f"flat sample range, {world} rank(s), no collective"},
+                       "plan_create_note": "resolving the 230 descriptors and uploading their records happens once, before the "
+                                           "timed region (the entities' elaboration); value excludes it, e2e includes it",
+                       "sharding": f"cost-balanced contiguous flat slices (bhw_shard_range_cost), {world} rank(s), no collective",
+                       "per_rank_ms": [round(x, 5) for x in per_rank_ms],
+                       "oracle_checked_windows": checked},
             "roofline": roof, "clocks": clocks.summary(),
             "e2e": e2e,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches * args.steps),
+            "gpu_launches_per_step": int(launches),
         }
+        if world == 1 and not args.no_configs:
+            scratch = torch.empty(1 << 28, dtype=torch.int32, device="cuda")
+            line["configs"] = config_lines(bhw, peak, int_peak, scratch)
+            del scratch
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_budget)
+            line["cpu_baseline"] = cpu_baseline("port", args.cpu_budget)
+            try:
+                line["cpu_baseline_hls"] = cpu_baseline("reference", min(args.cpu_budget, 8.0))
+            except Exception as ex:
+                line["cpu_baseline_hls"] = {"unavailable": str(ex)}
         print(json.dumps(line))
-    plan.destroy()
+    if plan is not None:
+        plan.destroy()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def _meta_bytes(nwin: int) -> int:
-    """Host->device bytes of one host-API call: the per-window records the library uploads
-    (224 B each), the window->record index (4 B each) and one table-job header; the descriptors
-    themselves are read on the host."""
-    return nwin * (224 + 4) + 256
+    """Host->device bytes of one host-API call: the per-window records the library uploads (224 B each),
+    the window->record index (4 B), the flat offsets (8 B), the group launch lists (32 B per window) and a
+    few table-job headers; the descriptors themselves are read on the host."""
+    return nwin * (224 + 4 + 8 + 32) + 16 * 1024
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "direct", "table"])
-    ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
-    ap.add_argument("--e2e-steps", type=int, default=10, help="0 skips the host-buffer leg")
+    ap.add_argument("--pw-max", type=int, default=PW_MAX, help="cap the sweep's PHI_WIDTH (tuning / smoke runs)")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="0 skips the host-buffer leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config sub-lines")
+    ap.add_argument("--check-all-ranks", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -74,6 +74,11 @@ def lib_path() -> str:
     return os.environ.get("BHW_LIB", os.path.join(_HERE, "libbhw.so"))
 
 
+class BhwLaunchRecord(C.Structure):
+    """bhw_launch_record (include/bhw.h)."""
+    _fields_ = [("kernel_class", C.c_int32), ("tag", C.c_uint32), ("bytes", C.c_uint64), ("ms", C.c_double)]
+
+
 def lib():
     """Load libbhw.so (built in-tree by csrc/build.sh / __graft_entry__.build()).  No fallback."""
     global _lib
@@ -121,6 +126,8 @@ def lib():
         "bhw_timing_enable": (C.c_int, [C.c_int]),
         "bhw_timing_reset": (C.c_int, []),
         "bhw_timing_read": (C.c_int, [C.c_int, P(C.c_double), P(C.c_uint64)]),
+        "bhw_timing_launches": (C.c_int, [P(BhwLaunchRecord), C.c_uint64, P(C.c_uint64)]),
+        "bhw_generate_repeat": (C.c_int, [D, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -137,6 +144,7 @@ ABI_SYMBOLS = (
     "bhw_atan2_validate", "bhw_atan2", "bhw_atan2_host", "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
     "bhw_device_count", "bhw_timing_enable", "bhw_timing_reset", "bhw_timing_read",
     "bhw_shard_windows", "bhw_plan_create", "bhw_plan_execute", "bhw_plan_total", "bhw_plan_destroy",
+    "bhw_timing_launches", "bhw_generate_repeat",
 )
 
 
@@ -425,6 +433,32 @@ def timing_read():
         _check(lib().bhw_timing_read(k, C.byref(ms), C.byref(n)), "bhw_timing_read")
         out[name] = (int(n.value), float(ms.value))
     return out
+
+
+def timing_launches():
+    """-> [{kernel, tag fields, bytes, ms}] for every launch recorded since the last reset, oldest first."""
+    n = C.c_uint64(0)
+    _check(lib().bhw_timing_launches(None, 0, C.byref(n)), "bhw_timing_launches")
+    buf = (BhwLaunchRecord * max(1, n.value))()
+    _check(lib().bhw_timing_launches(buf, n.value, C.byref(n)), "bhw_timing_launches")
+    out = []
+    for i in range(n.value):
+        r = buf[i]
+        t = r.tag
+        out.append({"kernel": KERNEL_NAMES[r.kernel_class], "terms": t & 0xFF, "table": (t >> 8) & 0xFF,
+                    "paired": (t >> 16) & 1, "spread": (t >> 17) & 1, "level": t >> 24, "bytes": int(r.bytes),
+                    "ms": float(r.ms)})
+    return out
+
+
+def generate_repeat(d: BhwDesc, out, reps: int, n0: int = 0, count: Optional[int] = None, out_stride: int = 0,
+                    out_slots: int = 0):
+    """`reps` back-to-back bhw_generate calls issued from C (bhw_generate_repeat)."""
+    torch = _torch()
+    if count is None:
+        count = (1 << d.phi_width) - n0
+    _check(lib().bhw_generate_repeat(C.byref(d), out.data_ptr(), n0, count, int(reps), int(out_stride), int(out_slots),
+                                     torch.cuda.current_stream().cuda_stream), "bhw_generate_repeat")
 
 
 def launch_count() -> int:

@@ -40,11 +40,12 @@ static int cuda_fail(cudaError_t e, const char* where) {
   } while (0)
 
 // ---- optional per-kernel timing (bhw_timing_*) -------------------------------------------------
-struct TimedSpan { int cls; int dev; cudaEvent_t a, b; };
+struct TimedSpan { int cls; int dev; cudaEvent_t a, b; uint32_t tag; uint64_t bytes; };
 static std::atomic<int> g_timing{0};
 static std::mutex g_timing_mu;
 static std::vector<TimedSpan> g_spans;                 // recorded, not yet read
 static std::vector<cudaEvent_t> g_event_pool[64];      // reusable events per device
+static std::vector<bhw_launch_record> g_launch_log;   // finished spans since the last reset (bhw_timing_launches)
 static double g_time_ms[BHW_KERNEL_CLASSES] = {0};
 static uint64_t g_time_n[BHW_KERNEL_CLASSES] = {0};
 
@@ -57,10 +58,12 @@ static cudaEvent_t pool_event(int dev) {
 
 // Brackets one launch with events on its stream when timing is on.
 struct LaunchTimer {
-  TimedSpan sp{0, 0, nullptr, nullptr};
+  TimedSpan sp{0, 0, nullptr, nullptr, 0, 0};
   cudaStream_t stream;
   bool on;
-  LaunchTimer(int cls, cudaStream_t s) : stream(s), on(g_timing.load() != 0) {
+  // tag: kernel-specific shape word (bhw_launch_record::tag); bytes: algorithmic bytes the launch writes
+  LaunchTimer(int cls, cudaStream_t s, uint32_t tag = 0, uint64_t bytes = 0) : stream(s), on(g_timing.load() != 0) {
+    sp.tag = tag; sp.bytes = bytes;
     if (!on) return;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { on = false; return; }
@@ -851,7 +854,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     table_ahead = false;
     cudaError_t ce;
     {
-      LaunchTimer tm(BHW_KERNEL_SYNTH, ls);
+      LaunchTimer tm(BHW_KERNEL_SYNTH, ls, 0, a.flat_count * 4);
       ce = launch_synth(a, ls);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "k_synth");
@@ -898,7 +901,9 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     cudaStream_t ls = fan.next();
     cudaError_t ce;
     {
-      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls);
+      const uint64_t bank_bytes = ntiles ? (uint64_t)ntiles * kBankTile * 4 : ((uint64_t)ba.nwin << run.sh.pw) * 4;
+      LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls, run.sh.m | ((uint32_t)(ntiles ? TAB_GLOBAL : run.tab_mode) << 8) |
+                     ((uint32_t)(ntiles ? 0 : run.pair) << 16) | (run.sh.pw << 24), bank_bytes);
       const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
       ce = ntiles ? launch_synth_bank(ba, TAB_GLOBAL, false, ls, pdl) : launch_synth_bank(ba, run.tab_mode, run.pair, ls, pdl);
       table_ahead = false;
@@ -987,7 +992,9 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       cudaStream_t ls = fan.next();
       cudaError_t ce;
       {
-        LaunchTimer tm(BHW_KERNEL_SYNTH_GROUP, ls);
+        LaunchTimer tm(BHW_KERNEL_SYNTH_GROUP, ls, gr.sh.m | ((uint32_t)tabm << 8) | ((uint32_t)(pass != 1) << 16) |
+                       ((uint32_t)(ga.spread ? 1 : 0) << 17) | (gr.sh.top << 24),
+                       (uint64_t)ga.nunits * kBankTile * (pass != 1 ? 8 : 4));
         const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
         ce = launch_synth_group(ga, tabm, pass != 1, ls, pdl);
         table_ahead = false;
@@ -1255,6 +1262,18 @@ int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, 
     if (st != 1) return st;
   }
   return run_batch(d, 1, n0, count, out_dev, (cudaStream_t)stream);
+}
+
+int bhw_generate_repeat(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, int reps, uint64_t out_stride,
+                        uint64_t out_slots, void* stream) {
+  if (reps < 0) return BHW_E_ARG;
+  const size_t esz = d && d->dat_width > 32 ? 8 : 4;
+  for (int i = 0; i < reps; i++) {
+    char* o = (char*)out_dev + (out_slots ? ((uint64_t)i % out_slots) * out_stride * esz : 0);
+    int st = bhw_generate(d, o, n0, count, stream);
+    if (st) return st;
+  }
+  return BHW_OK;
 }
 
 int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t count) {
@@ -1530,7 +1549,14 @@ static int timing_collect() {
     float ms = 0.f;
     cudaError_t e = cudaEventSynchronize(sp.b);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
-    if (e == cudaSuccess) { g_time_ms[sp.cls] += (double)ms; g_time_n[sp.cls]++; }
+    if (e == cudaSuccess) {
+      g_time_ms[sp.cls] += (double)ms; g_time_n[sp.cls]++;
+      if (g_launch_log.size() < (1u << 20)) {
+        bhw_launch_record rec;
+        rec.kernel_class = sp.cls; rec.tag = sp.tag; rec.bytes = sp.bytes; rec.ms = (double)ms;
+        g_launch_log.push_back(rec);
+      }
+    }
     else st = cuda_fail(e, "timing");
     g_event_pool[sp.dev].push_back(sp.a);
     g_event_pool[sp.dev].push_back(sp.b);
@@ -1544,6 +1570,7 @@ int bhw_timing_reset(void) {
   int st = timing_collect();
   std::lock_guard<std::mutex> lk(g_timing_mu);
   for (int i = 0; i < BHW_KERNEL_CLASSES; i++) { g_time_ms[i] = 0; g_time_n[i] = 0; }
+  g_launch_log.clear();
   return st;
 }
 
@@ -1553,6 +1580,16 @@ int bhw_timing_read(int kernel_class, double* total_ms, uint64_t* launches) {
   std::lock_guard<std::mutex> lk(g_timing_mu);
   if (total_ms) *total_ms = g_time_ms[kernel_class];
   if (launches) *launches = g_time_n[kernel_class];
+  return st;
+}
+
+int bhw_timing_launches(bhw_launch_record* out, uint64_t max_records, uint64_t* n_records) {
+  if (!n_records) return BHW_E_NULL;
+  int st = timing_collect();
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  *n_records = g_launch_log.size();
+  if (out)
+    for (uint64_t i = 0; i < max_records && i < g_launch_log.size(); i++) out[i] = g_launch_log[i];
   return st;
 }
 

@@ -75,25 +75,26 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
     const uint32_t ph_first = nbase * ks;
     const uint32_t span = (uint32_t)(kBankTile - 1) * ks;                 // meaningful when it does not overflow
     if (TAB == G_Q16) {
+      // image: cos16[Q] then sin16[Q], Q = 2^(top-2).  Quadrant q = phase >> 30 reads sin when q is odd, negated
+      // when q is 1 or 2; element index = (q & 1) * Q + (quarter-wave phase >> (32 - top)) = (phase & 0x7FFFFFFF)
+      // >> (32 - top): the table select rides in phase bit 30.
       const uint16_t* T16 = reinterpret_cast<const uint16_t*>(tab);
-      const uint32_t Q = 1u << (sh.top - 2);
-      const uint32_t rsh4 = 34u - sh.top;                                // (phase << 2) >> rsh4 = quarter-wave index
+      const uint32_t rsh = 32u - sh.top;
       const bool uni = ((((uint32_t)k * (uint32_t)(kBankTile - 1)) >> (pw - 2)) == 0u) &&
                        ((ph_first & 0x3FFFFFFFu) + span < 0x40000000u);
       if (uni) {
         const uint32_t q = ph_first >> 30;
-        const uint16_t* T = T16 + ((q & 1u) ? Q : 0u);
         const int32_t Ak = ((q + 1u) & 2u) ? -A[k] : A[k];
-        uint32_t ph4 = n * (ks << 2);
-        const uint32_t st4 = ks << 7;
+        uint32_t phx = (n * ks) & 0x7FFFFFFFu;                   // stays inside the quadrant: no carry into bit 30
+        const uint32_t st = ks << 5;
 #pragma unroll
         for (int j = 0; j < kBankJ; ++j) {
-          const int32_t c2 = (int32_t)((uint32_t)T[ph4 >> rsh4] * sh.tmul - sh.tbias);
+          const int32_t c2 = (int32_t)((uint32_t)T16[phx >> rsh] * sh.tmul - sh.tbias);
           const int64_t P = (int64_t)Ak * (int64_t)c2;
           const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
           Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
           if (PAIR) Sb[j] += (k & 1) ? (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32) : ba;
-          ph4 += st4;
+          phx += st;
         }
       } else {
         uint32_t ph = n * ks;
@@ -101,7 +102,7 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
 #pragma unroll
         for (int j = 0; j < kBankJ; ++j) {
           const uint32_t q = ph >> 30;
-          const uint32_t u = T16[((q & 1u) ? Q : 0u) + ((ph << 2) >> rsh4)];
+          const uint32_t u = T16[(ph & 0x7FFFFFFFu) >> rsh];
           int32_t c2 = (int32_t)(u * sh.tmul - sh.tbias);
           c2 = ((q + 1u) & 2u) ? -c2 : c2;
           const int64_t P = (int64_t)A[k] * (int64_t)c2;
@@ -112,36 +113,56 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
         }
       }
     } else {
-      // level this harmonic reads and its table (G_HALF32: the staged top level for every harmonic)
+      // Level this harmonic reads (G_HALF32: the staged top level for every harmonic).  Element index inside
+      // the pyramid (heap layout: level L starts at word 2^(L-1)): 2^(L-1) + (half-period phase >> (31 - L))
+      // = (phase | 2^31) >> (32 - L) - the level's offset rides in the top phase bit.
       uint32_t L = sh.top;
       const int32_t* T = reinterpret_cast<const int32_t*>(tab);
+      bool lin = false;
       if (TAB == G_GLOBAL) {
         const uint32_t want = pw - harmonic_log2(k);
-        L = want < sh.top ? want : sh.top;
-        T += (1u << (L - 1));
+        lin = want <= sh.top;                                    // the phase step is a whole number of entries
+        L = lin ? want : sh.top;
+      } else {
+        T -= (1u << (L - 1));                                    // the staged image is level `top` alone
       }
-      const uint32_t rsh2 = 33u - L;                                     // (phase << 1) >> rsh2 = half-period index
+      const uint32_t rsh = 32u - L;
       const bool uni = ((((uint32_t)k * (uint32_t)(kBankTile - 1)) >> (pw - 1)) == 0u) &&
                        ((ph_first & 0x7FFFFFFFu) + span < 0x80000000u);
       if (uni) {
         const int32_t Ak = (ph_first >> 31) ? -A[k] : A[k];
-        uint32_t ph2 = n * (ks << 1);
-        const uint32_t st2 = ks << 6;
+        uint32_t phx = (n * ks) | 0x80000000u;                   // stays inside the half period: no carry into bit 31
+        if (TAB == G_GLOBAL && lin) {
+          // whole-entry steps: sample lane + 32*j reads entry (first + b*(lane + 32*j)), b = k >> log2: one address,
+          // compile-time offsets
+          const int32_t* Tl = T + (phx >> rsh);
+          const uint32_t b = (uint32_t)k >> harmonic_log2(k);   // a constant once the harmonic loop is unrolled
 #pragma unroll
-        for (int j = 0; j < kBankJ; ++j) {
-          const int32_t c2 = T[ph2 >> rsh2];
-          const int64_t P = (int64_t)Ak * (int64_t)c2;
-          const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
-          Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
-          if (PAIR) Sb[j] += (k & 1) ? (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32) : ba;
-          ph2 += st2;
+          for (int j = 0; j < kBankJ; ++j) {
+            const int32_t c2 = Tl[(uint32_t)(32 * j) * b];
+            const int64_t P = (int64_t)Ak * (int64_t)c2;
+            const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
+            Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
+            if (PAIR) Sb[j] += (k & 1) ? (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32) : ba;
+          }
+        } else {
+          const uint32_t st = ks << 5;
+#pragma unroll
+          for (int j = 0; j < kBankJ; ++j) {
+            const int32_t c2 = T[phx >> rsh];
+            const int64_t P = (int64_t)Ak * (int64_t)c2;
+            const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
+            Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
+            if (PAIR) Sb[j] += (k & 1) ? (uint32_t)((P + (int64_t)(uint64_t)sh.rcn) >> 32) : ba;
+            phx += st;
+          }
         }
       } else {
         uint32_t ph = n * ks;
         const uint32_t st = ks << 5;
 #pragma unroll
         for (int j = 0; j < kBankJ; ++j) {
-          const int32_t t = T[(ph << 1) >> rsh2];
+          const int32_t t = T[(ph | 0x80000000u) >> rsh];
           const int32_t c2 = (ph >> 31) ? -t : t;
           const int64_t P = (int64_t)A[k] * (int64_t)c2;
           const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);

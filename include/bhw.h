@@ -163,6 +163,12 @@ BHW_API int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS
  * elements. Range: n0 + count <= 2^phi_width. */
 BHW_API int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, void* stream);
 
+/* `reps` back-to-back bhw_generate calls from one host call (a per-call latency measurement without a
+ * scripting language in the loop): call i writes to out_dev + (i % out_slots) * out_stride elements
+ * (out_slots = 0: always out_dev). */
+BHW_API int bhw_generate_repeat(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, int reps,
+                        uint64_t out_stride, uint64_t out_slots, void* stream);
+
 /* Same with a HOST output buffer: generates on the current device and copies
  * back (pinned staging, chunked, copy overlapped with generation).
  * Synchronises before returning. */
@@ -286,9 +292,21 @@ enum {
   BHW_KERNEL_SYNTH_GROUP = 6, /* k_synth_group: all windows of one family and entity, any PHI_WIDTHs  */
   BHW_KERNEL_CLASSES = 7
 };
+/* One finished launch of a timed region: its class, a kernel-specific shape word (k_synth_group /
+ * k_synth_bank: terms | table placement << 8 | paired << 16 | spread walk << 17 | top level or PHI_WIDTH
+ * << 24), the algorithmic bytes it wrote and its device time. */
+typedef struct bhw_launch_record {
+  int32_t kernel_class;
+  uint32_t tag;
+  uint64_t bytes;
+  double ms;
+} bhw_launch_record;
 BHW_API int bhw_timing_enable(int enabled);
 BHW_API int bhw_timing_reset(void);
 BHW_API int bhw_timing_read(int kernel_class, double* total_ms, uint64_t* launches);
+/* The launches recorded since the last reset, oldest first: writes up to max_records of them to `out`
+ * (may be NULL) and their total number to *n_records. */
+BHW_API int bhw_timing_launches(bhw_launch_record* out, uint64_t max_records, uint64_t* n_records);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,16 @@ def _worker(rank, world, port, q):
         t = bench.max_over_ranks(float(rank + 1))
         # bench.py's per-rank workload split
         wl = bench.rank_workload(rank, world, nwin_per_gpu=3)
-        q.put((rank, ok, t, b, c, wl))
+        # bench.py's headline split: the win_selector sweep cut into cost-balanced contiguous slices (strong
+        # scaling); every rank fills its slice from the windows it touches only, as bench.py plans them
+        sweep = bench.sweep_descs(pw_max=11)
+        sb, sc, first, touched, local = bench.rank_sweep(sweep, rank, world)
+        sub = [sweep[i] for i in range(first, first + touched)]
+        mine2 = H.orc_batch(sub, local, sc)
+        whole = H.orc_batch(list(sweep), 0, bhw.batch_total(sweep))
+        ok2 = np.array_equal(mine2, whole[sb:sb + sc])
+        times = bench.gather_ranks(float(10 * (rank + 1)))
+        q.put((rank, ok and ok2, t, b, c, wl, (sb, sc, int(bhw.batch_total(sweep))), times))
     finally:
         dist.destroy_process_group()
 
@@ -72,3 +81,7 @@ def test_two_rank_sharding_over_gloo():
     # weak scaling: global batch = world * per-GPU windows, rank r owns flat slice r
     (b0, c0, tot0), (b1, c1, tot1) = res[0][5], res[1][5]
     assert tot0 == tot1 and b0 == 0 and b0 + c0 == b1 and b1 + c1 == tot0 and c0 == c1
+    # strong scaling of the sweep: the two cost-balanced slices tile the flat range in order
+    (sb0, sc0, st0), (sb1, sc1, st1) = res[0][6], res[1][6]
+    assert st0 == st1 and sb0 == 0 and sb0 + sc0 == sb1 and sb1 + sc1 == st0 and sc0 > 0 and sc1 > 0
+    assert res[0][7] == [10.0, 20.0] and res[1][7] == [10.0, 20.0]      # per-rank times, gathered

@@ -17,7 +17,7 @@ from .api import (  # noqa: F401
     WinSelector, atan2, atan2_host, batch_total, cache_clear, desc_array, elem_bytes, generate, generate_batch,
     generate_batch_host, generate_host, launch_count, lib, lib_path, make_desc, quantize,
     set_side_streams, set_table_cache, shard_range, shard_range_cost, shard_windows, sincos, strerror, timing_enable, timing_read, timing_reset,
-    timing_launches, generate_repeat, BhwLaunchRecord,
+    timing_launches, generate_repeat, BhwLaunchRecord, apply, APPLY_EXACT, APPLY_ROUNDED,
     validate, variant_coeffs, variant_desc, win_function,
 )
 

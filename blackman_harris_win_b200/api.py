@@ -127,6 +127,7 @@ def lib():
         "bhw_timing_reset": (C.c_int, []),
         "bhw_timing_read": (C.c_int, [C.c_int, P(C.c_double), P(C.c_uint64)]),
         "bhw_timing_launches": (C.c_int, [P(BhwLaunchRecord), C.c_uint64, P(C.c_uint64)]),
+        "bhw_apply": (C.c_int, [D, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
         "bhw_generate_repeat": (C.c_int, [D, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     }
     for name, (res, args) in sig.items():
@@ -144,7 +145,7 @@ ABI_SYMBOLS = (
     "bhw_atan2_validate", "bhw_atan2", "bhw_atan2_host", "bhw_cache_clear", "bhw_set_table_cache", "bhw_set_side_streams", "bhw_launch_count", "bhw_last_cuda_error",
     "bhw_device_count", "bhw_timing_enable", "bhw_timing_reset", "bhw_timing_read",
     "bhw_shard_windows", "bhw_plan_create", "bhw_plan_execute", "bhw_plan_total", "bhw_plan_destroy",
-    "bhw_timing_launches", "bhw_generate_repeat",
+    "bhw_timing_launches", "bhw_generate_repeat", "bhw_apply",
 )
 
 
@@ -414,7 +415,7 @@ def set_table_cache(enabled: bool):
 
 
 KERNEL_TABLE_BUILD, KERNEL_SYNTH, KERNEL_DIRECT, KERNEL_SINCOS = 0, 1, 2, 3
-KERNEL_NAMES = ("k_table_build", "k_synth", "k_direct_window", "k_sincos", "k_synth_bank", "k_atan2", "k_synth_group")
+KERNEL_NAMES = ("k_table_build", "k_synth", "k_direct_window", "k_sincos", "k_synth_bank", "k_atan2", "k_synth_group", "k_apply_mul")
 
 
 def timing_enable(on: bool):
@@ -459,6 +460,25 @@ def generate_repeat(d: BhwDesc, out, reps: int, n0: int = 0, count: Optional[int
         count = (1 << d.phi_width) - n0
     _check(lib().bhw_generate_repeat(C.byref(d), out.data_ptr(), n0, count, int(reps), int(out_stride), int(out_slots),
                                      torch.cuda.current_stream().cuda_stream), "bhw_generate_repeat")
+
+
+APPLY_EXACT, APPLY_ROUNDED = 0, 1
+
+
+def apply(d: BhwDesc, x, mode: int = APPLY_EXACT, out=None):
+    """y[f, n] = x[f, n] * w[n] (bhw_apply): x an int32 CUDA tensor of shape (frames, N) or (N,); returns
+    int64 (APPLY_EXACT) or int32 (APPLY_ROUNDED) of the same shape."""
+    torch = _torch()
+    n = 1 << d.phi_width
+    if x.dtype != torch.int32 or not x.is_cuda or not x.is_contiguous() or x.numel() % n:
+        raise ValueError("x must be a contiguous int32 CUDA tensor of whole frames")
+    frames = x.numel() // n
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.int64 if mode == APPLY_EXACT else torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().bhw_apply(C.byref(d), int(mode), x.data_ptr(), out.data_ptr(), frames,
+                               torch.cuda.current_stream().cuda_stream), "bhw_apply")
+    return out
 
 
 def launch_count() -> int:

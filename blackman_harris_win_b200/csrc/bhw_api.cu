@@ -709,8 +709,12 @@ struct LaunchFan {
   ~LaunchFan() { join(); }
 };
 
+// fused apply step of bhw_apply: the plan's single whole window multiplies `frames` frames of x instead of
+// being stored
+struct ApplyInfo { const int32_t* x; void* y; uint64_t frames; int mode; int dw; };
+
 static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count, void* out_dev,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const ApplyInfo* ap = nullptr) {
   if (flat_begin > plan.total || flat_count > plan.total - flat_begin) return BHW_E_RANGE;
   if (!flat_count) return BHW_OK;
   if (!out_dev) return BHW_E_NULL;
@@ -785,6 +789,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     table_ahead = !tm_on && !(keep && !capturing);   // an event record sits between the two kernels otherwise
   }
   SynthArgs a;
+  memset(&a, 0, sizeof(a));
   a.recs = (const WinRec*)(plan.blob_dev + plan.o_recs);
   a.win_rec = !plan.all_same ? (const uint32_t*)(plan.blob_dev + plan.o_wr) : nullptr;
   a.flat_off = plan.uniform_pw < 0 ? (const uint64_t*)(plan.blob_dev + plan.o_off) : nullptr;
@@ -844,21 +849,51 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   LaunchFan fan;
   fan.begin(plan.dev, stream, runs_hit + group_launches);
   if (fan.err != cudaSuccess) return cuda_fail(fan.err, "side streams");
-  // one flat sub-range through the general kernel
+  // flat sub-ranges for the general kernel are collected and launched together (several disjoint ranges per
+  // launch): the win_selector sweep leaves ten little gaps of windows shorter than a tile pair
+  std::vector<Covered> pieces;
   auto general_raw = [&](uint64_t b, uint64_t e_) -> int {
-    if (b >= e_) return BHW_OK;
-    a.out = (int32_t*)out_dev + (b - flat_begin);
-    a.flat_begin = b;
-    a.flat_count = e_ - b;
-    cudaStream_t ls = fan.next();
-    table_ahead = false;
-    cudaError_t ce;
-    {
-      LaunchTimer tm(BHW_KERNEL_SYNTH, ls, 0, a.flat_count * 4);
-      ce = launch_synth(a, ls);
+    if (b < e_) pieces.push_back({b, e_});
+    return BHW_OK;
+  };
+  auto flush_pieces = [&]() -> int {
+    for (size_t i = 0; i < pieces.size();) {
+      const size_t n = pieces.size() - i < (size_t)kSynthMaxPieces ? pieces.size() - i : (size_t)kSynthMaxPieces;
+      uint64_t bytes = 0;
+      if (n == 1) {
+        a.npieces = 0;
+        a.out = (int32_t*)out_dev + (pieces[i].b - flat_begin);
+        a.flat_begin = pieces[i].b;
+        a.flat_count = pieces[i].e - pieces[i].b;
+        bytes = a.flat_count * 4;
+      } else {
+        a.npieces = (uint32_t)n;
+        a.out = out_dev;
+        a.out_flat0 = flat_begin;
+        a.flat_begin = pieces[i].b;
+        a.flat_count = 0;
+        uint32_t tiles = 0;
+        for (size_t j = 0; j < n; j++) {
+          a.piece_begin[j] = pieces[i + j].b;
+          a.piece_end[j] = pieces[i + j].e;
+          a.piece_tile0[j] = tiles;
+          tiles += (uint32_t)((pieces[i + j].e - pieces[i + j].b + 127) / 128);
+          bytes += (pieces[i + j].e - pieces[i + j].b) * 4;
+        }
+        a.piece_tile0[n] = tiles;
+      }
+      cudaStream_t ls = fan.next();
+      table_ahead = false;
+      cudaError_t ce;
+      {
+        LaunchTimer tm(BHW_KERNEL_SYNTH, ls, (uint32_t)n, bytes);
+        ce = launch_synth(a, ls);
+      }
+      if (ce != cudaSuccess) return cuda_fail(ce, "k_synth");
+      g_launches++;
+      i += n;
     }
-    if (ce != cudaSuccess) return cuda_fail(ce, "k_synth");
-    g_launches++;
+    pieces.clear();
     return BHW_OK;
   };
   // ... minus what the group launches cover
@@ -949,6 +984,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     cursor = hi;
   }
   int st = general(cursor, flat_end);
+  if (!st) st = flush_pieces();
   if (st) return st;
   // the group launches (after the small general pieces: these kernels fill the GPU)
   for (size_t g = 0; g < plan.groups.size(); g++) {
@@ -988,6 +1024,10 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
         ga.nwin = gk.nparts;
         ga.nunits = units;
         ga.sh.interleave = 0;
+      }
+      if (ap) {
+        ga.x = ap->x; ga.y = ap->y; ga.frames = ap->frames;
+        ga.apply_mode = (uint32_t)ap->mode + 1u; ga.apply_dw = (uint32_t)ap->dw;
       }
       cudaStream_t ls = fan.next();
       cudaError_t ce;
@@ -1274,6 +1314,45 @@ int bhw_generate_repeat(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t 
     if (st) return st;
   }
   return BHW_OK;
+}
+
+int bhw_apply(const bhw_desc* d, int mode, const int32_t* x_dev, void* y_dev, uint64_t frames, void* stream_) {
+  if (!d) return BHW_E_NULL;
+  int st = validate_desc(d, true);
+  if (st) return st;
+  if (d->dat_width > 32) return BHW_E_DAT_WIDTH;      // the multiplier ports are DAT_WIDTH bits, held in int32 here
+  if (mode != BHW_APPLY_EXACT && mode != BHW_APPLY_ROUNDED) return BHW_E_ARG;
+  if (!frames) return BHW_OK;
+  if (!x_dev || !y_dev) return BHW_E_NULL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return BHW_E_CAPTURE;
+  const uint64_t N = 1ull << d->phi_width;
+  bhw_plan plan;
+  plan.transient = true;
+  st = plan_build(plan, d, 1, 0, N, stream);
+  if (!st) {
+    if (plan.groups.size() == 1 && plan.win_group.size() == 1 && plan.win_group[0] == 0) {
+      // the window never reaches memory: k_synth_group multiplies it into the frames as it is produced
+      ApplyInfo ap{x_dev, y_dev, frames, mode, d->dat_width};
+      st = plan_execute(plan, 0, N, y_dev, stream, &ap);
+    } else {
+      // windows the fused kernel does not take: generate into scratch memory, then multiply
+      int32_t* w = nullptr;
+      cudaError_t e = plan_alloc(plan, (void**)&w, N * sizeof(int32_t), stream);
+      if (e != cudaSuccess) st = cuda_fail(e, "alloc(apply scratch)");
+      if (!st) st = plan_execute(plan, 0, N, w, stream);
+      if (!st) {
+        LaunchTimer tm(BHW_KERNEL_APPLY, stream, 0, N * frames * (mode == BHW_APPLY_EXACT ? 8 : 4));
+        e = launch_apply_mul(x_dev, w, y_dev, N, frames, mode + 1, d->dat_width, stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "k_apply_mul");
+        else g_launches++;
+      }
+      if (w) cudaFreeAsync(w, stream);
+    }
+  }
+  plan_free_device(plan, stream);
+  return st;
 }
 
 int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t count) {

@@ -16,7 +16,48 @@ namespace bhw {
 constexpr int kGroupThreads = 1024;
 constexpr int kGroupWarps = kGroupThreads / 32;
 
-template <int M, int TAB, bool PAIR>
+// Epilogue of one lane-tile.  APPLY 0: store the window samples (streaming, 128 B per warp instruction).
+// APPLY 1 / 2: the window is never written - every frame of the caller's signal is multiplied by it on the fly,
+// y = x * w as int_multNxN_dsp48 does (DAT_Q <= SIGNED(sig_a) * SIGNED(sig_b), 2*DTW bits,
+// src/int_multNxN_dsp48.vhd:82,105): 1 = the exact product (int64), 2 = the window entities' own use of DAT_Q,
+// r = DAT_Q[2DW-2 : DW-2], y = (r >> 1) + (r & 1) in DW bits (src/hamming_win.vhd:195-208) (int32).
+template <bool PAIR, int APPLY>
+__device__ __forceinline__ void group_epilogue(const GroupArgs& a, int32_t* o, size_t idx, size_t half, const int32_t* va,
+                                               const int32_t* vb) {
+  if (APPLY == 0) {
+    int32_t* ot = o + idx;
+#pragma unroll
+    for (int j = 0; j < kBankJ; ++j) {
+      __stcs(ot + 32 * j, va[j]);
+      if (PAIR) __stcs(ot + half + 32 * j, vb[j]);
+    }
+    return;
+  }
+  const int dw = (int)a.apply_dw;
+  const int xsh = 32 - dw;
+  for (uint64_t f = 0; f < a.frames; ++f) {
+    const size_t base = (size_t)f * (half * 2) + idx;
+    const int32_t* xf = a.x + base;
+#pragma unroll
+    for (int h = 0; h < (PAIR ? 2 : 1); ++h) {
+      int32_t xv[kBankJ];
+#pragma unroll
+      for (int j = 0; j < kBankJ; ++j) xv[j] = __ldcs(xf + h * half + 32 * j);
+#pragma unroll
+      for (int j = 0; j < kBankJ; ++j) {
+        const int64_t p = (int64_t)((int32_t)((uint32_t)xv[j] << xsh) >> xsh) * (int64_t)(h ? vb[j] : va[j]);
+        if (APPLY == 1) {
+          __stcs(reinterpret_cast<long long*>(a.y) + base + h * half + 32 * j, (long long)p);
+        } else {
+          const int64_t r = wrapb(p >> (dw - 2), dw + 1);
+          __stcs(reinterpret_cast<int32_t*>(a.y) + base + h * half + 32 * j, (int32_t)wrapb((r >> 1) + (r & 1), dw));
+        }
+      }
+    }
+  }
+}
+
+template <int M, int TAB, bool PAIR, int APPLY>
 __global__ void __launch_bounds__(kGroupThreads, 1)
 k_synth_group(const __grid_constant__ GroupArgs a) {
   extern __shared__ __align__(16) int32_t s_img[];
@@ -64,12 +105,7 @@ k_synth_group(const __grid_constant__ GroupArgs a) {
       if (!spread_tile(U, G, warp, i, &t)) continue;
       int32_t va[kBankJ], vb[kBankJ];
       group_lane_tile<M, TAB, PAIR>(sh, pw, A, S0, tab, t * kBankTile + n_first, lane, va, vb);
-      int32_t* ot = o + (size_t)t * kBankTile + lane;
-#pragma unroll
-      for (int j = 0; j < kBankJ; ++j) {
-        __stcs(ot + 32 * j, va[j]);
-        if (PAIR) __stcs(ot + half + 32 * j, vb[j]);
-      }
+      group_epilogue<PAIR, APPLY>(a, o, (size_t)t * kBankTile + lane, half, va, vb);
     }
     return;
   }
@@ -110,25 +146,19 @@ k_synth_group(const __grid_constant__ GroupArgs a) {
     const uint32_t t = u - w_begin + tile_first;
     int32_t va[kBankJ], vb[kBankJ];
     group_lane_tile<M, TAB, PAIR>(sh, pw, A, S0, tab, t * kBankTile + n_first, lane, va, vb);
-    int32_t* ot = o + (size_t)t * kBankTile + lane;
-    const size_t half = (size_t)1 << (pw - 1);
-#pragma unroll
-    for (int j = 0; j < kBankJ; ++j) {
-      __stcs(ot + 32 * j, va[j]);
-      if (PAIR) __stcs(ot + half + 32 * j, vb[j]);
-    }
+    group_epilogue<PAIR, APPLY>(a, o, (size_t)t * kBankTile + lane, (size_t)1 << (pw - 1), va, vb);
   }
 }
 
 size_t group_smem_limit() { return 192u * 1024u; }
 
-template <int M, int TAB, bool PAIR>
+template <int M, int TAB, bool PAIR, int APPLY>
 static cudaError_t launch_group_t(const GroupArgs& a, unsigned grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_synth_group<M, TAB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_synth_group<M, TAB, PAIR, APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)group_smem_limit());
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
@@ -144,21 +174,29 @@ static cudaError_t launch_group_t(const GroupArgs& a, unsigned grid, size_t smem
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_synth_group<M, TAB, PAIR>, a);
+  return cudaLaunchKernelEx(&cfg, k_synth_group<M, TAB, PAIR, APPLY>, a);
+}
+
+template <int M, int TAB>
+static cudaError_t launch_group_tab(const GroupArgs& a, bool pair, int apply, unsigned grid, size_t smem, cudaStream_t stream,
+                                    bool pdl) {
+  if (apply == 1) return pair ? launch_group_t<M, TAB, true, 1>(a, grid, smem, stream, pdl) : cudaErrorInvalidValue;
+  if (apply == 2) return pair ? launch_group_t<M, TAB, true, 2>(a, grid, smem, stream, pdl) : cudaErrorInvalidValue;
+  return pair ? launch_group_t<M, TAB, true, 0>(a, grid, smem, stream, pdl)
+              : launch_group_t<M, TAB, false, 0>(a, grid, smem, stream, pdl);
 }
 
 template <int M>
-static cudaError_t launch_group_m(const GroupArgs& a, int tab, bool pair, unsigned grid, size_t smem,
+static cudaError_t launch_group_m(const GroupArgs& a, int tab, bool pair, int apply, unsigned grid, size_t smem,
                                   cudaStream_t stream, bool pdl) {
-  if (tab == G_HALF32) return pair ? launch_group_t<M, G_HALF32, true>(a, grid, smem, stream, pdl)
-                                   : launch_group_t<M, G_HALF32, false>(a, grid, smem, stream, pdl);
-  if (tab == G_Q16) return pair ? launch_group_t<M, G_Q16, true>(a, grid, smem, stream, pdl)
-                                : launch_group_t<M, G_Q16, false>(a, grid, smem, stream, pdl);
-  return pair ? launch_group_t<M, G_GLOBAL, true>(a, grid, 0, stream, pdl)
-              : launch_group_t<M, G_GLOBAL, false>(a, grid, 0, stream, pdl);
+  if (tab == G_HALF32) return launch_group_tab<M, G_HALF32>(a, pair, apply, grid, smem, stream, pdl);
+  if (tab == G_Q16) return launch_group_tab<M, G_Q16>(a, pair, apply, grid, smem, stream, pdl);
+  return launch_group_tab<M, G_GLOBAL>(a, pair, apply, grid, 0, stream, pdl);
 }
 
 cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
+  const int apply = a.x ? (int)a.apply_mode : 0;
+  if (apply && (!a.y || !a.frames || apply > 2)) return cudaErrorInvalidValue;
   if (!a.nunits || !a.nwin) return cudaSuccess;
   if (a.spread && (tab != G_GLOBAL || a.nwin != 1 || a.unit_base || a.spread > (uint32_t)kGroupWarps)) return cudaErrorInvalidValue;
   const uint64_t ctas = a.spread ? ((uint64_t)a.nunits + a.spread - 1) / a.spread
@@ -170,11 +208,11 @@ cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStrea
   else if (tab == G_Q16) smem = (size_t)4 << (a.sh.top - 2);
   if (smem > group_smem_limit()) return cudaErrorInvalidValue;
   switch (a.sh.m) {
-    case 2: return launch_group_m<2>(a, tab, pair, grid, smem, stream, pdl);
-    case 3: return launch_group_m<3>(a, tab, pair, grid, smem, stream, pdl);
-    case 4: return launch_group_m<4>(a, tab, pair, grid, smem, stream, pdl);
-    case 5: return launch_group_m<5>(a, tab, pair, grid, smem, stream, pdl);
-    case 7: return launch_group_m<7>(a, tab, pair, grid, smem, stream, pdl);
+    case 2: return launch_group_m<2>(a, tab, pair, apply, grid, smem, stream, pdl);
+    case 3: return launch_group_m<3>(a, tab, pair, apply, grid, smem, stream, pdl);
+    case 4: return launch_group_m<4>(a, tab, pair, apply, grid, smem, stream, pdl);
+    case 5: return launch_group_m<5>(a, tab, pair, apply, grid, smem, stream, pdl);
+    case 7: return launch_group_m<7>(a, tab, pair, apply, grid, smem, stream, pdl);
     default: return cudaErrorInvalidValue;
   }
 }

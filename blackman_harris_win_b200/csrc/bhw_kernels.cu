@@ -95,18 +95,28 @@ __device__ __forceinline__ int find_window(const uint64_t* __restrict__ off, int
 }
 
 __global__ void __launch_bounds__(kSynthThreads)
-k_synth(SynthArgs a) {
+k_synth(const __grid_constant__ SynthArgs a) {
   __shared__ WinRec s_rec[kSynthWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WinRec& rec = s_rec[warp];
   int cur_w = -1, cur_r = -1;
-  const uint64_t ntiles = (a.flat_count + kTile - 1) / kTile;
+  const uint64_t ntiles = a.npieces ? (uint64_t)a.piece_tile0[a.npieces] : (a.flat_count + kTile - 1) / kTile;
   int32_t* const out = reinterpret_cast<int32_t*>(a.out);
   for (uint64_t tile = (uint64_t)blockIdx.x * kSynthWarps + warp; tile < ntiles;
        tile += (uint64_t)gridDim.x * kSynthWarps) {
-    const uint64_t o0 = tile * kTile;               // first output index of the tile
-    const uint64_t f0 = a.flat_begin + o0;          // its flat sample index
-    const uint64_t left = a.flat_count - o0;        // samples left in the request
+    uint64_t o0, f0, left;
+    if (a.npieces) {
+      // several disjoint ranges in one launch: piece of this tile (few pieces: linear search)
+      uint32_t p = 0;
+      while (p + 1 < a.npieces && (uint32_t)tile >= a.piece_tile0[p + 1]) ++p;
+      f0 = a.piece_begin[p] + (tile - a.piece_tile0[p]) * kTile;
+      left = a.piece_end[p] - f0;
+      o0 = f0 - a.out_flat0;
+    } else {
+      o0 = tile * kTile;                            // first output index of the tile
+      f0 = a.flat_begin + o0;                       // its flat sample index
+      left = a.flat_count - o0;                     // samples left in the request
+    }
     const uint32_t tile_n = left < kTile ? (uint32_t)left : kTile;
     int w;
     if (a.uniform_pw >= 0) w = (int)(f0 >> a.uniform_pw);
@@ -598,9 +608,31 @@ k_atan2_u(const __grid_constant__ Atan2Params p, const int32_t* __restrict__ x, 
   if (j < count) phi[j] = atan2_sample32_t<AW>(p, x[j], y[j]);
 }
 
+// The apply step for windows the fused kernel (k_synth_group) does not take (TAYLOR, the input-quadrant
+// CORDICs, 64-bit tails ...): y[f*N + n] = x[f*N + n] * w[n] from a window generated into scratch memory.
+// mode 1: the exact product DAT_Q (int64); mode 2: the entities' rounded slice of it (int32) - see group_epilogue.
+__global__ void __launch_bounds__(256)
+k_apply_mul(const int32_t* __restrict__ x, const int32_t* __restrict__ w, void* __restrict__ y, uint64_t n, uint64_t frames,
+            int mode, int dw) {
+  const int xsh = 32 - dw;
+  const uint64_t total = n * frames;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int32_t xv = (int32_t)((uint32_t)__ldcs(x + i) << xsh) >> xsh;
+    const int64_t p = (int64_t)xv * (int64_t)__ldg(w + (i % n));
+    if (mode == 1) {
+      __stcs(reinterpret_cast<long long*>(y) + i, (long long)p);
+    } else {
+      const int64_t r = wrapb(p >> (dw - 2), dw + 1);
+      __stcs(reinterpret_cast<int32_t*>(y) + i, (int32_t)wrapb((r >> 1) + (r & 1), dw));
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------
+cudaError_t launch_apply_mul(const int32_t* x, const int32_t* w, void* y, uint64_t n, uint64_t frames, int mode, int dw,
+                             cudaStream_t stream);
 static int g_sm_count[64] = {0};
 
 static int sm_count() {
@@ -652,8 +684,9 @@ cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream) {
 }
 
 cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
-  if (!a.flat_count) return cudaSuccess;
-  const uint64_t ntiles = (a.flat_count + kTile - 1) / kTile;
+  if (!a.npieces && !a.flat_count) return cudaSuccess;
+  const uint64_t ntiles = a.npieces ? (uint64_t)a.piece_tile0[a.npieces] : (a.flat_count + kTile - 1) / kTile;
+  if (!ntiles) return cudaSuccess;
   const unsigned grid = grid_for((ntiles + kSynthWarps - 1) / kSynthWarps, 8);
   k_synth<<<grid, kSynthThreads, 0, stream>>>(a);
   return cudaGetLastError();
@@ -782,6 +815,14 @@ cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* 
     const unsigned grid = grid_for((count + 255) / 256, 8);
     k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply_mul(const int32_t* x, const int32_t* w, void* y, uint64_t n, uint64_t frames, int mode, int dw,
+                             cudaStream_t stream) {
+  if (!n || !frames) return cudaSuccess;
+  const unsigned grid = grid_for((n * frames + 255) / 256, 8);
+  k_apply_mul<<<grid, 256, 0, stream>>>(x, w, y, n, frames, mode, dw);
   return cudaGetLastError();
 }
 

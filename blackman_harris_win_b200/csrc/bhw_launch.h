@@ -8,6 +8,8 @@
 
 namespace bhw {
 
+constexpr int kSynthMaxPieces = 24;
+
 struct SynthArgs {
   const WinRec* recs;        // [nrec] distinct window records
   const uint32_t* win_rec;   // [nwin] record of each window; NULL: record 0 for every window
@@ -19,6 +21,15 @@ struct SynthArgs {
   uint64_t flat_count;
   int32_t nwin;
   int32_t uniform_pw;        // >= 0: every window has 2^uniform_pw samples (no search needed)
+  // npieces > 0: the launch covers several disjoint flat ranges ("pieces", ascending) instead of
+  // [flat_begin, flat_begin + flat_count): piece p = [piece_begin[p], piece_end[p]), its 128-sample tiles are
+  // numbered from piece_tile0[p]; `out` is then element flat index `out_flat0` of the batch
+  uint32_t npieces;
+  uint32_t pad;
+  uint64_t out_flat0;
+  uint64_t piece_begin[kSynthMaxPieces];
+  uint64_t piece_end[kSynthMaxPieces];
+  uint32_t piece_tile0[kSynthMaxPieces + 1];
 };
 
 struct BankArgs {
@@ -45,6 +56,12 @@ struct GroupArgs {
   uint32_t unit_base;        // the launch covers units [unit_base, unit_base + nunits) of the list's numbering
   uint32_t nunits;           // tiles of 256 samples (sample pairs) in the launch
   uint32_t spread;           // G_GLOBAL, one whole window: G > 0 = warp j of G takes the j-th G-th of the window
+  // fused apply step (bhw_apply): x != NULL -> multiply every frame of x by the window instead of storing it
+  const int32_t* x;          // frames x N samples, frame-major; the low DAT_WIDTH bits are the sample
+  void* y;                   // frames x N products: int64 (mode 1) or int32 (mode 2)
+  uint64_t frames;
+  uint32_t apply_mode;       // BHW_APPLY_EXACT + 1 / BHW_APPLY_ROUNDED + 1
+  uint32_t apply_dw;         // DAT_WIDTH
 };
 
 struct DirectArgs {
@@ -104,6 +121,8 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl = false);
 // tab: G_HALF32 / G_Q16 / G_GLOBAL; pair: units are tiles of sample pairs (whole windows only)
 cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl = false);
+cudaError_t launch_apply_mul(const int32_t* x, const int32_t* w, void* y, uint64_t n, uint64_t frames, int mode, int dw,
+                             cudaStream_t stream);
 size_t group_smem_limit();  // bytes of shared memory a group launch may use for the staged table image
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 int device_sm_count();     // SMs of the current device (148 on B200)

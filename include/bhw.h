@@ -207,6 +207,24 @@ BHW_API int bhw_generate_batch_multi(const bhw_desc* descs, int nwin, int ngpus,
 BHW_API int bhw_shard_windows(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint64_t flat_count,
                       int* first_win, int* nwin_touched, uint64_t* local_begin);
 
+/* ---- the apply step: what the coefficient stream is for ------------------------------------ */
+/* Replaces: a win_selector instance feeding int_multNxN_dsp48 together with the signal, the way the
+ * window entities themselves use that multiplier (src/int_multNxN_dsp48.vhd:75-110:
+ * DAT_Q <= SIGNED(DAT_A) * SIGNED(DAT_B), DTW = DAT_WIDTH bits in, 2*DTW bits out; instantiated e.g.
+ * src/hamming_win.vhd:183-191).  x_dev holds `frames` frames of N = 2^phi_width samples, frame-major, one
+ * int32 per sample whose low DAT_WIDTH bits are the DAT_A port bits (sign bit = bit DAT_WIDTH-1).
+ * y[f*N + n] = x[f*N + n] * w[n] with w the stream bhw_generate(d) would write (stream_offset applies):
+ *   BHW_APPLY_EXACT   : DAT_Q itself, one int64 per sample
+ *   BHW_APPLY_ROUNDED : the entities' own slice of DAT_Q - r = DAT_Q[2DW-2 : DW-2],
+ *                       y = (r >> 1) + (r & 1) wrapped to DW bits (src/hamming_win.vhd:195-208) - one
+ *                       int32 per sample, sign-extended
+ * For the windows k_synth_group generates (cordic_dds / HLS families, 32-bit tail, N >= 512) the window
+ * is never written: it is produced in registers and multiplied into every frame on the fly (4 B read
+ * + 4 or 8 B written per sample); any other window is generated into scratch memory first.
+ * dat_width <= 32.  Stream-ordered; not capturable (BHW_E_CAPTURE). */
+enum { BHW_APPLY_EXACT = 0, BHW_APPLY_ROUNDED = 1 };
+BHW_API int bhw_apply(const bhw_desc* d, int mode, const int32_t* x_dev, void* y_dev, uint64_t frames, void* stream);
+
 /* ---- plans: resolve once, execute many times ------------------------------ */
 /* A plan is a batch resolved and resident on the current device: per-window records, trig-table
  * storage and (for TAYLOR) its own copy of every sine ROM the batch needs (any mix of DAT_WIDTH /
@@ -290,7 +308,8 @@ enum {
   BHW_KERNEL_SYNTH_BANK = 4,  /* k_synth_bank: whole windows of one shape, tables in shared memory */
   BHW_KERNEL_ATAN2 = 5,       /* k_atan2                                                          */
   BHW_KERNEL_SYNTH_GROUP = 6, /* k_synth_group: all windows of one family and entity, any PHI_WIDTHs  */
-  BHW_KERNEL_CLASSES = 7
+  BHW_KERNEL_APPLY = 7,       /* k_apply_mul: the unfused half of bhw_apply                           */
+  BHW_KERNEL_CLASSES = 8
 };
 /* One finished launch of a timed region: its class, a kernel-specific shape word (k_synth_group /
  * k_synth_bank: terms | table placement << 8 | paired << 16 | spread walk << 17 | top level or PHI_WIDTH

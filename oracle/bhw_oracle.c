@@ -429,6 +429,33 @@ int orc_window_i32(const bhw_desc* d, uint64_t n0, uint64_t count, int32_t* out)
   return BHW_OK;
 }
 
+/* The apply step: y[f*N + n] = x[f*N + n] * w[n] through int_multNxN_dsp48 - DAT_Q <= SIGNED(sig_a) *
+ * SIGNED(sig_b), DTW = DAT_WIDTH bits per port, 2*DTW bits out (src/int_multNxN_dsp48.vhd:77-82,105).  x: the
+ * low DAT_WIDTH bits are the DAT_A port.  mode 0: DAT_Q; mode 1: the window entities' own use of it,
+ * r = DAT_Q[2DW-2 : DW-2] (src/hamming_win.vhd:195), y = r[DW:1] (+1 when r[0]) in DW bits (:198-208). */
+int orc_apply(const bhw_desc* d, int mode, const int32_t* x, uint64_t frames, int64_t* y) {
+  int st = orc_validate(d);
+  if (st) return st;
+  if (d->dat_width > 32) return BHW_E_DAT_WIDTH;
+  if (mode != 0 && mode != 1) return BHW_E_ARG;
+  const int dw = d->dat_width;
+  const uint64_t N = 1ull << d->phi_width;
+  int64_t* w = (int64_t*)malloc(N * sizeof(int64_t));
+  if (!w) return BHW_E_ALLOC;
+  st = orc_window(d, 0, N, w);
+  for (uint64_t f = 0; !st && f < frames; f++)
+    for (uint64_t n = 0; n < N; n++) {
+      const int64_t a = (int64_t)((uint64_t)(int64_t)x[f * N + n] << (64 - dw)) >> (64 - dw);   /* DAT_A, signed DW bits */
+      const int64_t q = a * w[n];                                                                /* DAT_Q */
+      if (mode == 0) { y[f * N + n] = q; continue; }
+      const int64_t r = (int64_t)((uint64_t)(q >> (dw - 2)) << (63 - dw)) >> (63 - dw);          /* DW+1 bits */
+      const int64_t b = (r >> 1) + (r & 1);
+      y[f * N + n] = (int64_t)((uint64_t)b << (64 - dw)) >> (64 - dw);                           /* DW bits */
+    }
+  free(w);
+  return st;
+}
+
 typedef struct { const bhw_desc* d; uint64_t n0, count; int64_t* out; int st; } job_t;
 static void* mt_worker(void* p) {
   job_t* j = (job_t*)p;

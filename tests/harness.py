@@ -42,6 +42,7 @@ def oracle():
     L.orc_window_mt.argtypes = [D, C.c_uint64, C.c_uint64, I64P, C.c_int]
     L.orc_window_i32.argtypes = [D, C.c_uint64, C.c_uint64, P(C.c_int32)]
     L.orc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]
+    L.orc_apply.argtypes = [D, C.c_int, P(C.c_int32), C.c_uint64, I64P]
     L.orc_atan2.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_int32), P(C.c_int32), P(C.c_int32), C.c_uint64]
     L.orc_atan2_validate.argtypes = [C.c_int, C.c_int, C.c_int]
     L.orc_cordic_atan2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
@@ -83,6 +84,17 @@ def orc_atan2(iw: int, aw: int, prec: int, x: np.ndarray, y: np.ndarray) -> np.n
     if st:
         raise ValueError(f"orc_atan2: status {st}")
     return out
+
+
+def orc_apply(d: BhwDesc, x: np.ndarray, mode: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    n = 1 << d.phi_width
+    assert x.size % n == 0
+    y = _i64(x.size)
+    st = oracle().orc_apply(C.byref(d), mode, x.ctypes.data_as(P(C.c_int32)), x.size // n, _p(y))
+    if st:
+        raise ValueError(f"orc_apply status {st}")
+    return y.reshape(x.shape)
 
 
 def orc_window_status(d: BhwDesc) -> int:

@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 import blackman_harris_win_b200 as bhw
@@ -81,6 +82,32 @@ def test_validate_rejections():
     assert bhw.validate(bhw.make_desc(2, 10, 33, [1, 1], sin_type=bhw.SIN_TAYLOR)) == -6
     assert bhw.validate(bhw.make_desc(2, 20, 16, [1, 1], model=bhw.MODEL_HLS)) == -5  # NP > NW+2
     assert bhw.lib().bhw_validate(None) == -1
+
+
+def test_apply_argument_checks_need_no_gpu():
+    L = bhw.lib()
+    d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
+    assert L.bhw_apply(None, 0, None, None, 1, None) == -1
+    assert L.bhw_apply(C.byref(d.copy(dat_width=40, aa=[1, 1, 1, 1])), 0, None, None, 1, None) == -6
+    assert L.bhw_apply(C.byref(d), 2, None, None, 1, None) == -16
+    assert L.bhw_apply(C.byref(d), 0, None, None, 0, None) == 0          # no frames: nothing to do
+    assert L.bhw_apply(C.byref(d), 0, None, None, 1, None) == -1         # missing buffers
+
+
+def test_oracle_apply_step_matches_numpy():
+    """orc_apply against a direct numpy restatement of the product, the slice and the rounding."""
+    import harness as H
+    rng = np.random.default_rng(3)
+    for d in (bhw.variant_desc(1, 8, 16), bhw.variant_desc(10, 7, 32), bhw.variant_desc(6, 9, 17, model=bhw.MODEL_HLS)):
+        n, dw = 1 << d.phi_width, d.dat_width
+        x = rng.integers(-(1 << 31), 1 << 31, size=(2, n), dtype=np.int64).astype(np.int32)
+        w = H.orc_window(d)
+        a = ((x.astype(np.int64) << (64 - dw)) >> (64 - dw))
+        q = a * w[None, :]
+        assert np.array_equal(H.orc_apply(d, x, 0), q)
+        r = ((q >> (dw - 2)) << (63 - dw)) >> (63 - dw)
+        b = (r >> 1) + (r & 1)
+        assert np.array_equal(H.orc_apply(d, x, 1), (b << (64 - dw)) >> (64 - dw))
 
 
 def test_shard_ranges_partition_the_flat_range():

@@ -656,6 +656,51 @@ def test_stream_offset_long_windows_all_kernels():
         assert torch.equal(part, torch.roll(base, -1)[n - 1000:])
 
 
+def test_apply_step_fused_and_unfused():
+    """bhw_apply: y = x * w through int_multNxN_dsp48 (src/int_multNxN_dsp48.vhd:105), exact (2*DW bits) and as the
+    entities slice and round it (src/hamming_win.vhd:195-208) - bit-exact against the oracle for windows the fused
+    kernel takes (every table placement, spread walk) and for those that go through scratch memory."""
+    import torch
+    rng = np.random.default_rng(7)
+    hi = (1 << 31) - 1
+    shapes = [("fused, staged half period", bhw.variant_desc(1, 12, 16), 3),
+              ("fused, staged half period, 3 terms, DT_VLD order", bhw.variant_desc(4, 16, 16).copy(stream_offset=1), 2),
+              ("fused, uint16 quarter waves", bhw.variant_desc(6, 18, 17), 2),
+              ("fused, pyramid", bhw.variant_desc(9, 19, 24), 2),
+              ("fused, pyramid, 7 terms DW 32", bhw.variant_desc(10, 17, 32), 1),
+              ("fused, HLS family", bhw.variant_desc(6, 14, 17, model=bhw.MODEL_HLS), 2),
+              ("scratch: TAYLOR", bhw.variant_desc(3, 14, 24, sin_type=bhw.SIN_TAYLOR, lut_size=9), 2),
+              ("scratch: cordic_dds48", bhw.variant_desc(10, 12, 32, sin_type=bhw.SIN_CORDIC48), 2),
+              ("scratch: shorter than a tile pair", bhw.variant_desc(2, 6, 16), 5),
+              ("scratch: 64-bit tail", bhw.make_desc(4, 11, 32, [hi, hi - 1, hi - 2, hi - 3]), 2),
+              ("scratch: DIRECT", bhw.variant_desc(6, 12, 17, algo=bhw.ALGO_DIRECT), 1)]
+    for name, d, frames in shapes:
+        n = 1 << d.phi_width
+        x = rng.integers(-(1 << 31), 1 << 31, size=(frames, n), dtype=np.int64).astype(np.int32)   # upper bits are not port bits
+        x[0, :4] = [(1 << (d.dat_width - 1)) - 1, -(1 << (d.dat_width - 1)), 0, -1]
+        xd = torch.from_numpy(x).cuda()
+        for mode in (bhw.APPLY_EXACT, bhw.APPLY_ROUNDED):
+            bhw.timing_enable(True)
+            bhw.timing_reset()
+            got = bhw.apply(d, xd, mode)
+            kt = bhw.timing_read()
+            bhw.timing_enable(False)
+            assert got.dtype == (torch.int64 if mode == bhw.APPLY_EXACT else torch.int32)
+            want = H.orc_apply(d, x, mode)
+            assert np.array_equal(got.cpu().numpy().astype(np.int64), want), (name, mode)
+            assert (kt["k_apply_mul"][0] == 0) == name.startswith("fused"), (name, kt)
+    # a long window on the spread walk, one frame, spot-checked
+    d = bhw.variant_desc(9, 23, 24)
+    n = 1 << 23
+    xd = torch.randint(-(1 << 23), 1 << 23, (n,), dtype=torch.int32, device="cuda")
+    got = bhw.apply(d, xd, bhw.APPLY_EXACT)
+    w = bhw.generate(d)
+    assert torch.equal(got, xd.to(torch.int64) * w.to(torch.int64))
+    assert np.array_equal(w[:4096].cpu().numpy().astype(np.int64), H.orc_window(d, 0, 4096))
+    with pytest.raises(bhw.BhwError):
+        bhw.apply(bhw.variant_desc(10, 10, 40), torch.zeros(1024, dtype=torch.int32, device="cuda"))
+
+
 def test_cordic_atan2():
     import torch
     g = torch.Generator(device="cpu").manual_seed(11)

@@ -18,7 +18,7 @@ MAX_TERMS = 7
 VARIANT_NAMES = {
     1: "hamming", 2: "hann", 3: "blackman", 4: "blackman_harris_3", 5: "nuttall",
     6: "blackman_harris_4", 7: "blackman_nuttall", 8: "flat_top", 9: "blackman_harris_5",
-    10: "blackman_harris_7",
+    10: "blackman_harris_7", 11: "blackman_harris_7_readme", 12: "hamming_alt", 13: "flat_top_normalised",
 }
 _WIN_TYPE_NAMES = {"HAMMING": 2, "BH3TERM": 3, "BH4TERM": 4, "BH5TERM": 5, "BH7TERM": 7}
 _SIN_TYPE_NAMES = {"CORDIC": SIN_CORDIC, "TAYLOR": SIN_TAYLOR, "CORDIC48": SIN_CORDIC48,

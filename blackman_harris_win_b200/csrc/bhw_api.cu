@@ -27,6 +27,7 @@ namespace bhw {
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_cache_enabled{1};
 static std::atomic<int> g_side_streams{4};  // bhw_set_side_streams
+static std::atomic<int> g_defer_ctas{0};    // resident CTAs per SM of a table build that shares the GPU with synthesis
 static thread_local std::string t_cuda_err;
 
 static int cuda_fail(cudaError_t e, const char* where) {
@@ -217,6 +218,7 @@ struct bhw_plan {
     int tab_mode = 0;            // G_*
     int32_t* pyr = nullptr;      // 2^top words
     uint16_t* q16 = nullptr;     // G_Q16: 2^(top-1) uint16
+    int big_job = -1;            // index in big_jobs when the pyramid has a launch of its own
   };
   struct Group {
     int family = 0;
@@ -526,6 +528,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     init_pyramid_job(fam.canon, fam.lmin, fam.pyr, fam.q16, &j);
     if (j.work >= kBigTableWork && table_build_unrolled_ok(j)) {
       j.work_begin = 0;
+      fam.big_job = (int)plan.big_jobs.size();
       plan.big_jobs.push_back(j);
     } else {
       j.work_begin = work;
@@ -681,11 +684,28 @@ struct LaunchFan {
     if ((err = cudaEventRecord(ds->ev_fork, main)) != cudaSuccess) return;
     nside = want;
   }
+  unsigned reserved = 0;  // side streams handed out by reserve(): next() leaves them alone
+  // a side stream of its own for a chain of dependent launches (a family's table build and its groups);
+  // `main` when none is free
+  cudaStream_t reserve() {
+    for (int i = 0; i < nside; i++) {
+      if (reserved & (1u << i)) continue;
+      if (!(used & (1u << i))) {
+        cudaError_t e = cudaStreamWaitEvent(ds->side[i], ds->ev_fork, 0);
+        if (e != cudaSuccess) { err = e; return main; }
+        used |= 1u << i;
+      }
+      reserved |= 1u << i;
+      return ds->side[i];
+    }
+    return main;
+  }
   // stream of the next launch
   cudaStream_t next() {
     if (!nside) return main;
-    const unsigned slot = rr++ % (unsigned)(nside + 1);
-    if (slot == 0) return main;
+    unsigned slot = rr++ % (unsigned)(nside + 1);
+    for (int tries = 0; slot != 0 && (reserved & (1u << (slot - 1))) && tries <= nside; tries++) slot = rr++ % (unsigned)(nside + 1);
+    if (slot == 0 || (reserved & (1u << (slot - 1)))) return main;
     const unsigned i = slot - 1;
     if (!(used & (1u << i))) {
       cudaError_t e = cudaStreamWaitEvent(ds->side[i], ds->ev_fork, 0);
@@ -703,6 +723,7 @@ struct LaunchFan {
       if (e != cudaSuccess && err == cudaSuccess) err = e;
     }
     used = 0;
+    reserved = 0;
     nside = 0;
     return err;
   }
@@ -749,6 +770,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   cudaError_t e = cudaSuccess;
   bool table_ahead = false;  // k_table_build is the last thing enqueued on `stream`
   bool tm_on = false;
+  bool building = false, defer_family_builds = false;
   const bool have_jobs = !plan.jobs.empty() || !plan.big_jobs.empty();
   const bool keep = g_cache_enabled.load() != 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -770,23 +792,23 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       if (e != cudaSuccess) return cuda_fail(e, "k_table_build");
       g_launches++;
     }
-    for (const TabJob& j : plan.big_jobs) {
+    // A family's pyramid is read by that family's groups only: when the execute fans its launches out over
+    // side streams, such a build goes to a side stream of its own together with its groups (below), so that
+    // an integer-bound build overlaps the store-bound synthesis of the other families.
+    defer_family_builds = !capturing && g_side_streams.load() > 0 && g_defer_ctas.load() > 0 && plan.groups.size() >= 3;
+    for (size_t ji = 0; ji < plan.big_jobs.size(); ji++) {
+      bool deferred = false;
+      if (defer_family_builds)
+        for (const auto& fam : plan.families) if (fam.big_job == (int)ji) deferred = true;
+      if (deferred) continue;
       LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
       tm_on = tm.on;
-      e = launch_table_build_unrolled(j, stream);
+      e = launch_table_build_unrolled(plan.big_jobs[ji], stream);
       if (e != cudaSuccess) return cuda_fail(e, "k_table_build_u");
       g_launches++;
     }
-    // A build that is only captured has not happened: the flag stays clear, so an eager execute (or
-    // the next capture) builds again; replays of the graph rebuild the tables every time.
-    if (keep && !capturing) {
-      if (!plan.ev_built && (e = cudaEventCreateWithFlags(&plan.ev_built, cudaEventDisableTiming)) != cudaSuccess)
-        return cuda_fail(e, "cudaEventCreate(table build)");
-      if ((e = cudaEventRecord(plan.ev_built, stream)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(table build)");
-      plan.built_stream = stream;
-      plan.tables_built = true;
-    }
-    table_ahead = !tm_on && !(keep && !capturing);   // an event record sits between the two kernels otherwise
+    building = true;
+    table_ahead = !tm_on && !defer_family_builds;
   }
   SynthArgs a;
   memset(&a, 0, sizeof(a));
@@ -849,6 +871,24 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   LaunchFan fan;
   fan.begin(plan.dev, stream, runs_hit + group_launches);
   if (fan.err != cudaSuccess) return cuda_fail(fan.err, "side streams");
+  // deferred family builds: the largest first, each on a side stream of its own (or on `stream` when none is free)
+  std::vector<cudaStream_t> fam_stream(plan.families.size(), nullptr);
+  bool any_deferred = false;
+  if (building && defer_family_builds) {
+    std::vector<size_t> order;
+    for (size_t f = 0; f < plan.families.size(); f++) if (plan.families[f].big_job >= 0) order.push_back(f);
+    std::sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+      return plan.big_jobs[(size_t)plan.families[x].big_job].work > plan.big_jobs[(size_t)plan.families[y].big_job].work; });
+    for (size_t f : order) {
+      cudaStream_t fs = fan.reserve();
+      LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, fs);
+      e = launch_table_build_unrolled(plan.big_jobs[(size_t)plan.families[f].big_job], fs, fs == stream ? 8 : g_defer_ctas.load());
+      if (e != cudaSuccess) return cuda_fail(e, "k_table_build_u");
+      g_launches++;
+      fam_stream[f] = fs;
+      any_deferred = true;
+    }
+  }
   // flat sub-ranges for the general kernel are collected and launched together (several disjoint ranges per
   // launch): the win_selector sweep leaves ten little gaps of windows shorter than a tile pair
   std::vector<Covered> pieces;
@@ -984,6 +1024,20 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     cursor = hi;
   }
   int st = general(cursor, flat_end);
+  // with family builds on side streams, pieces that read a pyramid (the ragged ends of cut group windows) run
+  // after the join; the others now
+  std::vector<Covered> late;
+  if (!st && any_deferred) {
+    std::vector<Covered> now;
+    for (const Covered& pc : pieces) {
+      bool reads_pyramid = false;
+      size_t w = (size_t)(std::upper_bound(plan.flat_off.begin(), plan.flat_off.end(), pc.b) - plan.flat_off.begin());
+      for (w = w ? w - 1 : 0; w < (size_t)plan.nwin && plan.flat_off[w] < pc.e; w++)
+        if (plan.win_group[w] >= 0 && fam_stream[(size_t)plan.groups[(size_t)plan.win_group[w]].family]) reads_pyramid = true;
+      (reads_pyramid ? late : now).push_back(pc);
+    }
+    pieces.swap(now);
+  }
   if (!st) st = flush_pieces();
   if (st) return st;
   // the group launches (after the small general pieces: these kernels fill the GPU)
@@ -1029,7 +1083,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
         ga.x = ap->x; ga.y = ap->y; ga.frames = ap->frames;
         ga.apply_mode = (uint32_t)ap->mode + 1u; ga.apply_dw = (uint32_t)ap->dw;
       }
-      cudaStream_t ls = fan.next();
+      cudaStream_t ls = fam_stream[(size_t)gr.family] ? fam_stream[(size_t)gr.family] : fan.next();
       cudaError_t ce;
       {
         LaunchTimer tm(BHW_KERNEL_SYNTH_GROUP, ls, gr.sh.m | ((uint32_t)tabm << 8) | ((uint32_t)(pass != 1) << 16) |
@@ -1045,6 +1099,19 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   }
   e = fan.join();
   if (e != cudaSuccess) return cuda_fail(e, "side streams (join)");
+  if (!late.empty()) {
+    pieces.swap(late);
+    if ((st = flush_pieces())) return st;
+  }
+  // A build that is only captured has not happened: the flag stays clear, so an eager execute (or the next
+  // capture) builds again; replays of the graph rebuild the tables every time.
+  if (building && keep && !capturing) {
+    if (!plan.ev_built && (e = cudaEventCreateWithFlags(&plan.ev_built, cudaEventDisableTiming)) != cudaSuccess)
+      return cuda_fail(e, "cudaEventCreate(table build)");
+    if ((e = cudaEventRecord(plan.ev_built, stream)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord(table build)");
+    plan.built_stream = stream;
+    plan.tables_built = true;
+  }
   return BHW_OK;
 }
 
@@ -1603,6 +1670,13 @@ int bhw_cache_clear(void) {
 
 int bhw_set_table_cache(int enabled) {
   g_cache_enabled.store(enabled ? 1 : 0);
+  return BHW_OK;
+}
+
+// undocumented tuning knob: CTAs per SM of a deferred family table build (0 = do not defer)
+__attribute__((visibility("default"))) int bhw_debug_set_defer_ctas(int n) {
+  if (n < 0 || n > 8) return BHW_E_ARG;
+  g_defer_ctas.store(n);
   return BHW_OK;
 }
 

@@ -663,9 +663,9 @@ cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total
   return cudaGetLastError();
 }
 
-cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream) {
+cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream, int ctas_per_sm) {
   if (!j.work) return cudaSuccess;
-  const unsigned grid = grid_for(((uint64_t)j.work / (j.sp.kind == SRC_INQ ? 2 : 1) + 255) / 256, 8);
+  const unsigned grid = grid_for(((uint64_t)j.work / (j.sp.kind == SRC_INQ ? 2 : 1) + 255) / 256, ctas_per_sm);
   if (j.sp.kind == SRC_INQ) {
     switch (j.sp.n_xy) {
       case 16: k_table_build_inq_u<16><<<grid, 256, 0, stream>>>(j); break;

@@ -112,7 +112,9 @@ cudaError_t launch_table_build(const TabJob* jobs_dev, int njobs, uint32_t total
                                cudaStream_t stream);
 // a single large job of a 32-bit-core source with a stage count that has an unrolled instantiation
 // (DAT_WIDTH 16, 17, 24 and 32 of cordic_dds): its own launch, the job in the parameter block
-cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream);
+// ctas_per_sm: resident 256-thread CTAs per SM the grid is sized for (8 fills an SM; 2 leaves room for a
+// 1024-thread synthesis CTA of another stream next to it)
+cudaError_t launch_table_build_unrolled(const TabJob& j, cudaStream_t stream, int ctas_per_sm = 8);
 cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream);
 // tab: TAB_SMEM_FULL / TAB_SMEM_HALF / TAB_GLOBAL; pair: lanes own (n, n + N/2) sample pairs
 // pdl: launch with programmatic stream serialization (the kernel directly ahead in the stream is

@@ -3,6 +3,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "bhw_internal.h"
 #include "bhw_plan.h"
 
@@ -247,7 +249,7 @@ int resolve_window(const bhw_desc* d, WinParams* wp, SrcParams src[2]) {
 
 // ---- coefficient front end -----------------------------------------------------------------
 // Real-valued sets as the reference spells them (README.md:30-41 for the list of variants).
-static const double kCoef[10][BHW_MAX_TERMS] = {
+static const double kCoef[13][BHW_MAX_TERMS] = {
     {0.5434783, 1.0 - 0.5434783},                        // Hamming       src/tb/tb_windows.vhd:123-124
     {0.5, 0.5},                                          // Hann          src/hamming_win.vhd:14-16
     {0.42, 0.5, 0.08},                                   // Blackman      src/tb/tb_windows.vhd:114-116
@@ -259,11 +261,16 @@ static const double kCoef[10][BHW_MAX_TERMS] = {
     {0.3232153788877343, 0.4714921439576260, 0.1755341299601972, 0.0284969901061499,
      0.0012613570882927},                                // BH 5-term     src/bh_win_5term.vhd:14-19
     {0.271220360585039, 0.433444612327442, 0.218004122892930, 0.065785343295606, 0.010761867305342,
-     0.000770012710581, 0.000013680883060}};             // BH 7-term     src/tb/tb_windows.vhd:67-73
-static const int kTerms[10] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7};
+     0.000770012710581, 0.000013680883060},              // BH 7-term     src/tb/tb_windows.vhd:67-73
+    // the alternative sets the reference spells out next to the ones above
+    {0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803, 0.01081174209837,
+     0.00077658482522, 0.00001388721735},                // BH 7-term, README.md:45-51 (magnitudes; the entity alternates the signs)
+    {0.5383554, 0.4616446},                              // Hamming, second set  src/hamming_win.vhd:21-23
+    {0.215578950, 0.416631580, 0.277263158, 0.083578947, 0.006947368}};  // Flat-top, normalised  src/bh_win_5term.vhd:28-33
+static const int kTerms[13] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7, 7, 2, 5};
 
 static int variant_coeffs(int variant, int rule, double a[BHW_MAX_TERMS], int* nterms) {
-  if (variant < 1 || variant > 10) return BHW_E_VARIANT;
+  if (variant < 1 || variant > 13) return BHW_E_VARIANT;
   if (rule != BHW_RULE_TB && rule != BHW_RULE_HLS) return BHW_E_VARIANT;
   const int m = kTerms[variant - 1];
   for (int k = 0; k < BHW_MAX_TERMS; k++) a[k] = k < m ? kCoef[variant - 1][k] : 0.0;
@@ -367,83 +374,164 @@ int bhw_shard_range(uint64_t total, int rank, int nranks, uint64_t* begin, uint6
   return BHW_OK;
 }
 
-// Relative generation time of one sample of window d (1.0 = a paired 2-term window with its table in
-// shared memory, about 0.6 ps on B200), fitted to round-1 measurements (tools/window_costs.py,
-// DESIGN.md): an issue-bound estimate from the per-entity banks (terms, 64-bit tail, sources without
-// sample pairing) and, for tables that do not fit shared memory, a gather-bound estimate from the
-// big windows of the sweep - stride-k gathers when no phase bit is dropped (from L2, or from HBM
-// above ~100 MB), broadcast-friendly gathers otherwise.
-static double window_cost_per_sample(const bhw_desc& d) {
+// ---- cost model of bhw_shard_range_cost -----------------------------------------------------------
+// Estimated device time (us) of generating a flat slice of a batch with every trig table rebuilt, fitted to
+// round-2 measurements on B200 (bench.py roofline.by_instantiation, tools/r2_probe.py):
+//   * per sample, by how the window is generated: staged table (k_synth_group G_HALF32 0.70 ps, G_Q16 0.89 ps),
+//     pyramid gathers through L1/L2 (5 terms 1.2 ps, 7 terms 2.6 ps at 2^26 points, 10 % more per halving of
+//     the length), windows outside the groups by the round-1 fit; a window cut by the slice loses sample pairing;
+//   * per family and slice, the pyramid build: one CORDIC evaluation per quarter-wave phase of the top level
+//     the slice needs, ~0.4 ps per stage - 190 us for the 2^26-point DAT_WIDTH 32 family.  It is paid by
+//     EVERY rank that touches a window of that length, which is what bounds the strong scaling of the sweep.
+struct SliceCost {
+  // per-family state of the slice being grown
+  struct Fam { SrcParams key; int top; int stages; bool used; };
+  Fam fam[16];
+  int nfam = 0;
+  double us = 0.0;
+  void reset() { nfam = 0; us = 0.0; }
+};
+
+static double build_us(int top, int stages) { return 4.0 + ldexp(1.0, top - 2) * (double)stages * 0.4e-6; }
+
+// us per sample of window d when a slice holds `part` of its samples (1.0 = the whole window); *is_group: the
+// window belongs to a family (then *key / *res / *stages describe it)
+static double sample_cost_ps(const bhw_desc& d, bool whole, bool* is_group, SrcParams* key, int* res, int* stages) {
+  *is_group = false;
   const int m = d.win_type, pw = d.phi_width, dw = d.dat_width;
-  if (dw > 32) return 60.0 * (m - 1);                        // one-thread-per-sample int64 kernel
-  double a = m <= 3 ? 1.0 : m == 4 ? 1.05 : m == 5 ? 1.2 : 1.75;
-  if (d.model == BHW_MODEL_RTL && dw >= 31) {                // 64-bit tail, unless the ports keep dsp_pp in 32 bits
-    WinParams wp; SrcParams src[2];
-    if (resolve_window(&d, &wp, src) != BHW_OK || fast_tail_mode(wp, src) != TAILMODE_FAST32) a *= 1.55;
+  if (dw > 32) return 60.0 * (m - 1) * 0.7;                  // one-thread-per-sample int64 kernel
+  WinParams wp; SrcParams src[2];
+  if (resolve_window(&d, &wp, src) != BHW_OK) return 1.0;
+  if (group_eligible(d, wp, src) && family_source(d, BHW_MAX_PHI_WIDTH, key) == BHW_OK) {
+    *is_group = true;
+    *res = key->pw;
+    *stages = key->n_xy;
+    const int top = pw < *res ? pw : *res;                   // a lower bound of the family's top level
+    const int mode = group_tab_mode(*key, (uint32_t)(*res < 26 ? *res : 26), 192 * 1024);
+    double ps;
+    if (mode == G_HALF32) ps = 0.70;
+    else if (mode == G_Q16) ps = 0.62 + 0.09 * (m - 1);
+    else {
+      const double base = m <= 3 ? 0.9 : m == 4 ? 1.0 : m == 5 ? 1.22 : 2.56;
+      ps = base * (1.0 + 0.1 * (double)(26 - (pw > 26 ? 26 : pw)));
+      (void)top;
+    }
+    if (!whole) ps *= mode == G_GLOBAL ? 2.7 : 1.6;          // unpaired tiles, no spread walk (measured: 7-term 2^26 half 6.8 ps)
+    return ps;
   }
+  // windows outside the groups (TAYLOR, input-quadrant CORDICs, 64-bit tails, short windows): round-1 fit
+  double a = m <= 3 ? 1.0 : m == 4 ? 1.05 : m == 5 ? 1.2 : 1.75;
+  if (d.model == BHW_MODEL_RTL && dw >= 31 && fast_tail_mode(wp, src) != TAILMODE_FAST32) a *= 1.55;
   const bool taylor = d.model == BHW_MODEL_RTL && d.sin_type == BHW_SIN_TAYLOR;
   const bool inq = d.model == BHW_MODEL_RTL && (d.sin_type == BHW_SIN_CORDIC48 || d.sin_type == BHW_SIN_CORDIC_SCALED);
   const bool pair = !inq && !(taylor && dw < 19);
   if (!pair) a *= 1.7;
-  if (pw < 8) return a * 4.0;                                // general kernel, tiles straddle windows
-  const int idx_bits = (inq || taylor) ? pw : (pw < dw ? pw : dw);   // log2(table entries)
+  if (pw < 9) return a * 4.0 * 0.6;                          // general kernel
+  const int idx_bits = (inq || taylor) ? pw : (pw < dw ? pw : dw);
   const double table_bytes = 4.0 * (double)(1ull << idx_bits);
-  if (table_bytes / (pair ? 2.0 : 1.0) <= 192.0 * 1024.0) return a;
-  const bool dropped = !(inq || taylor) && pw > dw;
-  double g;
-  if (dropped) g = 1.0 + (m - 1) * (table_bytes > 8e6 ? 0.29 : 0.13);
-  else {
-    double per = table_bytes > 100e6 ? 0.42 : 0.2;
-    if (m >= 7 && pw >= 23)                                             // warps spread over the window (BankArgs::spread)
-      per = table_bytes > 200e6 ? 0.255 : table_bytes > 100e6 ? 0.19 : 0.135;
-    g = (double)(m * (m - 1) / 2) * per * (pair ? 1.0 : 2.0);
+  if (table_bytes / (pair ? 2.0 : 1.0) > 192.0 * 1024.0) {
+    const double per = table_bytes > 100e6 ? 0.42 : 0.2;
+    const double g = (double)(m * (m - 1) / 2) * per * (pair ? 1.0 : 2.0);
+    if (g > a) a = g;
   }
-  return a > g ? a : g;
+  return a * 0.6;
 }
-// launch + ramp of one more window in a mixed batch, in the same unit (samples of the cheapest kind);
-// windows of under 2^17 samples share one launch of the general kernel with their neighbours
-static double window_fixed_cost(const bhw_desc& d) { return d.phi_width < 17 ? 0.2e6 : 5.0e6; }
+
+// add samples [lo, hi) of window d (N samples) to the slice
+static void slice_add(SliceCost& sc, const bhw_desc& d, uint64_t lo, uint64_t hi) {
+  const uint64_t N = 1ull << d.phi_width;
+  bool grp; SrcParams key; int res = 0, stages = 0;
+  const double ps = sample_cost_ps(d, lo == 0 && hi == N, &grp, &key, &res, &stages);
+  sc.us += ps * 1e-6 * (double)(hi - lo);
+  if (!grp) { sc.us += d.phi_width < 17 ? 0.05 : 4.0; return; }          // a launch (or a share of one) of its own
+  const int top = d.phi_width < res ? d.phi_width : res;
+  int f = -1;
+  for (int i = 0; i < sc.nfam; i++) if (!memcmp(&sc.fam[i].key, &key, sizeof(key))) f = i;
+  if (f < 0 && sc.nfam < 16) {
+    f = sc.nfam++;
+    sc.fam[f].key = key; sc.fam[f].top = 0; sc.fam[f].stages = stages; sc.fam[f].used = true;
+    sc.us += 6.0;                                                        // the family's group launches
+  }
+  if (f >= 0 && top > sc.fam[f].top) {
+    if (sc.fam[f].top) sc.us -= build_us(sc.fam[f].top, stages);
+    sc.fam[f].top = top;
+    sc.us += build_us(top, stages);
+  }
+}
+
+// Greedy cut for a target slice time T: ranks take samples in order while their estimated time stays within T.
+// Cuts fall on window boundaries, or inside a window of >= 2^20 samples at multiples of 2^14 samples.
+// -> the cuts (nranks + 1 flat positions); returns false when nranks slices do not suffice.
+static bool cut_for_target(const bhw_desc* descs, int nwin, int nranks, double T, uint64_t total, uint64_t* cuts) {
+  int w = 0;
+  uint64_t in_w = 0, flat = 0;       // next sample to hand out: sample in_w of window w
+  cuts[0] = 0;
+  for (int r = 0; r < nranks; r++) {
+    SliceCost sc;
+    sc.reset();
+    while (w < nwin) {
+      const uint64_t N = 1ull << descs[w].phi_width;
+      SliceCost trial = sc;
+      slice_add(trial, descs[w], in_w, N);
+      if (trial.us <= T || r == nranks - 1) {                // the rest of this window fits (the last rank takes all)
+        sc = trial;
+        flat += N - in_w;
+        in_w = 0;
+        w++;
+        continue;
+      }
+      if (N >= (1ull << 20)) {                               // take a piece of it: bisect on the piece length
+        const uint64_t step = 1ull << 14;
+        uint64_t lo = 0, hi = (N - in_w) / step;             // pieces of `step` samples that fit
+        while (lo < hi) {
+          const uint64_t mid = (lo + hi + 1) / 2;
+          SliceCost t2 = sc;
+          slice_add(t2, descs[w], in_w, in_w + mid * step);
+          if (t2.us <= T) lo = mid; else hi = mid - 1;
+        }
+        // a piece shorter than an eighth of the window (or leaving less than that) is not worth the pyramid build
+        if (lo * step >= N / 8 && N - in_w - lo * step >= N / 8) {
+          slice_add(sc, descs[w], in_w, in_w + lo * step);
+          flat += lo * step;
+          in_w += lo * step;
+        }
+      }
+      break;
+    }
+    cuts[r + 1] = flat;
+    if (r == nranks - 1 && sc.us > T) return false;          // the last rank took the rest: it must fit as well
+  }
+  return flat == total;
+}
 
 int bhw_shard_range_cost(const bhw_desc* descs, int nwin, int rank, int nranks, uint64_t* begin,
                                     uint64_t* count) {
   if (!descs || !begin || !count) return BHW_E_NULL;
-  if (nwin <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return BHW_E_ARG;
-  double total_cost = 0.0;
+  if (nwin <= 0 || nranks < 1 || nranks > 1024 || rank < 0 || rank >= nranks) return BHW_E_ARG;
   uint64_t total = 0;
+  SliceCost all;
+  all.reset();
   for (int w = 0; w < nwin; w++) {
     if (descs[w].phi_width < BHW_MIN_PHI_WIDTH || descs[w].phi_width > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
     const uint64_t N = 1ull << descs[w].phi_width;
-    total_cost += window_cost_per_sample(descs[w]) * (double)N + window_fixed_cost(descs[w]);
+    slice_add(all, descs[w], 0, N);
     total += N;
   }
-  // flat index at which the cumulative cost reaches fraction r/nranks, rounded down to 4 samples
-  auto cut = [&](int r) -> uint64_t {
-    if (r <= 0) return 0;
-    if (r >= nranks) return total;
-    const double target = total_cost * (double)r / (double)nranks;
-    double acc = 0.0;
-    uint64_t off = 0;
-    for (int w = 0; w < nwin; w++) {
-      const uint64_t N = 1ull << descs[w].phi_width;
-      const double cw = window_cost_per_sample(descs[w]) + window_fixed_cost(descs[w]) / (double)N;   // per sample, fixed part spread
-      if (acc + cw * (double)N >= target) {
-        uint64_t in = (uint64_t)((target - acc) / cw);
-        if (in > N) in = N;
-        // a cut within an eighth of a window's length of its start or end moves onto that boundary: a
-        // whole window runs through the paired / spread walks of the bank kernel, a piece of one does
-        // not (one 2^26-point 7-term window: 0.23 ms whole, 0.63 ms for 96 % of it)
-        if (in < N / 8) in = 0;
-        else if (N - in < N / 8) in = N;
-        return (off + in) & ~(uint64_t)3;
-      }
-      acc += cw * (double)N;
-      off += N;
-    }
-    return total;
-  };
-  const uint64_t b = cut(rank), e = cut(rank + 1);
-  *begin = b;
-  *count = e > b ? e - b : 0;
+  std::vector<uint64_t> cuts((size_t)nranks + 1, 0), best((size_t)nranks + 1, 0);
+  // smallest target time for which the greedy cut needs no more than nranks slices
+  double lo = all.us / nranks, hi = all.us + 1.0;
+  bool have = false;
+  for (int it = 0; it < 60; it++) {
+    const double T = 0.5 * (lo + hi);
+    if (cut_for_target(descs, nwin, nranks, T, total, cuts.data())) { hi = T; best = cuts; have = true; }
+    else lo = T;
+    if (hi - lo < 1e-5 * all.us) break;
+  }
+  if (!have) {                                               // cannot happen (one rank can take everything within all.us)
+    for (int r = 0; r <= nranks; r++) best[(size_t)r] = r == 0 ? 0 : total;
+  }
+  *begin = best[(size_t)rank];
+  *count = best[(size_t)rank + 1] - best[(size_t)rank];
   return BHW_OK;
 }
 

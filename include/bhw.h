@@ -146,8 +146,12 @@ BHW_API int bhw_elem_bytes(const bhw_desc* d);
  * and hls/windows/win_function.cpp:176-355 (rule BHW_RULE_HLS).
  * variant: 1 Hamming, 2 Hann, 3 Blackman, 4 Blackman-Harris-3, 5 Nuttall,
  * 6 Blackman-Harris-4, 7 Blackman-Nuttall, 8 Flat-top, 9 Blackman-Harris-5,
- * 10 Blackman-Harris-7 (README.md:30-41).  Writes aa_out[0..6] (unused = 0)
- * and *win_type (2,3,4,5,7). */
+ * 10 Blackman-Harris-7 (README.md:30-41); and the alternative sets the reference
+ * prints beside them: 11 Blackman-Harris-7 as in README.md:45-51, 12 Hamming
+ * 0.5383554 / 0.4616446 (src/hamming_win.vhd:21-23), 13 Flat-top normalised
+ * (src/bh_win_5term.vhd:28-33).  Writes aa_out[0..6] (unused = 0) and *win_type
+ * (2,3,4,5,7).  (The 6- and 8..11-term sets of doc/blackman-harris coef.jpg have
+ * no entity in the reference - no adder tree, no rounding rule - and are not offered.) */
 enum { BHW_RULE_TB = 0, BHW_RULE_HLS = 1 };
 BHW_API int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS],
                  int32_t* win_type);

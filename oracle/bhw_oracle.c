@@ -555,7 +555,7 @@ int orc_atan2(int iw, int aw, int prec, const int32_t* x, const int32_t* y, int3
 
 /* ---- coefficient rules ---------------------------------------------------- */
 /* variants per README.md:30-41; values per the entity headers */
-static const double COEF[10][7] = {
+static const double COEF[13][7] = {
     {0.5434783, 1.0 - 0.5434783},                              /* 1 Hamming   tb :123-124 */
     {0.5, 0.5},                                                /* 2 Hann      hamming_win.vhd:14-16 */
     {0.42, 0.5, 0.08},                                         /* 3 Blackman  tb :114-116 */
@@ -567,11 +567,15 @@ static const double COEF[10][7] = {
     {0.3232153788877343, 0.4714921439576260, 0.1755341299601972, 0.0284969901061499,
      0.0012613570882927},                                      /* 9 BH5       bh_win_5term.vhd:14-19 */
     {0.271220360585039, 0.433444612327442, 0.218004122892930, 0.065785343295606,
-     0.010761867305342, 0.000770012710581, 0.000013680883060}};/* 10 BH7      tb :67-73 */
-static const int NTERMS[10] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7};
+     0.010761867305342, 0.000770012710581, 0.000013680883060}, /* 10 BH7      tb :67-73 */
+    {0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803, 0.01081174209837,
+     0.00077658482522, 0.00001388721735},                      /* 11 BH7, README.md:45-51 (magnitudes) */
+    {0.5383554, 0.4616446},                                    /* 12 Hamming, second set hamming_win.vhd:21-23 */
+    {0.215578950, 0.416631580, 0.277263158, 0.083578947, 0.006947368}}; /* 13 flat-top normalised bh_win_5term.vhd:28-33 */
+static const int NTERMS[13] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7, 7, 2, 5};
 
 int orc_quantize(int variant, int rule, int dw, int64_t aa[7], int32_t* win_type) {
-  if (variant < 1 || variant > 10 || (rule != BHW_RULE_TB && rule != BHW_RULE_HLS)) return BHW_E_VARIANT;
+  if (variant < 1 || variant > 13 || (rule != BHW_RULE_TB && rule != BHW_RULE_HLS)) return BHW_E_VARIANT;
   if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
   const int m = NTERMS[variant - 1];
   double scale;

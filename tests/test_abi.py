@@ -54,7 +54,7 @@ def test_quantize_matches_reference_rules():
             for dw in (8, 16, 17, 24, 32, 40, 48):
                 assert bhw.quantize(v, rule, dw) == H.orc_quantize(v, rule, dw)
     with pytest.raises(bhw.BhwError):
-        bhw.quantize(11, 0, 16)
+        bhw.quantize(14, 0, 16)
     with pytest.raises(bhw.BhwError):
         bhw.quantize(1, 2, 16)
     assert bhw.variant_coeffs(3, bhw.RULE_HLS) == [0.21, 0.25, 0.04]
@@ -82,6 +82,23 @@ def test_validate_rejections():
     assert bhw.validate(bhw.make_desc(2, 10, 33, [1, 1], sin_type=bhw.SIN_TAYLOR)) == -6
     assert bhw.validate(bhw.make_desc(2, 20, 16, [1, 1], model=bhw.MODEL_HLS)) == -5  # NP > NW+2
     assert bhw.lib().bhw_validate(None) == -1
+
+
+def test_alternative_coefficient_sets():
+    """Variants 11-13: the second sets the reference prints (README.md:45-51, src/hamming_win.vhd:21-23,
+    src/bh_win_5term.vhd:28-33), quantised by the same rules; library and oracle agree."""
+    import harness as H
+    assert bhw.quantize(11, bhw.RULE_TB, 32)[0] == [round(a * (2 ** 31 - 1)) for a in (
+        0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803, 0.01081174209837, 0.00077658482522,
+        0.00001388721735)]
+    assert bhw.quantize(12, bhw.RULE_TB, 16) == ([round(0.5383554 * 32767), round(0.4616446 * 32767), 0, 0, 0, 0, 0], 2)
+    assert bhw.quantize(13, bhw.RULE_TB, 24)[1] == 5
+    for v in (11, 12, 13):
+        for rule in (bhw.RULE_TB, bhw.RULE_HLS):
+            for dw in (12, 16, 24, 32):
+                assert bhw.quantize(v, rule, dw) == H.orc_quantize(v, rule, dw)
+    with pytest.raises(bhw.BhwError):
+        bhw.quantize(14, bhw.RULE_TB, 16)
 
 
 def test_apply_argument_checks_need_no_gpu():
@@ -178,13 +195,21 @@ def test_cost_balanced_shards_tile_the_batch():
     for r in range(8):
         b, c = bhw.shard_range_cost(same, r, 8)
         assert abs(c - total // 8) <= 4
-    # the sweep ends with the 7-term 32-bit windows: the last of 8 ranks must get far fewer samples
+    # the sweep ends with the 7-term 32-bit windows (costly samples, and a 190 us table build for whoever touches the
+    # 2^26-point one): the first rank takes far more samples than the ranks that share those windows
     total = bhw.batch_total(sweep)
-    _, c_last = bhw.shard_range_cost(sweep, 7, 8)
-    assert c_last < total // 16
-    # a cut that would land just inside a long window is moved onto its boundary: with 8 ranks the last rank
-    # gets exactly the 2^26-point 7-term window (whole windows run through the paired / spread walks)
-    b_last, c_last = bhw.shard_range_cost(sweep, 7, 8)
-    assert c_last == 1 << 26 and b_last == total - (1 << 26)
+    counts = [bhw.shard_range_cost(sweep, r, 8)[1] for r in range(8)]
+    assert counts[0] > 2 * total // 8 and max(counts[4:]) < total // 16
+    # cuts inside a window only for long windows, at multiples of 2^14 samples, never closer than an eighth of the
+    # window to one of its ends
+    offs = np.cumsum([0] + [1 << d.phi_width for d in sweep])
+    for world in (2, 3, 4, 8):
+        for r in range(1, world):
+            b, _ = bhw.shard_range_cost(sweep, r, world)
+            w = int(np.searchsorted(offs, b, side="right") - 1)
+            inside = b - int(offs[w])
+            if inside and b < total:
+                n = 1 << sweep[w].phi_width
+                assert n >= 1 << 20 and inside % (1 << 14) == 0 and n // 8 <= inside <= n - n // 8, (world, r, w, inside)
     with pytest.raises(bhw.BhwError):
         bhw.shard_range_cost(sweep, 8, 8)

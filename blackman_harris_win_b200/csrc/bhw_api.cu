@@ -165,6 +165,8 @@ struct PlanTable {
   uint32_t drop;
   uint32_t entries;
   int32_t* ptr;
+  uint32_t* exc = nullptr;   // input-quadrant CORDIC tables some bank run pairs: entries that break T[i+E/2] == ~T[i]
+  bool need_exc = false;
 };
 
 struct bhw_plan {
@@ -206,6 +208,7 @@ struct bhw_plan {
     // shape for a tile range inside one window of the run (unpaired, table read from global memory)
     bhw::BankShape sh_part;
     bool part_ok;
+    int exc_table = -1;      // paired over an input-quadrant CORDIC table: that table (its exception list feeds the patch pass)
   };
   std::vector<BankRun> runs;
   // families (one half-period pyramid each) and groups (bhw_group.cuh): windows that k_synth_group takes
@@ -277,6 +280,8 @@ static void plan_free_device(bhw_plan& plan, cudaStream_t stream) {
   if (plan.ev_built) { cudaEventDestroy(plan.ev_built); plan.ev_built = nullptr; }
   for (auto& pt : plan.tables)
     if (pt.ptr) { if (plan.transient) cudaFreeAsync(pt.ptr, stream); else cudaFree(pt.ptr); pt.ptr = nullptr; }
+  for (auto& pt : plan.tables)
+    if (pt.exc) { if (plan.transient) cudaFreeAsync(pt.exc, stream); else cudaFree(pt.exc); pt.exc = nullptr; }
   for (auto& f : plan.families) {
     if (f.pyr) { if (plan.transient) cudaFreeAsync(f.pyr, stream); else cudaFree(f.pyr); f.pyr = nullptr; }
     if (f.q16) { if (plan.transient) cudaFreeAsync(f.q16, stream); else cudaFree(f.q16); f.q16 = nullptr; }
@@ -312,6 +317,7 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
       ti[k].ptr = t < 0 ? nullptr : plan.tables[(size_t)t].ptr;
       ti[k].entries = t < 0 ? 0 : plan.tables[(size_t)t].entries;
       ti[k].antisym = t >= 0 && source_antisymmetric(plan.tables[(size_t)t].canon);
+      ti[k].inq_comp = t >= 0 && source_inq_complement(plan.tables[(size_t)t].canon);
     }
     if (bank_shape(r, ti, bank_smem_limit(), &sh, &mode, &pair)) {
       if (!plan.runs.empty()) {
@@ -327,6 +333,7 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
       int mode_p = 0;
       bool pair_p = false;
       run.part_ok = bank_shape(r, ti, 0, &run.sh_part, &mode_p, &pair_p, false) && mode_p == TAB_GLOBAL && !pair_p;
+      if (pair && sh.pair_adj) run.exc_table = rec_tab[(size_t)ri * BHW_MAX_TERMS + 1];
       plan.runs.push_back(run);
     }
     off += N;
@@ -342,6 +349,19 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
     if (((uint64_t)(run.w_end - run.w_begin) << run.sh.pw) >= min_run) plan.runs[keep++] = run;
   }
   plan.runs.resize(keep);
+  // Pairing over an input-quadrant CORDIC's table costs two more launches (exception scan, patch pass): below
+  // 2^23 samples the run keeps single samples (a one-shot N = 2^20 cordic_dds48 window: 40 us unpaired, 51 us paired)
+  for (bhw_plan::BankRun& run : plan.runs) {
+    if (run.exc_table < 0) continue;
+    if (((uint64_t)(run.w_end - run.w_begin) << run.sh.pw) < (1ull << 23) && run.part_ok) {
+      run.sh = run.sh_part;
+      run.tab_mode = TAB_GLOBAL;
+      run.pair = false;
+      run.exc_table = -1;
+    } else {
+      plan.tables[(size_t)run.exc_table].need_exc = true;
+    }
+  }
 }
 
 // Resolve a batch into `plan` and make it resident on the current device.  [hint_begin,
@@ -613,6 +633,11 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
     rec_tab[(size_t)tr.rec * BHW_MAX_TERMS + (size_t)tr.k] = tr.tab;
   }
   build_bank_runs(plan, rec_tab);
+  for (auto& pt : plan.tables) {
+    if (!pt.need_exc) continue;
+    cudaError_t ee = plan_alloc(plan, (void**)&pt.exc, ((size_t)pt.entries / 2 + 1) * sizeof(uint32_t), stream);
+    if (ee != cudaSuccess) return cuda_fail(ee, "alloc(exception list)");
+  }
 
   auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const bool need_off = plan.uniform_pw < 0, need_wr = !plan.all_same;
@@ -807,6 +832,15 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       if (e != cudaSuccess) return cuda_fail(e, "k_table_build_u");
       g_launches++;
     }
+    // tables some bank run pairs through the ones'-complement relation: list the entries that break it
+    for (const auto& pt : plan.tables) {
+      if (!pt.exc) continue;
+      LaunchTimer tm(BHW_KERNEL_TABLE_BUILD, stream);
+      tm_on = true;                                            // no longer directly behind the build: no PDL
+      e = launch_inq_exceptions(pt.ptr, pt.entries, (int32_t)(1u << table_tshift(pt.canon)), pt.exc, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "k_inq_exceptions");
+      g_launches++;
+    }
     building = true;
     table_ahead = !tm_on && !defer_family_builds;
   }
@@ -985,6 +1019,12 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "k_synth_bank");
     g_launches++;
+    if (!ntiles && run.exc_table >= 0) {                       // recompute the sample pairs that read an exception entry
+      LaunchTimer tm(BHW_KERNEL_SYNTH, ls, 0, 0);
+      ce = launch_inq_patch(ba, plan.tables[(size_t)run.exc_table].exc, ls);
+      if (ce != cudaSuccess) return cuda_fail(ce, "k_inq_patch");
+      g_launches++;
+    }
     return BHW_OK;
   };
   // samples [pa, pb) inside window widx of the run: whole tiles through the bank kernel (unpaired

@@ -1093,6 +1093,8 @@ struct BankShape {
   // 64-bit tail (RTL DAT_WIDTH 31..32): b = (int32)((AAk*C2 + prnd) >> psh), S in 64 bits,
   // out = sx(((S + fadd) >> fin), DW); A[k] are then the raw AAk and S0 the raw AA0
   uint32_t acc64, psh, prnd, prndn, fin, fadd, flsh;
+  uint32_t pair_adj;                    // pairing through the ones'-complement relation of the input-quadrant CORDICs:
+                                        // T[i + E/2] == -T[i] - pair_adj (pair_adj = 1 << tshift; 0: exact antisymmetry)
   uint32_t ntab;                        // distinct tables (1, or 2 for 3-term TAYLOR)
   uint32_t smem_words;                  // staged words in total
   uint32_t kstep[BHW_MAX_TERMS];
@@ -1184,7 +1186,11 @@ BHW_HD bool bank_tile_linear(const BankShape& sh, uint32_t nbase, uint32_t* base
 }
 
 // One lane's share of a linear tile: the look-ups of harmonic k are T[base + step*(lane + 32*j)].
-template <int M, int TAB, bool PAIR, bool W64>
+// PAIR: 0 = single samples; 1 = pairs (n, n + N/2) over an exactly antisymmetric table; 2 = pairs over an
+// input-quadrant CORDIC's table, where T[i + E/2] == ~T[i] (the ones' complement: the entity negates a wide
+// register and then floors, src/cordic_dds48.vhd:196-216,257-258) except at a few data-dependent entries that a
+// patch pass recomputes (k_inq_patch): the partner's product is A * -(C2 + pair_adj).
+template <int M, int TAB, int PAIR, bool W64>
 BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
                                uint32_t lane, const uint32_t* base, uint32_t neg, int32_t* va, int32_t* vb) {
   typedef typename BankAcc<W64>::type acc_t;
@@ -1203,7 +1209,7 @@ BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0
       const acc_t ba = bank_term<W64>(sh, P, false);
       Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
       if (PAIR) {
-        if (k & 1) Sb[j] += bank_term<W64>(sh, P, true);
+        if (k & 1) Sb[j] += bank_term<W64>(sh, PAIR == 2 ? (int64_t)Ak * (int64_t)(c2 + (int32_t)sh.pair_adj) : P, true);
         else Sb[j] += ba;
       }
     }
@@ -1218,7 +1224,7 @@ BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0
 // One lane's share of a tile: samples n + 32*j (j = 0..kBankJ-1) -> va[j], and their partners half a
 // window later -> vb[j] when PAIR.  `tabs[u]` is distinct table u as the kernel sees it (staged
 // or global).  A[k] are the window's pre-shifted coefficients, S0 its initial accumulator.
-template <int M, int TAB, bool PAIR, bool LANE_SIGN, bool W64>
+template <int M, int TAB, int PAIR, bool LANE_SIGN, bool W64>
 BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, const int32_t* const* tabs,
                            uint32_t n, uint32_t nbase, int32_t* va, int32_t* vb) {
   typedef typename BankAcc<W64>::type acc_t;
@@ -1243,7 +1249,8 @@ BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, co
       const acc_t ba = bank_term<W64>(sh, P, false);
       Sa[j] = (k & 1) ? Sa[j] - ba : Sa[j] + ba;
       if (PAIR) {
-        if (k & 1) Sb[j] += bank_term<W64>(sh, P, true);  // b(-P) = -bank_term(P, negated)
+        // b(-P) = -bank_term(P, negated)
+        if (k & 1) Sb[j] += bank_term<W64>(sh, PAIR == 2 ? (int64_t)Ae * (int64_t)(c2 + (int32_t)sh.pair_adj) : P, true);
         else Sb[j] += ba;
       }
     }

@@ -195,7 +195,7 @@ k_synth(const __grid_constant__ SynthArgs a) {
 constexpr int kBankThreads = 1024;
 constexpr int kBankWarps = kBankThreads / 32;
 
-template <int M, int TAB, bool PAIR, bool W64>
+template <int M, int TAB, int PAIR, bool W64>
 __global__ void __launch_bounds__(kBankThreads, 1)
 k_synth_bank(const __grid_constant__ BankArgs a) {
   extern __shared__ __align__(16) int32_t s_tab[];
@@ -224,7 +224,7 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
   // window): unit u is tile (u + tile_off) of the launch's windows
   // (only the unpaired global-table instantiations take tile ranges - launch_synth_bank() - so the
   // staged, paired kernels of whole-window banks carry none of this)
-  constexpr bool kRange = TAB == TAB_GLOBAL && !PAIR;
+  constexpr bool kRange = TAB == TAB_GLOBAL && PAIR == 0;
   const uint64_t U = kRange && a.ntiles ? (uint64_t)a.ntiles : (uint64_t)a.nwin << log_tpw;
   const uint64_t toff = kRange && a.ntiles ? (uint64_t)a.tile_off : 0;
   const uint64_t u0 = U * blockIdx.x / gridDim.x, u1 = U * (blockIdx.x + 1) / gridDim.x;
@@ -608,6 +608,43 @@ k_atan2_u(const __grid_constant__ Atan2Params p, const int32_t* __restrict__ x, 
   if (j < count) phi[j] = atan2_sample32_t<AW>(p, x[j], y[j]);
 }
 
+// Pairing over an input-quadrant CORDIC's table (BankShape::pair_adj): which entries break T[i + E/2] == -T[i] - adj?
+// exc[0] = their number (zeroed by the host before the launch), exc[1 ...] = the indices i < E/2, any order.
+__global__ void __launch_bounds__(256)
+k_inq_exceptions(const int32_t* __restrict__ tab, uint32_t entries, int32_t adj, uint32_t* __restrict__ exc) {
+  const uint32_t half = entries >> 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x)
+    if (tab[i + half] != -tab[i] - adj) exc[1 + atomicAdd(exc, 1u)] = i;
+}
+
+// ... and the samples that read them: for every window of the launch, exception i and odd harmonic k, the sample
+// pair (n, n + N/2) with k*n == i (mod N) is recomputed from the table itself (the general kernel's body).
+__global__ void __launch_bounds__(256)
+k_inq_patch(const WinRec* __restrict__ recs, const uint32_t* __restrict__ win_rec, uint32_t w_first, uint32_t nwin,
+            uint32_t pw, uint32_t m, const uint32_t* __restrict__ exc, int32_t* __restrict__ out) {
+  const uint32_t nexc = exc[0];
+  const uint32_t nodd = m / 2;                         // odd harmonics 1, 3, 5 below m
+  const uint64_t work = (uint64_t)nexc * nodd * nwin;
+  const uint32_t nmask = (1u << pw) - 1u, half = 1u << (pw - 1);
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = (uint32_t)(t % nwin);
+    const uint32_t r2 = (uint32_t)(t / nwin);
+    const uint32_t k = 2u * (r2 % nodd) + 1u;
+    const uint32_t i = exc[1 + r2 / nodd];
+    // inverse of the odd k modulo 2^32 (Newton), then n = i * k^-1 mod N
+    uint32_t inv = k;
+    inv *= 2u - k * inv; inv *= 2u - k * inv; inv *= 2u - k * inv; inv *= 2u - k * inv;
+    const uint32_t n = (i * inv) & nmask;
+    const WinRec& r = recs[win_rec ? win_rec[w_first + w] : 0u];
+    int32_t* o = out + ((size_t)w << pw);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t p = (n + (h ? half : 0u)) & nmask;   // phase index of the sample
+      o[(p - r.n_first) & nmask] = synth_sample(r, p);
+    }
+  }
+}
+
 // The apply step for windows the fused kernel (k_synth_group) does not take (TAYLOR, the input-quadrant
 // CORDICs, 64-bit tails ...): y[f*N + n] = x[f*N + n] * w[n] from a window generated into scratch memory.
 // mode 1: the exact product DAT_Q (int64); mode 2: the entities' rounded slice of it (int32) - see group_epilogue.
@@ -694,7 +731,7 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
 
 size_t bank_smem_limit() { return 192u * 1024u; }
 
-template <int M, int TAB, bool PAIR, bool W64>
+template <int M, int TAB, int PAIR, bool W64>
 static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -726,11 +763,16 @@ static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, 
 template <int M, bool W64>
 static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned grid, size_t smem,
                                  cudaStream_t stream, bool pdl) {
-  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, true, W64>(a, grid, smem, stream, pdl)
-                                        : launch_bank_t<M, TAB_SMEM_FULL, false, W64>(a, grid, smem, stream, pdl);
-  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, true, W64>(a, grid, smem, stream, pdl);
-  return pair ? launch_bank_t<M, TAB_GLOBAL, true, W64>(a, grid, 0, stream, pdl)
-              : launch_bank_t<M, TAB_GLOBAL, false, W64>(a, grid, 0, stream, pdl);
+  if (pair && a.sh.pair_adj) {       // ones'-complement pairing (input-quadrant CORDICs): 32-bit tail, no half-period staging
+    if (W64 || tab == TAB_SMEM_HALF) return cudaErrorInvalidValue;
+    return tab == TAB_SMEM_FULL ? launch_bank_t<M, TAB_SMEM_FULL, 2, false>(a, grid, smem, stream, pdl)
+                                : launch_bank_t<M, TAB_GLOBAL, 2, false>(a, grid, 0, stream, pdl);
+  }
+  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, 1, W64>(a, grid, smem, stream, pdl)
+                                        : launch_bank_t<M, TAB_SMEM_FULL, 0, W64>(a, grid, smem, stream, pdl);
+  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, 1, W64>(a, grid, smem, stream, pdl);
+  return pair ? launch_bank_t<M, TAB_GLOBAL, 1, W64>(a, grid, 0, stream, pdl)
+              : launch_bank_t<M, TAB_GLOBAL, 0, W64>(a, grid, 0, stream, pdl);
 }
 
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
@@ -815,6 +857,20 @@ cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* 
     const unsigned grid = grid_for((count + 255) / 256, 8);
     k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_inq_exceptions(const int32_t* tab, uint32_t entries, int32_t adj, uint32_t* exc, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(exc, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = grid_for(((uint64_t)entries / 2 + 255) / 256, 8);
+  k_inq_exceptions<<<grid, 256, 0, stream>>>(tab, entries, adj, exc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_inq_patch(const BankArgs& a, const uint32_t* exc, cudaStream_t stream) {
+  // the exception count lives on the device: a small fixed grid strides over whatever there is
+  k_inq_patch<<<(unsigned)sm_count(), 256, 0, stream>>>(a.recs, a.win_rec, a.w_first, a.nwin, a.sh.pw, a.sh.m, exc, a.out);
   return cudaGetLastError();
 }
 

@@ -126,6 +126,11 @@ cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStrea
 cudaError_t launch_apply_mul(const int32_t* x, const int32_t* w, void* y, uint64_t n, uint64_t frames, int mode, int dw,
                              cudaStream_t stream);
 size_t group_smem_limit();  // bytes of shared memory a group launch may use for the staged table image
+// pairing over input-quadrant CORDIC tables: find the entries that break the ones'-complement relation (exc[0] =
+// count, exc[1..] = indices; room for entries/2 + 1 words), and recompute the sample pairs of a paired bank launch
+// that read them
+cudaError_t launch_inq_exceptions(const int32_t* tab, uint32_t entries, int32_t adj, uint32_t* exc, cudaStream_t stream);
+cudaError_t launch_inq_patch(const BankArgs& a, const uint32_t* exc, cudaStream_t stream);
 size_t bank_smem_limit();  // bytes of shared memory a bank launch may use for staged tables
 int device_sm_count();     // SMs of the current device (148 on B200)
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);

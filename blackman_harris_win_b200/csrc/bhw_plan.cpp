@@ -311,6 +311,8 @@ bool source_antisymmetric(const SrcParams& sp) {
   }
 }
 
+bool source_inq_complement(const SrcParams& sp) { return sp.kind == SRC_INQ && sp.dw >= 8; }
+
 bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
                 int* tab_mode, bool* pair, bool allow_pair) {
   if (r.flags & WR_GENERIC) return false;
@@ -329,7 +331,7 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
     sh->fadd = sh->fin;               // (pp>>2)+((pp>>1)&1) == (pp+2)>>2 ; (pp>>1)+(pp&1) == (pp+1)>>1
     sh->flsh = 32 - r.dw;
   }
-  bool antisym = true, half_ok = true;
+  bool antisym = true, half_ok = true, inqc = true;
   for (uint32_t k = 1; k < r.m; k++) {
     if (!tk[k].ptr) return false;
     uint32_t u = 0;
@@ -344,13 +346,18 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
     sh->idx_rsh[k] = r.idx_rsh[k];
     sh->tsel[k] = u;
     if (!tk[k].antisym) antisym = false;
+    if (!tk[k].inq_comp) inqc = false;
     if ((uint64_t)r.kstep[k] * (uint64_t)(kBankTile - 1) >= (1ull << 31)) half_ok = false;
   }
   size_t words = 0;
   for (uint32_t u = 0; u < sh->ntab; u++) words += sh->tentries[u];
   if (sh->ntab == 1) { sh->tab[1] = sh->tab[0]; sh->tentries[1] = sh->tentries[0]; }
   const size_t limit = smem_limit_bytes / sizeof(int32_t);
-  const bool can_pair = allow_pair && antisym && r.pw >= (uint32_t)kBankTileLog2 + 1;
+  // exact antisymmetry, or the ones'-complement relation of the input-quadrant CORDICs (32-bit tail only; the
+  // exceptions are patched afterwards, see BankShape::pair_adj)
+  const bool comp_pair = !antisym && inqc && !(r.flags & WR_ACC64);
+  const bool can_pair = allow_pair && (antisym || comp_pair) && r.pw >= (uint32_t)kBankTileLog2 + 1;
+  if (can_pair && comp_pair) { sh->pair_adj = 1u << r.tshift; half_ok = false; }
   if (words <= limit) { *tab_mode = TAB_SMEM_FULL; *pair = can_pair; }
   else if (can_pair && half_ok && words / 2 <= limit) { *tab_mode = TAB_SMEM_HALF; *pair = true; }
   else { *tab_mode = TAB_GLOBAL; *pair = can_pair; }

@@ -226,6 +226,8 @@ def hostcheck():
     L.hc_walk.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     L.hc_lin_tiles.argtypes = [C.c_int]
     L.hc_lin_tiles.restype = C.c_uint64
+    L.hc_inq_exceptions.argtypes = [C.c_int]
+    L.hc_inq_exceptions.restype = C.c_uint64
     return L
 
 

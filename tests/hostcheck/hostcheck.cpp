@@ -225,6 +225,8 @@ int hc_table(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int f
 // force_mode: -1 = the planner's choice for `smem_limit` bytes, else TAB_* ; force_pair: -1/0/1.
 // Returns 1 when the window is not bank-eligible (or the forced combination is not legal).
 static uint64_t lin_tiles = 0;   // lane-tiles that took the linear path since the last reset
+static uint64_t inq_exceptions_seen = 0;
+uint64_t hc_inq_exceptions(int reset) { const uint64_t v = inq_exceptions_seen; if (reset) inq_exceptions_seen = 0; return v; }
 uint64_t hc_lin_tiles(int reset) { const uint64_t v = lin_tiles; if (reset) lin_tiles = 0; return v; }
 
 int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode, int force_pair) {
@@ -253,6 +255,7 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
     tk[k].ptr = r.tabp[k];
     tk[k].entries = (uint32_t)tabs[t.src].data.size();
     tk[k].antisym = source_antisymmetric(tabs[t.src].canon);
+    tk[k].inq_comp = source_inq_complement(tabs[t.src].canon);
   }
   BankShape sh;
   int mode; bool pair;
@@ -303,9 +306,12 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
       do { if (sh.acc64) HC_TILE2(M, TAB, PAIR, true); else HC_TILE2(M, TAB, PAIR, false); } while (0)
 #define HC_MODE(M)                                                                                 \
       do {                                                                                         \
-        if (mode == TAB_SMEM_FULL) { if (pair) HC_TILE(M, TAB_SMEM_FULL, true); else HC_TILE(M, TAB_SMEM_FULL, false); } \
-        else if (mode == TAB_SMEM_HALF) HC_TILE(M, TAB_SMEM_HALF, true);                           \
-        else { if (pair) HC_TILE(M, TAB_GLOBAL, true); else HC_TILE(M, TAB_GLOBAL, false); }       \
+        if (pair && sh.pair_adj) {      /* ones'-complement pairing: 32-bit tail, never the half-period placement */ \
+          if (mode == TAB_SMEM_FULL) HC_TILE2(M, TAB_SMEM_FULL, 2, false); else HC_TILE2(M, TAB_GLOBAL, 2, false);   \
+        }                                                                                          \
+        else if (mode == TAB_SMEM_FULL) { if (pair) HC_TILE(M, TAB_SMEM_FULL, 1); else HC_TILE(M, TAB_SMEM_FULL, 0); } \
+        else if (mode == TAB_SMEM_HALF) HC_TILE(M, TAB_SMEM_HALF, 1);                              \
+        else { if (pair) HC_TILE(M, TAB_GLOBAL, 1); else HC_TILE(M, TAB_GLOBAL, 0); }              \
       } while (0)
       switch (sh.m) {
         case 2: HC_MODE(2); break;
@@ -319,6 +325,28 @@ int hc_bank(const bhw_desc* d, int64_t* out, uint64_t smem_limit, int force_mode
         if (pair) out[half + t * kBankTile + lane + 32 * j] = vb[j];
       }
     }
+  }
+  if (pair && sh.pair_adj) {
+    // what k_inq_exceptions / k_inq_patch do: list the entries that break T[i + E/2] == -T[i] - adj, recompute the
+    // sample pairs that read them
+    if (mode == TAB_SMEM_HALF || sh.acc64) return -300;
+    const uint32_t E = sh.tentries[0], nmask = (1u << pw) - 1u;
+    const int32_t* T = sh.tab[0];
+    uint64_t nexc = 0;
+    for (uint32_t i = 0; i < E / 2; i++) {
+      if (T[i + E / 2] == -T[i] - (int32_t)sh.pair_adj) continue;
+      nexc++;
+      for (uint32_t k = 1; k < sh.m; k += 2) {
+        uint32_t inv = k;
+        inv *= 2u - k * inv; inv *= 2u - k * inv; inv *= 2u - k * inv; inv *= 2u - k * inv;
+        const uint32_t n = (i * inv) & nmask;
+        for (int h = 0; h < 2; h++) {
+          const uint32_t p = (n + (h ? half : 0u)) & nmask;
+          out[(p - r.n_first) & nmask] = synth_sample(r, p);
+        }
+      }
+    }
+    inq_exceptions_seen += nexc;
   }
   return 0;
 }

@@ -175,14 +175,17 @@ def test_bench_bank_shape_against_the_oracle():
 def test_bank_kernel_every_placement_against_the_oracle(m):
     """k_synth_bank on uniform banks, one instantiation per table placement and tail per entity: table staged
     whole (short windows), staged half period (N = 65536 at DAT_WIDTH 16), read from L2 (DAT_WIDTH 24), the
-    64-bit tail (DAT_WIDTH 32 with full-scale ports), an unpaired source (cordic_dds48) and TAYLOR."""
+    64-bit tail (DAT_WIDTH 32 with full-scale ports), the input-quadrant CORDICs (paired through the ones'-complement
+    relation, exceptions patched) and TAYLOR."""
     v = {2: 1, 3: 4, 4: 6, 5: 9, 7: 10}[m]
     hi = (1 << 31) - 1
     shapes = [("staged full", bhw.variant_desc(v, 12, 16), 64),
               ("staged half", bhw.variant_desc(v, 16, 16), 4),
               ("global", bhw.variant_desc(v, 17, 24), 2),
               ("64-bit tail", bhw.make_desc(m, 13, 32, [hi - 3 * k for k in range(m)]), 32),
-              ("unpaired", bhw.variant_desc(v, 13, 24, sin_type=bhw.SIN_CORDIC48), 32)]
+              ("cordic_dds48, paired by ones' complement + patch pass", bhw.variant_desc(v, 13, 24, sin_type=bhw.SIN_CORDIC48), 32),
+              ("cordic_dds_scaled, paired, table in L2", bhw.variant_desc(v, 17, 17, sin_type=bhw.SIN_CORDIC_SCALED), 3),
+              ("cordic_dds48 DW 32, table staged whole", bhw.variant_desc(v, 12, 32, sin_type=bhw.SIN_CORDIC48), 40)]
     if m <= 3:
         shapes.append(("taylor", bhw.variant_desc(v, 14, 24, sin_type=bhw.SIN_TAYLOR), 16))
     for name, d, nwin in shapes:
@@ -198,6 +201,28 @@ def test_bank_kernel_every_placement_against_the_oracle(m):
         plan.destroy()
         assert kt["k_synth_bank"][0] >= 1, (name, kt)
         assert np.array_equal(got, want), (m, name)
+
+
+def test_input_quadrant_cordic_banks_pair_through_ones_complement():
+    """cordic_dds48 / cordic_dds_scaled banks of >= 2^23 samples: k_synth_bank pairs samples through
+    T[i + E/2] == ~T[i], k_inq_exceptions lists the entries where that fails and k_inq_patch recomputes the pairs
+    that read them (src/cordic_dds48.vhd:170-258) - every sample against the oracle."""
+    for v, pw, dw, st, nwin in ((1, 17, 24, bhw.SIN_CORDIC48, 64), (6, 17, 17, bhw.SIN_CORDIC_SCALED, 64),
+                                (10, 14, 32, bhw.SIN_CORDIC48, 512)):
+        base = bhw.variant_desc(v, pw, dw, sin_type=st)
+        descs = [base.copy(aa=[int(a) - (3 * i + k) % 61 for k, a in enumerate(base.aa)], stream_offset=i & 1) for i in range(nwin)]
+        plan = bhw.Plan(descs)
+        bhw.timing_enable(True)
+        bhw.timing_reset()
+        got = plan.execute().cpu().numpy().astype(np.int64)
+        recs = bhw.timing_launches()
+        bhw.timing_enable(False)
+        plan.destroy()
+        banks = [r for r in recs if r["kernel"] == "k_synth_bank"]
+        assert len(banks) == 1 and banks[0]["paired"] == 1, recs
+        assert sum(r["kernel"] == "k_synth" for r in recs) == 1          # the patch pass
+        want = np.concatenate([H.orc_window(d, threads=8) for d in descs])
+        assert np.array_equal(got, want), (v, st, int(np.argmax(got != want)))
 
 
 def group_descs(variants, dw, pws, model=0):
@@ -461,6 +486,8 @@ def test_cost_balanced_shards_reassemble_and_cut_long_windows():
         parts = []
         for r in range(world):
             b, c = bhw.shard_range_cost(arr, r, world)
+            if c == 0:          # a batch dominated by one costly window may leave a rank without work
+                continue
             first, touched, local = bhw.shard_windows(arr, b, c)
             parts.append(bhw.generate_batch(descs[first:first + touched], local, c))
         assert torch.equal(torch.cat(parts), full), world

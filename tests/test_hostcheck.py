@@ -257,6 +257,32 @@ def test_bank_body_half_table_sign_boundaries():
     assert st == 0 and np.array_equal(got, H.orc_window(d))
 
 
+def test_bank_body_pairs_the_input_quadrant_cordics():
+    """cordic_dds48 / cordic_dds_scaled: the bank body pairs samples through T[i + E/2] == ~T[i] and a patch pass
+    recomputes the pairs that read one of the few entries where that fails (src/cordic_dds48.vhd:170-258) - every
+    sample must match the oracle, with and without exceptions present, and the relation must really have exceptions
+    somewhere (otherwise the patch pass is untested)."""
+    hc = H.hostcheck()
+    hc.hc_inq_exceptions(1)
+    n = 0
+    for st in (bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED):
+        for v in range(1, 11):
+            for pw in (9, 10, 12, 14):
+                for dw in sorted({cases.VARIANT_DW[v], 12, 16, 20, 24, 30}):
+                    d = bhw.variant_desc(v, pw, dw, sin_type=st).copy(stream_offset=(v + pw) & 1)
+                    if bhw.validate(d):
+                        continue
+                    want = H.orc_window(d)
+                    for mode in (-1, 2):
+                        st_, got = hc_bank(d, mode=mode, pair=1)
+                        assert st_ in (0, 1)
+                        if st_ == 0:
+                            n += 1
+                            assert np.array_equal(got, want), (st, v, pw, dw, mode, int(np.argmax(got != want)))
+    assert n > 300
+    assert hc.hc_inq_exceptions(0) > 20
+
+
 def test_bank_body_most_negative_coefficients_every_placement():
     """a_k = -2^(DW-1) pre-shifts to INT32_MIN, which the half-period placement cannot negate: such
     windows (RTL and HLS alike) must take the generic body, whatever placement is asked for."""

@@ -22,6 +22,16 @@
 #define BHW_CONSTANT static const
 #endif
 
+// Debug build (csrc/build.sh debug -> libbhw_debug.so, -DBHW_BOUNDS_CHECK): every table look-up and every store
+// of the synthesis kernels checks its index with a device-side assert.  compute-sanitizer is closed on the
+// B200 pool this was developed on; tools/sanitize_smoke.py run against the debug library is the stand-in.
+#if defined(BHW_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+#include <assert.h>
+#define BHW_CHECK(cond) assert(cond)
+#else
+#define BHW_CHECK(cond) ((void)0)
+#endif
+
 namespace bhw {
 
 struct I2 { int32_t x, y; };  // (cos, sin) ROM word of taylor_sincos
@@ -1204,6 +1214,7 @@ BHW_HD void bank_lane_tile_lin(const BankShape& sh, const int32_t* A, int32_t S0
     const int32_t Ak = (TAB == TAB_SMEM_HALF && ((neg >> k) & 1u)) ? -A[k] : A[k];
 #pragma unroll
     for (int j = 0; j < kBankJ; ++j) {
+      BHW_CHECK(base[k] + step * (lane + (uint32_t)(32 * j)) <= sh.lin_dmask[k]);
       const int32_t c2 = T[(uint32_t)(32 * j) * step];
       const int64_t P = (int64_t)Ak * (int64_t)c2;
       const acc_t ba = bank_term<W64>(sh, P, false);
@@ -1242,6 +1253,7 @@ BHW_HD void bank_lane_tile(const BankShape& sh, const int32_t* A, int32_t S0, co
     for (int j = 0; j < kBankJ; ++j) {
       const uint32_t ph = ph0 + (uint32_t)(32 * j) * ks;
       const uint32_t idx = TAB == TAB_SMEM_HALF ? ((ph << 1) >> (sh.idx_rsh[k] + 1)) : (ph >> sh.idx_rsh[k]);
+      BHW_CHECK(idx < (sh.tentries[sh.tsel[k]] >> (TAB == TAB_SMEM_HALF ? 1 : 0)));
       const int32_t c2 = T[idx];
       int32_t Ae = Ak;
       if (TAB == TAB_SMEM_HALF && LANE_SIGN) Ae = ((int32_t)ph < 0) ? -Ak : Ak;

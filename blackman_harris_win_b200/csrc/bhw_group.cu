@@ -24,6 +24,7 @@ constexpr int kGroupWarps = kGroupThreads / 32;
 template <bool PAIR, int APPLY>
 __device__ __forceinline__ void group_epilogue(const GroupArgs& a, int32_t* o, size_t idx, size_t half, const int32_t* va,
                                                const int32_t* vb) {
+  BHW_CHECK(idx + 32 * (kBankJ - 1) < 2 * half && (!PAIR || idx + 32 * (kBankJ - 1) < half));
   if (APPLY == 0) {
     int32_t* ot = o + idx;
 #pragma unroll

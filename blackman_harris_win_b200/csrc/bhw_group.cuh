@@ -89,6 +89,7 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
         const uint32_t st = ks << 5;
 #pragma unroll
         for (int j = 0; j < kBankJ; ++j) {
+          BHW_CHECK((phx >> rsh) < (1u << (sh.top - 1)));
           const int32_t c2 = (int32_t)((uint32_t)T16[phx >> rsh] * sh.tmul - sh.tbias);
           const int64_t P = (int64_t)Ak * (int64_t)c2;
           const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
@@ -102,6 +103,7 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
 #pragma unroll
         for (int j = 0; j < kBankJ; ++j) {
           const uint32_t q = ph >> 30;
+          BHW_CHECK(((ph & 0x7FFFFFFFu) >> rsh) < (1u << (sh.top - 1)));
           const uint32_t u = T16[(ph & 0x7FFFFFFFu) >> rsh];
           int32_t c2 = (int32_t)(u * sh.tmul - sh.tbias);
           c2 = ((q + 1u) & 2u) ? -c2 : c2;
@@ -139,6 +141,7 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
           const uint32_t b = (uint32_t)k >> harmonic_log2(k);   // a constant once the harmonic loop is unrolled
 #pragma unroll
           for (int j = 0; j < kBankJ; ++j) {
+            BHW_CHECK((phx >> rsh) + (uint32_t)(32 * j) * b >= (1u << (L - 1)) && (phx >> rsh) + (uint32_t)(32 * j) * b < (1u << L));
             const int32_t c2 = Tl[(uint32_t)(32 * j) * b];
             const int64_t P = (int64_t)Ak * (int64_t)c2;
             const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
@@ -149,6 +152,7 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
           const uint32_t st = ks << 5;
 #pragma unroll
           for (int j = 0; j < kBankJ; ++j) {
+            BHW_CHECK((phx >> rsh) >= (1u << (L - 1)) && (phx >> rsh) < (1u << L) && L >= sh.lmin);
             const int32_t c2 = T[phx >> rsh];
             const int64_t P = (int64_t)Ak * (int64_t)c2;
             const uint32_t ba = (uint32_t)((P + (int64_t)(uint64_t)sh.rc) >> 32);
@@ -162,6 +166,7 @@ BHW_HD void group_lane_tile(const GroupShape& sh, uint32_t pw, const int32_t* A,
         const uint32_t st = ks << 5;
 #pragma unroll
         for (int j = 0; j < kBankJ; ++j) {
+          BHW_CHECK(((ph | 0x80000000u) >> rsh) >= (1u << (L - 1)) && ((ph | 0x80000000u) >> rsh) < (1u << L) && L >= sh.lmin);
           const int32_t t = T[(ph | 0x80000000u) >> rsh];
           const int32_t c2 = (ph >> 31) ? -t : t;
           const int64_t P = (int64_t)A[k] * (int64_t)c2;

@@ -5,6 +5,11 @@ set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libbhw.so"
 OBJ="$HERE/../build"
+if [ "${1:-}" = "debug" ]; then   # bounds-checked build (device-side asserts), loaded with BHW_LIB=.../libbhw_debug.so
+  OUT="$HERE/../libbhw_debug.so"
+  OBJ="$HERE/../build/debug"
+  BHW_NVCC_EXTRA="${BHW_NVCC_EXTRA:-} -DBHW_BOUNDS_CHECK"
+fi
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden"
 mkdir -p "$OBJ"

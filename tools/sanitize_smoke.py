@@ -33,6 +33,18 @@ total = plan.total
 out = plan.execute(5, total - 9).cpu().numpy().astype(np.int64)
 assert np.array_equal(out, H.orc_batch(descs, 5, total - 9))
 plan.destroy()
+# the group kernel in its three table placements (mixed PHI_WIDTHs, a cut window), the apply step
+for variants, dw, pws in (((1, 3), 16, (9, 13, 17)), ((6,), 17, (10, 17, 18)), ((9, 10), 24, (9, 14, 18))):
+    gd = [bhw.variant_desc(v, pw, dw, stream_offset=pw & 1) for pw in pws for v in variants]
+    gt = bhw.batch_total(gd)
+    want = H.orc_batch(gd, 0, gt)
+    assert np.array_equal(bhw.generate_batch(gd).cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(bhw.generate_batch(gd, 777, gt - 5000).cpu().numpy().astype(np.int64), want[777:gt - 4223])
+    n_ok += 2
+xa = torch.randint(-(1 << 15), 1 << 15, (3, 1 << 12), dtype=torch.int32)
+da = bhw.variant_desc(6, 12, 17)
+assert np.array_equal(bhw.apply(da, xa.cuda(), bhw.APPLY_EXACT).cpu().numpy(), H.orc_apply(da, xa.numpy(), 0))
+assert np.array_equal(bhw.apply(da, xa.cuda(), bhw.APPLY_ROUNDED).cpu().numpy().astype(np.int64), H.orc_apply(da, xa.numpy(), 1))
 # host entry points, sincos, atan2
 assert np.array_equal(bhw.generate_batch_host(descs).astype(np.int64), H.orc_batch(descs, 0, total))
 d = bhw.make_desc(2, 12, 20, sin_type=bhw.SIN_CORDIC48)

@@ -466,8 +466,20 @@ def run_cuda(args):
                          "(use --impl reference for the CPU model)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries the one JSON line only: NCCL's banner ("NCCL version ...") goes to stderr - it is written by
+        # native code at communicator creation, so file descriptor 1 itself is pointed at stderr until that is done
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if world != args.gpus and rank == 0:
         print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
 
@@ -598,7 +610,7 @@ def run_cuda(args):
         link_s = time.perf_counter() - t0
         e2e = {"value": total * args.e2e_steps / e2e_s / 1e9, "unit": UNIT, "steps": args.e2e_steps,
                "d2h_gbs_per_gpu": count * 4 * args.e2e_steps / e2e_s / 1e9,
-               "d2h_box_gbs": max_over_ranks(count * 4 / link_s / 1e9) if count else None,
+               "d2h_box_gbs": max_over_ranks(count * 4 / link_s / 1e9 if count else 0.0),   # every rank joins the reduction
                "d2h_box_gbs_note": "plain pinned cudaMemcpy of this rank's slice, all ranks at once: the link ceiling of this box",
                "h2d_bytes_per_step": _meta_bytes(touched), "d2h_bytes_per_step": count * 4,
                "api": "bhw_generate_batch_host (descriptors in host memory, pinned host output, planning inside the timed region)"}

@@ -27,6 +27,8 @@ namespace bhw {
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_cache_enabled{1};
 static std::atomic<int> g_side_streams{4};  // bhw_set_side_streams
+static std::atomic<int> g_spread_min_terms{5}; // long windows over a pyramid in L2/HBM get a spread launch of their own from this many terms
+static std::atomic<int> g_prefetch_lines{0};    // spread launches: L1 prefetch of the next tile (0 = off)
 static std::atomic<int> g_defer_ctas{0};    // resident CTAs per SM of a table build that shares the GPU with synthesis
 static thread_local std::string t_cuda_err;
 
@@ -598,7 +600,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   }
   const uint32_t kSpreadG = 30;
   for (auto& gr : plan.groups) {
-    const bool can_spread = plan.families[(size_t)gr.family].tab_mode == G_GLOBAL && gr.sh.m >= 5;
+    const bool can_spread = plan.families[(size_t)gr.family].tab_mode == G_GLOBAL && (int)gr.sh.m >= g_spread_min_terms.load();
     uint32_t units = 0;
     for (uint32_t w : gr.wins) {
       GroupWin gw;
@@ -1104,6 +1106,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
         ga.nwin = 1;
         ga.nunits = gr.singles[2 * (size_t)si + 1].unit_begin;
         ga.spread = kSpreadG_;
+        ga.prefetch_lines = (uint32_t)g_prefetch_lines.load();
       } else {
         if (!gk.nparts) continue;
         uint32_t units = 0;
@@ -1712,6 +1715,12 @@ int bhw_set_table_cache(int enabled) {
   g_cache_enabled.store(enabled ? 1 : 0);
   return BHW_OK;
 }
+
+// undocumented tuning knob: terms from which long pyramid windows get their own spread launch (applies to plans created afterwards)
+__attribute__((visibility("default"))) int bhw_debug_set_spread_min_terms(int n) { g_spread_min_terms.store(n); return BHW_OK; }
+
+// undocumented tuning knob: L1 prefetch depth of the spread launches
+__attribute__((visibility("default"))) int bhw_debug_set_prefetch_lines(int n) { g_prefetch_lines.store(n); return BHW_OK; }
 
 // undocumented tuning knob: CTAs per SM of a deferred family table build (0 = do not defer)
 __attribute__((visibility("default"))) int bhw_debug_set_defer_ctas(int n) {

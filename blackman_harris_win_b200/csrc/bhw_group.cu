@@ -58,6 +58,33 @@ __device__ __forceinline__ void group_epilogue(const GroupArgs& a, int32_t* o, s
   }
 }
 
+// G_GLOBAL: pull the pyramid lines the tile at sample `nbase` is going to gather into L1 ahead of time (one
+// prefetch instruction per harmonic for up to 32 lines of 128 B), so that the gathers of the next tile find them
+// there instead of waiting ~300 cycles for L2: the kernel is otherwise bound by exactly that wait (ncu: long
+// scoreboard stalls, issue slots 54 % busy on a 2^26-point 5-term window).  A tile whose phase crosses a half
+// period is skipped (rare).  `max_lines`: L1 is finite - harmonics whose span needs more are left alone.
+template <int M>
+__device__ __forceinline__ void group_prefetch_tile(const GroupShape& sh, uint32_t pw, uint32_t nbase, uint32_t lane,
+                                                    uint32_t max_lines) {
+  const uint32_t sl = 32u - pw;
+#pragma unroll
+  for (int k = 1; k < M; ++k) {
+    const uint32_t ks = (uint32_t)k << sl;
+    const uint32_t ph = (nbase * ks) & 0x7FFFFFFFu;
+    const uint32_t span = (uint32_t)(kBankTile - 1) * ks;
+    if ((((uint32_t)k * (uint32_t)(kBankTile - 1)) >> (pw - 1)) != 0u || ph + span >= 0x80000000u) continue;
+    const uint32_t want = pw - harmonic_log2(k);
+    const uint32_t L = want < sh.top ? want : sh.top;
+    const uint32_t rsh = 32u - L;
+    const uint32_t i0 = (ph | 0x80000000u) >> rsh, i1 = ((ph + span) | 0x80000000u) >> rsh;   // heap element indices
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(sh.pyr + i0) & ~(uintptr_t)127;
+    const uintptr_t a1 = reinterpret_cast<uintptr_t>(sh.pyr + i1);
+    const uint32_t nlines = (uint32_t)((a1 - a0) >> 7) + 1u;
+    if (nlines > max_lines) continue;
+    if (lane < nlines) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + ((uintptr_t)lane << 7)));
+  }
+}
+
 template <int M, int TAB, bool PAIR, int APPLY>
 __global__ void __launch_bounds__(kGroupThreads, 1)
 k_synth_group(const __grid_constant__ GroupArgs a) {
@@ -104,6 +131,7 @@ k_synth_group(const __grid_constant__ GroupArgs a) {
     for (uint32_t i = i0; i < i1; ++i) {
       uint32_t t;
       if (!spread_tile(U, G, warp, i, &t)) continue;
+      if (a.prefetch_lines) group_prefetch_tile<M>(sh, pw, (t + 1) * kBankTile + n_first, lane, a.prefetch_lines);
       int32_t va[kBankJ], vb[kBankJ];
       group_lane_tile<M, TAB, PAIR>(sh, pw, A, S0, tab, t * kBankTile + n_first, lane, va, vb);
       group_epilogue<PAIR, APPLY>(a, o, (size_t)t * kBankTile + lane, half, va, vb);

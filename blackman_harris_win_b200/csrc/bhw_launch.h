@@ -62,6 +62,8 @@ struct GroupArgs {
   uint64_t frames;
   uint32_t apply_mode;       // BHW_APPLY_EXACT + 1 / BHW_APPLY_ROUNDED + 1
   uint32_t apply_dw;         // DAT_WIDTH
+  uint32_t prefetch_lines;   // spread walk: prefetch the next tile's pyramid lines into L1, harmonics of up to this many lines
+  uint32_t pad2;
 };
 
 struct DirectArgs {

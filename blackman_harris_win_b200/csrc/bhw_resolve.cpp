@@ -460,9 +460,13 @@ static void slice_add(SliceCost& sc, const bhw_desc& d, uint64_t lo, uint64_t hi
 }
 
 // Greedy cut for a target slice time T: ranks take samples in order while their estimated time stays within T.
-// Cuts fall on window boundaries, or inside a window of >= 2^20 samples at multiples of 2^14 samples.
+// Cuts fall on window boundaries, or inside a window of >= 2^20 samples at multiples of 2^14 samples (never
+// closer than an eighth of the window to one of its ends).  A window that fits no slice and yields no acceptable
+// piece - the 2^26-point 7-term window, whose table build alone exceeds the target at 8 ranks - becomes a slice of
+// its own ("atom"), exempt from T: the other ranks still balance among themselves.
 // -> the cuts (nranks + 1 flat positions); returns false when nranks slices do not suffice.
-static bool cut_for_target(const bhw_desc* descs, int nwin, int nranks, double T, uint64_t total, uint64_t* cuts) {
+static bool cut_for_target(const bhw_desc* descs, int nwin, int nranks, double T, double atom_cap, uint64_t total,
+                           uint64_t* cuts) {
   int w = 0;
   uint64_t in_w = 0, flat = 0;       // next sample to hand out: sample in_w of window w
   cuts[0] = 0;
@@ -473,13 +477,14 @@ static bool cut_for_target(const bhw_desc* descs, int nwin, int nranks, double T
       const uint64_t N = 1ull << descs[w].phi_width;
       SliceCost trial = sc;
       slice_add(trial, descs[w], in_w, N);
-      if (trial.us <= T || r == nranks - 1) {                // the rest of this window fits (the last rank takes all)
+      if (trial.us <= T) {                                   // the rest of this window fits
         sc = trial;
         flat += N - in_w;
         in_w = 0;
         w++;
         continue;
       }
+      bool took_piece = false;
       if (N >= (1ull << 20)) {                               // take a piece of it: bisect on the piece length
         const uint64_t step = 1ull << 14;
         uint64_t lo = 0, hi = (N - in_w) / step;             // pieces of `step` samples that fit
@@ -494,12 +499,18 @@ static bool cut_for_target(const bhw_desc* descs, int nwin, int nranks, double T
           slice_add(sc, descs[w], in_w, in_w + lo * step);
           flat += lo * step;
           in_w += lo * step;
+          took_piece = true;
         }
+      }
+      if (!took_piece && flat == cuts[r]) {                  // an empty slice and nothing fits: the window is an atom,
+        if (in_w != 0 || trial.us > atom_cap) return false;    // if whole and within the cap - else raise T
+        flat += N - in_w;
+        in_w = 0;
+        w++;
       }
       break;
     }
     cuts[r + 1] = flat;
-    if (r == nranks - 1 && sc.us > T) return false;          // the last rank took the rest: it must fit as well
   }
   return flat == total;
 }
@@ -523,9 +534,23 @@ int bhw_shard_range_cost(const bhw_desc* descs, int nwin, int rank, int nranks, 
   bool have = false;
   for (int it = 0; it < 60; it++) {
     const double T = 0.5 * (lo + hi);
-    if (cut_for_target(descs, nwin, nranks, T, total, cuts.data())) { hi = T; best = cuts; have = true; }
+    if (cut_for_target(descs, nwin, nranks, T, 0.0, total, cuts.data())) { hi = T; best = cuts; have = true; }
     else lo = T;
     if (hi - lo < 1e-5 * all.us) break;
+  }
+  // Second pass: hi is the makespan.  When a single costly window sets it, the greedy above has packed the other
+  // ranks up to it and left ranks idle; with windows of up to that cost allowed as slices of their own, find the
+  // smallest target for everybody else - same makespan by the model, but the other ranks finish early and errors
+  // of the model no longer add to the critical path.
+  if (have && nranks > 1) {
+    const double cap = hi * 1.0001;
+    double lo2 = all.us / nranks * 0.5, hi2 = hi;
+    for (int it = 0; it < 60; it++) {
+      const double T = 0.5 * (lo2 + hi2);
+      if (cut_for_target(descs, nwin, nranks, T, cap, total, cuts.data())) { hi2 = T; best = cuts; }
+      else lo2 = T;
+      if (hi2 - lo2 < 1e-5 * all.us) break;
+    }
   }
   if (!have) {                                               // cannot happen (one rank can take everything within all.us)
     for (int r = 0; r <= nranks; r++) best[(size_t)r] = r == 0 ? 0 : total;

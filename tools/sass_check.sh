@@ -5,7 +5,7 @@
 #   tools/sass_check.sh [mangled-name-substring] > /tmp/a.txt ; ... ; diff /tmp/a.txt /tmp/b.txt
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")/.." && pwd)"
-PAT="${1:-k_synth_bankILi4ELi1ELb1ELb0EE}"   # bench kernel: 4 terms, staged half table, paired, 32-bit tail
+PAT="${1:-k_synth_bankILi4ELi1ELi1ELb0EE}"   # bench kernel: 4 terms, staged half table, paired, 32-bit tail
 TMP="$(mktemp -d)"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -cubin \
   -I"$HERE/include" -o "$TMP/k.cubin" "$HERE/blackman_harris_win_b200/csrc/bhw_kernels.cu"

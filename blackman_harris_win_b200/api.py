@@ -37,7 +37,7 @@ class BhwError(RuntimeError):
 class BhwAtan2Desc(C.Structure):
     """struct bhw_atan2_desc - the generics of cordic_atan2 (src/cordic_atan2.vhd:64-69)."""
     _fields_ = [("input_width", C.c_int32), ("angle_width", C.c_int32), ("precision", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("stream_quadrant", C.c_int32)]
 
 
 class BhwDesc(C.Structure):
@@ -380,14 +380,15 @@ def cache_clear():
     _check(lib().bhw_cache_clear(), "bhw_cache_clear")
 
 
-def atan2(x, y, input_width: int, angle_width: int, precision: int = 1, out=None):
-    """cordic_atan2 over two int32 CUDA tensors (VEC_DX, VEC_DY) -> PHI_DT (int32 CUDA tensor)."""
+def atan2(x, y, input_width: int, angle_width: int, precision: int = 1, out=None, stream_quadrant: int = 0):
+    """cordic_atan2 over two int32 CUDA tensors (VEC_DX, VEC_DY) -> PHI_DT (int32 CUDA tensor).
+    stream_quadrant=1: as the entity streams it (pair t corrected with the quadrant of pair t+1)."""
     torch = _torch()
     assert x.is_cuda and y.is_cuda and x.dtype == torch.int32 and y.dtype == torch.int32 and x.shape == y.shape
     x, y = x.contiguous(), y.contiguous()
     if out is None:
         out = torch.empty_like(x)
-    d = BhwAtan2Desc(input_width, angle_width, precision, 0)
+    d = BhwAtan2Desc(input_width, angle_width, precision, stream_quadrant)
     with torch.cuda.device(x.device):
         st = lib().bhw_atan2(C.byref(d), x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(),
                              torch.cuda.current_stream().cuda_stream)
@@ -395,13 +396,14 @@ def atan2(x, y, input_width: int, angle_width: int, precision: int = 1, out=None
     return out
 
 
-def atan2_host(x: np.ndarray, y: np.ndarray, input_width: int, angle_width: int, precision: int = 1) -> np.ndarray:
+def atan2_host(x: np.ndarray, y: np.ndarray, input_width: int, angle_width: int, precision: int = 1,
+               stream_quadrant: int = 0) -> np.ndarray:
     """cordic_atan2 over two int32 numpy arrays (host buffers in, host buffer out)."""
     x = np.ascontiguousarray(x, dtype=np.int32)
     y = np.ascontiguousarray(y, dtype=np.int32)
     assert x.shape == y.shape
     out = np.empty(x.shape, np.int32)
-    d = BhwAtan2Desc(input_width, angle_width, precision, 0)
+    d = BhwAtan2Desc(input_width, angle_width, precision, stream_quadrant)
     _check(lib().bhw_atan2_host(C.byref(d), x.ctypes.data, y.ctypes.data, out.ctypes.data, x.size), "bhw_atan2_host")
     return out
 

@@ -1664,15 +1664,16 @@ int bhw_atan2_host(const bhw_atan2_desc* d, const int32_t* x_host, const int32_t
   cudaError_t e = pipe_ensure(hp);
   if (e != cudaSuccess) { pipe_release(hp); return cuda_fail(e, "host pipeline setup"); }
   // buf[0] = x | y (two halves), buf[1] = phi; one stream, chunk after chunk
-  const uint64_t chunk = hp.buf_bytes / 8;
+  const uint64_t chunk = hp.buf_bytes / 8 - 1;           // one spare pair: stream_quadrant looks one pair ahead
   int32_t* xd = (int32_t*)hp.buf[0];
-  int32_t* yd = xd + chunk;
+  int32_t* yd = xd + chunk + 1;
   int32_t* pd = (int32_t*)hp.buf[1];
   for (uint64_t done = 0; done < count && e == cudaSuccess; done += chunk) {
     const uint64_t cnt = count - done < chunk ? count - done : chunk;
-    if ((e = cudaMemcpyAsync(xd, x_host + done, cnt * 4, cudaMemcpyHostToDevice, hp.s_gen)) != cudaSuccess) break;
-    if ((e = cudaMemcpyAsync(yd, y_host + done, cnt * 4, cudaMemcpyHostToDevice, hp.s_gen)) != cudaSuccess) break;
-    if ((e = launch_atan2(p, xd, yd, pd, cnt, hp.s_gen)) != cudaSuccess) break;
+    const uint64_t avail = done + cnt < count ? cnt + 1 : cnt;
+    if ((e = cudaMemcpyAsync(xd, x_host + done, avail * 4, cudaMemcpyHostToDevice, hp.s_gen)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(yd, y_host + done, avail * 4, cudaMemcpyHostToDevice, hp.s_gen)) != cudaSuccess) break;
+    if ((e = launch_atan2(p, xd, yd, pd, cnt, hp.s_gen, avail)) != cudaSuccess) break;
     g_launches++;
     e = cudaMemcpyAsync(phi_host + done, pd, cnt * 4, cudaMemcpyDeviceToHost, hp.s_gen);
   }

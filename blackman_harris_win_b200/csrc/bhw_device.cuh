@@ -1006,6 +1006,8 @@ BHW_HD void direct_taylor_pair(const DirectTayParams& p, const I2* __restrict__ 
 struct Atan2Params {
   int32_t iw, aw, w;     // INPUT_WIDTH, ANGLE_WIDTH, ANGLE_WIDTH + PRECISION
   int32_t fast32;        // 1: W <= 32, the 32-bit body applies
+  int32_t skew;          // 1: PHI_DT of pair t takes the quadrant of pair t+1 (bhw_atan2_desc::stream_quadrant)
+  int32_t pad;
   int64_t rom64[48];     // ROM_TABLE(ii) (:97-108) left-aligned to bit 63; aw-1 entries used
   uint32_t rom32[32];    // the same words left-aligned to bit 31 (fast32)
 };
@@ -1014,10 +1016,14 @@ struct Atan2Params {
 // of Y turns the three conditional add/subtracts into multiply-adds (mod 2^32 = the W-bit wrap).
 // AW > 0: ANGLE_WIDTH as a compile-time constant (stage count, shifts and masks become immediates);
 // AW == 0: run-time loop.
+// (qx, qy): the pair whose sign bits select the output quadrant - the pair itself, or (Atan2Params::skew) the NEXT
+// pair of the stream, which is what the entity as written does: its quadrant shift registers are one stage shorter
+// than the data path (src/cordic_atan2.vhd:127-129 vs :136-184; found by executing the VHDL, oracle/vhdl_sim.py).
 template <int AW>
-BHW_HD int32_t atan2_sample32_t(const Atan2Params& p, int32_t xin, int32_t yin) {
+BHW_HD int32_t atan2_sample32_t(const Atan2Params& p, int32_t xin, int32_t yin, int32_t qx, int32_t qy) {
   const int aw = AW > 0 ? AW : p.aw, ax = 32 - p.w;
   const uint32_t sxb = ((uint32_t)xin >> (p.iw - 1)) & 1u, syb = ((uint32_t)yin >> (p.iw - 1)) & 1u;
+  const uint32_t qxb = ((uint32_t)qx >> (p.iw - 1)) & 1u, qyb = ((uint32_t)qy >> (p.iw - 1)) & 1u;
   const uint32_t mag_mask = (1u << (aw - 1)) - 1u;
   const int32_t mx = (int32_t)(~0u << ax);
   uint32_t X = (((uint32_t)xin ^ (0u - sxb)) & mag_mask) << ax;
@@ -1044,7 +1050,7 @@ BHW_HD int32_t atan2_sample32_t(const Atan2Params& p, int32_t xin, int32_t yin) 
   const int32_t phi = (int32_t)Z >> (32 - aw);                // top ANGLE_WIDTH bits, sign-extended
   const int32_t pi = 1 << (aw - 2);
   int32_t o;
-  switch ((sxb << 1) | syb) {
+  switch ((qxb << 1) | qyb) {
     case 0: o = phi; break;
     case 1: o = (int32_t)((uint32_t)phi + (uint32_t)pi); break;
     case 2: o = (int32_t)(0u - (uint32_t)phi); break;
@@ -1052,12 +1058,17 @@ BHW_HD int32_t atan2_sample32_t(const Atan2Params& p, int32_t xin, int32_t yin) 
   }
   return wrapb32(o, aw);
 }
-BHW_HD int32_t atan2_sample32(const Atan2Params& p, int32_t xin, int32_t yin) { return atan2_sample32_t<0>(p, xin, yin); }
+template <int AW>
+BHW_HD int32_t atan2_sample32_t(const Atan2Params& p, int32_t xin, int32_t yin) { return atan2_sample32_t<AW>(p, xin, yin, xin, yin); }
+BHW_HD int32_t atan2_sample32(const Atan2Params& p, int32_t xin, int32_t yin, int32_t qx, int32_t qy) {
+  return atan2_sample32_t<0>(p, xin, yin, qx, qy);
+}
 
-BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin) {
-  if (p.fast32) return atan2_sample32(p, xin, yin);
+BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin, int32_t qx, int32_t qy) {
+  if (p.fast32) return atan2_sample32(p, xin, yin, qx, qy);
   const int aw = p.aw, ax = 64 - p.w;
   const uint32_t sxb = ((uint32_t)xin >> (p.iw - 1)) & 1u, syb = ((uint32_t)yin >> (p.iw - 1)) & 1u;
+  const uint32_t qxb = ((uint32_t)qx >> (p.iw - 1)) & 1u, qyb = ((uint32_t)qy >> (p.iw - 1)) & 1u;
   // init_x(ii) = VEC_DX(ii) xor VEC_DX(INPUT_WIDTH-1), ii = 0..ANGLE_WIDTH-2; upper bits zero (:136-146)
   const uint32_t mag_mask = aw - 1 >= 32 ? 0xFFFFFFFFu : ((1u << (aw - 1)) - 1u);
   const uint64_t ix = ((uint32_t)xin ^ (0u - sxb)) & mag_mask, iy = ((uint32_t)yin ^ (0u - syb)) & mag_mask;
@@ -1075,7 +1086,7 @@ BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin) {
   const int64_t phi = (int64_t)Z >> (64 - aw);
   const int64_t pi = (int64_t)1 << (aw - 2);              // PHI_PI: only bit ANGLE_WIDTH-2 set (:121)
   int64_t o;
-  switch ((sxb << 1) | syb) {                             // quadrant = sign(X) & sign(Y) (:129-131,203-208)
+  switch ((qxb << 1) | qyb) {                             // quadrant = sign(X) & sign(Y) (:129-131,203-208)
     case 0: o = phi; break;
     case 1: o = phi + pi; break;
     case 2: o = -phi; break;
@@ -1083,6 +1094,7 @@ BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin) {
   }
   return (int32_t)wrapb(o, aw);
 }
+BHW_HD int32_t atan2_sample(const Atan2Params& p, int32_t xin, int32_t yin) { return atan2_sample(p, xin, yin, xin, yin); }
 
 // ============================================================================================
 // Bank synthesis body (k_synth_bank): whole windows of one shape

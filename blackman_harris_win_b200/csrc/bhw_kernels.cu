@@ -582,10 +582,15 @@ k_sincos(const __grid_constant__ SinCosArgs a, OutT* __restrict__ out_sin, OutT*
 // ~10 instructions per stage make it integer-issue-bound long before HBM.
 __global__ void __launch_bounds__(256)
 k_atan2(const __grid_constant__ Atan2Params p, const int32_t* __restrict__ x, const int32_t* __restrict__ y,
-        int32_t* __restrict__ phi, uint64_t count) {
+        int32_t* __restrict__ phi, uint64_t count, uint64_t avail) {
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count;
        j += (uint64_t)gridDim.x * blockDim.x)
-    __stcs(phi + j, atan2_sample(p, __ldcs(x + j), __ldcs(y + j)));
+  {
+    const int32_t xv = __ldcs(x + j), yv = __ldcs(y + j);
+    // stream_quadrant: the quadrant of the next pair of the stream (the inputs after the last pair read 0)
+    const int32_t qx = !p.skew ? xv : (j + 1 < avail ? __ldg(x + j + 1) : 0), qy = !p.skew ? yv : (j + 1 < avail ? __ldg(y + j + 1) : 0);
+    __stcs(phi + j, atan2_sample(p, xv, yv, qx, qy));
+  }
 }
 
 // ANGLE_WIDTH known at compile time (W <= 32): unrolled stages, 4 pairs per thread, 128-bit accesses
@@ -844,9 +849,10 @@ cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStrea
 }
 
 cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, uint64_t avail) {
+  if (avail < count) avail = count;
   if (!count) return cudaSuccess;
-  const bool vec = p.fast32 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+  const bool vec = p.fast32 && !p.skew && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                                  reinterpret_cast<uintptr_t>(phi)) & 15) == 0;
   const unsigned gridv = grid_for((count / 4 + 255) / 256 + 1, 8);
   if (vec && p.aw == 16) k_atan2_u<16><<<gridv, 256, 0, stream>>>(p, x, y, phi, count);
@@ -855,7 +861,7 @@ cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* 
   else if (vec && p.aw == 12) k_atan2_u<12><<<gridv, 256, 0, stream>>>(p, x, y, phi, count);
   else {
     const unsigned grid = grid_for((count + 255) / 256, 8);
-    k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count);
+    k_atan2<<<grid, 256, 0, stream>>>(p, x, y, phi, count, avail);
   }
   return cudaGetLastError();
 }

@@ -138,8 +138,9 @@ int device_sm_count();     // SMs of the current device (148 on B200)
 cudaError_t launch_direct_window(const DirectArgs& a, void* out, cudaStream_t stream);
 cudaError_t launch_direct32(const Direct32Args& a, int32_t* out, cudaStream_t stream);
 cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream);
+// avail: input pairs present in x / y (>= count): with Atan2Params::skew pair count-1 reads the quadrant of pair `count`
 cudaError_t launch_atan2(const Atan2Params& p, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count,
-                         cudaStream_t stream);
+                         cudaStream_t stream, uint64_t avail = 0);
 cudaError_t launch_sincos(const SinCosArgs& a, void* out_sin, void* out_cos, bool elem64, cudaStream_t stream);
 
 }  // namespace bhw

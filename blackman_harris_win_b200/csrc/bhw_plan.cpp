@@ -244,7 +244,7 @@ bool direct_taylor_params(const WinParams& wp, const SrcParams* src, DirectTayPa
 int resolve_atan2(const bhw_atan2_desc* d, Atan2Params* p) {
   if (!d) return BHW_E_NULL;
   const int prec = d->precision == 0 ? 1 : d->precision;
-  if (d->reserved != 0) return BHW_E_ARG;
+  if (d->stream_quadrant != 0 && d->stream_quadrant != 1) return BHW_E_ARG;
   if (d->angle_width < 4 || d->angle_width > 32) return BHW_E_DAT_WIDTH;
   if (d->input_width > 32 || d->input_width < d->angle_width - 1) return BHW_E_PHI_WIDTH;
   if (prec < 1 || prec > 7) return BHW_E_PRECISION;
@@ -257,6 +257,7 @@ int resolve_atan2(const bhw_atan2_desc* d, Atan2Params* p) {
     if (p->w <= 32 && i < 32) p->rom32[i] = (uint32_t)((uint64_t)r << (32 - p->w));
   }
   p->fast32 = p->w <= 32 ? 1 : 0;
+  p->skew = d->stream_quadrant;
   return BHW_OK;
 }
 

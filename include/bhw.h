@@ -271,7 +271,11 @@ typedef struct bhw_atan2_desc {
   int32_t input_width;   /* INPUT_WIDTH */
   int32_t angle_width;   /* ANGLE_WIDTH */
   int32_t precision;     /* PRECISION, 0 = the entity default 1 */
-  int32_t reserved;      /* must be 0 */
+  int32_t stream_quadrant; /* 0: every pair is corrected with its own quadrant (the evident intent);
+                              1: as the entity really streams - its quadrant shift registers are one stage
+                              shorter than the data path (src/cordic_atan2.vhd:127-129 vs :136-184), so on a
+                              stream of one pair per clock PHI_DT of pair t takes the quadrant of pair t+1
+                              (the inputs after the last pair read 0).  Found by executing the VHDL. */
 } bhw_atan2_desc;
 BHW_API int bhw_atan2_validate(const bhw_atan2_desc* d);
 BHW_API int bhw_atan2(const bhw_atan2_desc* d, const int32_t* x_dev, const int32_t* y_dev, int32_t* phi_dev,

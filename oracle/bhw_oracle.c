@@ -518,10 +518,20 @@ int orc_atan2_validate(int iw, int aw, int prec) {
   return BHW_OK;
 }
 
+/* (qx, qy): the pair whose sign bits select the quadrant at the output.  In the entity as written the quadrant
+ * shift registers quadz1/quadz2 are ANGLE_WIDTH stages long (:127-129) while the data takes ANGLE_WIDTH + 1 clocks
+ * to reach dat_phi (init_x/init_y :136-146, sigX(0) :160, ANGLE_WIDTH-1 stages :166-184), so on a stream of pairs
+ * PHI_DT for pair t is corrected with the quadrant of pair t+1 (seen by executing the VHDL: oracle/vhdl_sim.py,
+ * tests/golden/rtl_sim_vectors.npz).  orc_cordic_atan2 = the aligned reading (qx, qy) = (vx, vy). */
+int64_t orc_cordic_atan2_q(int iw, int aw, int prec, int64_t vx, int64_t vy, int64_t qx, int64_t qy);
 int64_t orc_cordic_atan2(int iw, int aw, int prec, int64_t vx, int64_t vy) {
+  return orc_cordic_atan2_q(iw, aw, prec, vx, vy, vx, vy);
+}
+int64_t orc_cordic_atan2_q(int iw, int aw, int prec, int64_t vx, int64_t vy, int64_t qx, int64_t qy) {
   if (prec == 0) prec = 1;
   const int w = aw + prec;                                 /* dat_array / phi_array element width :117-118 */
   const int sxb = (int)((vx >> (iw - 1)) & 1), syb = (int)((vy >> (iw - 1)) & 1);
+  const int qxb = (int)((qx >> (iw - 1)) & 1), qyb = (int)((qy >> (iw - 1)) & 1);
   int64_t x = 0, y = 0, z = 0;                             /* init_z <= 0 :149 */
   for (int ii = 0; ii <= aw - 2; ii++) {                   /* pr_abs :136-146 */
     x |= (int64_t)(((vx >> ii) & 1) ^ sxb) << ii;
@@ -537,7 +547,7 @@ int64_t orc_cordic_atan2(int iw, int aw, int prec, int64_t vx, int64_t vy) {
   }
   const int64_t dat_phi = sx(z >> prec, aw);               /* sigZ(AW-1)(w-1 downto PRECISION) :188 */
   const int64_t phi_pi = (int64_t)1 << (aw - 2);           /* (ANGLE_WIDTH-2 => '1', others => '0') :121 */
-  switch ((sxb << 1) | syb) {                              /* quadrant = quadz1 & quadz2 :129-131; case :203-208 */
+  switch ((qxb << 1) | qyb) {                              /* quadrant = quadz1 & quadz2 :129-131; case :203-208 */
     case 0: return dat_phi;
     case 1: return sx(dat_phi + phi_pi, aw);
     case 2: return sx(~dat_phi + 1, aw);
@@ -550,6 +560,17 @@ int orc_atan2(int iw, int aw, int prec, const int32_t* x, const int32_t* y, int3
   if (st) return st;
   for (uint64_t j = 0; j < count; j++)
     phi[j] = (int32_t)orc_cordic_atan2(iw, aw, prec, (int64_t)(uint32_t)x[j], (int64_t)(uint32_t)y[j]);
+  return BHW_OK;
+}
+
+/* PHI_DT as the entity streams it: pair t with the quadrant of pair t+1; after the last pair the inputs are 0. */
+int orc_atan2_stream(int iw, int aw, int prec, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count) {
+  int st = orc_atan2_validate(iw, aw, prec);
+  if (st) return st;
+  for (uint64_t j = 0; j < count; j++) {
+    const int64_t qx = j + 1 < count ? (int64_t)(uint32_t)x[j + 1] : 0, qy = j + 1 < count ? (int64_t)(uint32_t)y[j + 1] : 0;
+    phi[j] = (int32_t)orc_cordic_atan2_q(iw, aw, prec, (int64_t)(uint32_t)x[j], (int64_t)(uint32_t)y[j], qx, qy);
+  }
   return BHW_OK;
 }
 

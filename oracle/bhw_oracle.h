@@ -47,6 +47,7 @@ int orc_atan2(int input_width, int angle_width, int precision, const int32_t* x,
 /* multi-threaded fill used by bench.py's CPU legs (pthreads, one contiguous slice per thread) */
 int orc_window_mt(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out, int nthreads);
 int orc_window_i32(const bhw_desc* d, uint64_t n0, uint64_t count, int32_t* out);
+int orc_atan2_stream(int iw, int aw, int prec, const int32_t* x, const int32_t* y, int32_t* phi, uint64_t count);
 int orc_apply(const bhw_desc* d, int mode, const int32_t* x, uint64_t frames, int64_t* y);
 
 #ifdef __cplusplus

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Golden vectors of the RTL entities, produced by EXECUTING the reference's own VHDL (oracle/vhdl_sim.py reads
+/root/reference/src/*.vhd where they lie and clocks the elaborated entities).  Runs in the container that has the
+reference checkout; the vectors travel in tests/golden/rtl_sim_vectors.npz (+ rtl_sim_cases.json) and pin
+oracle/bhw_oracle.c (tests/test_rtl_vhdl_sim.py) and the CUDA path (tests/test_gpu_parity.py) wherever the reference
+itself is absent.
+
+  python tests/golden/make_rtl_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import vhdl_sim as V  # noqa: E402
+import blackman_harris_win_b200 as bhw  # noqa: E402  (bhw_quantize only: the testbench's coefficient rules)
+
+
+def phases_for(pw, rng, n=192):
+    N = 1 << pw
+    if N <= 1024:
+        return list(range(N))
+    fixed = [0, 1, 2, 3, N // 4 - 1, N // 4, N // 4 + 1, N // 2 - 1, N // 2, N // 2 + 1, 3 * N // 4 - 1, 3 * N // 4, N - 2, N - 1]
+    return sorted(set(fixed + [int(x) for x in rng.integers(0, N, n)]))
+
+
+def main():
+    lib = V.reference_library()
+    rng = np.random.default_rng(20261018)
+    arrays, cases = {}, {"dds": [], "windows": [], "atan2": [], "source": "oracle/vhdl_sim.py over /root/reference/src/*.vhd"}
+
+    # ---- the DDS entities: PH_IN -> (DT_SIN, DT_COS), valid flag from DT_VAL
+    dds_sets = {"cordic_dds": [(4, 8), (10, 16), (11, 16), (8, 12), (6, 10), (16, 17), (14, 24), (20, 32), (24, 24), (26, 16), (12, 8), (9, 40)],
+                "cordic_dds48": [(4, 8), (10, 16), (14, 12), (16, 24), (20, 32), (9, 47), (12, 8)],
+                "cordic_dds_scaled": [(4, 8), (10, 16), (14, 12), (16, 24), (20, 32), (12, 8), (26, 17), (9, 21)]}
+    for ent, sets in dds_sets.items():
+        for pw, dw in sets:
+            ph = phases_for(pw, rng)
+            out, lat = V.run_dds(lib, ent, pw, dw, ph)
+            key = f"dds/{ent}/pw{pw}_dw{dw}"
+            arrays[key + "/phases"] = np.array(ph, np.int64)
+            arrays[key + "/sin"] = np.array([o[0] for o in out], np.int64)
+            arrays[key + "/cos"] = np.array([o[1] for o in out], np.int64)
+            cases["dds"].append({"entity": ent, "phase_width": pw, "data_width": dw, "key": key, "dt_val_latency": lat})
+            print(key, "latency", lat, flush=True)
+
+    # ---- the window entities: ENABLE held high, DT_WIN / DT_VLD per clock
+    def window_case(ent, gen, aa, tag):
+        pw, dw = gen["PHI_WIDTH"], gen["DAT_WIDTH"]
+        N = 1 << pw
+        clocks = 2 * N + dw + 24
+        out = V.run_window(lib, ent, gen, aa, clocks)
+        win = np.array([o[0] for o in out], np.int64)
+        vld = [o[1] for o in out]
+        key = f"win/{ent}/pw{pw}_dw{dw}_{tag}"
+        arrays[key + "/aa"] = np.array(aa, np.int64)
+        arrays[key + "/dt_win_per_clock"] = win
+        arrays[key + "/dt_vld_per_clock"] = np.array(vld, np.int8)
+        cases["windows"].append({"entity": ent, "generics": gen, "key": key, "clocks": clocks, "first_dt_vld_clock": vld.index(1)})
+        print(key, "first DT_VLD clock", vld.index(1), flush=True)
+
+    ent_of = {2: "hamming_win", 3: "bh_win_3term", 4: "bh_win_4term", 5: "bh_win_5term", 7: "bh_win_7term"}
+    shapes = {1: [(7, 16), (10, 16), (5, 12)], 2: [(7, 16), (8, 8)], 3: [(8, 16), (6, 24)], 4: [(8, 16)], 5: [(8, 17)], 6: [(8, 17), (10, 17), (6, 31)],
+              7: [(7, 17)], 8: [(8, 24), (7, 32)], 9: [(8, 24), (9, 16)], 10: [(7, 32), (8, 24), (7, 16), (6, 40)],
+              11: [(7, 32)], 12: [(7, 16)], 13: [(7, 24)]}
+    for v, lst in shapes.items():
+        for pw, dw in lst:
+            aa, m = bhw.quantize(v, bhw.RULE_TB, dw)
+            gen = {"PHI_WIDTH": pw, "DAT_WIDTH": dw}
+            if m <= 3:
+                gen["SIN_TYPE"] = "CORDIC"
+            window_case(ent_of[m], gen, [int(a) for a in aa[:m]], f"variant{v}")
+    # port edge cases: negative, most negative, all ones (unsigned reading), zeros
+    for m, pw, dw in ((2, 6, 16), (3, 6, 12), (4, 6, 17), (5, 6, 24), (7, 6, 32), (4, 6, 32), (7, 6, 31)):
+        lo, hi = -(1 << (dw - 1)), (1 << (dw - 1)) - 1
+        gen = {"PHI_WIDTH": pw, "DAT_WIDTH": dw}
+        if m <= 3:
+            gen["SIN_TYPE"] = "CORDIC"
+        for tag, aa in (("hi", [hi] * m), ("lo", [lo] * m), ("mixed", [lo if k & 1 else hi for k in range(m)]),
+                        ("small", [-3, 5, -7, 11, -13, 17, -19][:m]), ("zero", [0] * m)):
+            window_case(ent_of[m], gen, aa, tag)
+    # the selector on top (src/win_selector.vhd:93-199)
+    for wt, m, pw, dw, v in (("HAMMING", 2, 6, 16, 1), ("BH3TERM", 3, 6, 16, 4), ("BH4TERM", 4, 6, 17, 6), ("BH5TERM", 5, 6, 24, 9), ("BH7TERM", 7, 6, 32, 10)):
+        aa, _ = bhw.quantize(v, bhw.RULE_TB, dw)
+        window_case("win_selector", {"PHI_WIDTH": pw, "DAT_WIDTH": dw, "WIN_TYPE": wt, "SIN_TYPE": "CORDIC"}, [int(a) for a in aa[:7]], f"sel_{wt.lower()}")
+
+    # ---- cordic_atan2: one pair per clock, PHI_DT / PHI_VL per clock
+    for iw, aw, prec in ((16, 16, 1), (24, 24, 1), (15, 16, 2), (32, 32, 1), (12, 12, 3), (20, 12, 1), (31, 32, 7)):
+        n = 160
+        lim = 1 << (iw - 1)
+        x = rng.integers(-lim, lim, n)
+        y = rng.integers(-lim, lim, n)
+        x[:8] = [0, lim - 1, -lim, 1, -1, 0, lim - 1, -lim]
+        y[:8] = [0, 0, 0, -1, 1, lim - 1, lim - 1, -lim]
+        out = V.run_atan2(lib, iw, aw, prec, [(int(a), int(b)) for a, b in zip(x, y)])
+        key = f"atan2/iw{iw}_aw{aw}_p{prec}"
+        arrays[key + "/x"] = x.astype(np.int64)
+        arrays[key + "/y"] = y.astype(np.int64)
+        arrays[key + "/phi_dt_per_clock"] = np.array([o[0] for o in out], np.int64)
+        arrays[key + "/phi_vl_per_clock"] = np.array([o[1] for o in out], np.int8)
+        cases["atan2"].append({"input_width": iw, "angle_width": aw, "precision": prec, "key": key})
+        print(key, flush=True)
+
+    np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
+    print("wrote", len(arrays), "arrays")
+
+
+if __name__ == "__main__":
+    main()

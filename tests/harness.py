@@ -45,6 +45,7 @@ def oracle():
     L.orc_apply.argtypes = [D, C.c_int, P(C.c_int32), C.c_uint64, I64P]
     L.orc_atan2.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_int32), P(C.c_int32), P(C.c_int32), C.c_uint64]
     L.orc_atan2_validate.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.orc_atan2_stream.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_int32), P(C.c_int32), P(C.c_int32), C.c_uint64]
     L.orc_cordic_atan2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]
     L.orc_cordic_atan2.restype = C.c_int64
     L.orc_cordic_dds.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, I64P, I64P]
@@ -75,12 +76,14 @@ def orc_window(d: BhwDesc, n0=0, count=None, threads=1) -> np.ndarray:
     return out
 
 
-def orc_atan2(iw: int, aw: int, prec: int, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+def orc_atan2(iw: int, aw: int, prec: int, x: np.ndarray, y: np.ndarray, stream: bool = False) -> np.ndarray:
+    """stream=True: PHI_DT as the entity streams it (pair t with the quadrant of pair t+1, see orc_cordic_atan2_q)."""
     x = np.ascontiguousarray(x, dtype=np.int32)
     y = np.ascontiguousarray(y, dtype=np.int32)
     out = np.empty(x.shape, np.int32)
     p32 = P(C.c_int32)
-    st = oracle().orc_atan2(iw, aw, prec, x.ctypes.data_as(p32), y.ctypes.data_as(p32), out.ctypes.data_as(p32), x.size)
+    fn = oracle().orc_atan2_stream if stream else oracle().orc_atan2
+    st = fn(iw, aw, prec, x.ctypes.data_as(p32), y.ctypes.data_as(p32), out.ctypes.data_as(p32), x.size)
     if st:
         raise ValueError(f"orc_atan2: status {st}")
     return out

@@ -499,13 +499,15 @@ int hc_atan2(const bhw_atan2_desc* d, const int32_t* x, const int32_t* y, int32_
   int st = resolve_atan2(d, &p);
   if (st) return st;
   for (uint64_t j = 0; j < count; j++) {
-    phi[j] = atan2_sample(p, x[j], y[j]);
+    // the quadrant source the kernel picks: the pair itself, or (stream_quadrant) the next pair / zeros after the last
+    const int32_t qx = !p.skew ? x[j] : (j + 1 < count ? x[j + 1] : 0), qy = !p.skew ? y[j] : (j + 1 < count ? y[j + 1] : 0);
+    phi[j] = atan2_sample(p, x[j], y[j], qx, qy);
     if (p.fast32) {   // the stage-unrolled instantiations k_atan2_u uses
       int32_t u = phi[j];
-      if (p.aw == 12) u = atan2_sample32_t<12>(p, x[j], y[j]);
-      else if (p.aw == 16) u = atan2_sample32_t<16>(p, x[j], y[j]);
-      else if (p.aw == 20) u = atan2_sample32_t<20>(p, x[j], y[j]);
-      else if (p.aw == 24) u = atan2_sample32_t<24>(p, x[j], y[j]);
+      if (p.aw == 12) u = atan2_sample32_t<12>(p, x[j], y[j], qx, qy);
+      else if (p.aw == 16) u = atan2_sample32_t<16>(p, x[j], y[j], qx, qy);
+      else if (p.aw == 20) u = atan2_sample32_t<20>(p, x[j], y[j], qx, qy);
+      else if (p.aw == 24) u = atan2_sample32_t<24>(p, x[j], y[j], qx, qy);
       if (u != phi[j]) return -100;
     }
   }

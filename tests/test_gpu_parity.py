@@ -744,6 +744,62 @@ def test_cordic_atan2():
     xh = torch.randint(-(1 << 23), 1 << 23, (n,), generator=g, dtype=torch.int32).numpy()
     yh = torch.randint(-(1 << 23), 1 << 23, (n,), generator=g, dtype=torch.int32).numpy()
     assert np.array_equal(bhw.atan2_host(xh, yh, 24, 24, 2), H.orc_atan2(24, 24, 2, xh, yh))
+    # stream_quadrant=1 (the entity's own pairing, tests/test_rtl_vhdl_sim.py): the look-ahead crosses chunk borders
+    assert np.array_equal(bhw.atan2_host(xh, yh, 24, 24, 2, stream_quadrant=1), H.orc_atan2(24, 24, 2, xh, yh, stream=True))
+    n = (1 << 20) + 77
+    for aw, iw, prec in [(16, 16, 1), (24, 32, 2), (32, 32, 7), (12, 20, 1)]:
+        got = bhw.atan2(x[:n].cuda(), y[:n].cuda(), iw, aw, prec, stream_quadrant=1).cpu().numpy()
+        assert np.array_equal(got, H.orc_atan2(iw, aw, prec, x[:n].numpy(), y[:n].numpy(), stream=True)), (aw, iw, prec)
+    with pytest.raises(bhw.BhwError):
+        bhw.atan2(x.cuda(), y.cuda(), 16, 16, 1, stream_quadrant=2)
+
+
+def test_rtl_golden_vectors_on_gpu():
+    """The CUDA path against what the reference's VHDL entities output when executed (tests/golden/rtl_sim_vectors.npz,
+    made by tests/golden/make_rtl_golden.py through oracle/vhdl_sim.py) - no oracle in between."""
+    import json
+    import torch
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "rtl_sim_vectors.npz"))
+    cases = json.load(open(os.path.join(gold, "rtl_sim_cases.json")))
+    sin_of = {"cordic_dds": bhw.SIN_CORDIC, "cordic_dds48": bhw.SIN_CORDIC48, "cordic_dds_scaled": bhw.SIN_CORDIC_SCALED}
+    for c in cases["dds"]:
+        d = bhw.make_desc(2, c["phase_width"], c["data_width"], sin_type=sin_of[c["entity"]])
+        ph = z[c["key"] + "/phases"]
+        if c["phase_width"] <= 20:
+            s, co = bhw.sincos(d)
+            s, co = s.cpu().numpy().astype(np.int64)[ph], co.cpu().numpy().astype(np.int64)[ph]
+        else:
+            pairs = [bhw.sincos(d, int(p), 1) for p in ph]
+            s = np.array([int(a[0]) for a, _ in pairs], np.int64)
+            co = np.array([int(b[0]) for _, b in pairs], np.int64)
+        assert np.array_equal(s, z[c["key"] + "/sin"]) and np.array_equal(co, z[c["key"] + "/cos"]), c["key"]
+    terms = {"hamming_win": 2, "bh_win_3term": 3, "bh_win_4term": 4, "bh_win_5term": 5, "bh_win_7term": 7,
+             "HAMMING": 2, "BH3TERM": 3, "BH4TERM": 4, "BH5TERM": 5, "BH7TERM": 7}
+    descs, wants = [], []
+    for c in cases["windows"]:
+        g = c["generics"]
+        m = terms[g["WIN_TYPE"] if c["entity"] == "win_selector" else c["entity"]]
+        N = 1 << g["PHI_WIDTH"]
+        vld = z[c["key"] + "/dt_vld_per_clock"].astype(bool)
+        stream = z[c["key"] + "/dt_win_per_clock"][vld][:N]                    # w[1] ... w[N-1], w[0]
+        d = bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], [int(a) for a in z[c["key"] + "/aa"][:m]])
+        for name, dd in both_algos(d):
+            assert np.array_equal(gpu_window(dd), np.roll(stream, 1)), (name, c["key"])
+        assert np.array_equal(gpu_window(d.copy(stream_offset=1)), stream), c["key"]
+        if g["DAT_WIDTH"] <= 32:
+            descs.append(d.copy(stream_offset=1))
+            wants.append(stream)
+    # and all the int32 ones as one plan (group / bank kernels)
+    got = bhw.generate_batch(descs).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, np.concatenate(wants))
+    for c in cases["atan2"]:
+        aw = c["angle_width"]
+        x = torch.from_numpy(z[c["key"] + "/x"].astype(np.int32)).cuda()
+        y = torch.from_numpy(z[c["key"] + "/y"].astype(np.int32)).cuda()
+        want = z[c["key"] + "/phi_dt_per_clock"][aw + 1:aw + 1 + x.numel()]
+        got = bhw.atan2(x, y, c["input_width"], aw, c["precision"], stream_quadrant=1).cpu().numpy().astype(np.int64)
+        assert np.array_equal(got & ((1 << aw) - 1), want & ((1 << aw) - 1)), c["key"]
 
 
 def test_win_selector_and_errors():

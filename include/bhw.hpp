@@ -123,14 +123,17 @@ inline std::vector<int32_t> win_function(char win_type, int nphase, int nwidth, 
   return out;
 }
 
-// entity cordic_atan2 (src/cordic_atan2.vhd:64-78): PHI_DT for every (VEC_DX, VEC_DY) pair, in order
+// entity cordic_atan2 (src/cordic_atan2.vhd:64-78): PHI_DT for every (VEC_DX, VEC_DY) pair, in order.
+// stream_quadrant = true: as the entity streams it (the quadrant of pair t+1 corrects pair t, src/cordic_atan2.vhd:110-205)
 inline std::vector<int32_t> cordic_atan2(int input_width, int angle_width, const std::vector<int32_t>& vec_dx,
-                                         const std::vector<int32_t>& vec_dy, int precision = 1) {
+                                         const std::vector<int32_t>& vec_dy, int precision = 1,
+                                         bool stream_quadrant = false) {
   if (vec_dx.size() != vec_dy.size()) throw error(BHW_E_ARG, "cordic_atan2: VEC_DX and VEC_DY differ in length");
   bhw_atan2_desc d = bhw_atan2_desc();
   d.input_width = input_width;
   d.angle_width = angle_width;
   d.precision = precision;
+  d.stream_quadrant = stream_quadrant ? 1 : 0;
   std::vector<int32_t> phi(vec_dx.size());
   check(bhw_atan2_host(&d, vec_dx.data(), vec_dy.data(), phi.data(), vec_dx.size()), "bhw_atan2_host");
   return phi;

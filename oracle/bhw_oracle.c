@@ -8,8 +8,11 @@
  * restates rather than like an optimised implementation.
  *
  * Parity: HLS and CPP models are pinned against the compiled reference
- * (oracle/_ref); the RTL model is unpinned by the reference (no simulator, no
- * golden files) and anchored by oracle/rtl_bitvec.py + tests/golden KATs.
+ * (oracle/_ref).  The RTL model is pinned by vectors recorded while EXECUTING
+ * the reference's src/*.vhd in oracle/vhdl_sim.py (tests/golden/rtl_sim_vectors.npz,
+ * tests/test_rtl_vhdl_sim.py); for the TAYLOR path that execution relies on our
+ * behavioural model of the third-party DSP48E1/E2 primitives and on libm for
+ * ieee.math_real.  Second anchors: oracle/rtl_bitvec.py + tests/golden KATs.
  */
 #include "bhw_oracle.h"
 

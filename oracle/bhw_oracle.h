@@ -7,11 +7,15 @@
  *
  * Parity status: the HLS-model and CPP-model functions are pinned against the
  * reference's own C++ compiled here (oracle/_ref, see oracle/Makefile).  The
- * RTL-model functions have NO executable reference in this image (no VHDL
- * simulator): they are "parity unpinned" by the reference and are anchored by
- * an independent bit-vector restatement (oracle/rtl_bitvec.py, checked against this
- * file by tests/test_rtl_bitvec.py) and the
- * known-answer hashes in tests/golden/.
+ * RTL-model functions are pinned by golden vectors recorded while executing the
+ * reference's own VHDL in oracle/vhdl_sim.py (a cycle simulator written for
+ * this repo: no ghdl / nvc / vendor simulator exists in the image) - see
+ * tests/golden/make_rtl_golden.py and tests/test_rtl_vhdl_sim.py.  The TAYLOR
+ * entities sit on Xilinx DSP48E1/E2 primitives and ieee.math_real, which the
+ * reference does not carry: those two are modelled (vhdl_sim.Dsp48, libm), so
+ * TAYLOR is pinned "up to the primitive model".  An independent bit-vector
+ * restatement (oracle/rtl_bitvec.py, tests/test_rtl_bitvec.py) and the
+ * known-answer hashes in tests/golden/ remain as second anchors.
  */
 #ifndef BHW_ORACLE_H_
 #define BHW_ORACLE_H_
@@ -38,7 +42,8 @@ int orc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin,
 int orc_quantize(int variant, int rule, int dat_width, int64_t aa_out[7], int32_t* win_type);
 
 /* cordic_atan2 (src/cordic_atan2.vhd): PHI_DT of one (VEC_DX, VEC_DY) pair, sign-extended from
- * ANGLE_WIDTH bits.  RTL-only entity: parity unpinned (see header comment). */
+ * ANGLE_WIDTH bits.  RTL-only entity: pinned by the executed VHDL (see header comment); the entity's own
+ * stream pairs PHI_DT of pair t with the quadrant of pair t+1 - orc_atan2_stream restates that. */
 int orc_atan2_validate(int input_width, int angle_width, int precision);
 int64_t orc_cordic_atan2(int input_width, int angle_width, int precision, int64_t vec_dx, int64_t vec_dy);
 int orc_atan2(int input_width, int angle_width, int precision, const int32_t* x, const int32_t* y, int32_t* phi,

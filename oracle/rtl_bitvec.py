@@ -7,7 +7,8 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product imports this.  It exists becau
 executable reference in this image (no VHDL simulator): oracle/bhw_oracle.c restates the entities
 with integer arithmetic + explicit wraps, this file restates them with bit vectors, and
 tests/test_rtl_bitvec.py requires the two to agree on randomised generics, ports and phases.
-Agreement of two restatements is a regression anchor, not ground truth ("parity unpinned").
+Agreement of two restatements is a regression anchor, not ground truth; since round 2 the ground truth is
+oracle/vhdl_sim.py, which executes the reference's VHDL itself (tests/test_rtl_vhdl_sim.py).
 
 Covered: cordic_dds (src/cordic_dds.vhd:97-249), cordic_dds48 (src/cordic_dds48.vhd:110-259), int_multNxN_dsp48 (src/int_multNxN_dsp48.vhd:105),
 the tails of hamming_win (src/hamming_win.vhd:133-231), bh_win_3term (src/bh_win_3term.vhd:151-306),

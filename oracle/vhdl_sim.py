@@ -22,11 +22,21 @@ What is implemented is what those files need, with the semantics of the packages
   * an assignment whose value length differs from its target's raises - the check a real elaborator does
 Every signal is two-valued here: 'U' / 'X' are not modelled (registers start at 0 instead of 'U'), `after`
 delays are ignored (they are shorter than a clock), processes sensitive to a clock are evaluated on the rising
-edge only (the asynchronous reset of cordic_dds48 / cordic_dds_scaled acts at the next edge).  The UNISIM
-primitives under taylor_sincos / tay1_order are not modelled: TAYLOR stays outside.
+edge only (the asynchronous reset of cordic_dds48 / cordic_dds_scaled acts at the next edge).
+
+The TAYLOR path (src/taylor_sincos.vhd, src/tay1_order.vhd, src/mults/mlt35x2{5,7}_dsp48e{1,2}.vhd) is executed the
+same way, with two additions the reference does not carry itself:
+  * ieee.math_real (MATH_PI, sin, cos, round) and the real -> integer conversion, evaluated in IEEE doubles with the
+    C library's sin / cos and round-half-away-from-zero - what the usual simulators do for the ROM constant functions;
+  * the Xilinx UNISIM primitives DSP48E1 / DSP48E2 (third party, not in the reference tree, no version pinned there):
+    class Dsp48 below is a behavioural model of the configuration these files use - A/B/C/M/P pipeline registers,
+    the X/Y/Z/W multiplexers selected by OPMODE, the four ALUMODE sums, synchronous resets, PCIN/PCOUT cascade with
+    the 17-bit shift - written from the published port semantics (UG479 / UG579).  Any generic or port value outside
+    that configuration raises instead of being guessed.
 """
 from __future__ import annotations
 
+import math
 import os
 import re
 
@@ -63,24 +73,44 @@ class BV:
         return f"BV{self.w}'{self.v:x}"
 
 
+class UBV(BV):
+    """the result of UNSIGNED(x): same bits, read as an unsigned number by conv_integer"""
+    __slots__ = ()
+
+    def signed(self):
+        return self.v
+
+
 class SL(int):
     """std_logic value, '0' or '1'."""
 
 
 class Arr:
-    """constrained array (lo to hi) of anything"""
-    __slots__ = ("lo", "hi", "items")
+    """constrained array of anything; items are stored by ascending index, `down` = declared (hi downto lo)"""
+    __slots__ = ("lo", "hi", "items", "down")
 
-    def __init__(self, lo, hi, items):
-        self.lo, self.hi, self.items = lo, hi, items
+    def __init__(self, lo, hi, items, down=False):
+        self.lo, self.hi, self.items, self.down = lo, hi, items, down
 
     def get(self, i):
         if not self.lo <= i <= self.hi:
             raise IndexError(f"array index {i} outside ({self.lo} to {self.hi})")
         return self.items[i - self.lo]
 
+    def seq(self):
+        """elements left to right"""
+        return list(reversed(self.items)) if self.down else list(self.items)
+
+    def sub(self, a, b):
+        """slice (a downto b) / (b to a) with a >= b"""
+        if a < b:
+            return Arr(b, a, [], self.down)
+        if b < self.lo or a > self.hi:
+            raise IndexError(f"array slice ({a}, {b}) outside ({self.lo} to {self.hi})")
+        return Arr(b, a, self.items[b - self.lo:a - self.lo + 1], self.down)
+
     def copy(self):
-        return Arr(self.lo, self.hi, [x.copy() if isinstance(x, Arr) else x for x in self.items])
+        return Arr(self.lo, self.hi, [x.copy() if isinstance(x, Arr) else x for x in self.items], self.down)
 
 
 def as_bv(x, w=None):
@@ -371,13 +401,14 @@ class Parser:
             self.eat("if")
             cond = self.expr()
             self.eat("generate")
+            decls = self.generate_decls()
             body = self.concurrent_statements(("end",))
             self.eat("end")
             self.eat("generate")
             if self.peek()[0] == "id":
                 self.ident()
             self.eat(";")
-            return ("ifgen", label, cond, body)
+            return ("ifgen", label, cond, body, decls)
         if self.at("for"):
             self.eat("for")
             var = self.ident()
@@ -388,18 +419,23 @@ class Parser:
                 self.eat("downto")
             b = self.expr()
             self.eat("generate")
+            decls = self.generate_decls()
             body = self.concurrent_statements(("end",))
             self.eat("end")
             self.eat("generate")
             if self.peek()[0] == "id":
                 self.ident()
             self.eat(";")
-            return ("forgen", label, var, a, b, down, body)
-        if self.at("entity"):
-            self.eat("entity")
-            self.eat("work")
-            self.eat(".")
-            ent = self.ident()
+            return ("forgen", label, var, a, b, down, body, decls)
+        component = label is not None and self.peek()[0] == "id" and (self.at("generic", 1) or self.at("port", 1))
+        if self.at("entity") or component:
+            if component:                         # label: DSP48E2 generic map (...) port map (...);
+                ent = self.ident()
+            else:
+                self.eat("entity")
+                self.eat("work")
+                self.eat(".")
+                ent = self.ident()
             gmap, pmap = [], []
             if self.opt("generic"):
                 self.eat("map")
@@ -428,6 +464,13 @@ class Parser:
             break
         self.eat(";")
         return ("cassign", label, target, waves)
+
+    def generate_decls(self):
+        """optional declarative part of a generate statement: [declarations] begin"""
+        decls = self.declarations()
+        if decls or self.at("begin"):
+            self.eat("begin")
+        return decls
 
     def assoc_list(self):
         self.eat("(")
@@ -740,7 +783,7 @@ class Instance:
             lo, hi = self.ev(t[1], scope), self.ev(t[2], scope)
             if t[3]:
                 lo, hi = hi, lo
-            return ("array", lo, hi, self.resolve_type(t[4], scope))
+            return ("array", lo, hi, self.resolve_type(t[4], scope), bool(t[3]))
         name = t[1]
         if name in ("std_logic", "std_ulogic", "bit"):
             return ("sl",)
@@ -759,9 +802,11 @@ class Instance:
         if typ[0] == "sl":
             return SL(0)
         if typ[0] == "array":
-            return Arr(typ[1], typ[2], [self.default(typ[3]) for _ in range(typ[1], typ[2] + 1)])
+            return Arr(typ[1], typ[2], [self.default(typ[3]) for _ in range(typ[1], typ[2] + 1)], typ[4])
         if typ[0] == "int":
             return 0
+        if typ[0] == "real":
+            return 0.0
         return None
 
     def check_type(self, sig, typ, what):
@@ -797,16 +842,16 @@ class Instance:
             return val
         if typ[0] == "array":
             n = typ[2] - typ[1] + 1
+            down = typ[4]
             if isinstance(val, tuple) and val[0] == "others":
-                return Arr(typ[1], typ[2], [self.conform(val[1], typ[3], what) for _ in range(n)])
+                return Arr(typ[1], typ[2], [self.conform(val[1], typ[3], what) for _ in range(n)], down)
+            if isinstance(val, Arr):
+                val = ("positional", val.seq())                      # arrays are assigned left to right
             if isinstance(val, tuple) and val[0] == "positional":
                 if len(val[1]) != n:
                     raise ValueError(f"{self.path}: {what}: {len(val[1])} elements for an array of {n}")
-                return Arr(typ[1], typ[2], [self.conform(x, typ[3], what) for x in val[1]])
-            if isinstance(val, Arr):
-                if val.hi - val.lo + 1 != n:
-                    raise ValueError(f"{self.path}: {what}: array length mismatch")
-                return Arr(typ[1], typ[2], [self.conform(x, typ[3], what) for x in val.items])
+                items = [self.conform(x, typ[3], what) for x in val[1]]
+                return Arr(typ[1], typ[2], list(reversed(items)) if down else items, down)
             raise TypeError(f"{self.path}: {what}: {val!r} is not an array")
         if typ[0] == "int":
             if isinstance(val, (BV, SL)) and not isinstance(val, bool):
@@ -845,13 +890,16 @@ class Instance:
                 (self.clocked if clocked else self.comb).append(("cassign", st[2], st[3], scope))
             elif k == "ifgen":
                 if self.truth(self.ev(st[2], scope)):
-                    self.elab_stmts(st[3], scope)
+                    s2 = Scope(scope)
+                    self.declare(st[4], s2)
+                    self.elab_stmts(st[3], s2)
             elif k == "forgen":
                 a, b = self.ev(st[3], scope), self.ev(st[4], scope)
                 rng = range(a, b - 1, -1) if st[5] else range(a, b + 1)
                 for i in rng:
                     s2 = Scope(scope)
                     s2.d[st[2]] = i
+                    self.declare(st[7], s2)
                     self.elab_stmts(st[6], s2)
             elif k == "inst":
                 self.instantiate(st, scope)
@@ -861,21 +909,33 @@ class Instance:
     def instantiate(self, st, scope):
         _, label, ent, gmap, pmap = st
         gens = {f: self.ev(a, scope) for f, a in gmap}
-        child_ent = self.lib.units[ent]["entity"]
-        modes = {p["name"]: p["mode"] for p in child_ent["ports"]}
-        port_sigs, drives = {}, []
+        prim = PRIMITIVES.get(ent)
+        if prim is not None:
+            modes = {n: m for n, (m, _) in prim.PORTS.items()}
+        elif ent in self.lib.units:
+            modes = {p["name"]: p["mode"] for p in self.lib.units[ent]["entity"]["ports"]}
+        else:
+            raise NameError(f"{self.path}: no entity or primitive {ent!r}")
+        port_sigs, drives, taps = {}, [], []
         for formal, actual in pmap:
             if actual is None:
                 continue
-            if actual[0] == "name" and isinstance(scope.get(actual[1]), Sig):
+            if formal not in modes:
+                raise NameError(f"{self.path}: {ent} has no port {formal!r}")
+            if actual[0] == "name" and scope.has(actual[1]) and isinstance(scope.get(actual[1]), Sig):
                 port_sigs[formal] = scope.get(actual[1])          # the port IS the actual signal
             elif modes[formal] == "in":
                 drives.append((formal, actual))                     # an expression drives an input port
+            elif actual[0] == "slice":
+                taps.append((formal, actual))                       # an output port drives a slice of a signal
             else:
                 raise NotImplementedError(f"{self.path}: output port {formal} mapped to an expression")
-        child = Instance(self.lib, ent, gens, port_sigs, self.path + "/" + (label or ent))
+        path = self.path + "/" + (label or ent)
+        child = prim(self, gens, port_sigs, path) if prim is not None else Instance(self.lib, ent, gens, port_sigs, path)
         for formal, actual in drives:
             self.comb.append(("drive", child.ports[formal], actual, scope))
+        for formal, actual in taps:
+            self.comb.append(("tap", child.ports[formal], actual, scope))
         self.children.append(child)
 
     # ---- expression evaluation
@@ -909,11 +969,14 @@ class Instance:
             if isinstance(base, BV):
                 return {"left": base.left, "right": base.right, "high": base.left, "low": base.right, "length": base.w}[a]
             if isinstance(base, Arr):
-                return {"left": base.lo, "right": base.hi, "high": base.hi, "low": base.lo, "length": base.hi - base.lo + 1}[a]
+                return {"left": base.hi if base.down else base.lo, "right": base.lo if base.down else base.hi,
+                        "high": base.hi, "low": base.lo, "length": base.hi - base.lo + 1}[a]
             raise TypeError(f"attribute {a} of {base!r}")
         if k == "slice":
             base = self.ev(e[1], scope)
             hi, lo = self.ev(e[2], scope), self.ev(e[3], scope)
+            if isinstance(base, Arr):
+                return base.sub(hi, lo)
             return as_bv(base).slice(hi, lo)
         if k == "call":
             return self.call(e, scope)
@@ -941,6 +1004,8 @@ class Instance:
     def builtin_name(self, name):
         if name in ("true", "false"):
             return name == "true"
+        if name == "math_pi":
+            return math.pi
         raise NameError(f"{self.path}: unknown name {name!r}")
 
     def call(self, e, scope):
@@ -957,8 +1022,29 @@ class Instance:
                 return self.index(base, self.ev(args[0], scope))
             if nm == "rising_edge":
                 return True                      # statements that mention it are evaluated on the rising edge only
-            if nm in ("signed", "unsigned", "std_logic_vector"):
-                return as_bv(self.ev(args[0], scope))
+            if nm == "unsigned":
+                b = as_bv(self.ev(args[0], scope))
+                return UBV(b.w, b.v, b.left, b.right)
+            if nm in ("signed", "std_logic_vector"):
+                b = as_bv(self.ev(args[0], scope))
+                return BV(b.w, b.v, b.left, b.right)
+            if nm == "conv_signed":
+                return BV(self.ev(args[1], scope), int(self.ev(args[0], scope)))
+            if nm == "sxt":                                   # std_logic_arith: sign-extend to n bits
+                b, n = as_bv(self.ev(args[0], scope)), self.ev(args[1], scope)
+                if n < b.w:
+                    raise ValueError("SXT to fewer bits")
+                return BV(n, b.signed())
+            if nm == "real":
+                return float(self.as_int(self.ev(args[0], scope)))
+            if nm == "integer":                               # real -> integer rounds to nearest, halves away from zero
+                v = self.ev(args[0], scope)
+                return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1) if isinstance(v, float) else int(v)
+            if nm == "round":
+                v = self.ev(args[0], scope)
+                return float(math.floor(abs(v) + 0.5)) * (1.0 if v >= 0 else -1.0)
+            if nm in ("sin", "cos"):
+                return getattr(math, nm)(self.ev(args[0], scope))
             if nm == "conv_std_logic_vector":
                 return BV(self.ev(args[1], scope), int(self.as_int(self.ev(args[0], scope))))
             if nm in ("conv_integer", "to_integer"):
@@ -1006,6 +1092,8 @@ class Instance:
                 return a + b if op == "+" else a - b
             return int(a) + int(b) if op == "+" else int(a) - int(b)
         if op == "&":
+            if isinstance(a, Arr) or isinstance(b, Arr):
+                return ("positional", (a.seq() if isinstance(a, Arr) else [a]) + (b.seq() if isinstance(b, Arr) else [b]))
             x, y = as_bv(a), as_bv(b)
             return BV(x.w + y.w, (x.v << y.w) | y.v)
         if op == "*":
@@ -1140,7 +1228,7 @@ def store(cur, path, v):
     p = path[0]
     if p[0] == "index":
         if isinstance(cur, Arr):
-            new = Arr(cur.lo, cur.hi, list(cur.items))
+            new = Arr(cur.lo, cur.hi, list(cur.items), cur.down)
             new.items[p[1] - cur.lo] = store(cur.get(p[1]), path[1:], v)
             return new
         if isinstance(cur, BV):
@@ -1213,6 +1301,11 @@ class Simulator:
         elif blk[0] == "drive":
             _, sig, actual, scope = blk
             pending.append((sig, [], inst.conform(inst.ev(actual, scope), sig.typ, "port drive")))
+        elif blk[0] == "tap":
+            _, sig, target, scope = blk
+            inst.assign(target, sig.val, scope, pending)
+        elif blk[0] == "prim":
+            blk[1].clock(pending)
 
     def commit(self, pending):
         changed = False
@@ -1245,16 +1338,160 @@ class Simulator:
         self.settle()
 
 
+# --------------------------------------------------------------------------------------------- primitives
+
+
+class Dsp48:
+    """Behavioural DSP48E1 / DSP48E2 (Xilinx UNISIM; absent from the reference tree) for the configuration
+    src/tay1_order.vhd and src/mults/*.vhd instantiate: USE_MULT = MULTIPLY, direct A / B inputs, no pre-adder,
+    AREG = BREG in {1, 2}, CREG = MREG = PREG = 1, registered OPMODE / ALUMODE, all clock enables '1', synchronous
+    resets.  Per rising edge (all right-hand sides are the values before the edge):
+        A2 <= A (AREG = 1) | A1 (AREG = 2);  A1 <= A;  likewise B;  C' <= C
+        M  <= signed(A2[AW-1:0]) * signed(B2[17:0])            AW = 25 (E1) / 27 (E2)
+        P  <= alu(X, Y, Z, W)                                    48 bits, wrapping
+    X = OPMODE[1:0]: 00 -> 0, 01 -> M (with Y = 01), 10 -> P;   Y = OPMODE[3:2]: 00 -> 0, 01 -> M, 11 -> C
+    Z = OPMODE[6:4]: 000 -> 0, 001 -> PCIN, 010 -> P, 011 -> C, 101 -> PCIN >> 17 (arithmetic), 110 -> P >> 17
+    W = OPMODE[8:7] (E2 only): 00 -> 0, 01 -> P, 11 -> C
+    ALUMODE 0000: Z + W + X + Y;  0011: Z - (W + X + Y);  0001: -Z + (W + X + Y) - 1;  0010: -(Z + W + X + Y) - 1
+    PCOUT = P.  Anything else raises."""
+    AW = 25
+    OPW = 7
+    DW = 25
+    _IN = dict(a=30, b=18, c=48, pcin=48, acin=30, bcin=18, alumode=4, carryinsel=3, inmode=5,
+               carryin=None, carrycascin=None, multsignin=None, clk=None)
+    _CE = ("cea1", "cea2", "cead", "cealumode", "ceb1", "ceb2", "cec", "cecarryin", "cectrl", "ced", "ceinmode", "cem", "cep")
+    _RST = ("rsta", "rstallcarryin", "rstalumode", "rstb", "rstc", "rstctrl", "rstd", "rstinmode", "rstm", "rstp")
+    _OUT = dict(p=48, pcout=48, acout=30, bcout=18)
+    _GEN_OK = dict(a_input="DIRECT", b_input="DIRECT", use_dport=False, use_mult="MULTIPLY", use_simd="ONE48",
+                   amultsel="A", bmultsel="B", preaddinsel="A", creg=1, mreg=1, preg=1, opmodereg=1, alumodereg=1,
+                   carryinreg=1, carryinselreg=1, inmodereg=1, acascreg=None, bcascreg=None, adreg=None, dreg=None)
+
+    @classmethod
+    def ports_table(cls):
+        t = {n: ("in", w) for n, w in cls._IN.items()}
+        t["d"] = ("in", cls.DW)
+        t["opmode"] = ("in", cls.OPW)
+        t.update({n: ("in", None) for n in cls._CE + cls._RST})
+        t.update({n: ("out", w) for n, w in cls._OUT.items()})
+        return t
+
+    def __init__(self, parent, generics, port_sigs, path):
+        self.path = path
+        g = {k.lower(): v for k, v in generics.items()}
+        for k, v in g.items():
+            if k in ("areg", "breg"):
+                if v not in (1, 2):
+                    raise NotImplementedError(f"{path}: {k} = {v}")
+            elif k not in self._GEN_OK:
+                raise NotImplementedError(f"{path}: generic {k} is not modelled")
+            elif self._GEN_OK[k] is not None and v != self._GEN_OK[k]:
+                raise NotImplementedError(f"{path}: {k} = {v!r} is not modelled")
+        self.areg, self.breg = g.get("areg", 1), g.get("breg", 1)
+        self.ports = {}
+        for name, (mode, w) in self.PORTS.items():
+            typ = ("sl",) if w is None else ("slv", w - 1, 0)
+            sig = port_sigs.get(name)
+            if sig is None:
+                sig = Sig(path + "." + name, typ, SL(1 if name in self._CE else 0) if w is None else BV(w, 0))
+            else:
+                have = sig.val.w if isinstance(sig.val, BV) else None
+                if have != w:
+                    raise TypeError(f"{path}: port {name} is {w} bits, actual {sig.name} is {have}")
+            sig_typ = typ
+            self.ports[name] = sig
+            if sig.typ is None:
+                sig.typ = sig_typ
+        self.comb, self.clocked, self.children = [], [("prim", self)], []
+        self.a1 = self.a2 = self.b1 = self.b2 = self.c = self.m = 0
+        self.opmode = self.alumode = 0
+
+    def all_instances(self):
+        return [self]
+
+    # the Simulator calls these two through run_block / conform on port drives
+    def conform(self, val, typ, what="value"):
+        raise NotImplementedError
+
+    def _in(self, name, signed=True):
+        v = self.ports[name].val
+        if isinstance(v, BV):
+            return v.signed() if signed else v.v
+        return int(v)
+
+    @staticmethod
+    def _sx(v, w):
+        v &= (1 << w) - 1
+        return v - (1 << w) if v >> (w - 1) else v
+
+    def clock(self, pending):
+        for n in self._CE:
+            if self._in(n) != 1:
+                raise NotImplementedError(f"{self.path}: clock enable {n} is not '1'")
+        for n in ("carryin", "carrycascin", "multsignin", "carryinsel", "inmode"):
+            if self._in(n, False) != 0:
+                raise NotImplementedError(f"{self.path}: {n} /= 0")
+        rst = {n: self._in(n) for n in self._RST}
+        p_old = self.ports["p"].val.signed()
+        op, alu = self.opmode, self.alumode
+        x, y, z, w = op & 3, (op >> 2) & 3, (op >> 4) & 7, (op >> 7) & 3
+        if (x == 1) != (y == 1):
+            raise NotImplementedError(f"{self.path}: OPMODE {op:b}: X and Y must select M together")
+        pcin = self._in("pcin")
+        xv = {0: 0, 1: self.m, 2: p_old}.get(x)
+        yv = {0: 0, 1: 0, 3: self.c}.get(y)
+        zv = {0: 0, 1: pcin, 2: p_old, 3: self.c, 5: pcin >> 17, 6: p_old >> 17}.get(z)
+        wv = {0: 0, 1: p_old, 3: self.c}.get(w)
+        if None in (xv, yv, zv, wv):
+            raise NotImplementedError(f"{self.path}: OPMODE {op:b} selects an input that is not modelled")
+        s = wv + xv + yv
+        if alu == 0:
+            p_new = zv + s
+        elif alu == 3:
+            p_new = zv - s
+        elif alu == 1:
+            p_new = -zv + s - 1
+        elif alu == 2:
+            p_new = -(zv + s) - 1
+        else:
+            raise NotImplementedError(f"{self.path}: ALUMODE {alu:b}")
+        a_in, b_in = self._in("a", False), self._in("b", False)
+        m_new = self._sx(self.a2, self.AW) * self._sx(self.b2, 18)
+        a2_new = a_in if self.areg == 1 else self.a1
+        b2_new = b_in if self.breg == 1 else self.b1
+        self.a1, self.b1 = (0 if rst["rsta"] else a_in), (0 if rst["rstb"] else b_in)
+        self.a2, self.b2 = (0 if rst["rsta"] else a2_new), (0 if rst["rstb"] else b2_new)
+        self.c = 0 if rst["rstc"] else self._in("c")
+        self.m = 0 if rst["rstm"] else m_new
+        self.opmode = 0 if rst["rstctrl"] else self._in("opmode", False)
+        self.alumode = 0 if rst["rstalumode"] else self._in("alumode", False)
+        p_bv = BV(48, 0 if rst["rstp"] else p_new)
+        pending.append((self.ports["p"], [], p_bv))
+        pending.append((self.ports["pcout"], [], BV(48, p_bv.v)))
+
+
+class Dsp48E1(Dsp48):
+    AW, OPW, DW = 25, 7, 25
+
+
+class Dsp48E2(Dsp48):
+    AW, OPW, DW = 27, 9, 27
+
+
+Dsp48E1.PORTS = Dsp48E1.ports_table()
+Dsp48E2.PORTS = Dsp48E2.ports_table()
+PRIMITIVES = {"dsp48e1": Dsp48E1, "dsp48e2": Dsp48E2}
+
+
 # --------------------------------------------------------------------------------------------- drivers
 
 REF_SRC = "/root/reference/src"
 RTL_FILES = ("cordic_dds.vhd", "cordic_dds48.vhd", "cordic_dds_scaled.vhd", "cordic_atan2.vhd", "int_multNxN_dsp48.vhd",
-             "hamming_win.vhd", "bh_win_3term.vhd", "bh_win_4term.vhd", "bh_win_5term.vhd", "bh_win_7term.vhd", "win_selector.vhd")
+             "hamming_win.vhd", "bh_win_3term.vhd", "bh_win_4term.vhd", "bh_win_5term.vhd", "bh_win_7term.vhd", "win_selector.vhd",
+             "taylor_sincos.vhd", "tay1_order.vhd", "mults/mlt35x25_dsp48e1.vhd", "mults/mlt35x27_dsp48e2.vhd")
 
 
 def reference_library(src=REF_SRC, files=RTL_FILES):
-    """The reference's RTL, parsed where it lies (taylor_sincos / tay1_order / mults are left out: hamming_win and
-    bh_win_3term only reach them through `if (SIN_TYPE = "TAYLOR") generate`, which is not elaborated for CORDIC)."""
+    """The reference's RTL, parsed where it lies."""
     return Library([os.path.join(src, f) for f in files])
 
 
@@ -1312,4 +1549,35 @@ def run_atan2(lib, input_width, angle_width, precision, pairs):
         else:
             sim.step(reset=0, vec_en=0, vec_dx=0, vec_dy=0)
         out.append((sim.get("phi_dt"), sim.get("phi_vl")))
+    return out
+
+
+def run_taylor(lib, phase_width, data_width, lut_size, xseries, clocks, start=0):
+    """Clock taylor_sincos with PHI_ENA high (its phase counter is internal): -> per-clock list of (OUT_SIN, OUT_COS).
+    start: value deposited into the phase counter `cnt` after reset (a simulator `force -deposit`), so that a long
+    period can be entered anywhere without clocking up to it."""
+    sim = Simulator(lib, "taylor_sincos", {"PHASE_WIDTH": phase_width, "DATA_WIDTH": data_width, "LUT_SIZE": lut_size, "XSERIES": xseries})
+    for _ in range(4):
+        sim.step(rst=1, phi_ena=0)
+    if start:
+        cnt = sim.top.scope.get("cnt")
+        cnt.val = BV(phase_width, start, cnt.val.left, cnt.val.right)
+        sim.settle()
+    out = []
+    for _ in range(clocks):
+        sim.step(rst=0, phi_ena=1)
+        out.append((sim.get("out_sin"), sim.get("out_cos")))
+    return out
+
+
+def run_mult(lib, dtw, pairs):
+    """Clock int_multNxN_dsp48 with one (DAT_A, DAT_B) per clock: -> per-clock DAT_Q (signed)."""
+    sim = Simulator(lib, "int_multNxN_dsp48", {"DTW": dtw})
+    for _ in range(2):
+        sim.step(rst=1, dat_a=0, dat_b=0)
+    out = []
+    for t in range(len(pairs) + 4):
+        a, b = pairs[t] if t < len(pairs) else (0, 0)
+        sim.step(rst=0, dat_a=a, dat_b=b)
+        out.append(sim.get("dat_q"))
     return out

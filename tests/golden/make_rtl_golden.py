@@ -106,6 +106,51 @@ def main():
         cases["atan2"].append({"input_width": iw, "angle_width": aw, "precision": prec, "key": key})
         print(key, flush=True)
 
+    # ---- taylor_sincos (src/taylor_sincos.vhd + tay1_order.vhd + mults/*.vhd, DSP48 primitives modelled by
+    #      vhdl_sim.Dsp48): PHI_ENA held high, OUT_SIN / OUT_COS per clock; `start` = deposited phase counter
+    cases["taylor"] = []
+    for pw, dw, lut, xs, start, clocks in (
+            (10, 16, 5, "ULTRA", 0, 1100), (10, 12, 5, "7SERIES", 0, 1100), (11, 18, 9, "ULTRA", 0, 2100), (10, 16, 9, "ULTRA", 0, 1100),
+            (9, 16, 9, "ULTRA", 0, 600), (8, 8, 4, "ULTRA", 0, 300), (12, 16, 7, "ULTRA", 0, 4200), (12, 24, 6, "ULTRA", 0, 4200),
+            (11, 24, 6, "7SERIES", 0, 2100), (11, 32, 5, "ULTRA", 0, 2100), (10, 19, 5, "ULTRA", 0, 1100), (10, 18, 5, "7SERIES", 0, 1100),
+            (14, 16, 9, "ULTRA", 0, 700), (14, 16, 9, "ULTRA", (1 << 12) - 300, 700), (14, 24, 9, "ULTRA", (1 << 13) - 300, 700),
+            (20, 24, 9, "ULTRA", 3 * (1 << 18) - 300, 700), (24, 16, 10, "ULTRA", (1 << 24) - 300, 700), (16, 17, 9, "7SERIES", (1 << 15) - 200, 500),
+            (26, 16, 11, "ULTRA", (1 << 24) - 200, 500), (13, 32, 8, "ULTRA", (1 << 11) - 200, 500)):
+        out = V.run_taylor(lib, pw, dw, lut, xs, clocks, start)
+        key = f"taylor/pw{pw}_dw{dw}_lut{lut}_{xs.lower()}_s{start}"
+        arrays[key + "/sin_per_clock"] = np.array([o[0] for o in out], np.int64)
+        arrays[key + "/cos_per_clock"] = np.array([o[1] for o in out], np.int64)
+        cases["taylor"].append({"phase_width": pw, "data_width": dw, "lut_size": lut, "xseries": xs, "start": start, "clocks": clocks, "key": key})
+        print(key, flush=True)
+
+    # ---- the window entities with SIN_TYPE = "TAYLOR"
+    for ent, v, pw, dw, lut, xs in (("hamming_win", 1, 10, 16, 5, "ULTRA"), ("hamming_win", 1, 8, 16, 9, "ULTRA"), ("hamming_win", 2, 10, 24, 5, "ULTRA"),
+                                    ("hamming_win", 1, 11, 32, 6, "7SERIES"), ("hamming_win", 12, 9, 12, 5, "7SERIES"), ("bh_win_3term", 3, 10, 16, 5, "ULTRA"),
+                                    ("bh_win_3term", 4, 10, 24, 5, "7SERIES"), ("bh_win_3term", 3, 11, 12, 6, "ULTRA"), ("bh_win_3term", 4, 9, 32, 4, "ULTRA"),
+                                    ("bh_win_3term", 3, 7, 16, 9, "ULTRA")):
+        aa, m = bhw.quantize(v, bhw.RULE_TB, dw)
+        window_case(ent, {"PHI_WIDTH": pw, "DAT_WIDTH": dw, "SIN_TYPE": "TAYLOR", "LUT_SIZE": lut, "XSERIES": xs}, [int(a) for a in aa[:m]], f"taylor_lut{lut}_{xs.lower()}_variant{v}")
+    for wt, m, pw, dw, v, lut in (("HAMMING", 2, 9, 16, 1, 5), ("BH3TERM", 3, 9, 16, 4, 4)):
+        aa, _ = bhw.quantize(v, bhw.RULE_TB, dw)
+        window_case("win_selector", {"PHI_WIDTH": pw, "DAT_WIDTH": dw, "WIN_TYPE": wt, "SIN_TYPE": "TAYLOR", "LUT_SIZE": lut, "XSERIES": "ULTRA"},
+                    [int(a) for a in aa[:7]], f"sel_{wt.lower()}_taylor_lut{lut}")
+
+    # ---- int_multNxN_dsp48: DAT_Q per clock
+    cases["mult"] = []
+    for dtw in (8, 16, 17, 24, 32):
+        lim = 1 << (dtw - 1)
+        a = rng.integers(-lim, lim, 64)
+        b = rng.integers(-lim, lim, 64)
+        a[:6] = [lim - 1, -lim, -lim, 0, -1, lim - 1]
+        b[:6] = [lim - 1, -lim, lim - 1, -lim, -1, -1]
+        q = V.run_mult(lib, dtw, [(int(x), int(y)) for x, y in zip(a, b)])
+        key = f"mult/dtw{dtw}"
+        arrays[key + "/a"] = a.astype(np.int64)
+        arrays[key + "/b"] = b.astype(np.int64)
+        arrays[key + "/q_per_clock"] = np.array(q, np.int64)
+        cases["mult"].append({"dtw": dtw, "key": key})
+        print(key, flush=True)
+
     np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
     json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
     print("wrote", len(arrays), "arrays")

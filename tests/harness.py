@@ -243,3 +243,43 @@ def sha_lines(values) -> str:
 def sha_pairs(s, c) -> str:
     """sha256 of 's c\\n' lines (cpp/cordic_sincos.cpp:138 output format)."""
     return hashlib.sha256("".join(f"{int(a)} {int(b)}\n" for a, b in zip(s, c)).encode()).hexdigest()
+
+
+# ---- tests/golden/rtl_sim_cases.json helpers (vectors made by executing the reference VHDL, oracle/vhdl_sim.py)
+_RTL_TERMS = {"hamming_win": 2, "bh_win_3term": 3, "bh_win_4term": 4, "bh_win_5term": 5, "bh_win_7term": 7,
+              "HAMMING": 2, "BH3TERM": 3, "BH4TERM": 4, "BH5TERM": 5, "BH7TERM": 7}
+
+
+def rtl_case_terms(case) -> int:
+    return _RTL_TERMS[case["generics"]["WIN_TYPE"] if case["entity"] == "win_selector" else case["entity"]]
+
+
+def rtl_case_is_taylor(case) -> bool:
+    return case["generics"].get("SIN_TYPE", "CORDIC") == "TAYLOR" and rtl_case_terms(case) <= 3
+
+
+def rtl_case_desc(case, aa, stream_offset=0) -> BhwDesc:
+    """The descriptor that names what a simulated window entity was elaborated with."""
+    import blackman_harris_win_b200 as bhw
+    g, m = case["generics"], rtl_case_terms(case)
+    tay = rtl_case_is_taylor(case)
+    return bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], [int(a) for a in aa[:m]], stream_offset=stream_offset,
+                         sin_type=bhw.SIN_TAYLOR if tay else bhw.SIN_CORDIC, lut_size=g["LUT_SIZE"] if tay else 0)
+
+
+def rtl_case_first_vld(case) -> int:
+    """Clock index (ENABLE raised at clock 0) of the first DT_VLD = the entity's ADD_DELAY + 1
+    (src/hamming_win.vhd find_delay, src/bh_win_3term.vhd:120-140, +1 / +2 in the 4/5- and 7-term entities)."""
+    g, m = case["generics"], rtl_case_terms(case)
+    if rtl_case_is_taylor(case):
+        if g["PHI_WIDTH"] - g["LUT_SIZE"] <= 2:
+            return 11
+        return 14 if g["DAT_WIDTH"] < 19 else 17
+    return g["DAT_WIDTH"] + {2: 8, 3: 8, 4: 9, 5: 9, 7: 10}[m]
+
+
+def rtl_taylor_latency(pw: int, dw: int, lut: int) -> int:
+    """Clocks from the phase counter value to OUT_SIN / OUT_COS (src/taylor_sincos.vhd:170-215)."""
+    if pw - lut <= 2:
+        return 3
+    return 6 if dw < 19 else 9

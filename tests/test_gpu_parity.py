@@ -774,16 +774,29 @@ def test_rtl_golden_vectors_on_gpu():
             s = np.array([int(a[0]) for a, _ in pairs], np.int64)
             co = np.array([int(b[0]) for _, b in pairs], np.int64)
         assert np.array_equal(s, z[c["key"] + "/sin"]) and np.array_equal(co, z[c["key"] + "/cos"]), c["key"]
-    terms = {"hamming_win": 2, "bh_win_3term": 3, "bh_win_4term": 4, "bh_win_5term": 5, "bh_win_7term": 7,
-             "HAMMING": 2, "BH3TERM": 3, "BH4TERM": 4, "BH5TERM": 5, "BH7TERM": 7}
+    for c in cases["taylor"]:
+        pw, dw, lut = c["phase_width"], c["data_width"], c["lut_size"]
+        N, L = 1 << pw, H.rtl_taylor_latency(pw, dw, lut)
+        d = bhw.make_desc(2, pw, dw, sin_type=bhw.SIN_TAYLOR, lut_size=lut)
+        n = c["clocks"] - L
+        if N <= 4096:
+            s, co = bhw.sincos(d)
+            idx = (c["start"] + np.arange(n)) % N
+            s, co = s.cpu().numpy().astype(np.int64)[idx], co.cpu().numpy().astype(np.int64)[idx]
+        else:
+            first = min(n, N - c["start"])                                      # may run across the end of the period
+            parts = [bhw.sincos(d, c["start"], first)] + ([bhw.sincos(d, 0, n - first)] if first < n else [])
+            s = np.concatenate([p[0].cpu().numpy().astype(np.int64) for p in parts])
+            co = np.concatenate([p[1].cpu().numpy().astype(np.int64) for p in parts])
+        assert np.array_equal(s, z[c["key"] + "/sin_per_clock"][L:]), c["key"]
+        assert np.array_equal(co, z[c["key"] + "/cos_per_clock"][L:]), c["key"]
     descs, wants = [], []
     for c in cases["windows"]:
         g = c["generics"]
-        m = terms[g["WIN_TYPE"] if c["entity"] == "win_selector" else c["entity"]]
         N = 1 << g["PHI_WIDTH"]
         vld = z[c["key"] + "/dt_vld_per_clock"].astype(bool)
         stream = z[c["key"] + "/dt_win_per_clock"][vld][:N]                    # w[1] ... w[N-1], w[0]
-        d = bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], [int(a) for a in z[c["key"] + "/aa"][:m]])
+        d = H.rtl_case_desc(c, z[c["key"] + "/aa"])
         for name, dd in both_algos(d):
             assert np.array_equal(gpu_window(dd), np.roll(stream, 1)), (name, c["key"])
         assert np.array_equal(gpu_window(d.copy(stream_offset=1)), stream), c["key"]

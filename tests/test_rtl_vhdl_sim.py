@@ -27,10 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 REF_SRC = "/root/reference/src"
 SIN_OF = {"cordic_dds": bhw.SIN_CORDIC, "cordic_dds48": bhw.SIN_CORDIC48, "cordic_dds_scaled": bhw.SIN_CORDIC_SCALED}
-TERMS_OF = {"hamming_win": 2, "bh_win_3term": 3, "bh_win_4term": 4, "bh_win_5term": 5, "bh_win_7term": 7}
-SEL_TERMS = {"HAMMING": 2, "BH3TERM": 3, "BH4TERM": 4, "BH5TERM": 5, "BH7TERM": 7}
-# clock index (ENABLE raised at clock 0) of the first DT_VLD, minus DAT_WIDTH, per term count
-VLD_AFTER = {2: 8, 3: 8, 4: 9, 5: 9, 7: 10}
+ENTITIES = {"hamming_win", "bh_win_3term", "bh_win_4term", "bh_win_5term", "bh_win_7term", "win_selector"}
 
 
 @pytest.fixture(scope="module")
@@ -40,16 +37,8 @@ def gold():
     return z, cases
 
 
-def window_terms(case):
-    if case["entity"] == "win_selector":
-        return SEL_TERMS[case["generics"]["WIN_TYPE"]]
-    return TERMS_OF[case["entity"]]
-
-
-def window_desc(case, aa, stream_offset=0):
-    g = case["generics"]
-    m = window_terms(case)
-    return bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], [int(a) for a in aa[:m]], stream_offset=stream_offset)
+window_terms = H.rtl_case_terms
+window_desc = H.rtl_case_desc
 
 
 def valid_stream(z, case):
@@ -61,10 +50,12 @@ def valid_stream(z, case):
 
 def test_case_inventory(gold):
     z, cases = gold
-    assert len(cases["dds"]) == 27 and len(cases["windows"]) == 64 and len(cases["atan2"]) == 7
+    assert len(cases["dds"]) == 27 and len(cases["windows"]) == 76 and len(cases["atan2"]) == 7
+    assert len(cases["taylor"]) == 20 and len(cases["mult"]) == 5
     assert {c["entity"] for c in cases["dds"]} == set(SIN_OF)
-    assert {c["entity"] for c in cases["windows"]} == set(TERMS_OF) | {"win_selector"}
-    for grp in ("dds", "windows", "atan2"):
+    assert {c["entity"] for c in cases["windows"]} == ENTITIES
+    assert sum(H.rtl_case_is_taylor(c) for c in cases["windows"]) == 12
+    for grp in ("dds", "windows", "atan2", "taylor", "mult"):
         for c in cases[grp]:
             assert any(f.startswith(c["key"] + "/") for f in z.files), c["key"]
 
@@ -120,7 +111,7 @@ def test_oracle_windows_match_rtl_stream(gold):
         assert np.array_equal(H.orc_window(window_desc(c, aa, stream_offset=1)), stream[:N]), c["key"]
         first = c["first_dt_vld_clock"]
         assert vld[first:].all() and not vld[:first].any(), c["key"]          # one gap-free burst
-        assert first == c["generics"]["DAT_WIDTH"] + VLD_AFTER[window_terms(c)], c["key"]
+        assert first == H.rtl_case_first_vld(c), c["key"]
 
 
 def test_hostcheck_windows_match_rtl(gold):
@@ -140,6 +131,10 @@ def test_hostcheck_windows_match_rtl(gold):
         st = hc.hc_table(C.byref(d), 0, N, got.ctypes.data_as(H.I64P), 0)
         # 1 = the planner keeps this window on the generic tail (wide DAT_WIDTH, extreme coefficients): no TABLE body
         assert st in (0, 1) and (st == 0 or "variant" not in c["key"] or c["generics"]["DAT_WIDTH"] > 32), c["key"]
+        if H.rtl_case_is_taylor(c):
+            st = hc.hc_direct_taylor(C.byref(d), 0, N, got.ctypes.data_as(H.I64P))   # 1: no fast TAYLOR body (wide)
+            assert st == (0 if c["generics"]["DAT_WIDTH"] <= 24 else st) and st in (0, 1), c["key"]
+            assert st or np.array_equal(got, want), ("direct_taylor", c["key"])
         n_table += st == 0
         assert st or np.array_equal(got, want), ("table", c["key"])
     assert n_table >= 40
@@ -153,11 +148,66 @@ def test_selector_equals_entity(gold):
         m = window_terms(sel)
         g = sel["generics"]
         aa = z[sel["key"] + "/aa"]
-        w = H.orc_window(bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], [int(a) for a in aa[:m]]))
+        w = H.orc_window(window_desc(sel, aa))
         stream, _ = valid_stream(z, sel)
         assert np.array_equal(stream[:len(w)], np.roll(w, -1)), sel["key"]
-        assert sel["first_dt_vld_clock"] == g["DAT_WIDTH"] + VLD_AFTER[m]
+        assert sel["first_dt_vld_clock"] == H.rtl_case_first_vld(sel)
     assert by_key  # the plain entities are in the same file
+
+
+def taylor_expect(c, fn):
+    """(sin, cos) the oracle / product gives for the clocks a taylor case recorded, and the slice of clocks they cover."""
+    pw, dw, lut = c["phase_width"], c["data_width"], c["lut_size"]
+    N, L = 1 << pw, H.rtl_taylor_latency(pw, dw, lut)
+    d = bhw.make_desc(2, pw, dw, sin_type=bhw.SIN_TAYLOR, lut_size=lut)
+    n = c["clocks"] - L
+    if N <= 4096:
+        s, co = fn(d, 0, N)
+        idx = (c["start"] + np.arange(n)) % N
+        return s[idx], co[idx], L
+    first = min(n, N - c["start"])                       # a case may run across the end of the period
+    s, co = fn(d, c["start"], first)
+    if first < n:
+        s2, co2 = fn(d, 0, n - first)
+        s, co = np.concatenate([s, s2]), np.concatenate([co, co2])
+    return s, co, L
+
+
+def test_oracle_taylor_sincos_matches_rtl(gold):
+    """taylor_sincos executed (ROM from math_real, tay1_order, the DSP48E1/E2 cascades under mults/): OUT_SIN / OUT_COS
+    appear 3 (ROM only), 6 (DATA_WIDTH < 19) or 9 clocks after the phase counter value, both XSERIES give the same
+    numbers, and orc_sincos(SIN_TAYLOR) equals them over whole periods and across every quadrant border."""
+    z, cases = gold
+    seen = set()
+    for c in cases["taylor"]:
+        s, co, L = taylor_expect(c, H.orc_sincos)
+        assert np.array_equal(z[c["key"] + "/sin_per_clock"][L:], s), c["key"]
+        assert np.array_equal(z[c["key"] + "/cos_per_clock"][L:], co), c["key"]
+        seen.add((L, c["xseries"]))
+    assert seen == {(3, "ULTRA"), (6, "ULTRA"), (9, "ULTRA"), (6, "7SERIES"), (9, "7SERIES")}
+
+
+def test_hostcheck_taylor_sincos_matches_rtl(gold):
+    z, cases = gold
+    hc = H.hostcheck()
+
+    def body(d, n0, n):
+        s, co = np.empty(n, np.int64), np.empty(n, np.int64)
+        assert hc.hc_sincos(C.byref(d), n0, n, s.ctypes.data_as(H.I64P), co.ctypes.data_as(H.I64P)) == 0
+        return s, co
+    for c in cases["taylor"]:
+        s, co, L = taylor_expect(c, body)
+        assert np.array_equal(z[c["key"] + "/sin_per_clock"][L:], s), c["key"]
+        assert np.array_equal(z[c["key"] + "/cos_per_clock"][L:], co), c["key"]
+
+
+def test_multiplier_entity(gold):
+    """int_multNxN_dsp48 (src/int_multNxN_dsp48.vhd:88-104): DAT_Q = A * B, full 2*DTW bits, two clocks later - the
+    product bhw_apply's EXACT mode returns and whose slice [2*DTW-2 : DTW-2] the window entities round."""
+    z, cases = gold
+    for c in cases["mult"]:
+        a, b, q = z[c["key"] + "/a"], z[c["key"] + "/b"], z[c["key"] + "/q_per_clock"]
+        assert np.array_equal(q[1:1 + len(a)], a * b), c["key"]
 
 
 def atan2_views(z, c):

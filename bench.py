@@ -449,6 +449,17 @@ def config_lines(bhw, peak_gbs, int_peak, scratch):
                             "gsamples_per_s": round(total / bms / 1e6, 1), "frac_hbm": round(4 * total / bms / 1e6 / peak_gbs, 4),
                             "frac_int_issue": round(ops * total / (bms * 1e-3) / int_peak, 4) if int_peak else None,
                             "tables": "rebuilt every step", "kernel_ms": {k: round(v[1] / 4, 5) for k, v in kt.items() if v[0]}}
+            if d.dat_width <= 16:
+                # the same bank in the optional int16 container (BHW_OUT_INT16): 2 algorithmic bytes per sample
+                plan = bhw.Plan([x.copy(out_format=bhw.OUT_INT16) for x in descs])
+                o16 = scratch.view(torch.int16)[:total]
+                bhw.set_table_cache(False)
+                pms = _time_loop(lambda: plan.execute(out=o16), 20)
+                bhw.set_table_cache(True)
+                plan.destroy()
+                line["bank_int16"] = {"windows": nbank, "bytes": 2 * total, "ms_per_step": round(pms, 5),
+                                      "gsamples_per_s": round(total / pms / 1e6, 1), "frac_hbm": round(2 * total / pms / 1e6 / peak_gbs, 4),
+                                      "note": "group kernel with int16 stores; the int32 bank above goes through the bank kernel"}
         out.append(line)
     return out
 
@@ -614,6 +625,48 @@ def run_cuda(args):
                "d2h_box_gbs_note": "plain pinned cudaMemcpy of this rank's slice, all ranks at once: the link ceiling of this box",
                "h2d_bytes_per_step": _meta_bytes(touched), "d2h_bytes_per_step": count * 4,
                "api": "bhw_generate_batch_host (descriptors in host memory, pinned host output, planning inside the timed region)"}
+        # the same request with the optional int16 container (bhw_desc.out_format = BHW_OUT_INT16) for the windows
+        # whose DAT_WIDTH fits it - in the sweep's variant-major order they are a prefix of every rank's slice:
+        # one packed call for that prefix, one int32 call for the rest.  Reported beside e2e, not instead of it.
+        n16 = 0
+        while n16 < touched and mine[n16].dat_width <= 16:
+            n16 += 1
+        pre = sum(1 << mine[i].phi_width for i in range(n16)) - local if n16 else 0
+        c16 = max_over_ranks(float(min(count, max(pre, 0))))          # every rank joins, even with nothing to pack
+        if c16 > 0:
+            c16 = int(min(count, max(pre, 0)))
+            packed = bhw.desc_array([bhw.BhwDesc.from_buffer_copy(bytes(mine[i])).copy(out_format=bhw.OUT_INT16) for i in range(n16)]) if n16 else None
+            rest = bhw.desc_array([mine[i] for i in range(n16, touched)]) if touched > n16 else None
+            h16 = torch.empty(max(c16, 1), dtype=torch.int16, pin_memory=True)
+            h32 = torch.empty(max(count - c16, 1), dtype=torch.int32, pin_memory=True)
+
+            def step_packed():
+                if c16:
+                    st = L.bhw_generate_batch_host(packed, n16, local, c16, h16.data_ptr())
+                    if st:
+                        raise bhw.BhwError(st, "bhw_generate_batch_host (int16)")
+                if count - c16:
+                    st = L.bhw_generate_batch_host(rest, touched - n16, 0 if n16 else local, count - c16, h32.data_ptr())
+                    if st:
+                        raise bhw.BhwError(st, "bhw_generate_batch_host")
+
+            step_packed()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                step_packed()
+            barrier()
+            p_s = max_over_ranks(time.perf_counter() - t0)
+            if c16 and not torch.equal(h16[:c16].to(torch.int32), host[:c16]):
+                raise SystemExit("bench.py: packed host output differs from the int32 host output")
+            if count - c16 and not torch.equal(h32[:count - c16], host[c16:count]):
+                raise SystemExit("bench.py: int32 remainder of the packed request differs")
+            e2e["packed16"] = {"value": total * args.e2e_steps / p_s / 1e9, "unit": UNIT,
+                               "d2h_bytes_per_step": c16 * 2 + (count - c16) * 4,
+                               "int16_samples": c16, "int32_samples": count - c16,
+                               "api": "bhw_generate_batch_host twice per step: out_format BHW_OUT_INT16 for the DAT_WIDTH <= 16 windows "
+                                      "(variants 1-4), int32 for the rest; same integers, checked against the int32 result"}
+            del h16, h32
         del host
 
     # ---- roofline of the dominant kernel class -------------------------------------------------------------

@@ -12,7 +12,7 @@ Reference interfaces mirrored (paths relative to the reference checkout):
   * ``cordic_atan2`` generics/ports          src/cordic_atan2.vhd:64-78   -> :func:`atan2`
 """
 from .api import (  # noqa: F401
-    ALGO_AUTO, ALGO_DIRECT, ALGO_TABLE, MODEL_CPP, MODEL_HLS, MODEL_RTL, RULE_HLS, RULE_TB,
+    ALGO_AUTO, ALGO_DIRECT, ALGO_TABLE, OUT_DEFAULT, OUT_INT16, MODEL_CPP, MODEL_HLS, MODEL_RTL, RULE_HLS, RULE_TB,
     SIN_CORDIC, SIN_CORDIC48, SIN_CORDIC_SCALED, SIN_TAYLOR, VARIANT_NAMES, BhwAtan2Desc, BhwDesc, BhwError, Plan,
     WinSelector, atan2, atan2_host, batch_total, cache_clear, desc_array, elem_bytes, generate, generate_batch,
     generate_batch_host, generate_host, launch_count, lib, lib_path, make_desc, quantize,

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SIN_CORDIC, SIN_TAYLOR, SIN_CORDIC48, SIN_CORDIC_SCALED = 0, 1, 2, 3
 MODEL_RTL, MODEL_HLS, MODEL_CPP = 0, 1, 2
 ALGO_AUTO, ALGO_DIRECT, ALGO_TABLE = 0, 1, 2
+OUT_DEFAULT, OUT_INT16 = 0, 1
 RULE_TB, RULE_HLS = 0, 1
 MAX_TERMS = 7
 VARIANT_NAMES = {
@@ -46,7 +47,7 @@ class BhwDesc(C.Structure):
         ("win_type", C.c_int32), ("sin_type", C.c_int32), ("model", C.c_int32),
         ("phi_width", C.c_int32), ("dat_width", C.c_int32), ("precision", C.c_int32),
         ("lut_size", C.c_int32), ("stream_offset", C.c_int32), ("algo", C.c_int32),
-        ("reserved", C.c_int32), ("aa", C.c_int64 * MAX_TERMS),
+        ("out_format", C.c_int32), ("aa", C.c_int64 * MAX_TERMS),
     ]
 
     def copy(self, **changes) -> "BhwDesc":
@@ -61,9 +62,10 @@ class BhwDesc(C.Structure):
 
     def __repr__(self):
         return ("BhwDesc(win_type=%d, sin_type=%d, model=%d, phi_width=%d, dat_width=%d, precision=%d, "
-                "lut_size=%d, stream_offset=%d, algo=%d, aa=%s)" % (
+                "lut_size=%d, stream_offset=%d, algo=%d%s, aa=%s)" % (
                     self.win_type, self.sin_type, self.model, self.phi_width, self.dat_width,
                     self.precision, self.lut_size, self.stream_offset, self.algo,
+                    ", out_format=%d" % self.out_format if self.out_format else "",
                     list(self.aa)[: max(self.win_type, 1)]))
 
 
@@ -161,11 +163,11 @@ def strerror(status: int) -> str:
 # ---- descriptors -----------------------------------------------------------------------------
 def make_desc(win_type: int, phi_width: int, dat_width: int, aa: Sequence[int] = (), *,
               sin_type: int = SIN_CORDIC, model: int = MODEL_RTL, precision: int = 0,
-              lut_size: int = 0, stream_offset: int = 0, algo: int = ALGO_AUTO) -> BhwDesc:
+              lut_size: int = 0, stream_offset: int = 0, algo: int = ALGO_AUTO, out_format: int = 0) -> BhwDesc:
     d = BhwDesc()
     d.win_type, d.sin_type, d.model = int(win_type), int(sin_type), int(model)
     d.phi_width, d.dat_width, d.precision = int(phi_width), int(dat_width), int(precision)
-    d.lut_size, d.stream_offset, d.algo, d.reserved = int(lut_size), int(stream_offset), int(algo), 0
+    d.lut_size, d.stream_offset, d.algo, d.out_format = int(lut_size), int(stream_offset), int(algo), int(out_format)
     for i, v in enumerate(aa):
         d.aa[i] = int(v)
     return d
@@ -243,11 +245,11 @@ def _torch():
 
 
 def _np_dtype(esz: int):
-    return np.int64 if esz == 8 else np.int32
+    return {8: np.int64, 4: np.int32, 2: np.int16}[esz]
 
 
 def _dev_out(torch, esz, count, out, device):
-    dt = torch.int64 if esz == 8 else torch.int32
+    dt = {8: torch.int64, 4: torch.int32, 2: torch.int16}[esz]
     if out is None:
         out = torch.empty(count, dtype=dt, device=device if device is not None else "cuda")
     else:

@@ -175,6 +175,7 @@ struct bhw_plan {
   int dev = 0;
   int nwin = 0;
   bool elem64 = false;
+  bool pack16 = false;   // BHW_OUT_INT16: int16 output through k_synth<short> / k_synth_group<.., 3>, no bank runs
   bool transient = false;        // one-shot plan: device memory comes from / returns to the stream pool
   uint64_t total = 0;            // flat samples of the whole batch
   // DAT_WIDTH <= 32: table + synthesis path
@@ -305,6 +306,7 @@ static cudaError_t plan_alloc(bhw_plan& plan, void** p, size_t bytes, cudaStream
 
 static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
   plan.runs.clear();
+  if (plan.pack16) return;   // the bank kernel stores int32 only: packed plans use the group and general kernels
   uint64_t off = 0;
   for (int w = 0; w < plan.nwin; w++) {
     const uint32_t ri = plan.win_rec[(size_t)w];
@@ -372,13 +374,13 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
 // into a long window through the direct body instead of building a table for it.
 static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t hint_begin,
                       uint64_t hint_count, cudaStream_t stream) {
-  int st = current_device(&plan.dev);
+  size_t esz_ = 4;
+  int st = batch_elem_bytes(descs, nwin, &esz_);   // before anything touches a device: the error is the caller's
   if (st) return st;
+  if ((st = current_device(&plan.dev))) return st;
   plan.nwin = nwin;
-  bool any64 = false, any32 = false;
-  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
-  if (any64 && any32) return BHW_E_ELEM;
-  plan.elem64 = any64;
+  plan.elem64 = esz_ == 8;
+  plan.pack16 = esz_ == 2;
   plan.flat_off.resize((size_t)nwin + 1);
   uint64_t off = 0;
   for (int w = 0; w < nwin; w++) {
@@ -414,7 +416,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   for (int w = 0; w < nwin;) {
     int e = w + 1;
     while (e < nwin && same_shape(descs[w], descs[e])) e++;
-    if (e - w >= 2 && ((uint64_t)(e - w) << descs[w].phi_width) >= (1ull << 17))
+    if (!plan.pack16 && e - w >= 2 && ((uint64_t)(e - w) << descs[w].phi_width) >= (1ull << 17))
       for (int i = w; i < e; i++) banked[(size_t)i] = 1;
     w = e;
   }
@@ -855,6 +857,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   a.rom = plan.rom;
   a.nwin = plan.nwin;
   a.uniform_pw = plan.uniform_pw;
+  a.pack16 = plan.pack16 ? 1u : 0u;
   // whole windows of bank runs go to the bank kernel, everything in between to the general one
   const uint64_t flat_end = flat_begin + flat_count;
   size_t runs_hit = 0;
@@ -938,10 +941,10 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       uint64_t bytes = 0;
       if (n == 1) {
         a.npieces = 0;
-        a.out = (int32_t*)out_dev + (pieces[i].b - flat_begin);
+        a.out = (char*)out_dev + (pieces[i].b - flat_begin) * (plan.pack16 ? 2 : 4);
         a.flat_begin = pieces[i].b;
         a.flat_count = pieces[i].e - pieces[i].b;
-        bytes = a.flat_count * 4;
+        bytes = a.flat_count * (plan.pack16 ? 2 : 4);
       } else {
         a.npieces = (uint32_t)n;
         a.out = out_dev;
@@ -954,7 +957,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
           a.piece_end[j] = pieces[i + j].e;
           a.piece_tile0[j] = tiles;
           tiles += (uint32_t)((pieces[i + j].e - pieces[i + j].b + 127) / 128);
-          bytes += (pieces[i + j].e - pieces[i + j].b) * 4;
+          bytes += (pieces[i + j].e - pieces[i + j].b) * (plan.pack16 ? 2 : 4);
         }
         a.piece_tile0[n] = tiles;
       }
@@ -1093,7 +1096,9 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
       memset(&ga, 0, sizeof(ga));
       ga.sh = gr.sh;
       ga.recs = a.recs;
-      ga.out = (int32_t*)out_dev - flat_begin;                  // GroupWin::out_off is a flat index of the batch
+      ga.out = plan.pack16 ? (int32_t*)((int16_t*)out_dev - flat_begin)   // GroupWin::out_off is a flat index of the batch
+                           : (int32_t*)out_dev - flat_begin;
+      ga.pack16 = plan.pack16 ? 1u : 0u;
       if (pass == 0) {
         if (gk.i1 == gk.i0) continue;
         ga.wins = (const GroupWin*)(plan.blob_dev + gr.o_list) + gk.i0;
@@ -1193,12 +1198,12 @@ static int run_batch(const bhw_desc* descs, int nwin, uint64_t flat_begin, uint6
     int st = validate_desc(&descs[w], true);
     if (st) return st;
   }
-  bool any64 = false, any32 = false;
-  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
-  if (any64 && any32) return BHW_E_ELEM;
+  size_t esz = 4;
+  int st = batch_elem_bytes(descs, nwin, &esz);
+  if (st) return st;
   int first = 0, touched = 0;
   uint64_t local = 0;
-  int st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
+  st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
   if (st) return st;
   if (!touched) return BHW_OK;
   // a one-shot call uploads its records from a stack-lifetime buffer: it cannot be recorded into a
@@ -1257,13 +1262,12 @@ static int run_batch_host(const bhw_desc* descs, int nwin, uint64_t flat_begin, 
     int st = validate_desc(&descs[w], true);
     if (st) return st;
   }
-  bool any64 = false, any32 = false;
-  for (int i = 0; i < nwin; i++) (descs[i].dat_width > 32 ? any64 : any32) = true;
-  if (any64 && any32) return BHW_E_ELEM;
-  const size_t esz = any64 ? 8 : 4;
+  size_t esz = 4;
+  int st = batch_elem_bytes(descs, nwin, &esz);
+  if (st) return st;
   int first = 0, touched = 0;
   uint64_t local = 0;
-  int st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
+  st = shard_windows(descs, nwin, flat_begin, flat_count, &first, &touched, &local);
   if (st) return st;
   if (!touched) return BHW_OK;
   int dev;
@@ -1354,6 +1358,7 @@ static int run_direct(const bhw_desc* d, uint64_t n0, uint64_t count, void* out_
     // whole window: evaluate the units once per sample pair (n, n + N/2)
     at.pair = (n0 == 0 && count == N && N >= 8 && at.p.unit[0].pw == d->phi_width &&
                (at.p.m == 2 || at.p.unit[1].pw == d->phi_width - 1)) ? 1u : 0u;
+    if (at.pair && direct_taylor_quad_ok(at.p, d->phi_width)) at.pair = 2u;
     LaunchTimer tm(BHW_KERNEL_DIRECT, stream);
     e = launch_direct_taylor(at, (int32_t*)out_dev, stream);
   } else if (fast32) {
@@ -1406,6 +1411,7 @@ int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, 
   const uint64_t N = 1ull << d->phi_width;
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
   if (!out_dev && count) return BHW_E_NULL;
+  if (d->out_format == BHW_OUT_INT16) return run_batch(d, 1, n0, count, out_dev, (cudaStream_t)stream);  // plan kernels only
   if (d->dat_width > 32 || d->algo == BHW_ALGO_DIRECT) return run_direct(d, n0, count, out_dev, (cudaStream_t)stream);
   if (d->algo == BHW_ALGO_AUTO && auto_prefers_direct(d, n0, count)) {
     st = run_direct(d, n0, count, out_dev, (cudaStream_t)stream, true);
@@ -1417,7 +1423,7 @@ int bhw_generate(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, 
 int bhw_generate_repeat(const bhw_desc* d, void* out_dev, uint64_t n0, uint64_t count, int reps, uint64_t out_stride,
                         uint64_t out_slots, void* stream) {
   if (reps < 0) return BHW_E_ARG;
-  const size_t esz = d && d->dat_width > 32 ? 8 : 4;
+  const size_t esz = (size_t)bhw_elem_bytes(d);
   for (int i = 0; i < reps; i++) {
     char* o = (char*)out_dev + (out_slots ? ((uint64_t)i % out_slots) * out_stride * esz : 0);
     int st = bhw_generate(d, o, n0, count, stream);
@@ -1431,6 +1437,7 @@ int bhw_apply(const bhw_desc* d, int mode, const int32_t* x_dev, void* y_dev, ui
   int st = validate_desc(d, true);
   if (st) return st;
   if (d->dat_width > 32) return BHW_E_DAT_WIDTH;      // the multiplier ports are DAT_WIDTH bits, held in int32 here
+  if (d->out_format != BHW_OUT_DEFAULT) return BHW_E_ARG;   // the products have their own containers
   if (mode != BHW_APPLY_EXACT && mode != BHW_APPLY_ROUNDED) return BHW_E_ARG;
   if (!frames) return BHW_OK;
   if (!x_dev || !y_dev) return BHW_E_NULL;
@@ -1474,8 +1481,8 @@ int bhw_generate_host(const bhw_desc* d, void* out_host, uint64_t n0, uint64_t c
   if (!out_host && count) return BHW_E_NULL;
   // a short request (one staging chunk) that bhw_generate would send to a register-resident
   // direct kernel: one launch + one copy instead of planning, table build and two launches
-  if (count && d->dat_width <= 32 && d->algo == BHW_ALGO_AUTO && count * 4 <= kHostChunkBytes &&
-      auto_prefers_direct(d, n0, count)) {
+  if (count && d->dat_width <= 32 && d->out_format == BHW_OUT_DEFAULT && d->algo == BHW_ALGO_AUTO &&
+      count * 4 <= kHostChunkBytes && auto_prefers_direct(d, n0, count)) {
     int dev;
     if ((st = current_device(&dev))) return st;
     DeviceState& ds = g_dev[dev];

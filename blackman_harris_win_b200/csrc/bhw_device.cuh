@@ -997,6 +997,74 @@ BHW_HD void direct_taylor_pair(const DirectTayParams& p, const I2* __restrict__ 
   wb = (int32_t)(Sb << p.lsh) >> p.rsh;
 }
 
+// Sixteen samples from two ROM words: four consecutive samples n0 .. n0+3 of the first quarter window
+// (n0 a multiple of 4, stream offset 0) and their partners a quarter, a half and three quarters of a window
+// later, TAY_WIDE datapath.  What is shared:
+//   * the four samples address one ROM word per unit (its counter bits below the ROM address are >= 2 wide)
+//     and sit in one quadrant, so the word, the quadrant mux and the product rounding constants are loaded
+//     once and pi*acnt advances by `pi` per sample (0 <= pi*acnt < 2^20: the 24-bit ROM word never wraps);
+//   * a quarter window later the first unit's quadrant advances by one: cos = vc, -vs, -vc, vs
+//     (src/taylor_sincos.vhd:237-255); TAY_WIDE values lie in [0, 2^(dw-1)-1] so the DW-bit negation is plain;
+//   * the product of a negated value is taken from the same 64-bit product with the other rounding addend:
+//     b(-P) = -hi32(P + rcn), rcn = 2^32 - 1 - rc (BankShape comment);
+//   * the second unit of bh_win_3term counts PHI_WIDTH-1 bits (src/bh_win_3term.vhd:221-233): a quarter
+//     window is half its period, so its value alternates v, -v, v, -v over the four partners.
+// w[r][e] = sample n0 + e + r*N/4.  Same integers as direct_taylor_sample (tests/hostcheck).
+BHW_HD void taylor_wide4(const TayUnit& u, int dw, const I2* __restrict__ rom, uint32_t t0, int32_t* vs, int32_t* vc) {
+  const I2 w = rom[t0 >> u.ashift];
+  const int32_t c0 = w.x, s0 = w.y;
+  const int32_t sat = (int32_t)((1u << (dw - 1)) - 1u);
+  const int xs = u.xs;
+  int32_t mpi = u.pi * (int32_t)(t0 & ((1u << u.cbits) - 1u));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int32_t m1 = (int32_t)(((int64_t)s0 * (int64_t)mpi) >> xs);               // src/tay1_order.vhd:585
+    const int32_t m2 = (int32_t)(((int64_t)c0 * (int64_t)mpi) >> xs);               // :586
+    const uint32_t cp = (uint32_t)(c0 - m1), sp = (uint32_t)s0 + (uint32_t)m2;      // :595-596
+    vc[e] = (int32_t)(cp < (uint32_t)sat ? cp : (uint32_t)sat);                     // negative (huge unsigned) -> max positive
+    vs[e] = (int32_t)(sp < (uint32_t)sat ? sp : (uint32_t)sat);
+    mpi += u.pi;
+  }
+}
+
+BHW_HD void direct_taylor_quad4(const DirectTayParams& p, const I2* __restrict__ rom, uint32_t n0, int32_t (*w)[4]) {
+  const int64_t rc = (int64_t)(uint64_t)p.rc, rcn = (int64_t)(uint64_t)(0xFFFFFFFFu - p.rc);
+  uint32_t S[4][4];
+  {
+    int32_t vs[4], vc[4];
+    taylor_wide4(p.unit[0], p.dw, rom, n0, vs, vc);                                // n0 < N/4: quadrant 0, low bits = n0
+    const int64_t A1 = p.A[1];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t Pc = A1 * (int64_t)(int32_t)((uint32_t)vc[e] << p.tshift);
+      const int64_t Ps = A1 * (int64_t)(int32_t)((uint32_t)vs[e] << p.tshift);
+      S[0][e] = (uint32_t)p.S0 - (uint32_t)((Pc + rc) >> 32);                      // - b( vc)
+      S[1][e] = (uint32_t)p.S0 + (uint32_t)((Ps + rcn) >> 32);                     // - b(-vs)
+      S[2][e] = (uint32_t)p.S0 + (uint32_t)((Pc + rcn) >> 32);                     // - b(-vc)
+      S[3][e] = (uint32_t)p.S0 - (uint32_t)((Ps + rc) >> 32);                      // - b( vs)
+    }
+  }
+  if (p.m > 2) {
+    const TayUnit& u = p.unit[1];
+    const uint32_t q1 = n0 >> (u.pw - 2);                                          // 0 or 1: n0 < N/4 = half its period
+    int32_t vs[4], vc[4];
+    taylor_wide4(u, p.dw, rom, n0 & ((1u << (u.pw - 2)) - 1u), vs, vc);
+    const int64_t A2 = p.A[2];
+    const int64_t r_even = q1 ? rcn : rc, r_odd = q1 ? rc : rcn;                   // quadrant 1: cos = -vs
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t P = A2 * (int64_t)(int32_t)((uint32_t)(q1 ? vs[e] : vc[e]) << p.tshift);
+      const uint32_t he = (uint32_t)((P + r_even) >> 32), ho = (uint32_t)((P + r_odd) >> 32);
+      const uint32_t be = q1 ? 0u - he : he, bo = q1 ? ho : 0u - ho;              // b(cos) at even / odd partners
+      S[0][e] += be; S[1][e] += bo; S[2][e] += be; S[3][e] += bo;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[r][e] = (int32_t)(S[r][e] << p.lsh) >> p.rsh;
+}
+
 // ============================================================================================
 // cordic_atan2 (src/cordic_atan2.vhd:80-220)
 // ============================================================================================

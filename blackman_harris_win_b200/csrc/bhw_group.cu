@@ -34,6 +34,16 @@ __device__ __forceinline__ void group_epilogue(const GroupArgs& a, int32_t* o, s
     }
     return;
   }
+  if (APPLY == 3) {
+    // packed output (BHW_OUT_INT16, DAT_WIDTH <= 16): `o` already points at the window's first int16 element
+    short* ot = reinterpret_cast<short*>(o) + idx;
+#pragma unroll
+    for (int j = 0; j < kBankJ; ++j) {
+      __stcs(ot + 32 * j, (short)va[j]);
+      if (PAIR) __stcs(ot + half + 32 * j, (short)vb[j]);
+    }
+    return;
+  }
   const int dw = (int)a.apply_dw;
   const int xsh = 32 - dw;
   for (uint64_t f = 0; f < a.frames; ++f) {
@@ -123,7 +133,7 @@ k_synth_group(const __grid_constant__ GroupArgs a) {
     for (int k = 1; k < M; ++k) A[k] = __ldg(&r->A[k]);
     const int32_t S0 = __ldg(&r->S0);
     const uint32_t n_first = __ldg(&r->n_first);
-    int32_t* o = a.out + gw->out_off;
+    int32_t* o = APPLY == 3 ? reinterpret_cast<int32_t*>(reinterpret_cast<short*>(a.out) + gw->out_off) : a.out + gw->out_off;
     const size_t half = (size_t)1 << (pw - 1);
     const uint32_t L = spread_steps(U, G);
     const uint32_t i0 = (uint32_t)((uint64_t)L * blockIdx.x / gridDim.x);
@@ -163,7 +173,7 @@ k_synth_group(const __grid_constant__ GroupArgs a) {
       w_next = gw[1].unit_begin;
       pw = gw->pw;
       tile_first = gw->tile_first;
-      o = a.out + gw->out_off;
+      o = APPLY == 3 ? reinterpret_cast<int32_t*>(reinterpret_cast<short*>(a.out) + gw->out_off) : a.out + gw->out_off;
       const WinRec* r = a.recs + gw->rec;
       A[0] = 0;
 #pragma unroll
@@ -211,6 +221,8 @@ static cudaError_t launch_group_tab(const GroupArgs& a, bool pair, int apply, un
                                     bool pdl) {
   if (apply == 1) return pair ? launch_group_t<M, TAB, true, 1>(a, grid, smem, stream, pdl) : cudaErrorInvalidValue;
   if (apply == 2) return pair ? launch_group_t<M, TAB, true, 2>(a, grid, smem, stream, pdl) : cudaErrorInvalidValue;
+  if (apply == 3) return pair ? launch_group_t<M, TAB, true, 3>(a, grid, smem, stream, pdl)
+                              : launch_group_t<M, TAB, false, 3>(a, grid, smem, stream, pdl);
   return pair ? launch_group_t<M, TAB, true, 0>(a, grid, smem, stream, pdl)
               : launch_group_t<M, TAB, false, 0>(a, grid, smem, stream, pdl);
 }
@@ -224,8 +236,8 @@ static cudaError_t launch_group_m(const GroupArgs& a, int tab, bool pair, int ap
 }
 
 cudaError_t launch_synth_group(const GroupArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
-  const int apply = a.x ? (int)a.apply_mode : 0;
-  if (apply && (!a.y || !a.frames || apply > 2)) return cudaErrorInvalidValue;
+  const int apply = a.x ? (int)a.apply_mode : a.pack16 ? 3 : 0;
+  if (a.x && (!a.y || !a.frames || apply > 2 || a.pack16)) return cudaErrorInvalidValue;
   if (!a.nunits || !a.nwin) return cudaSuccess;
   if (a.spread && (tab != G_GLOBAL || a.nwin != 1 || a.unit_base || a.spread > (uint32_t)kGroupWarps)) return cudaErrorInvalidValue;
   const uint64_t ctas = a.spread ? ((uint64_t)a.nunits + a.spread - 1) / a.spread

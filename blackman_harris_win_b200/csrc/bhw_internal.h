@@ -95,6 +95,7 @@ struct WinParams {
 
 // Host-side resolution (bhw_resolve.cpp).  All return a bhw_status.
 int validate_desc(const bhw_desc* d, bool for_window);
+int batch_elem_bytes(const bhw_desc* descs, int nwin, size_t* esz);   // one container per batch, else BHW_E_ELEM
 int resolve_source(const bhw_desc* d, int unit, SrcParams* out);     // unit: 0, or 1 = 2nd Taylor unit
 int resolve_window(const bhw_desc* d, WinParams* wp, SrcParams src[2]);
 TabLookup table_lookup_for(const SrcParams& sp);

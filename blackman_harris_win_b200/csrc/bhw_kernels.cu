@@ -70,18 +70,19 @@ constexpr int kSynthThreads = 256;
 constexpr int kSynthWarps = kSynthThreads / 32;
 constexpr int kTile = 128;  // samples per warp tile: 4 per lane, lane-interleaved
 
-template <int M>
-__device__ __forceinline__ void synth_tile(const WinRec& r, uint32_t n, int32_t* __restrict__ out,
+// OutT = int32_t, or short for the packed output (BHW_OUT_INT16)
+template <int M, typename OutT>
+__device__ __forceinline__ void synth_tile(const WinRec& r, uint32_t n, OutT* __restrict__ out,
                                            uint32_t valid) {
   // lane owns samples n, n+32, n+64, n+96 of the tile; `valid` = samples left from this lane's first
   if (r.flags & WR_ACC64) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if ((uint32_t)(32 * j) < valid) out[32 * j] = synth_sample64<M>(r, n + 32 * j);
+      if ((uint32_t)(32 * j) < valid) out[32 * j] = (OutT)synth_sample64<M>(r, n + 32 * j);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if ((uint32_t)(32 * j) < valid) out[32 * j] = synth_sample32<M>(r, n + 32 * j);
+      if ((uint32_t)(32 * j) < valid) out[32 * j] = (OutT)synth_sample32<M>(r, n + 32 * j);
   }
 }
 
@@ -94,6 +95,7 @@ __device__ __forceinline__ int find_window(const uint64_t* __restrict__ off, int
   return lo;
 }
 
+template <typename OutT>
 __global__ void __launch_bounds__(kSynthThreads)
 k_synth(const __grid_constant__ SynthArgs a) {
   __shared__ WinRec s_rec[kSynthWarps];
@@ -101,7 +103,7 @@ k_synth(const __grid_constant__ SynthArgs a) {
   WinRec& rec = s_rec[warp];
   int cur_w = -1, cur_r = -1;
   const uint64_t ntiles = a.npieces ? (uint64_t)a.piece_tile0[a.npieces] : (a.flat_count + kTile - 1) / kTile;
-  int32_t* const out = reinterpret_cast<int32_t*>(a.out);
+  OutT* const out = reinterpret_cast<OutT*>(a.out);
   for (uint64_t tile = (uint64_t)blockIdx.x * kSynthWarps + warp; tile < ntiles;
        tile += (uint64_t)gridDim.x * kSynthWarps) {
     uint64_t o0, f0, left;
@@ -140,22 +142,22 @@ k_synth(const __grid_constant__ SynthArgs a) {
         cur_w = w;
       }
       const uint32_t n = (uint32_t)(f0 - wbeg) + rec.n_first + lane;
-      int32_t* o = out + o0 + lane;
+      OutT* o = out + o0 + lane;
       const uint32_t valid = tile_n > (uint32_t)lane ? tile_n - lane : 0;
       if (rec.flags & WR_GENERIC) {
         const GenRec& g = a.gens[rec.gen_idx];
         const uint64_t nmask = (1ull << g.wp.pw) - 1;
         for (int j = 0; j < 4; ++j)
           if ((uint32_t)(32 * j) < valid)
-            o[32 * j] = (int32_t)direct_sample_generic(g.wp, g.src, a.rom + g.rom_off,
-                                                       (uint64_t)(n + 32 * j) & nmask);
+            o[32 * j] = (OutT)direct_sample_generic(g.wp, g.src, a.rom + g.rom_off,
+                                                    (uint64_t)(n + 32 * j) & nmask);
       } else {
         switch (rec.m) {
-          case 2: synth_tile<2>(rec, n, o, valid); break;
-          case 3: synth_tile<3>(rec, n, o, valid); break;
-          case 4: synth_tile<4>(rec, n, o, valid); break;
-          case 5: synth_tile<5>(rec, n, o, valid); break;
-          default: synth_tile<7>(rec, n, o, valid); break;
+          case 2: synth_tile<2, OutT>(rec, n, o, valid); break;
+          case 3: synth_tile<3, OutT>(rec, n, o, valid); break;
+          case 4: synth_tile<4, OutT>(rec, n, o, valid); break;
+          case 5: synth_tile<5, OutT>(rec, n, o, valid); break;
+          default: synth_tile<7, OutT>(rec, n, o, valid); break;
         }
       }
     } else {
@@ -179,7 +181,7 @@ k_synth(const __grid_constant__ SynthArgs a) {
         } else {
           v = synth_sample(r, n);
         }
-        out[o0 + i] = v;
+        out[o0 + i] = (OutT)v;
       }
     }
   }
@@ -516,6 +518,20 @@ k_direct_taylor(const __grid_constant__ DirectTayArgs a, int32_t* __restrict__ o
   for (uint32_t i = threadIdx.x; i < p.rom_entries; i += blockDim.x) s_rom[i] = a.rom[i];
   __syncthreads();
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (a.pair == 2 && TMODE == TMODE_WIDE && aligned) {
+    // whole long window: 4 consecutive samples of the first quarter and their three partners (direct_taylor_quad4)
+    const uint64_t quarter = a.count / 4;
+    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quarter / 4;
+         qd += (uint64_t)gridDim.x * blockDim.x) {
+      const uint64_t j = qd * 4;
+      int32_t w[4][4];
+      direct_taylor_quad4(p, s_rom, (uint32_t)j, w);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        __stcs(reinterpret_cast<int4*>(out + r * quarter + j), make_int4(w[r][0], w[r][1], w[r][2], w[r][3]));
+    }
+    return;
+  }
   if (a.pair) {
     // whole window: 4 consecutive samples of the first half and their partners half a window later
     const uint64_t half = a.count / 2;
@@ -730,7 +746,8 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
   const uint64_t ntiles = a.npieces ? (uint64_t)a.piece_tile0[a.npieces] : (a.flat_count + kTile - 1) / kTile;
   if (!ntiles) return cudaSuccess;
   const unsigned grid = grid_for((ntiles + kSynthWarps - 1) / kSynthWarps, 8);
-  k_synth<<<grid, kSynthThreads, 0, stream>>>(a);
+  if (a.pack16) k_synth<short><<<grid, kSynthThreads, 0, stream>>>(a);
+  else k_synth<int32_t><<<grid, kSynthThreads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -840,7 +857,8 @@ cudaError_t launch_direct32(const Direct32Args& a_in, int32_t* out, cudaStream_t
 
 cudaError_t launch_direct_taylor(const DirectTayArgs& a, int32_t* out, cudaStream_t stream) {
   if (!a.count) return cudaSuccess;
-  const unsigned grid = grid_for(((a.count / (a.pair ? 2 : 1) + 3) / 4 + 255) / 256, 8);
+  const bool quad = a.pair == 2 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const unsigned grid = grid_for(((a.count / (quad ? 4 : a.pair ? 2 : 1) + 3) / 4 + 255) / 256, 8);
   const size_t smem = (size_t)a.p.rom_entries * sizeof(I2);  // <= 32 KB (LUT_SIZE <= 12)
   if (a.p.tmode == TMODE_ROM) k_direct_taylor<TMODE_ROM><<<grid, 256, smem, stream>>>(a, out);
   else if (a.p.tmode == TMODE_DSP) k_direct_taylor<TMODE_DSP><<<grid, 256, smem, stream>>>(a, out);

@@ -16,7 +16,7 @@ struct SynthArgs {
   const uint64_t* flat_off;  // [nwin+1] first flat sample of each window; unused when uniform_pw >= 0
   const GenRec* gens;        // parameters of WR_GENERIC windows
   const I2* rom;             // Taylor ROM words (generic body only)
-  void* out;                 // int32 output, element 0 = flat sample flat_begin
+  void* out;                 // int32 (pack16: int16) output, element 0 = flat sample flat_begin
   uint64_t flat_begin;
   uint64_t flat_count;
   int32_t nwin;
@@ -25,7 +25,7 @@ struct SynthArgs {
   // [flat_begin, flat_begin + flat_count): piece p = [piece_begin[p], piece_end[p]), its 128-sample tiles are
   // numbered from piece_tile0[p]; `out` is then element flat index `out_flat0` of the batch
   uint32_t npieces;
-  uint32_t pad;
+  uint32_t pack16;           // 1: `out` is an int16 array (BHW_OUT_INT16, every window DAT_WIDTH <= 16)
   uint64_t out_flat0;
   uint64_t piece_begin[kSynthMaxPieces];
   uint64_t piece_end[kSynthMaxPieces];
@@ -63,7 +63,7 @@ struct GroupArgs {
   uint32_t apply_mode;       // BHW_APPLY_EXACT + 1 / BHW_APPLY_ROUNDED + 1
   uint32_t apply_dw;         // DAT_WIDTH
   uint32_t prefetch_lines;   // spread walk: prefetch the next tile's pyramid lines into L1, harmonics of up to this many lines
-  uint32_t pad2;
+  uint32_t pack16;           // 1: `out` is an int16 array (BHW_OUT_INT16); not together with x
 };
 
 struct DirectArgs {
@@ -96,9 +96,12 @@ struct DirectTayArgs {
   const I2* rom;    // Taylor ROM (global)
   uint64_t n0;      // first sample (the stream offset lives in p.n_first)
   uint64_t count;
-  uint32_t pair;    // whole window (n0 = 0, count = N >= 8, bh_win_3term's second unit one bit narrower): one
-                    // evaluation serves samples n and n + N/2 (direct_taylor_pair).  (All four quarter-window
-                    // partners from one evaluation measured no faster: config 4 32.8 vs 30.8 us.)
+  uint32_t pair;    // whole window (n0 = 0, count = N >= 8, bh_win_3term's second unit one bit narrower): 1 = one
+                    // evaluation serves samples n and n + N/2 (direct_taylor_pair); 2 = long TAY_WIDE window,
+                    // stream offset 0: two ROM words serve 4 consecutive samples and their three quarter-window
+                    // partners (direct_taylor_quad4, direct_taylor_quad_ok).  (Round 1 tried the four partners
+                    // with the per-sample body and measured no gain, 32.8 vs 30.8 us on config 4: the cost was the
+                    // per-sample ROM look-up, mode and quadrant logic, which quad4 hoists out.)
 };
 
 struct SinCosArgs {

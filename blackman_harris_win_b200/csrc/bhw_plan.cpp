@@ -239,6 +239,18 @@ bool direct_taylor_params(const WinParams& wp, const SrcParams* src, DirectTayPa
   return true;
 }
 
+// direct_taylor_quad4 applies: TAY_WIDE, stream offset 0, the window's units are (PHI_WIDTH[, PHI_WIDTH-1]) and
+// four aligned consecutive samples share every unit's ROM word (>= 2 counter bits below the ROM address).
+bool direct_taylor_quad_ok(const DirectTayParams& p, int phi_width) {
+  if (p.tmode != TMODE_WIDE || p.n_first != 0 || phi_width < 12) return false;
+  if (p.unit[0].pw != phi_width || (p.m > 2 && p.unit[1].pw != phi_width - 1)) return false;
+  for (int k = 1; k < p.m; k++) {
+    const TayUnit& u = p.unit[k - 1];
+    if (u.mode != TAY_WIDE || u.cbits < 2 || u.ashift != u.cbits) return false;
+  }
+  return true;
+}
+
 // cordic_atan2 generics -> kernel parameters.  ROM_TABLE(ii) = "0" & ROM_LUT(ii)(47 downto
 // 47-(W-2)): the top W-1 bits of the 48-bit word (src/cordic_atan2.vhd:97-108).
 int resolve_atan2(const bhw_atan2_desc* d, Atan2Params* p) {

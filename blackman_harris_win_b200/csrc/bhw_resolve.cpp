@@ -92,7 +92,8 @@ int validate_desc(const bhw_desc* d, bool for_window) {
   if (d->algo < BHW_ALGO_AUTO || d->algo > BHW_ALGO_TABLE) return BHW_E_ARG;
   if (!for_window) return BHW_OK;
   if (d->stream_offset != 0 && d->stream_offset != 1) return BHW_E_ARG;
-  if (d->reserved != 0) return BHW_E_ARG;
+  if (d->out_format != BHW_OUT_DEFAULT && d->out_format != BHW_OUT_INT16) return BHW_E_ARG;
+  if (d->out_format == BHW_OUT_INT16 && dw > 16) return BHW_E_DAT_WIDTH;
   for (int k = 0; k < d->win_type; k++) {
     const int64_t v = d->aa[k];
     // an AAk port is DAT_WIDTH raw bits: accept the signed or the unsigned reading of them
@@ -280,6 +281,18 @@ static int variant_coeffs(int variant, int rule, double a[BHW_MAX_TERMS], int* n
   return BHW_OK;
 }
 
+// element size of a batch: one container for all its windows (BHW_E_ELEM otherwise)
+int batch_elem_bytes(const bhw_desc* descs, int nwin, size_t* esz) {
+  bool any64 = false, any32 = false, any16 = false;
+  for (int i = 0; i < nwin; i++) {
+    if (descs[i].out_format == BHW_OUT_INT16) any16 = true;
+    else (descs[i].dat_width > 32 ? any64 : any32) = true;
+  }
+  if ((int)any64 + (int)any32 + (int)any16 > 1) return BHW_E_ELEM;
+  *esz = any16 ? 2 : any64 ? 8 : 4;
+  return BHW_OK;
+}
+
 }  // namespace bhw
 
 using namespace bhw;
@@ -314,7 +327,11 @@ const char* bhw_strerror(int s) {
 
 int bhw_validate(const bhw_desc* d) { return validate_desc(d, true); }
 
-int bhw_elem_bytes(const bhw_desc* d) { return d && d->dat_width > 32 ? 8 : 4; }
+int bhw_elem_bytes(const bhw_desc* d) {
+  if (d && d->out_format == BHW_OUT_INT16) return 2;
+  return d && d->dat_width > 32 ? 8 : 4;
+}
+
 
 int bhw_variant_coeffs(int variant, int rule, double a_out[BHW_MAX_TERMS], int32_t* nterms) {
   if (!a_out) return BHW_E_NULL;

@@ -99,6 +99,12 @@ enum {
   BHW_MODEL_CPP = 2  /* cpp/cordic_sincos.cpp (sin/cos table only: bhw_sincos)    */
 };
 
+/* Output container (bhw_desc.out_format). */
+enum {
+  BHW_OUT_DEFAULT = 0, /* int32, or int64 when DAT_WIDTH > 32 */
+  BHW_OUT_INT16 = 1    /* int16; DAT_WIDTH <= 16 only (BHW_E_DAT_WIDTH otherwise) */
+};
+
 /* Evaluation strategy (results are identical; this is a performance knob). */
 enum {
   BHW_ALGO_AUTO = 0,
@@ -125,7 +131,13 @@ typedef struct bhw_desc {
   int32_t stream_offset; /* 0: out[j] = w[n0+j]; 1: the DT_VLD-gated order
                             w[1], w[2], ..., w[N-1], w[0] (DESIGN.md "stream order") */
   int32_t algo;          /* BHW_ALGO_*                                             */
-  int32_t reserved;      /* must be 0 (XSERIES has no numeric effect)              */
+  int32_t out_format;    /* BHW_OUT_*: container of one output sample.  0: int32
+                            (int64 for DAT_WIDTH > 32).  BHW_OUT_INT16: int16, for
+                            DAT_WIDTH <= 16 (DT_WIN is DAT_WIDTH bits wide,
+                            src/hamming_win.vhd:60-82) - half the bytes in HBM and
+                            over the host link; batch / plan entry points and
+                            bhw_generate[_host] only, one format per batch.
+                            (XSERIES needs no field: it has no numeric effect.)      */
   int64_t aa[BHW_MAX_TERMS]; /* raw two's-complement AA0..AA6 port values; terms
                                 beyond win_type are ignored                        */
 } bhw_desc;

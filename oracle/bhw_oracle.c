@@ -9,7 +9,7 @@
  *
  * Parity: HLS and CPP models are pinned against the compiled reference
  * (oracle/_ref).  The RTL model is pinned by vectors recorded while EXECUTING
- * the reference's src/*.vhd in oracle/vhdl_sim.py (tests/golden/rtl_sim_vectors.npz,
+ * the reference's VHDL sources (src/, every .vhd) in oracle/vhdl_sim.py (tests/golden/rtl_sim_vectors.npz,
  * tests/test_rtl_vhdl_sim.py); for the TAYLOR path that execution relies on our
  * behavioural model of the third-party DSP48E1/E2 primitives and on libm for
  * ieee.math_real.  Second anchors: oracle/rtl_bitvec.py + tests/golden KATs.
@@ -318,7 +318,9 @@ int orc_validate(const bhw_desc* d) {
   int st = validate_source(d, 1);
   if (st) return st;
   if (d->stream_offset != 0 && d->stream_offset != 1) return BHW_E_ARG;
-  if (d->reserved != 0) return BHW_E_ARG;
+  /* the container of the output is not the oracle's business (it returns int64), its legality is */
+  if (d->out_format != BHW_OUT_DEFAULT && d->out_format != BHW_OUT_INT16) return BHW_E_ARG;
+  if (d->out_format == BHW_OUT_INT16 && d->dat_width > 16) return BHW_E_DAT_WIDTH;
   const int dw = d->dat_width;
   for (int k = 0; k < m; k++) {
     const int64_t v = d->aa[k];

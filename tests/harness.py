@@ -218,6 +218,7 @@ def hostcheck():
     L.hc_table.argtypes = [D, C.c_uint64, C.c_uint64, I64P, C.c_int]
     L.hc_direct32.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
     L.hc_direct_taylor.argtypes = [D, C.c_uint64, C.c_uint64, I64P]
+    L.hc_taylor_quad_ok.argtypes = [D]
     from blackman_harris_win_b200.api import BhwAtan2Desc
     L.hc_atan2.argtypes = [P(BhwAtan2Desc), P(C.c_int32), P(C.c_int32), P(C.c_int32), C.c_uint64]
     L.hc_sincos.argtypes = [D, C.c_uint64, C.c_uint64, I64P, I64P]

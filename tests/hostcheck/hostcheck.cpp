@@ -134,7 +134,27 @@ int hc_direct_taylor(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* ou
       if (wa != out[j] || wb != out[partner - n0]) return -101;
     }
   }
+  // the quarter-window body (long whole TAY_WIDE windows in the kernel): 16 samples per call
+  if (n0 == 0 && count == N && direct_taylor_quad_ok(p, d->phi_width)) {
+    for (uint64_t j = 0; j < N / 4; j += 4) {
+      int32_t w[4][4];
+      direct_taylor_quad4(p, rom.data(), (uint32_t)j, w);
+      for (int r = 0; r < 4; r++)
+        for (int e = 0; e < 4; e++)
+          if (w[r][e] != out[r * (N / 4) + j + e]) return -102;
+    }
+  }
   return 0;
+}
+
+// 1 when hc_direct_taylor(d, 0, N) also runs the quarter-window body (k_direct_taylor's pair == 2 branch)
+int hc_taylor_quad_ok(const bhw_desc* d) {
+  WinParams wp; SrcParams src[2];
+  int st = resolve_window(d, &wp, src);
+  if (st) return st;
+  DirectTayParams p;
+  if (wp.elem64 || !direct_taylor_params(wp, src, &p)) return 0;
+  return direct_taylor_quad_ok(p, d->phi_width) ? 1 : 0;
 }
 
 // the 32-bit register-resident direct body (k_direct32); returns 1 when the window is not eligible

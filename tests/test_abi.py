@@ -73,7 +73,10 @@ def test_validate_rejections():
     assert bhw.validate(ok.copy(precision=2)) == -7
     assert bhw.validate(ok.copy(aa=[1 << 17, 0, 0, 0])) == -9
     assert bhw.validate(ok.copy(stream_offset=2)) == -16
-    assert bhw.validate(ok.copy(reserved=1)) == -16
+    assert bhw.validate(ok.copy(out_format=2)) == -16
+    assert bhw.validate(ok.copy(out_format=bhw.OUT_INT16)) == -6             # DAT_WIDTH 17 does not fit int16
+    ok16 = bhw.make_desc(2, 10, 16, [17808, 14959], out_format=bhw.OUT_INT16)
+    assert bhw.validate(ok16) == 0 and bhw.elem_bytes(ok16) == 2 and bhw.elem_bytes(ok) == 4
     t3 = bhw.make_desc(3, 12, 16, [1, 1, 1], sin_type=bhw.SIN_TAYLOR, lut_size=9)
     assert bhw.validate(t3) == -8                                         # PHI_WIDTH - LUT_SIZE == 3
     assert bhw.validate(t3.copy(phi_width=13)) == 0
@@ -164,6 +167,25 @@ def test_generate_without_gpu_fails_loudly():
     out = np.full(1024, 12345, np.int32)
     st = bhw.lib().bhw_generate_host(C.byref(bhw.make_desc(2, 10, 16, [17808, 14959])), out.ctypes.data, 0, 1024)
     assert st in (-12, -13) and (out == 12345).all()
+
+
+def test_one_container_per_batch():
+    """BHW_OUT_INT16 (bhw_desc.out_format): a batch has one element size - int16, int32 or int64 - and says so
+    before it looks for a device (BHW_E_ELEM); int16 needs DAT_WIDTH <= 16; the apply step has its own containers."""
+    import numpy as np
+    d16 = bhw.make_desc(2, 10, 16, [17808, 14959], out_format=bhw.OUT_INT16)
+    d32 = bhw.make_desc(2, 10, 16, [17808, 14959])
+    d64 = bhw.variant_desc(10, 10, 40)
+    out = np.zeros(4096, np.int64)
+    for mix in ([d16, d32], [d32, d64], [d16, d64], [d32, d16, d32]):
+        arr = bhw.desc_array(mix)
+        assert bhw.lib().bhw_generate_batch_host(arr, len(mix), 0, 2048, out.ctypes.data) == -11, mix
+        plan = C.c_void_p()
+        assert bhw.lib().bhw_plan_create(arr, len(mix), C.byref(plan)) == -11
+    assert bhw.lib().bhw_generate_batch_host(bhw.desc_array([d32.copy(dat_width=17, out_format=1)]), 1, 0, 1024, out.ctypes.data) == -6
+    assert bhw.lib().bhw_apply(C.byref(d16), 0, None, None, 0, None) == -16
+    assert [bhw.elem_bytes(d) for d in (d16, d32, d64)] == [2, 4, 8]
+    assert H.orc_window_status(d16) == 0 and H.orc_window_status(d32.copy(dat_width=17, out_format=1)) == -6
 
 
 def test_win_selector_mirror():

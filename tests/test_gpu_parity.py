@@ -754,6 +754,103 @@ def test_cordic_atan2():
         bhw.atan2(x.cuda(), y.cuda(), 16, 16, 1, stream_quadrant=2)
 
 
+def test_taylor_long_window_quarter_body():
+    """k_direct_taylor's quarter-window branch (direct_taylor_quad4: 16 samples from two ROM words) on whole TAY_WIDE
+    windows, every sample against the oracle; the shapes around it (DT_VLD order, a range, the DSP datapath) keep
+    the per-sample / pair branches and are checked the same way."""
+    rng = np.random.default_rng(17)
+    shapes = [(3, 12, 19, 5), (4, 14, 24, 9), (1, 16, 24, 9), (2, 18, 32, 11), (3, 20, 24, 9), (4, 13, 31, 4), (1, 22, 20, 12)]
+    for v, pw, dw, lut in shapes:
+        d = bhw.variant_desc(v, pw, dw, sin_type=bhw.SIN_TAYLOR, lut_size=lut, algo=bhw.ALGO_DIRECT)
+        n = 1 << pw
+        got = gpu_window(d)
+        if n <= (1 << 18):
+            assert np.array_equal(got, H.orc_window(d)), d
+        else:
+            for n0 in (0, n // 4 - 4096, n // 2 - 4096, 3 * (n // 4) - 4096, n - 8192):
+                assert np.array_equal(got[n0:n0 + 8192], H.orc_window(d, n0, 8192)), (d, n0)
+        assert np.array_equal(gpu_window(d.copy(stream_offset=1)), np.roll(got, -1)), d
+        assert np.array_equal(gpu_window(d, 1000, 3000), got[1000:4000]), d
+    for it in range(12):
+        m, pw, dw = int(rng.integers(2, 4)), int(rng.integers(12, 17)), int(rng.integers(19, 33))
+        lut = int(rng.integers(4, min(pw - 4, 12) + 1))
+        lim = 1 << (dw - 1)
+        aa = [lim - 1] * m if it % 4 == 0 else [-lim] * m if it % 5 == 0 else [int(x) for x in rng.integers(-lim, lim, m)]
+        d = bhw.make_desc(m, pw, dw, aa, sin_type=bhw.SIN_TAYLOR, lut_size=lut, algo=bhw.ALGO_DIRECT)
+        assert np.array_equal(gpu_window(d), H.orc_window(d)), d
+
+
+def test_packed_int16_output():
+    """BHW_OUT_INT16 (bhw_desc.out_format): the same integers in an int16 container, for every window kind whose
+    DAT_WIDTH fits - through the group kernel (every table placement, paired / cut / spread walk), the general kernel
+    (short windows, TAYLOR and input-quadrant tables, the generic body), one-shot, host and plan entry points, ragged
+    ranges.  Reference for each: the int32 output of the same batch, itself oracle-checked elsewhere, plus the oracle
+    directly on the small ones."""
+    import torch
+    P = bhw.OUT_INT16
+    small = []
+    for pw in (4, 5, 7, 8, 9, 10, 12, 13, 15):
+        for v in (1, 2, 3, 4):
+            small.append(bhw.variant_desc(v, pw, 16))
+        small.append(bhw.variant_desc(6, pw, 14))
+        small.append(bhw.variant_desc(9, pw, 16))
+        small.append(bhw.variant_desc(10, pw, 12))
+        small.append(bhw.variant_desc(1, pw, 16, sin_type=bhw.SIN_CORDIC48))
+        small.append(bhw.variant_desc(3, pw, 16, sin_type=bhw.SIN_CORDIC_SCALED).copy(stream_offset=1))
+        if pw >= 8:
+            small.append(bhw.variant_desc(4, pw, 16, sin_type=bhw.SIN_TAYLOR, lut_size=pw - 4))
+            small.append(bhw.variant_desc(6, pw, 16, model=bhw.MODEL_HLS))
+    small.append(bhw.make_desc(2, 9, 16, [-32768, -32768]))
+    small.append(bhw.make_desc(3, 9, 8, [127, -128, 127]))
+    small += [bhw.make_desc(2, 10, 16, [17808 + i, 14959 - i]) for i in range(300)]        # a bank-shaped run
+    for d in small:
+        assert bhw.validate(d) == 0, d
+    packed = [d.copy(out_format=P) for d in small]
+    total = bhw.batch_total(bhw.desc_array(small))
+    want = bhw.generate_batch(small).cpu().numpy()
+    assert np.abs(want).max() < (1 << 15)
+    got = bhw.generate_batch(packed)
+    assert got.dtype == torch.int16 and got.numel() == total
+    assert np.array_equal(got.cpu().numpy().astype(np.int32), want)
+    assert np.array_equal(want[:4096].astype(np.int64), H.orc_batch(small, 0, 4096))
+    for b, c in ((1, 777), (12345, 100001), (total - 5000, 5000), (3, total - 7)):
+        g = bhw.generate_batch(packed, b, c).cpu().numpy()
+        assert np.array_equal(g.astype(np.int32), want[b:b + c]), (b, c)
+    h = bhw.generate_batch_host(packed)
+    assert h.dtype == np.int16 and np.array_equal(h.astype(np.int32), want)
+    h = bhw.generate_batch_host(packed, 1001, 54321)
+    assert np.array_equal(h.astype(np.int32), want[1001:1001 + 54321])
+    plan = bhw.Plan(packed)
+    assert plan.elem_bytes == 2
+    for b, c in ((0, total), (257, 99999)):
+        assert np.array_equal(plan.execute(b, c).cpu().numpy().astype(np.int32), want[b:b + c])
+    plan.destroy()
+    # one window through bhw_generate / bhw_generate_host
+    d = bhw.variant_desc(4, 14, 16)
+    w32 = bhw.generate(d).cpu().numpy()
+    assert np.array_equal(bhw.generate(d.copy(out_format=P)).cpu().numpy().astype(np.int32), w32)
+    assert np.array_equal(bhw.generate(d.copy(out_format=P), 100, 1000).cpu().numpy().astype(np.int32), w32[100:1100])
+    assert np.array_equal(bhw.generate_host(d.copy(out_format=P)).astype(np.int32), w32)
+    # long windows: pyramid gathers, the spread walk of a 7-term window, a long TAYLOR window
+    for d in (bhw.variant_desc(2, 22, 16), bhw.variant_desc(10, 23, 16), bhw.variant_desc(9, 21, 16),
+              bhw.variant_desc(3, 20, 16, sin_type=bhw.SIN_TAYLOR, lut_size=9)):
+        a = bhw.generate_batch([d.copy(out_format=P)])
+        b_ = bhw.generate_batch([d])
+        assert a.dtype == torch.int16 and torch.equal(a.to(torch.int32), b_), d
+        assert np.array_equal(b_[:2048].cpu().numpy().astype(np.int64), H.orc_window(d, 0, 2048))
+    # the launches of a packed batch are the library's own kernels, no bank kernel and no conversion pass
+    bhw.timing_enable(True)
+    bhw.timing_reset()
+    bhw.generate_batch(packed)
+    kt = bhw.timing_read()
+    bhw.timing_enable(False)
+    assert kt["k_synth_bank"][0] == 0 and kt["k_synth_group"][0] > 0, kt
+    with pytest.raises(bhw.BhwError):
+        bhw.generate_batch([small[0], packed[1]])                          # one container per batch
+    with pytest.raises(bhw.BhwError):
+        bhw.apply(packed[0], torch.zeros(16, dtype=torch.int32, device="cuda"))
+
+
 def test_rtl_golden_vectors_on_gpu():
     """The CUDA path against what the reference's VHDL entities output when executed (tests/golden/rtl_sim_vectors.npz,
     made by tests/golden/make_rtl_golden.py through oracle/vhdl_sim.py) - no oracle in between."""

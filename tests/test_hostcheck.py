@@ -67,6 +67,37 @@ def test_rtl_sweep_all_variants_widths_sources():
     assert len(DIRECT_TAYLOR_SEEN) > 50  # and so did the TAYLOR one
 
 
+def test_taylor_quarter_window_body():
+    """direct_taylor_quad4 (k_direct_taylor's long-window branch: 16 samples from two ROM words) against the
+    per-sample body and the oracle over whole windows - every coefficient sign, DAT_WIDTH 19..32, both entities,
+    ROM depths from 4 to PHI_WIDTH-4, and the shapes that must NOT take it (DSP datapath, DT_VLD order, short)."""
+    hc = H.hostcheck()
+    rng = np.random.default_rng(5)
+    taken = 0
+    shapes = [(3, 14, 24, 9, 0), (4, 16, 24, 9, 0), (1, 14, 24, 9, 0), (3, 12, 19, 5, 0), (4, 15, 31, 10, 0), (4, 18, 24, 12, 0),
+              (1, 16, 32, 9, 0), (3, 13, 16, 5, 0), (3, 14, 24, 9, 1), (1, 11, 24, 5, 0)]
+    descs = [(bhw.variant_desc(v, pw, dw, sin_type=bhw.SIN_TAYLOR, lut_size=lut).copy(stream_offset=so), None) for v, pw, dw, lut, so in shapes]
+    for it in range(40):
+        m, pw, dw = int(rng.integers(2, 4)), int(rng.integers(12, 16)), int(rng.integers(19, 33))
+        lut = int(rng.integers(4, pw - 4 + 1))
+        lim = 1 << (dw - 1)
+        aa = [lim - 1] * m if it % 5 == 0 else [-lim] * m if it % 7 == 0 else [int(x) for x in rng.integers(-lim, lim, m)]
+        descs.append((bhw.make_desc(m, pw, dw, aa, sin_type=bhw.SIN_TAYLOR, lut_size=min(lut, 12)), None))
+    for d, _ in descs:
+        if bhw.validate(d) != 0:
+            continue
+        n = 1 << d.phi_width
+        got = np.empty(n, np.int64)
+        st = hc.hc_direct_taylor(C.byref(d), 0, n, got.ctypes.data_as(H.I64P))     # -102: quad body differs
+        assert st in (0, 1), (st, d)
+        q = hc.hc_taylor_quad_ok(C.byref(d))
+        assert q == int(st == 0 and d.dat_width >= 19 and d.stream_offset == 0 and d.phi_width >= 12 and d.phi_width - d.lut_size - 2 - (d.win_type == 3) >= 2), d
+        taken += q
+        if st == 0:
+            assert np.array_equal(got, H.orc_window(d)), d
+    assert taken >= 30
+
+
 def test_validation_agrees_with_oracle():
     n = 0
     for v in range(1, 11):

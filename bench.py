@@ -459,7 +459,8 @@ def config_lines(bhw, peak_gbs, int_peak, scratch):
                 plan.destroy()
                 line["bank_int16"] = {"windows": nbank, "bytes": 2 * total, "ms_per_step": round(pms, 5),
                                       "gsamples_per_s": round(total / pms / 1e6, 1), "frac_hbm": round(2 * total / pms / 1e6 / peak_gbs, 4),
-                                      "note": "group kernel with int16 stores; the int32 bank above goes through the bank kernel"}
+                                      "note": "same bank kernel, int16 store instantiation (k_synth_bank<2, ., ., false, short>): half the bytes, "
+                                              "so the kernel is no longer HBM-bound - the fraction is of the HBM peak at 2 B per sample"}
         out.append(line)
     return out
 

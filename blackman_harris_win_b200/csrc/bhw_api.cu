@@ -175,7 +175,7 @@ struct bhw_plan {
   int dev = 0;
   int nwin = 0;
   bool elem64 = false;
-  bool pack16 = false;   // BHW_OUT_INT16: int16 output through k_synth<short> / k_synth_group<.., 3>, no bank runs
+  bool pack16 = false;   // BHW_OUT_INT16: int16 output - k_synth<short>, k_synth_group<.., 3>, k_synth_bank<.., short> (2/3 terms)
   bool transient = false;        // one-shot plan: device memory comes from / returns to the stream pool
   uint64_t total = 0;            // flat samples of the whole batch
   // DAT_WIDTH <= 32: table + synthesis path
@@ -239,6 +239,16 @@ struct bhw_plan {
   };
   std::vector<Family> families;
   std::vector<Group> groups;
+  // what an execute asks of each group: the piece [i0, i1) of its launch list, up to two windows the range cuts,
+  // the windows launched singly; `covered` = the flat intervals those launches write (ascending, merged)
+  struct Covered { uint64_t b, e; };
+  struct GroupWork { uint32_t i0 = 0, i1 = 0; bhw::GroupWin part[2]; uint32_t nparts = 0; std::vector<uint32_t> singles; };
+  // ... of an execute of the whole batch, kept from the first one (a bank of 65,536 short windows: the walk over
+  // the windows costs more host time than the kernels take)
+  bool whole_cached = false;
+  std::vector<GroupWork> whole_gwork;
+  std::vector<Covered> whole_covered;
+  size_t whole_group_launches = 0;
   std::vector<int32_t> win_group;        // [nwin] group of each window, -1: none
   std::vector<uint32_t> win_gidx;        // [nwin] index of the window in its group's list (or in `singles`, bit 31 set)
   // DAT_WIDTH > 32: one direct launch per window
@@ -306,7 +316,6 @@ static cudaError_t plan_alloc(bhw_plan& plan, void** p, size_t bytes, cudaStream
 
 static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
   plan.runs.clear();
-  if (plan.pack16) return;   // the bank kernel stores int32 only: packed plans use the group and general kernels
   uint64_t off = 0;
   for (int w = 0; w < plan.nwin; w++) {
     const uint32_t ri = plan.win_rec[(size_t)w];
@@ -323,7 +332,8 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
       ti[k].antisym = t >= 0 && source_antisymmetric(plan.tables[(size_t)t].canon);
       ti[k].inq_comp = t >= 0 && source_inq_complement(plan.tables[(size_t)t].canon);
     }
-    if (bank_shape(r, ti, bank_smem_limit(), &sh, &mode, &pair)) {
+    // a packed plan (int16 output) has bank kernels for 2- and 3-term shapes with the 32-bit tail only
+    if (bank_shape(r, ti, bank_smem_limit(), &sh, &mode, &pair) && (!plan.pack16 || (sh.m <= 3 && !sh.acc64))) {
       if (!plan.runs.empty()) {
         bhw_plan::BankRun& last = plan.runs.back();
         if (last.w_end == w && last.tab_mode == mode && last.pair == pair && !memcmp(&last.sh, &sh, sizeof(sh))) {
@@ -355,9 +365,16 @@ static void build_bank_runs(bhw_plan& plan, const std::vector<int>& rec_tab) {
   plan.runs.resize(keep);
   // Pairing over an input-quadrant CORDIC's table costs two more launches (exception scan, patch pass): below
   // 2^23 samples the run keeps single samples (a one-shot N = 2^20 cordic_dds48 window: 40 us unpaired, 51 us paired)
+  // (a packed plan has no bank kernel for that pairing: it keeps single samples, or leaves the run to k_synth)
+  if (plan.pack16) {
+    keep = 0;
+    for (size_t i = 0; i < plan.runs.size(); i++)
+      if (plan.runs[i].exc_table < 0 || plan.runs[i].part_ok) plan.runs[keep++] = plan.runs[i];
+    plan.runs.resize(keep);
+  }
   for (bhw_plan::BankRun& run : plan.runs) {
     if (run.exc_table < 0) continue;
-    if (((uint64_t)(run.w_end - run.w_begin) << run.sh.pw) < (1ull << 23) && run.part_ok) {
+    if ((((uint64_t)(run.w_end - run.w_begin) << run.sh.pw) < (1ull << 23) || plan.pack16) && run.part_ok) {
       run.sh = run.sh_part;
       run.tab_mode = TAB_GLOBAL;
       run.pair = false;
@@ -416,7 +433,7 @@ static int plan_build(bhw_plan& plan, const bhw_desc* descs, int nwin, uint64_t 
   for (int w = 0; w < nwin;) {
     int e = w + 1;
     while (e < nwin && same_shape(descs[w], descs[e])) e++;
-    if (!plan.pack16 && e - w >= 2 && ((uint64_t)(e - w) << descs[w].phi_width) >= (1ull << 17))
+    if ((!plan.pack16 || descs[w].win_type <= 3) && e - w >= 2 && ((uint64_t)(e - w) << descs[w].phi_width) >= (1ull << 17))
       for (int i = w; i < e; i++) banked[(size_t)i] = 1;
     w = e;
   }
@@ -868,13 +885,22 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   // Groups (bhw_group.cuh): the member windows that lie wholly inside the range form one contiguous piece of
   // their group's launch list -> one paired launch per group; a member window the range cuts contributes its
   // whole 256-sample tiles to an unpaired launch (inline list); `covered` collects what these launches write.
-  struct Covered { uint64_t b, e; };
+  using Covered = bhw_plan::Covered;
+  using GroupWork = bhw_plan::GroupWork;
   const uint32_t kSpreadG_ = 30;
   std::vector<Covered> covered;
-  struct GroupWork { uint32_t i0 = 0, i1 = 0; GroupWin part[2]; uint32_t nparts = 0; std::vector<uint32_t> singles; };
   std::vector<GroupWork> gwork(plan.groups.size());
   size_t group_launches = 0;
-  if (!plan.groups.empty()) {
+  const bool whole = flat_begin == 0 && flat_count == plan.total;
+  auto cover = [&](uint64_t b, uint64_t e_) {
+    if (!covered.empty() && covered.back().e == b) covered.back().e = e_;
+    else covered.push_back({b, e_});
+  };
+  if (whole && plan.whole_cached) {
+    gwork = plan.whole_gwork;
+    covered = plan.whole_covered;
+    group_launches = plan.whole_group_launches;
+  } else if (!plan.groups.empty()) {
     size_t w = (size_t)(std::upper_bound(plan.flat_off.begin(), plan.flat_off.end(), flat_begin) - plan.flat_off.begin());
     w = w ? w - 1 : 0;
     for (; w < (size_t)plan.nwin && plan.flat_off[w] < flat_end; w++) {
@@ -891,7 +917,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
           if (gk.i1 == gk.i0) { gk.i0 = gi; group_launches++; }
           gk.i1 = gi + 1;
         }
-        covered.push_back({wb, we});
+        cover(wb, we);
       } else {
         const uint64_t ta = (lo - wb + kBankTile - 1) / kBankTile, tb = (hi - wb) / kBankTile;
         if (tb <= ta || gk.nparts >= 2) continue;
@@ -903,8 +929,14 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
         pw_.out_off = (int64_t)wb;
         pw_.unit_begin = (uint32_t)(tb - ta);                   // tile count for now; prefix-summed at launch
         if (!gk.nparts++) group_launches++;
-        covered.push_back({wb + ta * kBankTile, wb + tb * kBankTile});
+        cover(wb + ta * kBankTile, wb + tb * kBankTile);
       }
+    }
+    if (whole) {
+      plan.whole_gwork = gwork;
+      plan.whole_covered = covered;
+      plan.whole_group_launches = group_launches;
+      plan.whole_cached = true;
     }
   }
   LaunchFan fan;
@@ -991,10 +1023,12 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   auto bank = [&](const bhw_plan::BankRun& run, uint64_t out_flat, uint32_t wa, uint32_t wb, uint32_t tile_off,
                   uint32_t ntiles) -> int {
     BankArgs ba;
+    memset(&ba, 0, sizeof(ba));
     ba.sh = ntiles ? run.sh_part : run.sh;
     ba.recs = a.recs;
     ba.win_rec = a.win_rec;
-    ba.out = (int32_t*)out_dev + (out_flat - flat_begin);
+    ba.out = (int32_t*)((char*)out_dev + (out_flat - flat_begin) * (plan.pack16 ? 2 : 4));
+    ba.pack16 = plan.pack16 ? 1u : 0u;
     ba.w_first = (uint32_t)run.w_begin + wa;
     ba.nwin = wb - wa;
     ba.tile_off = tile_off;
@@ -1015,7 +1049,7 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
     cudaStream_t ls = fan.next();
     cudaError_t ce;
     {
-      const uint64_t bank_bytes = ntiles ? (uint64_t)ntiles * kBankTile * 4 : ((uint64_t)ba.nwin << run.sh.pw) * 4;
+      const uint64_t bank_bytes = (ntiles ? (uint64_t)ntiles * kBankTile : ((uint64_t)ba.nwin << run.sh.pw)) * (plan.pack16 ? 2 : 4);
       LaunchTimer tm(BHW_KERNEL_SYNTH_BANK, ls, run.sh.m | ((uint32_t)(ntiles ? TAB_GLOBAL : run.tab_mode) << 8) |
                      ((uint32_t)(ntiles ? 0 : run.pair) << 16) | (run.sh.pw << 24), bank_bytes);
       const bool pdl = table_ahead && !fan.nside && !tm.on && ls == stream;
@@ -1105,6 +1139,9 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
         ga.nwin = gk.i1 - gk.i0;
         ga.unit_base = gr.list[gk.i0].unit_begin;
         ga.nunits = gr.list[gk.i1].unit_begin - ga.unit_base;
+        // the interleaved walk jumps gridDim * 8 units per step: over a list of short windows that is a window search
+        // per unit (65,536 windows of 1024 samples: 0.11 ms instead of 0.05) - such lists are walked contiguously
+        if (ga.nunits / ga.nwin < 64u) ga.sh.interleave = 0;
       } else if (pass >= 2) {
         const uint32_t si = gk.singles[(size_t)pass - 2];
         ga.wins = (const GroupWin*)(plan.blob_dev + gr.o_singles) + 2 * si;

@@ -167,7 +167,13 @@ k_synth_group(const __grid_constant__ GroupArgs a) {
   bool loaded = false;
   for (; u < u_end; u += u_step) {
     if (!loaded || u >= w_next) {
-      if (loaded) { do { ++w; } while (u >= wins[w + 1].unit_begin); }
+      if (loaded) {
+        // the next window is usually the neighbour; an interleaved walk over a list of short windows jumps far
+        // (65,536 windows of 1024 samples: hundreds of windows per step) - then search instead of walking
+        uint32_t hops = 0;
+        do { ++w; } while (u >= wins[w + 1].unit_begin && ++hops < 16u);
+        if (u >= wins[w + 1].unit_begin) w = group_find_window(wins, a.nwin, u);
+      }
       const GroupWin* gw = wins + w;
       w_begin = gw->unit_begin;
       w_next = gw[1].unit_begin;

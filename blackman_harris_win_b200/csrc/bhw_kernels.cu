@@ -197,7 +197,8 @@ k_synth(const __grid_constant__ SynthArgs a) {
 constexpr int kBankThreads = 1024;
 constexpr int kBankWarps = kBankThreads / 32;
 
-template <int M, int TAB, int PAIR, bool W64>
+// OutT: int32_t, or short for the packed output of DAT_WIDTH <= 16 windows (BHW_OUT_INT16)
+template <int M, int TAB, int PAIR, bool W64, typename OutT = int32_t>
 __global__ void __launch_bounds__(kBankThreads, 1)
 k_synth_bank(const __grid_constant__ BankArgs a) {
   extern __shared__ __align__(16) int32_t s_tab[];
@@ -252,12 +253,12 @@ k_synth_bank(const __grid_constant__ BankArgs a) {
       bank_lane_tile<M, TAB, PAIR, true, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
     else
       bank_lane_tile<M, TAB, PAIR, false, W64>(sh, p.A, p.S0, tabs, n, nbase, va, vb);
-    int32_t* o = a.out + ((uint64_t)w << pw) + t * kBankTile + lane;
+    OutT* o = reinterpret_cast<OutT*>(a.out) + ((uint64_t)w << pw) + t * kBankTile + lane;
     if (kRange) o -= toff * kBankTile;
 #pragma unroll
     for (int j = 0; j < kBankJ; ++j) {
-      __stcs(o + 32 * j, va[j]);
-      if (PAIR) __stcs(o + half + 32 * j, vb[j]);
+      __stcs(o + 32 * j, (OutT)va[j]);
+      if (PAIR) __stcs(o + half + 32 * j, (OutT)vb[j]);
     }
   };
   Ports cur;
@@ -753,13 +754,13 @@ cudaError_t launch_synth(const SynthArgs& a, cudaStream_t stream) {
 
 size_t bank_smem_limit() { return 192u * 1024u; }
 
-template <int M, int TAB, int PAIR, bool W64>
+template <int M, int TAB, int PAIR, bool W64, typename OutT = int32_t>
 static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48 * 1024 && dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_synth_bank<M, TAB, PAIR, W64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_synth_bank<M, TAB, PAIR, W64, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)bank_smem_limit());
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
@@ -776,9 +777,9 @@ static cudaError_t launch_bank_t(const BankArgs& a, unsigned grid, size_t smem, 
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_synth_bank<M, TAB, PAIR, W64>, a);
+    return cudaLaunchKernelEx(&cfg, k_synth_bank<M, TAB, PAIR, W64, OutT>, a);
   }
-  k_synth_bank<M, TAB, PAIR, W64><<<grid, kBankThreads, smem, stream>>>(a);
+  k_synth_bank<M, TAB, PAIR, W64, OutT><<<grid, kBankThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -797,6 +798,18 @@ static cudaError_t launch_bank_m(const BankArgs& a, int tab, bool pair, unsigned
               : launch_bank_t<M, TAB_GLOBAL, 0, W64>(a, grid, 0, stream, pdl);
 }
 
+// packed output: 2- and 3-term banks only (what DAT_WIDTH <= 16 windows are in practice; the rest of a packed
+// plan goes through k_synth_group / k_synth), 32-bit tail, no ones'-complement pairing
+template <int M>
+static cudaError_t launch_bank_m16(const BankArgs& a, int tab, bool pair, unsigned grid, size_t smem, cudaStream_t stream,
+                                   bool pdl) {
+  if (tab == TAB_SMEM_FULL) return pair ? launch_bank_t<M, TAB_SMEM_FULL, 1, false, short>(a, grid, smem, stream, pdl)
+                                        : launch_bank_t<M, TAB_SMEM_FULL, 0, false, short>(a, grid, smem, stream, pdl);
+  if (tab == TAB_SMEM_HALF) return launch_bank_t<M, TAB_SMEM_HALF, 1, false, short>(a, grid, smem, stream, pdl);
+  return pair ? launch_bank_t<M, TAB_GLOBAL, 1, false, short>(a, grid, 0, stream, pdl)
+              : launch_bank_t<M, TAB_GLOBAL, 0, false, short>(a, grid, 0, stream, pdl);
+}
+
 cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_t stream, bool pdl) {
   if (!a.nwin) return cudaSuccess;
   if (tab == TAB_SMEM_HALF && !pair) return cudaErrorInvalidValue;
@@ -810,6 +823,12 @@ cudaError_t launch_synth_bank(const BankArgs& a, int tab, bool pair, cudaStream_
   const unsigned grid = (unsigned)(ctas < (uint64_t)sm_count() ? ctas : (uint64_t)sm_count());
   const size_t smem = tab == TAB_GLOBAL ? 0 : (size_t)a.sh.smem_words * sizeof(int32_t);
   const bool w64 = a.sh.acc64 != 0;
+  if (a.pack16) {
+    if (w64 || (pair && a.sh.pair_adj)) return cudaErrorInvalidValue;
+    if (a.sh.m == 2) return launch_bank_m16<2>(a, tab, pair, grid, smem, stream, pdl);
+    if (a.sh.m == 3) return launch_bank_m16<3>(a, tab, pair, grid, smem, stream, pdl);
+    return cudaErrorInvalidValue;
+  }
   switch (a.sh.m) {
     case 2: return w64 ? launch_bank_m<2, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<2, false>(a, tab, pair, grid, smem, stream, pdl);
     case 3: return w64 ? launch_bank_m<3, true>(a, tab, pair, grid, smem, stream, pdl) : launch_bank_m<3, false>(a, tab, pair, grid, smem, stream, pdl);

@@ -36,13 +36,15 @@ struct BankArgs {
   BankShape sh;
   const WinRec* recs;        // per-window records (A[k], S0, n_first are read)
   const uint32_t* win_rec;   // record of each window; NULL: record 0 for every window
-  int32_t* out;              // sample 0 of window w_first
+  int32_t* out;              // sample 0 of window w_first (an int16 array when pack16)
   uint32_t w_first;          // first window of the launch (index into win_rec)
   uint32_t nwin;             // whole windows to generate
   uint32_t tile_off;         // ntiles > 0: tiles [tile_off, tile_off + ntiles) of window w_first only
   uint32_t ntiles;           //             (unpaired shape); `out` is then the first of those tiles
   uint32_t win_minor;        // TAB_GLOBAL, whole windows: walk the bank tile by tile across its windows
   uint32_t spread;           // TAB_GLOBAL, one whole window: G > 0 = warp j of G takes the j-th G-th of the window
+  uint32_t pack16;           // 1: `out` is an int16 array (BHW_OUT_INT16); 2- and 3-term shapes, 32-bit tail only
+  uint32_t pad3;
 };
 
 struct GroupArgs {

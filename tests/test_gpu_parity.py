@@ -838,13 +838,22 @@ def test_packed_int16_output():
         b_ = bhw.generate_batch([d])
         assert a.dtype == torch.int16 and torch.equal(a.to(torch.int32), b_), d
         assert np.array_equal(b_[:2048].cpu().numpy().astype(np.int64), H.orc_window(d, 0, 2048))
-    # the launches of a packed batch are the library's own kernels, no bank kernel and no conversion pass
+    # the launches of a packed batch are the same kernel classes as for int32 (the bank-shaped run through the
+    # bank kernel's int16 instantiation), no conversion pass
     bhw.timing_enable(True)
     bhw.timing_reset()
     bhw.generate_batch(packed)
     kt = bhw.timing_read()
     bhw.timing_enable(False)
-    assert kt["k_synth_bank"][0] == 0 and kt["k_synth_group"][0] > 0, kt
+    assert kt["k_synth_bank"][0] == 1 and kt["k_synth_group"][0] > 0 and kt["k_apply_mul"][0] == 0, kt
+    # banks the int16 bank kernel does not take (4 and more terms; an input-quadrant CORDIC) still come out right
+    for base in (bhw.variant_desc(6, 10, 16), bhw.variant_desc(10, 9, 16), bhw.variant_desc(1, 11, 16, sin_type=bhw.SIN_CORDIC48),
+                 bhw.variant_desc(3, 12, 16), bhw.variant_desc(2, 8, 12)):
+        bank = [base.copy(aa=[int(a) - i if k == 0 else int(a) for k, a in enumerate(base.aa)]) for i in range(600)]
+        a = bhw.generate_batch([d.copy(out_format=P) for d in bank])
+        b_ = bhw.generate_batch(bank)
+        assert torch.equal(a.to(torch.int32), b_), base
+        assert np.array_equal(b_[:3000].cpu().numpy().astype(np.int64), H.orc_batch(bank[:16], 0, 3000)), base
     with pytest.raises(bhw.BhwError):
         bhw.generate_batch([small[0], packed[1]])                          # one container per batch
     with pytest.raises(bhw.BhwError):

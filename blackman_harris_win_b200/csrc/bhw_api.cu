@@ -1648,6 +1648,7 @@ int bhw_sincos(const bhw_desc* d, void* out_sin_dev, void* out_cos_dev, uint64_t
   if (!d) return BHW_E_NULL;
   int st = validate_desc(d, false);
   if (st) return st;
+  if (d->out_format != BHW_OUT_DEFAULT) return BHW_E_ARG;   // DT_SIN / DT_COS come in the default container
   const uint64_t N = 1ull << d->phi_width;
   if (n0 > N || count > N - n0) return BHW_E_RANGE;
   int dev;

@@ -184,6 +184,7 @@ def test_one_container_per_batch():
         assert bhw.lib().bhw_plan_create(arr, len(mix), C.byref(plan)) == -11
     assert bhw.lib().bhw_generate_batch_host(bhw.desc_array([d32.copy(dat_width=17, out_format=1)]), 1, 0, 1024, out.ctypes.data) == -6
     assert bhw.lib().bhw_apply(C.byref(d16), 0, None, None, 0, None) == -16
+    assert bhw.lib().bhw_sincos(C.byref(d16), None, None, 0, 0, None) == -16
     assert [bhw.elem_bytes(d) for d in (d16, d32, d64)] == [2, 4, 8]
     assert H.orc_window_status(d16) == 0 and H.orc_window_status(d32.copy(dat_width=17, out_format=1)) == -6
 

@@ -465,6 +465,45 @@ def config_lines(bhw, peak_gbs, int_peak, scratch):
     return out
 
 
+def apply_lines(bhw, peak_gbs, scratch):
+    """SURVEY section 8 f3, bhw_apply: y[f, n] = x[f, n] * w[n] with the window generated on the fly (never written):
+    2048 frames of the config-2 window (BH4, N = 65536, DAT_WIDTH 17) and 8 frames of a 2^24-point Blackman-Harris 3
+    window.  Algorithmic bytes: 4 read + 8 written (exact product, int64) or 4 + 4 (the entities' rounded slice)."""
+    import torch
+    out = []
+    for name, d, frames in (("BH4 N=65536 DW17, 2048 frames", bhw.make_desc(4, 16, 17, list(BH4_AA)), 2048),
+                            ("BH3 N=16M DW16, 8 frames", bhw.variant_desc(4, 24, 16), 8)):
+        n = 1 << d.phi_width
+        x = scratch[:frames * n].view(frames, n)
+        x.random_(-(1 << (d.dat_width - 1)), 1 << (d.dat_width - 1))
+        line = {"window": name, "samples": frames * n}
+        for mode, mname, ybytes in ((bhw.APPLY_EXACT, "exact_int64", 8), (bhw.APPLY_ROUNDED, "rounded_int32", 4)):
+            y = torch.empty((frames, n), dtype=torch.int64 if ybytes == 8 else torch.int32, device="cuda")
+            ms = _time_loop(lambda: bhw.apply(d, x, mode, out=y), 10)
+            bhw.timing_enable(True)
+            bhw.timing_reset()
+            bhw.apply(d, x, mode, out=y)
+            torch.cuda.synchronize()
+            kt = bhw.timing_read()
+            bhw.timing_enable(False)
+            w = bhw.generate(d).to(torch.int64)
+            f = frames // 2
+            want = x[f].to(torch.int64) * w
+            if ybytes == 4:
+                r = want >> (d.dat_width - 2)
+                r = ((r + (1 << d.dat_width)) & ((1 << (d.dat_width + 1)) - 1)) - (1 << d.dat_width)    # wrap to DW+1 bits
+                want = (r >> 1) + (r & 1)
+                want = ((want + (1 << (d.dat_width - 1))) & ((1 << d.dat_width) - 1)) - (1 << (d.dat_width - 1))
+            if not torch.equal(y[f].to(torch.int64), want):
+                raise SystemExit(f"bench.py: bhw_apply {mname} differs from x * w")
+            line[mname] = {"ms": round(ms, 5), "gsamples_per_s": round(frames * n / ms / 1e6, 1),
+                           "bytes": (4 + ybytes) * frames * n, "frac_hbm": round((4 + ybytes) * frames * n / ms / 1e6 / peak_gbs, 4),
+                           "kernels": {k: v[0] for k, v in kt.items() if v[0]}}
+            del y
+        out.append(line)
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -747,6 +786,7 @@ def run_cuda(args):
         if world == 1 and not args.no_configs:
             scratch = torch.empty(1 << 28, dtype=torch.int32, device="cuda")
             line["configs"] = config_lines(bhw, peak, int_peak, scratch)
+            line["apply"] = apply_lines(bhw, peak, scratch)
             del scratch
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline("port", args.cpu_budget)

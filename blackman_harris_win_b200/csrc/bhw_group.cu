@@ -46,7 +46,10 @@ __device__ __forceinline__ void group_epilogue(const GroupArgs& a, int32_t* o, s
   }
   const int dw = (int)a.apply_dw;
   const int xsh = 32 - dw;
-  for (uint64_t f = 0; f < a.frames; ++f) {
+  // the frames are split over gridDim.y (launch_synth_group): a short window has too few tiles to fill the GPU,
+  // so several CTAs generate the same tile and each multiplies its share of the frames
+  const uint64_t f_begin = a.frames * blockIdx.y / gridDim.y, f_end = a.frames * (blockIdx.y + 1) / gridDim.y;
+  for (uint64_t f = f_begin; f < f_end; ++f) {
     const size_t base = (size_t)f * (half * 2) + idx;
     const int32_t* xf = a.x + base;
 #pragma unroll
@@ -199,6 +202,13 @@ size_t group_smem_limit() { return 192u * 1024u; }
 
 template <int M, int TAB, bool PAIR, int APPLY>
 static cudaError_t launch_group_t(const GroupArgs& a, unsigned grid, size_t smem, cudaStream_t stream, bool pdl) {
+  // fused apply step: fewer CTAs than two per SM -> split the frames over gridDim.y
+  unsigned fy = 1;
+  if ((APPLY == 1 || APPLY == 2) && a.frames > 1) {
+    const unsigned want = 2u * (unsigned)device_sm_count();
+    if (grid < want) fy = (want + grid - 1) / grid;
+    if ((uint64_t)fy > a.frames) fy = (unsigned)a.frames;
+  }
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -210,7 +220,7 @@ static cudaError_t launch_group_t(const GroupArgs& a, unsigned grid, size_t smem
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3(grid, fy);
   cfg.blockDim = dim3(kGroupThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;

@@ -696,6 +696,9 @@ def test_apply_step_fused_and_unfused():
               ("fused, pyramid", bhw.variant_desc(9, 19, 24), 2),
               ("fused, pyramid, 7 terms DW 32", bhw.variant_desc(10, 17, 32), 1),
               ("fused, HLS family", bhw.variant_desc(6, 14, 17, model=bhw.MODEL_HLS), 2),
+              ("fused, frames split over the grid (short window, many frames)", bhw.variant_desc(1, 12, 16), 301),
+              ("fused, frames split, one tile per window", bhw.variant_desc(6, 9, 17), 1000),
+              ("fused, frames split, pyramid", bhw.variant_desc(9, 13, 24), 77),
               ("scratch: TAYLOR", bhw.variant_desc(3, 14, 24, sin_type=bhw.SIN_TAYLOR, lut_size=9), 2),
               ("scratch: cordic_dds48", bhw.variant_desc(10, 12, 32, sin_type=bhw.SIN_CORDIC48), 2),
               ("scratch: shorter than a tile pair", bhw.variant_desc(2, 6, 16), 5),

@@ -15,11 +15,13 @@ MODEL_RTL, MODEL_HLS, MODEL_CPP = 0, 1, 2
 ALGO_AUTO, ALGO_DIRECT, ALGO_TABLE = 0, 1, 2
 OUT_DEFAULT, OUT_INT16 = 0, 1
 RULE_TB, RULE_HLS = 0, 1
-MAX_TERMS = 7
+MAX_TERMS = 11
 VARIANT_NAMES = {
     1: "hamming", 2: "hann", 3: "blackman", 4: "blackman_harris_3", 5: "nuttall",
     6: "blackman_harris_4", 7: "blackman_nuttall", 8: "flat_top", 9: "blackman_harris_5",
     10: "blackman_harris_7", 11: "blackman_harris_7_readme", 12: "hamming_alt", 13: "flat_top_normalised",
+    # minimum-sidelobe sets of doc/blackman-harris coef.jpg without a reference entity (BHW_WIN_MTERM_*)
+    14: "min_sidelobe_6", 15: "min_sidelobe_8", 16: "min_sidelobe_9", 17: "min_sidelobe_10", 18: "min_sidelobe_11",
 }
 _WIN_TYPE_NAMES = {"HAMMING": 2, "BH3TERM": 3, "BH4TERM": 4, "BH5TERM": 5, "BH7TERM": 7}
 _SIN_TYPE_NAMES = {"CORDIC": SIN_CORDIC, "TAYLOR": SIN_TAYLOR, "CORDIC48": SIN_CORDIC48,

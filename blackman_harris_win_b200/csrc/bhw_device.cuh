@@ -668,7 +668,7 @@ struct WinRec {
   const int32_t* tabp[BHW_MAX_TERMS];  // tabp[k], k = 1..m-1: trig table of harmonic k
   uint32_t pad2[2];
 };
-static_assert(sizeof(WinRec) == 224, "WinRec is copied to shared memory as 56 words");
+static_assert(sizeof(WinRec) == 320 && sizeof(WinRec) % 16 == 0, "WinRec is copied to shared memory word by word");
 enum : uint32_t {
   WR_ACC64 = 2u,    // accumulator / shifts need more than 32 bits: 64-bit tail on table values
   WR_HLS = 4u,      // HLS tail
@@ -736,7 +736,12 @@ BHW_HD int32_t synth_sample(const WinRec& r, uint32_t n) {
     case 3: return synth_sample_m<3>(r, n);
     case 4: return synth_sample_m<4>(r, n);
     case 5: return synth_sample_m<5>(r, n);
-    default: return synth_sample_m<7>(r, n);
+    case 6: return synth_sample_m<6>(r, n);     // 6 and 8..11 terms: BHW_WIN_MTERM_* (general kernel only)
+    case 7: return synth_sample_m<7>(r, n);
+    case 8: return synth_sample_m<8>(r, n);
+    case 9: return synth_sample_m<9>(r, n);
+    case 10: return synth_sample_m<10>(r, n);
+    default: return synth_sample_m<11>(r, n);
   }
 }
 

@@ -157,7 +157,11 @@ k_synth(const __grid_constant__ SynthArgs a) {
           case 3: synth_tile<3, OutT>(rec, n, o, valid); break;
           case 4: synth_tile<4, OutT>(rec, n, o, valid); break;
           case 5: synth_tile<5, OutT>(rec, n, o, valid); break;
-          default: synth_tile<7, OutT>(rec, n, o, valid); break;
+          case 7: synth_tile<7, OutT>(rec, n, o, valid); break;
+          default:   // 6 and 8..11 terms (BHW_WIN_MTERM_*): the run-time form
+            for (int j = 0; j < 4; ++j)
+              if ((uint32_t)(32 * j) < valid) o[32 * j] = (OutT)synth_sample(rec, n + 32 * j);
+            break;
         }
       }
     } else {

@@ -329,6 +329,7 @@ bool source_inq_complement(const SrcParams& sp) { return sp.kind == SRC_INQ && s
 bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_bytes, BankShape* sh,
                 int* tab_mode, bool* pair, bool allow_pair) {
   if (r.flags & WR_GENERIC) return false;
+  if (!kernel_terms((int)r.m)) return false;
   if (r.pw < (uint32_t)kBankTileLog2) return false;  // a window must hold at least one tile
   memset(sh, 0, sizeof(*sh));
   sh->m = r.m; sh->pw = r.pw;
@@ -395,7 +396,12 @@ bool bank_shape(const WinRec& r, const BankTableInfo* tk, size_t smem_limit_byte
 
 
 // ---- families and groups --------------------------------------------------------------------------
+// term counts the group and bank kernels are instantiated for (the reference's entities); 6 and 8..11 terms
+// (BHW_WIN_MTERM_*) go through the general and the direct kernels
+bool kernel_terms(int m) { return m == 2 || m == 3 || m == 4 || m == 5 || m == 7; }
+
 bool group_eligible(const bhw_desc& d, const WinParams& wp, const SrcParams* src) {
+  if (!kernel_terms(wp.m)) return false;
   if (d.algo == BHW_ALGO_DIRECT || wp.nsrc != 1 || wp.pw < kBankTileLog2 + 1 || wp.elem64) return false;
   const SrcParams& sp = src[0];
   if (sp.kind != SRC_DDS && sp.kind != SRC_HLS) return false;

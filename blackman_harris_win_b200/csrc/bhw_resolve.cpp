@@ -36,7 +36,11 @@ int validate_desc(const bhw_desc* d, bool for_window) {
   const int pw = d->phi_width, dw = d->dat_width;
   if (for_window) {
     const int m = d->win_type;
-    if (m != 2 && m != 3 && m != 4 && m != 5 && m != 7) return BHW_E_WIN_TYPE;
+    if (m < 2 || m > BHW_MAX_TERMS) return BHW_E_WIN_TYPE;
+    // 6 and 8..11 terms (BHW_WIN_MTERM_*) are the RTL structure extended, with a CORDIC source: the HLS model has
+    // no such type (win_function.cpp:380-422) and only hamming_win / bh_win_3term take TAYLOR
+    const bool entity = m == 2 || m == 3 || m == 4 || m == 5 || m == 7;
+    if (!entity && (d->model != BHW_MODEL_RTL || d->sin_type == BHW_SIN_TAYLOR)) return BHW_E_WIN_TYPE;
   }
   if (pw < BHW_MIN_PHI_WIDTH || pw > BHW_MAX_PHI_WIDTH) return BHW_E_PHI_WIDTH;
   switch (d->model) {
@@ -250,7 +254,7 @@ int resolve_window(const bhw_desc* d, WinParams* wp, SrcParams src[2]) {
 
 // ---- coefficient front end -----------------------------------------------------------------
 // Real-valued sets as the reference spells them (README.md:30-41 for the list of variants).
-static const double kCoef[13][BHW_MAX_TERMS] = {
+static const double kCoef[18][BHW_MAX_TERMS] = {
     {0.5434783, 1.0 - 0.5434783},                        // Hamming       src/tb/tb_windows.vhd:123-124
     {0.5, 0.5},                                          // Hann          src/hamming_win.vhd:14-16
     {0.42, 0.5, 0.08},                                   // Blackman      src/tb/tb_windows.vhd:114-116
@@ -267,12 +271,28 @@ static const double kCoef[13][BHW_MAX_TERMS] = {
     {0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803, 0.01081174209837,
      0.00077658482522, 0.00001388721735},                // BH 7-term, README.md:45-51 (magnitudes; the entity alternates the signs)
     {0.5383554, 0.4616446},                              // Hamming, second set  src/hamming_win.vhd:21-23
-    {0.215578950, 0.416631580, 0.277263158, 0.083578947, 0.006947368}};  // Flat-top, normalised  src/bh_win_5term.vhd:28-33
-static const int kTerms[13] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7, 7, 2, 5};
+    {0.215578950, 0.416631580, 0.277263158, 0.083578947, 0.006947368},   // Flat-top, normalised  src/bh_win_5term.vhd:28-33
+    // 14..18: the 6- and 8..11-term minimum-sidelobe sets the reference only tabulates (doc/blackman-harris coef.jpg,
+    // "Table 1. Coefficients of minimum sidelobe windows"); BHW_WIN_MTERM_* - no reference entity
+    {2.935578950102797e-001, 4.519357723474506e-001, 2.014164714263962e-001, 4.792610922105837e-002,
+     5.026196426859393e-003, 1.375555679558877e-004},
+    {2.533176817029088e-001, 4.163269305810218e-001, 2.288396213719708e-001, 8.157508425925879e-002,
+     1.773592450349622e-002, 2.096702749032688e-003, 1.067741302205525e-004, 1.280702090361482e-006},
+    {2.384331152777942e-001, 4.005545348643820e-001, 2.358242530472107e-001, 9.527918858383112e-002,
+     2.537395516617152e-002, 4.152432907505835e-003, 3.685604163298180e-004, 1.384355593917030e-005,
+     1.161808358932861e-007},
+    {2.257345387130214e-001, 3.860122949150963e-001, 2.401294214106057e-001, 1.070542338664613e-001,
+     3.325916184016952e-002, 6.873374952321475e-003, 8.751673238035159e-004, 6.008598932721187e-005,
+     1.710716472110202e-006, 1.027272130265191e-008},
+    {2.151527506679809e-001, 3.731348357785249e-001, 2.424243358446660e-001, 1.166907592689211e-001,
+     4.077422105878731e-002, 1.000904500852923e-002, 1.639806917362033e-003, 1.651660820997142e-004,
+     8.884663168541479e-006, 1.938617116029048e-007, 8.482485599330470e-010}};
+static const int kTerms[18] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7, 7, 2, 5, 6, 8, 9, 10, 11};
 
 static int variant_coeffs(int variant, int rule, double a[BHW_MAX_TERMS], int* nterms) {
-  if (variant < 1 || variant > 13) return BHW_E_VARIANT;
+  if (variant < 1 || variant > 18) return BHW_E_VARIANT;
   if (rule != BHW_RULE_TB && rule != BHW_RULE_HLS) return BHW_E_VARIANT;
+  if (variant > 13 && rule != BHW_RULE_TB) return BHW_E_VARIANT;   // the HLS model has no such window type
   const int m = kTerms[variant - 1];
   for (int k = 0; k < BHW_MAX_TERMS; k++) a[k] = k < m ? kCoef[variant - 1][k] : 0.0;
   if (rule == BHW_RULE_HLS && variant == 3)  // the HLS Blackman uses 0.21/0.25/0.04 (win_function.cpp:206-208)
@@ -356,7 +376,7 @@ int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TE
     if (m == 3) scale = ldexp(1.0, dat_width) - 16.0;
     else if (m == 4) scale = ldexp(1.0, dat_width) - 1.0;
     else if (m == 5) scale = ldexp(1.0, dat_width - 2) - 1.0;
-    else scale = ldexp(1.0, dat_width - 1) - 1.0;
+    else scale = ldexp(1.0, dat_width - 1) - 1.0;   // 2 and 7 terms; 6 and 8..11 terms follow the 7-term entity
   } else {
     // round(a * (2^(NW-1)-1)) for types 1-4, 2^(NW-2)-1 for 5 and 7 (win_function.cpp:176-355)
     scale = m >= 5 ? ldexp(1.0, dat_width - 2) - 1.0 : ldexp(1.0, dat_width - 1) - 1.0;

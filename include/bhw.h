@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define BHW_VERSION 0x000100 /* 0.1.0 */
-#define BHW_MAX_TERMS 7
+#define BHW_MAX_TERMS 11  /* bh_win_7term is the reference's widest entity; 6 and 8..11 terms: see BHW_WIN_MTERM_* */
 #define BHW_MIN_PHI_WIDTH 4   /* 16 points ...                                  */
 #define BHW_MAX_PHI_WIDTH 26  /* ... 64M points, the reference's range (README.md:2) */
 
@@ -48,7 +48,8 @@ extern "C" {
 typedef enum bhw_status {
   BHW_OK = 0,
   BHW_E_NULL = -1,        /* a required pointer is NULL                       */
-  BHW_E_WIN_TYPE = -2,    /* win_type is not 2,3,4,5,7                        */
+  BHW_E_WIN_TYPE = -2,    /* win_type is not 2..11, or 6 / 8..11 outside the
+                             RTL model with a CORDIC source                   */
   BHW_E_SIN_TYPE = -3,    /* unknown sin_type, or not available for the entity
                              (4/5/7-term have no TAYLOR: src/bh_win_4term.vhd:57-61) */
   BHW_E_MODEL = -4,       /* unknown model, or model/sin_type/op mismatch     */
@@ -79,7 +80,18 @@ enum {
   BHW_WIN_BH3TERM = 3, /* "BH3TERM" -> bh_win_3term (src/bh_win_3term.vhd:68-90) */
   BHW_WIN_BH4TERM = 4, /* "BH4TERM" -> bh_win_4term (src/bh_win_4term.vhd:56-75) */
   BHW_WIN_BH5TERM = 5, /* "BH5TERM" -> bh_win_5term (src/bh_win_5term.vhd:70-90) */
-  BHW_WIN_BH7TERM = 7  /* "BH7TERM" -> bh_win_7term (src/bh_win_7term.vhd:58-80) */
+  BHW_WIN_BH7TERM = 7, /* "BH7TERM" -> bh_win_7term (src/bh_win_7term.vhd:58-80) */
+  /* Extension, not a reference entity: the minimum-sidelobe sets with 6 and 8..11 terms that the reference
+   * only tabulates (doc/blackman-harris coef.jpg).  The window is what the structure shared by
+   * bh_win_3term .. bh_win_7term gives for M terms: one cordic_dds (or pin-compatible CORDIC) per harmonic
+   * k = 1..M-1 at phase k*n, each product sliced and rounded as in every entity
+   * (src/bh_win_7term.vhd:350-400), the alternating sum AA0 - b1 + b2 - ... in DAT_WIDTH+2 bits and the
+   * rounding on bit 1 (src/bh_win_3term.vhd:295-306).  BHW_MODEL_RTL with a CORDIC source only. */
+  BHW_WIN_MTERM_6 = 6,
+  BHW_WIN_MTERM_8 = 8,
+  BHW_WIN_MTERM_9 = 9,
+  BHW_WIN_MTERM_10 = 10,
+  BHW_WIN_MTERM_11 = 11
 };
 
 /* SIN_TYPE generic (src/win_selector.vhd:65) plus the two pin-compatible
@@ -138,7 +150,7 @@ typedef struct bhw_desc {
                             over the host link; batch / plan entry points and
                             bhw_generate[_host] only, one format per batch.
                             (XSERIES needs no field: it has no numeric effect.)      */
-  int64_t aa[BHW_MAX_TERMS]; /* raw two's-complement AA0..AA6 port values; terms
+  int64_t aa[BHW_MAX_TERMS]; /* raw two's-complement AA0..AA10 port values; terms
                                 beyond win_type are ignored                        */
 } bhw_desc;
 
@@ -161,9 +173,10 @@ BHW_API int bhw_elem_bytes(const bhw_desc* d);
  * 10 Blackman-Harris-7 (README.md:30-41); and the alternative sets the reference
  * prints beside them: 11 Blackman-Harris-7 as in README.md:45-51, 12 Hamming
  * 0.5383554 / 0.4616446 (src/hamming_win.vhd:21-23), 13 Flat-top normalised
- * (src/bh_win_5term.vhd:28-33).  Writes aa_out[0..6] (unused = 0) and *win_type
- * (2,3,4,5,7).  (The 6- and 8..11-term sets of doc/blackman-harris coef.jpg have
- * no entity in the reference - no adder tree, no rounding rule - and are not offered.) */
+ * (src/bh_win_5term.vhd:28-33); 14..18: the 6-, 8-, 9-, 10- and 11-term
+ * minimum-sidelobe sets of doc/blackman-harris coef.jpg (rule TB only, scaled like
+ * the 7-term entity's: 2^(DAT_WIDTH-1)-1) for the BHW_WIN_MTERM_* extension.
+ * Writes aa_out[0..10] (unused = 0) and *win_type (the number of terms). */
 enum { BHW_RULE_TB = 0, BHW_RULE_HLS = 1 };
 BHW_API int bhw_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS],
                  int32_t* win_type);

@@ -99,6 +99,25 @@ class win_selector {
   bhw_desc d_;
 };
 
+// Extension (no reference entity): a window of `terms` = 6 or 8..11 cosine terms built like bh_win_7term
+// (BHW_WIN_MTERM_*), coefficients by quantize variant 14..18 (doc/blackman-harris coef.jpg) or raw ports.
+inline bhw_desc mterm_desc(int terms, int PHI_WIDTH, int DAT_WIDTH, const std::vector<int64_t>& aa = {},
+                           int sin_type = BHW_SIN_CORDIC) {
+  bhw_desc d = bhw_desc();
+  d.win_type = terms; d.phi_width = PHI_WIDTH; d.dat_width = DAT_WIDTH; d.sin_type = sin_type;
+  if (aa.empty()) {
+    const int variant = terms == 6 ? 14 : terms + 7;   // 8 -> 15 ... 11 -> 18
+    int32_t wt = 0;
+    check(bhw_quantize(variant, BHW_RULE_TB, DAT_WIDTH, d.aa, &wt), "bhw_quantize");
+    if (wt != terms) throw error(BHW_E_WIN_TYPE, "mterm_desc");
+  } else {
+    if (aa.size() > (size_t)BHW_MAX_TERMS) throw error(BHW_E_ARG, "mterm_desc: more than AA0..AA10");
+    for (size_t k = 0; k < aa.size(); k++) d.aa[k] = aa[k];
+  }
+  check(bhw_validate(&d), "mterm_desc");
+  return d;
+}
+
 // HLS win_function for i = i0 .. i0+count-1; win_type codes as in the reference (1 Hamming, 2 Hann,
 // 3 Blackman(-Harris 3), 4 BH4, 5 BH5, 7 BH7); any other code yields zeros like win_empty().
 inline std::vector<int32_t> win_function(char win_type, int nphase, int nwidth, uint64_t i0 = 0, uint64_t count = 0) {

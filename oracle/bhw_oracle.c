@@ -314,7 +314,13 @@ static int validate_source(const bhw_desc* d, int for_window) {
 int orc_validate(const bhw_desc* d) {
   if (!d) return BHW_E_NULL;
   const int m = d->win_type;
-  if (m != 2 && m != 3 && m != 4 && m != 5 && m != 7) return BHW_E_WIN_TYPE;
+  if (m < 2 || m > BHW_MAX_TERMS) return BHW_E_WIN_TYPE;
+  /* 6 and 8..11 terms: the structure of bh_win_3term .. bh_win_7term continued (one cordic_dds per harmonic, the
+   * same product rounding, the same DW+2-bit sum and rounding on bit 1) for the coefficient sets the reference only
+   * tabulates (doc/blackman-harris coef.jpg).  Not a reference entity: RTL model, CORDIC sources only. */
+  if (m == 6 || m > 7) {
+    if (d->model != BHW_MODEL_RTL || d->sin_type == BHW_SIN_TAYLOR) return BHW_E_WIN_TYPE;
+  }
   int st = validate_source(d, 1);
   if (st) return st;
   if (d->stream_offset != 0 && d->stream_offset != 1) return BHW_E_ARG;
@@ -581,7 +587,7 @@ int orc_atan2_stream(int iw, int aw, int prec, const int32_t* x, const int32_t* 
 
 /* ---- coefficient rules ---------------------------------------------------- */
 /* variants per README.md:30-41; values per the entity headers */
-static const double COEF[13][7] = {
+static const double COEF[18][BHW_MAX_TERMS] = {
     {0.5434783, 1.0 - 0.5434783},                              /* 1 Hamming   tb :123-124 */
     {0.5, 0.5},                                                /* 2 Hann      hamming_win.vhd:14-16 */
     {0.42, 0.5, 0.08},                                         /* 3 Blackman  tb :114-116 */
@@ -597,17 +603,34 @@ static const double COEF[13][7] = {
     {0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803, 0.01081174209837,
      0.00077658482522, 0.00001388721735},                      /* 11 BH7, README.md:45-51 (magnitudes) */
     {0.5383554, 0.4616446},                                    /* 12 Hamming, second set hamming_win.vhd:21-23 */
-    {0.215578950, 0.416631580, 0.277263158, 0.083578947, 0.006947368}}; /* 13 flat-top normalised bh_win_5term.vhd:28-33 */
-static const int NTERMS[13] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7, 7, 2, 5};
+    {0.215578950, 0.416631580, 0.277263158, 0.083578947, 0.006947368},  /* 13 flat-top normalised bh_win_5term.vhd:28-33 */
+    /* 14..18: the 6- and 8..11-term minimum-sidelobe sets the reference only tabulates (doc/blackman-harris coef.jpg,
+       "Table 1. Coefficients of minimum sidelobe windows"); BHW_WIN_MTERM_* - no reference entity */
+    {2.935578950102797e-001, 4.519357723474506e-001, 2.014164714263962e-001, 4.792610922105837e-002,
+     5.026196426859393e-003, 1.375555679558877e-004},
+    {2.533176817029088e-001, 4.163269305810218e-001, 2.288396213719708e-001, 8.157508425925879e-002,
+     1.773592450349622e-002, 2.096702749032688e-003, 1.067741302205525e-004, 1.280702090361482e-006},
+    {2.384331152777942e-001, 4.005545348643820e-001, 2.358242530472107e-001, 9.527918858383112e-002,
+     2.537395516617152e-002, 4.152432907505835e-003, 3.685604163298180e-004, 1.384355593917030e-005,
+     1.161808358932861e-007},
+    {2.257345387130214e-001, 3.860122949150963e-001, 2.401294214106057e-001, 1.070542338664613e-001,
+     3.325916184016952e-002, 6.873374952321475e-003, 8.751673238035159e-004, 6.008598932721187e-005,
+     1.710716472110202e-006, 1.027272130265191e-008},
+    {2.151527506679809e-001, 3.731348357785249e-001, 2.424243358446660e-001, 1.166907592689211e-001,
+     4.077422105878731e-002, 1.000904500852923e-002, 1.639806917362033e-003, 1.651660820997142e-004,
+     8.884663168541479e-006, 1.938617116029048e-007, 8.482485599330470e-010}};
+static const int NTERMS[18] = {2, 2, 3, 3, 4, 4, 4, 5, 5, 7, 7, 2, 5, 6, 8, 9, 10, 11};
 
-int orc_quantize(int variant, int rule, int dw, int64_t aa[7], int32_t* win_type) {
-  if (variant < 1 || variant > 13 || (rule != BHW_RULE_TB && rule != BHW_RULE_HLS)) return BHW_E_VARIANT;
+int orc_quantize(int variant, int rule, int dw, int64_t aa[BHW_MAX_TERMS], int32_t* win_type) {
+  if (variant < 1 || variant > 18 || (rule != BHW_RULE_TB && rule != BHW_RULE_HLS)) return BHW_E_VARIANT;
+  if (variant > 13 && rule != BHW_RULE_TB) return BHW_E_VARIANT;
   if (dw < 4 || dw > 48) return BHW_E_DAT_WIDTH;
   const int m = NTERMS[variant - 1];
   double scale;
   if (rule == BHW_RULE_TB) {        /* src/tb/tb_windows.vhd:75-127 */
     switch (m) {
-      case 2: case 7: scale = ldexp(1.0, dw - 1) - 1.0; break; /* :75-81, :126-127 */
+      case 2: case 7: case 6: case 8: case 9: case 10: case 11:
+        scale = ldexp(1.0, dw - 1) - 1.0; break;               /* :75-81, :126-127; the M-term extension follows the 7-term rule */
       case 3: scale = ldexp(1.0, dw) - 16.0; break;            /* :118-120 */
       case 4: scale = ldexp(1.0, dw) - 1.0; break;             /* :108-111 */
       default: scale = ldexp(1.0, dw - 2) - 1.0; break;        /* 5-term :96-100 */
@@ -615,7 +638,7 @@ int orc_quantize(int variant, int rule, int dw, int64_t aa[7], int32_t* win_type
   } else {                          /* hls/windows/win_function.cpp:176-355 */
     scale = (m >= 5) ? ldexp(1.0, dw - 2) - 1.0 : ldexp(1.0, dw - 1) - 1.0;
   }
-  for (int k = 0; k < 7; k++) aa[k] = 0;
+  for (int k = 0; k < BHW_MAX_TERMS; k++) aa[k] = 0;
   for (int k = 0; k < m; k++) {
     double a = COEF[variant - 1][k];
     if (rule == BHW_RULE_HLS && variant == 3) a *= 0.5;        /* 0.21/0.25/0.04: :206-208 */

@@ -39,7 +39,7 @@ void orc_cpp_cordic(int pw, int dw, int theta, int* s, int* c);
 int orc_validate(const bhw_desc* d);
 int orc_window(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out);
 int orc_sincos(const bhw_desc* d, uint64_t n0, uint64_t count, int64_t* out_sin, int64_t* out_cos);
-int orc_quantize(int variant, int rule, int dat_width, int64_t aa_out[7], int32_t* win_type);
+int orc_quantize(int variant, int rule, int dat_width, int64_t aa_out[BHW_MAX_TERMS], int32_t* win_type);
 
 /* cordic_atan2 (src/cordic_atan2.vhd): PHI_DT of one (VEC_DX, VEC_DY) pair, sign-extended from
  * ANGLE_WIDTH bits.  RTL-only entity: pinned by the executed VHDL (see header comment); the entity's own

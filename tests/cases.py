@@ -33,6 +33,27 @@ def rtl_sweep(pws=(4, 5, 7, 10, 13), extra_dws=(8, 12, 20, 31, 32, 33, 47),
     return out
 
 
+def mterm_sweep(pws=(4, 6, 9, 12), dws=(8, 16, 17, 24, 31, 32, 33, 40),
+                sin_types=(bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED)):
+    """The 6- and 8..11-term extension (BHW_WIN_MTERM_*, quantize variants 14..18) over widths and CORDIC sources,
+    plus port edge cases."""
+    out = []
+    for v in range(14, 19):
+        for pw in pws:
+            for dw in dws:
+                for st in sin_types:
+                    d = bhw.variant_desc(v, pw, dw, sin_type=st)
+                    if bhw.validate(d) == 0:
+                        out.append(d)
+    for m in (6, 8, 9, 10, 11):
+        for dw in (12, 24, 32):
+            lo, hi = -(1 << (dw - 1)), (1 << (dw - 1)) - 1
+            for aa in ([hi] * m, [lo] * m, [lo if k & 1 else hi for k in range(m)], [(-1) ** k * (k + 3) for k in range(m)], [0] * m):
+                out.append(bhw.make_desc(m, 8, dw, aa))
+                out.append(bhw.make_desc(m, 8, dw, aa, stream_offset=1))
+    return out
+
+
 def hls_sweep(cfgs):
     out = []
     for (np_, nw) in cfgs:

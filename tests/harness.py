@@ -115,7 +115,7 @@ def orc_sincos(d: BhwDesc, n0=0, count=None):
 
 
 def orc_quantize(variant, rule, dw):
-    aa = (C.c_int64 * 7)()
+    aa = (C.c_int64 * 11)()
     wt = C.c_int32(0)
     st = oracle().orc_quantize(variant, rule, dw, aa, C.byref(wt))
     if st:

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(bhw.BhwDesc) == 10 * 4 + 7 * 8
+    assert C.sizeof(bhw.BhwDesc) == 10 * 4 + 11 * 8 and api.MAX_TERMS == 11      # BHW_MAX_TERMS
     assert bhw.BhwDesc.aa.offset == 40
 
 
@@ -43,18 +43,18 @@ def test_version_and_strerror():
 
 def test_quantize_matches_reference_rules():
     # src/tb/tb_windows.vhd:75-127 worked examples
-    assert bhw.quantize(1, bhw.RULE_TB, 16) == ([17808, 14959, 0, 0, 0, 0, 0], 2)
-    assert bhw.quantize(2, bhw.RULE_TB, 16) == ([16384, 16384, 0, 0, 0, 0, 0], 2)   # 16383.5 ties up
+    assert bhw.quantize(1, bhw.RULE_TB, 16) == ([17808, 14959] + [0] * 9, 2)
+    assert bhw.quantize(2, bhw.RULE_TB, 16) == ([16384, 16384] + [0] * 9, 2)   # 16383.5 ties up
     assert bhw.quantize(6, bhw.RULE_TB, 17)[0][:4] == [47022, 64001, 18518, 1531]
     assert bhw.quantize(3, bhw.RULE_TB, 24)[0][:3] == [7046424, 8388600, 1342176]
-    assert bhw.quantize(10, bhw.RULE_TB, 32)[0] == [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379]
+    assert bhw.quantize(10, bhw.RULE_TB, 32)[0] == [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379, 0, 0, 0, 0]
     assert bhw.quantize(8, bhw.RULE_TB, 16)[0][:5] == [16383, 31619, 21134, 6357, 491]
     for v in range(1, 11):
         for rule in (0, 1):
             for dw in (8, 16, 17, 24, 32, 40, 48):
                 assert bhw.quantize(v, rule, dw) == H.orc_quantize(v, rule, dw)
     with pytest.raises(bhw.BhwError):
-        bhw.quantize(14, 0, 16)
+        bhw.quantize(19, 0, 16)
     with pytest.raises(bhw.BhwError):
         bhw.quantize(1, 2, 16)
     assert bhw.variant_coeffs(3, bhw.RULE_HLS) == [0.21, 0.25, 0.04]
@@ -63,7 +63,7 @@ def test_quantize_matches_reference_rules():
 def test_validate_rejections():
     ok = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
     assert bhw.validate(ok) == 0
-    assert bhw.validate(ok.copy(win_type=6)) == -2
+    assert bhw.validate(ok.copy(win_type=12)) == -2 and bhw.validate(ok.copy(win_type=1)) == -2   # 6 and 8..11: BHW_WIN_MTERM_*
     assert bhw.validate(ok.copy(sin_type=bhw.SIN_TAYLOR)) == -3          # 4-term has no TAYLOR
     assert bhw.validate(ok.copy(sin_type=9)) == -3
     assert bhw.validate(ok.copy(model=7)) == -4
@@ -91,17 +91,17 @@ def test_alternative_coefficient_sets():
     """Variants 11-13: the second sets the reference prints (README.md:45-51, src/hamming_win.vhd:21-23,
     src/bh_win_5term.vhd:28-33), quantised by the same rules; library and oracle agree."""
     import harness as H
-    assert bhw.quantize(11, bhw.RULE_TB, 32)[0] == [round(a * (2 ** 31 - 1)) for a in (
+    assert bhw.quantize(11, bhw.RULE_TB, 32)[0][:7] == [round(a * (2 ** 31 - 1)) for a in (
         0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803, 0.01081174209837, 0.00077658482522,
         0.00001388721735)]
-    assert bhw.quantize(12, bhw.RULE_TB, 16) == ([round(0.5383554 * 32767), round(0.4616446 * 32767), 0, 0, 0, 0, 0], 2)
+    assert bhw.quantize(12, bhw.RULE_TB, 16) == ([round(0.5383554 * 32767), round(0.4616446 * 32767)] + [0] * 9, 2)
     assert bhw.quantize(13, bhw.RULE_TB, 24)[1] == 5
     for v in (11, 12, 13):
         for rule in (bhw.RULE_TB, bhw.RULE_HLS):
             for dw in (12, 16, 24, 32):
                 assert bhw.quantize(v, rule, dw) == H.orc_quantize(v, rule, dw)
     with pytest.raises(bhw.BhwError):
-        bhw.quantize(14, bhw.RULE_TB, 16)
+        bhw.quantize(19, bhw.RULE_TB, 16)
 
 
 def test_apply_argument_checks_need_no_gpu():
@@ -167,6 +167,40 @@ def test_generate_without_gpu_fails_loudly():
     out = np.full(1024, 12345, np.int32)
     st = bhw.lib().bhw_generate_host(C.byref(bhw.make_desc(2, 10, 16, [17808, 14959])), out.ctypes.data, 0, 1024)
     assert st in (-12, -13) and (out == 12345).all()
+
+
+def test_mterm_extension_front_end():
+    """BHW_WIN_MTERM_* (6, 8..11 terms): the coefficient sets of doc/blackman-harris coef.jpg as quantize variants
+    14..18 (each sums to 1 and nearly cancels at n = 0, which any transcription slip would break), quantised by
+    the 7-term testbench rule; library and oracle agree; legal for the RTL model with a CORDIC source only."""
+    import harness as H
+    for v, m in zip(range(14, 19), (6, 8, 9, 10, 11)):
+        a = bhw.variant_coeffs(v, bhw.RULE_TB)
+        assert len(a) == m and abs(sum(a) - 1.0) < 1e-14 and 0 < sum((-1) ** k * x for k, x in enumerate(a)) < 2e-6
+        assert all(a[k] > a[k + 1] for k in range(1, m - 1))
+        for dw in (12, 16, 24, 32, 40):
+            aa, wt = bhw.quantize(v, bhw.RULE_TB, dw)
+            assert wt == m and (list(aa), wt) == H.orc_quantize(v, bhw.RULE_TB, dw)
+            assert list(aa[:m]) == [round(x * ((1 << (dw - 1)) - 1)) for x in a] and not any(aa[m:])
+        with pytest.raises(bhw.BhwError):
+            bhw.quantize(v, bhw.RULE_HLS, 16)
+        d = bhw.variant_desc(v, 10, 24)
+        assert bhw.validate(d) == 0 and H.orc_window_status(d) == 0
+        for bad in (d.copy(model=bhw.MODEL_HLS), d.copy(sin_type=bhw.SIN_TAYLOR, lut_size=5)):
+            assert bhw.validate(bad) == -2 and H.orc_window_status(bad) == -2
+        assert bhw.validate(d.copy(sin_type=bhw.SIN_CORDIC48)) == 0 and bhw.validate(d.copy(sin_type=bhw.SIN_CORDIC_SCALED)) == 0
+    assert bhw.validate(bhw.make_desc(12, 10, 16, [1] * 11)) == -2 and bhw.validate(bhw.make_desc(1, 10, 16, [1])) == -2
+    # the oracle window at the two points the coefficient identities speak about.  The CORDIC amplitude is 2^(DW-2), so
+    # the harmonics enter at half weight, and DT_WIN is dsp_pp[DW+1:2], a quarter of the sum (src/bh_win_3term.vhd:
+    # 295-306): w[N/2] ~ (a0 + (1 - a0)/2) / 4, w[0] ~ (a0 - (a1 - a2 + ...)/2) / 4
+    for v in range(14, 19):
+        a = bhw.variant_coeffs(v, bhw.RULE_TB)
+        d = bhw.variant_desc(v, 12, 24)
+        w = H.orc_window(d)
+        S = (1 << 23) - 1
+        assert abs(int(w[2048]) - S * (a[0] + (1 - a[0]) / 2) / 4) < 64
+        assert abs(int(w[0]) - S * (a[0] - sum((-1) ** (k + 1) * a[k] for k in range(1, len(a))) / 2) / 4) < 64
+        assert int(w.argmax()) == 2048
 
 
 def test_one_container_per_batch():

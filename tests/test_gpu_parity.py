@@ -757,6 +757,52 @@ def test_cordic_atan2():
         bhw.atan2(x.cuda(), y.cuda(), 16, 16, 1, stream_quadrant=2)
 
 
+def test_mterm_extension():
+    """BHW_WIN_MTERM_* (6 and 8..11 terms, quantize variants 14..18): every strategy against the oracle over widths,
+    CORDIC sources and port edge cases; long windows; mixed into batches with the reference's entities; the int16
+    container, the 64-bit container and the apply step."""
+    import torch
+    descs = cases.mterm_sweep()
+    assert len(descs) > 500
+    for d in descs:
+        want = H.orc_window(d)
+        for name, dd in both_algos(d):
+            assert np.array_equal(gpu_window(dd), want), (name, d)
+    for v, pw, dw in ((14, 16, 24), (18, 16, 32), (15, 18, 16), (17, 14, 40), (16, 20, 17)):
+        d = bhw.variant_desc(v, pw, dw)
+        n = 1 << pw
+        got = gpu_window(d)
+        for n0 in (0, n // 2 - 2048, n - 4096):
+            assert np.array_equal(got[n0:n0 + 4096], H.orc_window(d, n0, 4096)), (d, n0)
+        assert np.array_equal(gpu_window(d.copy(stream_offset=1)), np.roll(got, -1)), d
+        assert np.array_equal(gpu_window(d, 777, 5000), got[777:5777]), d
+    # batches: M-term windows between group, bank-shaped and short windows; ragged ranges; a resident plan
+    mix = []
+    for pw in (5, 9, 12, 14):
+        mix += [bhw.variant_desc(1, pw, 16), bhw.variant_desc(14, pw, 16), bhw.variant_desc(6, pw, 16), bhw.variant_desc(18, pw, 16),
+                bhw.variant_desc(10, pw, 16), bhw.variant_desc(16, pw, 16, sin_type=bhw.SIN_CORDIC48)]
+    mix += [bhw.variant_desc(15, 10, 16).copy(aa=[int(a) - i if k == 0 else int(a) for k, a in enumerate(bhw.variant_desc(15, 10, 16).aa)])
+            for i in range(200)]
+    total = bhw.batch_total(bhw.desc_array(mix))
+    want = H.orc_batch(mix, 0, total)
+    assert np.array_equal(bhw.generate_batch(mix).cpu().numpy().astype(np.int64), want)
+    for b, c in ((3, 10001), (total - 70000, 70000)):
+        assert np.array_equal(bhw.generate_batch(mix, b, c).cpu().numpy().astype(np.int64), want[b:b + c]), (b, c)
+    assert np.array_equal(bhw.generate_batch_host(mix).astype(np.int64), want)
+    plan = bhw.Plan(mix)
+    assert np.array_equal(plan.execute(5, total - 9).cpu().numpy().astype(np.int64), want[5:total - 4])
+    plan.destroy()
+    packed = bhw.generate_batch([d.copy(out_format=bhw.OUT_INT16) for d in mix])
+    assert packed.dtype == torch.int16 and np.array_equal(packed.cpu().numpy().astype(np.int64), want)
+    # the apply step (scratch path: these term counts are outside the fused kernel)
+    d = bhw.variant_desc(17, 12, 24)
+    x = torch.randint(-(1 << 23), 1 << 23, (3, 4096), dtype=torch.int32, device="cuda")
+    for mode in (bhw.APPLY_EXACT, bhw.APPLY_ROUNDED):
+        assert np.array_equal(bhw.apply(d, x, mode).cpu().numpy().astype(np.int64), H.orc_apply(d, x.cpu().numpy(), mode))
+    with pytest.raises(bhw.BhwError):
+        bhw.generate(bhw.make_desc(8, 10, 16, [1] * 8, model=bhw.MODEL_HLS))
+
+
 def test_taylor_long_window_quarter_body():
     """k_direct_taylor's quarter-window branch (direct_taylor_quad4: 16 samples from two ROM words) on whole TAY_WIDE
     windows, every sample against the oracle; the shapes around it (DT_VLD order, a range, the DSP datapath) keep
@@ -938,7 +984,7 @@ def test_win_selector_and_errors():
         bhw.generate(good.copy(dat_width=50))
     import torch
     out = torch.full((1024,), 7, dtype=torch.int32, device="cuda")
-    st = bhw.lib().bhw_generate(C.byref(good.copy(win_type=6)), out.data_ptr(), 0, 1024, None)
+    st = bhw.lib().bhw_generate(C.byref(good.copy(win_type=12)), out.data_ptr(), 0, 1024, None)
     assert st == -2 and bool((out == 7).all())                            # errors write nothing
 
 

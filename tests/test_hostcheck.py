@@ -67,6 +67,20 @@ def test_rtl_sweep_all_variants_widths_sources():
     assert len(DIRECT_TAYLOR_SEEN) > 50  # and so did the TAYLOR one
 
 
+def test_mterm_extension_bodies():
+    """6 and 8..11 terms (BHW_WIN_MTERM_*): the direct, 32-bit direct, table and generic bodies against the oracle;
+    the bank / group placements decline these term counts (they stay with the general and direct kernels)."""
+    descs = cases.mterm_sweep()
+    assert len(descs) > 500
+    n32 = len(DIRECT32_SEEN)
+    for d in descs:
+        check(d, cnt_cap=1024)
+        full = np.zeros(1 << d.phi_width, np.int64)
+        if d.phi_width >= 8 and d.dat_width <= 32:
+            assert H.hostcheck().hc_bank(C.byref(d), full.ctypes.data_as(H.I64P), 192 * 1024, -1, -1) == 1, d
+    assert len(DIRECT32_SEEN) - n32 > 100
+
+
 def test_taylor_quarter_window_body():
     """direct_taylor_quad4 (k_direct_taylor's long-window branch: 16 samples from two ROM words) against the
     per-sample body and the oracle over whole windows - every coefficient sign, DAT_WIDTH 19..32, both entities,

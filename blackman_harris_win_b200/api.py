@@ -192,7 +192,7 @@ def elem_bytes(d: BhwDesc) -> int:
 
 
 def quantize(variant: int, rule: int, dat_width: int):
-    """-> (aa[7], win_type): the reference's own quantisation rules (src/tb/tb_windows.vhd:75-127,
+    """-> (aa[11], win_type): the reference's own quantisation rules (src/tb/tb_windows.vhd:75-127,
     hls/windows/win_function.cpp:176-355)."""
     aa = (C.c_int64 * MAX_TERMS)()
     wt = C.c_int32(0)

@@ -125,7 +125,7 @@ enum {
 };
 
 /* ---- the descriptor: one field per generic / port ---------------------- */
-/* Mirrors win_selector's generic list and AA0..AA6 ports
+/* Mirrors win_selector's generic list and AA0..AA6 ports (AA7..AA10: BHW_WIN_MTERM_*)
  * (src/win_selector.vhd:60-87).  For BHW_MODEL_HLS, phi_width/dat_width are
  * NPHASE/NWIDTH (hls/windows/win_function.h:51-52) and aa[] are the a_k
  * integers the HLS functions derive from their double constants

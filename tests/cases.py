@@ -91,7 +91,7 @@ def edge_coeff_descs():
     return out
 
 
-def random_descs(count, seed, max_pw=12, models=("rtl", "hls")):
+def random_descs(count, seed, max_pw=12, models=("rtl", "hls"), terms=(2, 3, 4, 5, 7)):
     """Seeded random descriptors over everything the library accepts: entity, widths, source, model,
     stream offset, strategy, and ports drawn from {full-range random, small, real-window-like,
     extremes} so that every tail route (32-bit, bounded 32-bit at DAT_WIDTH 31..32, 64-bit, generic)
@@ -100,7 +100,7 @@ def random_descs(count, seed, max_pw=12, models=("rtl", "hls")):
     rng = random.Random(seed)
     out = []
     while len(out) < count:
-        m = rng.choice((2, 3, 4, 5, 7))
+        m = rng.choice(terms)
         pw = rng.randint(4, max_pw)
         model = rng.choice(models)
         if model == "hls":

@@ -564,6 +564,29 @@ def test_random_descriptors_one_shot_and_in_one_plan():
     plan.destroy()
 
 
+def test_random_descriptors_with_the_extensions():
+    """The same fuzz over the round-2 additions: 6 and 8..11 terms among the entities, and every DAT_WIDTH <= 16
+    descriptor of the seed once more in the int16 container - one shot, in one batch, in ragged ranges of a plan."""
+    import torch
+    descs = cases.random_descs(260, seed=20261019, max_pw=13, terms=(2, 3, 4, 5, 6, 7, 8, 9, 10, 11))
+    assert sum(d.win_type in (6, 8, 9, 10, 11) for d in descs) > 60
+    for d in descs:
+        assert np.array_equal(gpu_window(d), H.orc_window(d)), d
+    small = [d.copy(algo=bhw.ALGO_AUTO, out_format=bhw.OUT_INT16) for d in descs if d.dat_width <= 16]
+    assert len(small) > 50
+    for d in small[:40]:
+        got = bhw.generate(d)
+        assert got.dtype == torch.int16 and np.array_equal(got.cpu().numpy().astype(np.int64), H.orc_window(d)), d
+    total = bhw.batch_total(small)
+    want = H.orc_batch(small, 0, total)
+    assert np.array_equal(bhw.generate_batch(small).cpu().numpy().astype(np.int64), want)
+    plan = bhw.Plan(small)
+    for b, c in ((0, total), (1, total - 2), (total // 3, total // 2), (total - 300, 300)):
+        assert np.array_equal(plan.execute(b, c).cpu().numpy().astype(np.int64), want[b:b + c]), (b, c)
+    plan.destroy()
+    assert np.array_equal(bhw.generate_batch_host(small, 17, total - 40).astype(np.int64), want[17:total - 23])
+
+
 def test_host_entry_points():
     d = bhw.make_desc(4, 16, 17, [47022, 64001, 18518, 1531])
     want = H.orc_window(d)

@@ -18,6 +18,21 @@ KAT = json.load(open(os.path.join(GOLD, "reference_kat.json")))
 RTL = json.load(open(os.path.join(GOLD, "rtl_kat.json")))
 
 
+MTERM = json.load(open(os.path.join(GOLD, "mterm_kat.json")))
+
+
+@pytest.mark.parametrize("e", MTERM["windows"], ids=lambda e: f"v{e['variant']}_pw{e['phi_width']}_dw{e['dat_width']}_s{e['sin_type']}")
+def test_mterm_definition_is_frozen(e):
+    """6 and 8..11 terms have no reference entity: tests/golden/mterm_kat.json freezes the oracle's answer (a definition,
+    not parity) together with the ports bhw_quantize produced for it."""
+    d = bhw.variant_desc(e["variant"], e["phi_width"], e["dat_width"], sin_type=e["sin_type"])
+    assert d.win_type == e["win_type"] and list(d.aa)[:d.win_type] == e["aa"]
+    w = H.orc_window(d)
+    for i, v in e["values"].items():
+        assert int(w[int(i)]) == v
+    assert H.sha_lines(w) == e["sha256"]
+
+
 def hls_desc(np_, nw, t):
     return bhw.variant_desc(cases.HLS_TYPES[t], np_, nw, model=bhw.MODEL_HLS)
 

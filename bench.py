@@ -774,7 +774,10 @@ def run_cuda(args):
                        "tables": "rebuilt every step (table cache off)",
                        "plan_create_ms": round(1e3 * t_plan, 3),
                        "plan_create_note": "resolving the 230 descriptors and uploading their records happens once, before the "
-                                           "timed region (the entities' elaboration); value excludes it, e2e includes it",
+                                           "timed region (the entities' elaboration); value excludes it, e2e includes it. "
+                                           "This is the first plan of the process (first device allocations included): a "
+                                           "repeated create takes 1.2 ms, and a one-shot bhw_generate_batch of the whole sweep - "
+                                           "resolve, upload, build, synthesis, release - 1.73 ms (profiles/r2_one_shot.json)",
                        "sharding": f"cost-balanced contiguous flat slices (bhw_shard_range_cost), {world} rank(s), no collective",
                        "per_rank_ms": [round(x, 5) for x in per_rank_ms],
                        "oracle_checked_windows": checked},

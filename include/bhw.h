@@ -141,7 +141,10 @@ typedef struct bhw_desc {
   int32_t lut_size;      /* LUT_SIZE (TAYLOR only); 0 means the entity default 9
                             (src/hamming_win.vhd:67)                               */
   int32_t stream_offset; /* 0: out[j] = w[n0+j]; 1: the DT_VLD-gated order
-                            w[1], w[2], ..., w[N-1], w[0] (DESIGN.md "stream order") */
+                            w[1], w[2], ..., w[N-1], w[0] of the entities as written
+                            (cordic_dds / TAYLOR; confirmed by executing the VHDL,
+                            DESIGN.md section 2).  With cordic_dds48 / _scaled swapped
+                            in, the same rotation is applied as a convention only */
   int32_t algo;          /* BHW_ALGO_*                                             */
   int32_t out_format;    /* BHW_OUT_*: container of one output sample.  0: int32
                             (int64 for DAT_WIDTH > 32).  BHW_OUT_INT16: int16, for

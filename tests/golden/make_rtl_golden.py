@@ -29,6 +29,46 @@ def phases_for(pw, rng, n=192):
     return sorted(set(fixed + [int(x) for x in rng.integers(0, N, n)]))
 
 
+def swapped_cases(lib, arrays, cases):
+    """BASELINE config 3 names a composition the reference never elaborates: a window entity with cordic_dds48 (or
+    cordic_dds_scaled) in place of cordic_dds.  The three DDS entities have the same port list, so the swap is made
+    here by binding the name cordic_dds to the other entity and clocking the unmodified window entity."""
+    import copy
+    ent_of = {2: "hamming_win", 3: "bh_win_3term", 4: "bh_win_4term", 5: "bh_win_5term", 7: "bh_win_7term"}
+    cases["windows_swapped"] = []
+    for dds in ("cordic_dds48", "cordic_dds_scaled"):
+        l2 = copy.copy(lib)
+        l2.units = dict(lib.units)
+        l2.units["cordic_dds"] = lib.units[dds]
+        for v, pw, dw in ((10, 6, 32), (10, 8, 16), (10, 7, 24), (6, 7, 17), (1, 6, 16), (9, 6, 24), (3, 6, 12), (8, 7, 20)):
+            aa, m = bhw.quantize(v, bhw.RULE_TB, dw)
+            gen = {"PHI_WIDTH": pw, "DAT_WIDTH": dw}
+            if m <= 3:
+                gen["SIN_TYPE"] = "CORDIC"
+            clocks = 2 * (1 << pw) + dw + 30
+            out = V.run_window(l2, ent_of[m], gen, [int(a) for a in aa[:m]], clocks)
+            vld = [o[1] for o in out]
+            key = f"winswap/{dds}/{ent_of[m]}/pw{pw}_dw{dw}_variant{v}"
+            arrays[key + "/aa"] = np.array([int(a) for a in aa[:m]], np.int64)
+            arrays[key + "/dt_win_per_clock"] = np.array([o[0] for o in out], np.int64)
+            arrays[key + "/dt_vld_per_clock"] = np.array(vld, np.int8)
+            cases["windows_swapped"].append({"dds": dds, "entity": ent_of[m], "generics": gen, "key": key, "clocks": clocks,
+                                             "first_dt_vld_clock": vld.index(1)})
+            print(key, "first DT_VLD clock", vld.index(1), flush=True)
+
+
+def update_only_swapped():
+    """python tests/golden/make_rtl_golden.py swapped: add the swapped compositions to the existing files."""
+    lib = V.reference_library()
+    z = np.load(os.path.join(HERE, "rtl_sim_vectors.npz"))
+    arrays = {k: z[k] for k in z.files if not k.startswith("winswap/")}
+    cases = json.load(open(os.path.join(HERE, "rtl_sim_cases.json")))
+    swapped_cases(lib, arrays, cases)
+    np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
+    print("wrote", len(arrays), "arrays")
+
+
 def main():
     lib = V.reference_library()
     rng = np.random.default_rng(20261018)
@@ -151,10 +191,14 @@ def main():
         cases["mult"].append({"dtw": dtw, "key": key})
         print(key, flush=True)
 
+    swapped_cases(lib, arrays, cases)
     np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
     json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
     print("wrote", len(arrays), "arrays")
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["swapped"]:
+        update_only_swapped()
+    else:
+        main()

@@ -981,6 +981,20 @@ def test_rtl_golden_vectors_on_gpu():
         if g["DAT_WIDTH"] <= 32:
             descs.append(d.copy(stream_offset=1))
             wants.append(stream)
+    # config 3's composition: the window entities over cordic_dds48 / cordic_dds_scaled (the name cordic_dds bound to
+    # the other entity in the simulator); w[0] reaches DT_WIN one clock after DT_VLD has risen
+    sin_sw = {"cordic_dds48": bhw.SIN_CORDIC48, "cordic_dds_scaled": bhw.SIN_CORDIC_SCALED}
+    for c in cases["windows_swapped"]:
+        g = c["generics"]
+        m = H.rtl_case_terms(c)
+        N = 1 << g["PHI_WIDTH"]
+        d = bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], [int(a) for a in z[c["key"] + "/aa"]], sin_type=sin_sw[c["dds"]])
+        L = c["first_dt_vld_clock"] + 1
+        want = z[c["key"] + "/dt_win_per_clock"][L:L + N]
+        for name, dd in both_algos(d):
+            assert np.array_equal(gpu_window(dd), want), (name, c["key"])
+        descs.append(d)
+        wants.append(want)
     # and all the int32 ones as one plan (group / bank kernels)
     got = bhw.generate_batch(descs).cpu().numpy().astype(np.int64)
     assert np.array_equal(got, np.concatenate(wants))

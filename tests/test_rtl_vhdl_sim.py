@@ -55,7 +55,7 @@ def test_case_inventory(gold):
     assert {c["entity"] for c in cases["dds"]} == set(SIN_OF)
     assert {c["entity"] for c in cases["windows"]} == ENTITIES
     assert sum(H.rtl_case_is_taylor(c) for c in cases["windows"]) == 12
-    for grp in ("dds", "windows", "atan2", "taylor", "mult"):
+    for grp in ("dds", "windows", "atan2", "taylor", "mult", "windows_swapped"):
         for c in cases[grp]:
             assert any(f.startswith(c["key"] + "/") for f in z.files), c["key"]
 
@@ -208,6 +208,33 @@ def test_multiplier_entity(gold):
     for c in cases["mult"]:
         a, b, q = z[c["key"] + "/a"], z[c["key"] + "/b"], z[c["key"] + "/q_per_clock"]
         assert np.array_equal(q[1:1 + len(a)], a * b), c["key"]
+
+
+def test_windows_with_the_dds_entity_swapped(gold):
+    """BASELINE config 3's composition - a window entity over cordic_dds48 / cordic_dds_scaled - executed by binding
+    the name cordic_dds to the other, pin-compatible entity: the window values are the oracle's for sin_type
+    CORDIC48 / CORDIC_SCALED bit for bit.  Those DDS entities are two clocks longer than cordic_dds while the window's
+    ADD_DELAY stays DAT_WIDTH+7 (+1, +2), so here DT_VLD rises one clock BEFORE w[0] reaches DT_WIN: for these
+    sources stream_offset is a rotation convention of the API, not something a swapped entity would stream."""
+    z, cases = gold
+    sin_of = {"cordic_dds48": bhw.SIN_CORDIC48, "cordic_dds_scaled": bhw.SIN_CORDIC_SCALED}
+    hc = H.hostcheck()
+    assert len(cases["windows_swapped"]) == 16
+    for c in cases["windows_swapped"]:
+        g = c["generics"]
+        m = H.rtl_case_terms(c)
+        N = 1 << g["PHI_WIDTH"]
+        aa = [int(a) for a in z[c["key"] + "/aa"]]
+        d = bhw.make_desc(m, g["PHI_WIDTH"], g["DAT_WIDTH"], aa, sin_type=sin_of[c["dds"]])
+        w = H.orc_window(d)
+        win = z[c["key"] + "/dt_win_per_clock"]
+        L = c["first_dt_vld_clock"] + 1                      # w[0] is on DT_WIN one clock after DT_VLD has risen
+        assert c["first_dt_vld_clock"] == g["DAT_WIDTH"] + {2: 8, 3: 8, 4: 9, 5: 9, 7: 10}[m], c["key"]
+        assert np.array_equal(win[L:], w[np.arange(len(win) - L) % N]), c["key"]
+        got = np.empty(N, np.int64)
+        assert hc.hc_direct(C.byref(d), 0, N, got.ctypes.data_as(H.I64P)) == 0 and np.array_equal(got, w), c["key"]
+        st = hc.hc_table(C.byref(d), 0, N, got.ctypes.data_as(H.I64P), 0)
+        assert st in (0, 1) and (st or np.array_equal(got, w)), c["key"]
 
 
 def atan2_views(z, c):

@@ -818,7 +818,8 @@ static int plan_execute(bhw_plan& plan, uint64_t flat_begin, uint64_t flat_count
   bool tm_on = false;
   bool building = false, defer_family_builds = false;
   const bool have_jobs = !plan.jobs.empty() || !plan.big_jobs.empty();
-  const bool keep = g_cache_enabled.load() != 0;
+  // a one-shot plan lives for one call: the chunks of a host-buffer request share the tables its first chunk built
+  const bool keep = plan.transient || g_cache_enabled.load() != 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
   const bool capturing = cap != cudaStreamCaptureStatusNone;

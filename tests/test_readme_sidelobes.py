@@ -1,0 +1,131 @@
+"""The reference's one published table of results for this path: README.md:30-41, "Side lobe lvl (dB)" per
+component, plus README.md:53 ("up to 180 dB") and README.md:5-6 ("1 digital bit equals 6dB ... Blackman-Harris
+4-term (-92dB) ... total optimal bit width = 17").  These are spectral figures, not integers, so they pin the
+*meaning* of the generated tables where the bit-exact vectors (tests/golden/) pin their bits: the integer
+window an entity streams is transformed (float64 FFT, zero-padded 16x) and its highest side lobe is compared
+with the table.
+
+How the table is reached: the CORDIC cores have amplitude 2^(DAT_WIDTH-2), so a window entity
+computes (AA0 - AA1 cos / 2 + AA2 cos / 2 - ...) / 4 - the harmonics carry an extra 1/2 relative to AA0.  With
+the testbench's equal-scale ports (src/tb/tb_windows.vhd:75-127) the stream is therefore the textbook window
+on a pedestal; the published side-lobe levels appear when AA0 is passed at HALF the scale of AA1.. (or with the
+TAYLOR source, whose amplitude is 2^(DAT_WIDTH-1)-1, at equal scale).  INTEGRATION.md section 4 says the same
+to callers.
+
+Two things the table does not say and this test records:
+  * "Nuttall -93": src/bh_win_4term.vhd:16-17 spells a2 = 0.144323; the literature's window is 0.144232 (two
+    digits transposed).  The entity fed the reference's own number gives -87.3 dB; with 0.144232 it gives the
+    published -93.3 dB.
+  * "Hamming -43" is the level of the second set the reference prints (0.5383554 / 0.4616446,
+    src/hamming_win.vhd:21-23: -43.2 dB); the testbench's 0.5434783 gives -41.7 dB.  "Flat-top -69" is
+    conservative for the testbench's set (-75.6 dB); the normalised set of src/bh_win_5term.vhd:28-33 gives -93.
+"""
+import numpy as np
+import pytest
+
+import blackman_harris_win_b200 as bhw
+import harness as H
+
+# README.md:30-41 (variant numbering as bhw_quantize)
+README_DB = {1: -43, 2: -32, 3: -58, 4: -71, 5: -93, 6: -92, 7: -98, 8: -69, 9: -124, 10: -180}
+
+
+def sidelobe_db(w, terms, pad=16):
+    """Highest side lobe of the integer window `w` relative to its main lobe, in dB.  An M-term cosine-sum
+    window has its first null at bin M: walk down from just inside it to the local minimum, take the maximum
+    beyond."""
+    n = len(w)
+    s = np.abs(np.fft.rfft(np.asarray(w, dtype=np.float64), n * pad))
+    s /= s.max()
+    i = int((terms - 0.5) * pad)
+    while s[i + 1] < s[i]:
+        i += 1
+    assert abs(i / pad - terms) < 0.3, f"main lobe ends at bin {i / pad}, expected {terms}"
+    return float(20 * np.log10(s[i:].max()))
+
+
+def published_form(d):
+    """AA0 at half scale for the CORDIC sources (see the module docstring); TAYLOR keeps equal scale."""
+    if d.sin_type == bhw.SIN_TAYLOR:
+        return d
+    aa = [int(a) for a in d.aa]
+    aa[0] = (aa[0] + 1) // 2
+    return d.copy(aa=aa)
+
+
+# (variant, DAT_WIDTH, what the entity gives in dB).  DAT_WIDTH per variant as the README advises ("maximum
+# possible data width", 6 dB per bit): wide enough for the level to be the coefficients', not the quantisation's.
+CASES = [
+    (1, 16, -41.7), (2, 16, -31.5), (3, 16, -58.1), (4, 24, -71.5),
+    (5, 24, -87.3),          # the reference's transposed a2; see test_nuttall_coefficient_as_printed_and_as_published
+    (6, 24, -92.0), (7, 24, -98.2),
+    (8, 24, -75.6), (9, 32, -125.4), (10, 40, -180.5),
+    (11, 40, -180.2),        # README.md:45-51, the set printed under "7-term Blackman-Harris window coefficients"
+    (12, 16, -43.2),         # Hamming, second set: the README's -43
+    (13, 24, -93.0),         # Flat-top, normalised
+]
+
+
+@pytest.mark.parametrize("variant,dw,level", CASES)
+@pytest.mark.parametrize("sin_type", [bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR])
+def test_published_sidelobe_levels_on_the_oracle(variant, dw, level, sin_type):
+    d = bhw.variant_desc(variant, 12 if dw <= 32 else 13, dw, sin_type=sin_type)
+    if bhw.validate(d):
+        pytest.skip("combination the entities do not elaborate")
+    d = published_form(d)
+    got = sidelobe_db(H.orc_window(d), d.win_type)
+    assert abs(got - level) < 0.5, (variant, dw, sin_type, got)
+    if variant in README_DB and variant != 5:
+        # at least as good as published, to the table's own rounding (Hamming: see the docstring)
+        assert got < README_DB[variant] + 1.5, (variant, got, README_DB[variant])
+
+
+def test_nuttall_coefficient_as_printed_and_as_published():
+    """src/bh_win_4term.vhd:16-17 prints a2 = 0.144323 (-87.3 dB through the entity); the README's -93 dB is the
+    literature's 0.144232.  Both through bh_win_4term, testbench scale 2^DAT_WIDTH - 1 (src/tb/tb_windows.vhd:108-111)."""
+    dw = 24
+    for a2, level in ((0.144323, -87.3), (0.144232, -93.3)):
+        aa = [int(round(a * ((1 << dw) - 1))) for a in (0.355768, 0.487396, a2, 0.012604)]
+        d = published_form(bhw.make_desc(4, 12, dw, aa))
+        assert abs(sidelobe_db(H.orc_window(d), 4) - level) < 0.3
+    printed, _ = bhw.quantize(5, bhw.RULE_TB, dw)
+    assert printed[2] == int(round(0.144323 * ((1 << dw) - 1)))      # bhw_quantize keeps the reference's number
+
+
+def test_six_db_per_bit_rule_of_the_readme():
+    """README.md:5-6: Blackman-Harris 4-term (-92 dB) needs 16 bits plus sign = DAT_WIDTH 17.  At 17 bits the entity is
+    within 1.5 dB of the level; every bit less costs about 6 dB."""
+    levels = {}
+    for dw in (12, 14, 17, 24):
+        d = published_form(bhw.variant_desc(6, 12, dw))
+        levels[dw] = sidelobe_db(H.orc_window(d), 4)
+    assert levels[17] < -92 + 1.5
+    assert abs(levels[24] - (-92.0)) < 0.3
+    assert levels[12] > levels[14] > levels[17]
+    assert 3.0 < (levels[12] - levels[14]) / 2 < 9.0, levels        # dB per bit while quantisation-limited
+
+
+def test_equal_scale_ports_give_the_window_on_a_pedestal():
+    """What the testbench's own ports stream: the published window plus a constant, AA0 / 8 (AA0 / 4
+    for the 2-term entity) - a rectangular window riding on the real one.  On the N-point DFT grid that only adds
+    to bin 0; between the bins it is the -13 dB Dirichlet skirt, which is why the equal-scale stream measures
+    -24 .. -32 dB where the README promises -92."""
+    d = bhw.variant_desc(6, 12, 24)
+    w_tb = H.orc_window(d).astype(np.float64)
+    w_pub = H.orc_window(published_form(d)).astype(np.float64)
+    ped = w_tb - w_pub
+    assert np.abs(ped - ped.mean()).max() <= 1.0           # a constant, up to the final rounding
+    aa0 = int(d.aa[0])
+    assert abs(ped.mean() - (aa0 - (aa0 + 1) // 2) / 4) < 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,pw,dw,level", [(6, 16, 17, -91.4), (2, 14, 16, -31.5), (9, 14, 24, -123.8), (10, 14, 32, -179.5)])
+def test_published_sidelobe_levels_on_the_gpu(variant, pw, dw, level):
+    """The same figures from the CUDA path (BASELINE config-2 / sweep shapes)."""
+    d = published_form(bhw.variant_desc(variant, pw, dw))
+    w = bhw.generate(d).cpu().numpy().astype(np.int64)
+    assert np.array_equal(w, H.orc_window(d))
+    got = sidelobe_db(w, d.win_type)
+    assert abs(got - level) < 0.5, got
+    assert got < README_DB[variant] + 1.5

@@ -57,6 +57,55 @@ def swapped_cases(lib, arrays, cases):
             print(key, "first DT_VLD clock", vld.index(1), flush=True)
 
 
+TB_FILE = os.path.join(V.REF_SRC, "tb", "tb_windows.vhd")
+# constant prefix in the testbench -> (README variant whose real-valued set it spells, number of terms)
+TB_SETS = {"cnt7": (10, 7), "cnt5": (8, 5), "cnt4": (6, 4), "cnt3": (3, 3), "cnt2": (1, 2)}
+
+
+def tb_constants(width):
+    """The integer port constants CNT*_STD* of the reference's testbench (src/tb/tb_windows.vhd:64-127), obtained by
+    ELABORATING the declarative part of its architecture with the simulator - the reals, 2.0**(CONST_WIDTH-1)-1.0 and
+    friends, INTEGER(real) and conv_std_logic_vector are evaluated from the reference's own text.  The statement part
+    (clock / reset processes with `wait for`, the one live taylor_sincos instance) is not needed for constants and is
+    left out, as are the two `time` constants; `width` replaces the literal 16 of `constant CONST_WIDTH : integer:=16`
+    (the line a user of the testbench edits).  -> {prefix: [signed ints]}"""
+    import re
+    src = open(TB_FILE, encoding="latin-1").read()
+    m = re.search(r"architecture\s+testbench\s+of\s+tb_windows\s+is(.*?)\nbegin\b", src, re.S | re.I)
+    decl = "\n".join(l for l in m.group(1).split("\n") if not re.search(r":\s*time\s*:=", l))
+    decl, n = re.subn(r"(constant\s+CONST_WIDTH\s*:\s*integer\s*:=\s*)16", r"\g<1>%d" % width, decl)
+    assert n == 1
+    text = ("library ieee; use ieee.std_logic_1164.all;\nentity tb_consts is end tb_consts;\n"
+            "architecture a of tb_consts is\n" + decl + "\nbegin\nend a;\n")
+    lib = V.Library([])
+    for name, u in V.Parser(text).design_file().items():
+        lib.units.setdefault(name, {}).update(u)
+    inst = V.Instance(lib, "tb_consts")
+    out = {}
+    for prefix, (_, terms) in TB_SETS.items():
+        out[prefix] = [int(inst.scope.d[f"{prefix}_std{k}"].signed()) for k in range(terms)]
+    return out
+
+
+def tb_constant_cases(cases):
+    """CONST_WIDTH 8 .. 32: every product a_k * scale stays inside VHDL's 32-bit INTEGER (the largest, flat-top
+    1.93 * (2**30 - 1), is 2.07e9), so a conforming simulator elaborates all of them."""
+    cases["tb_constants"] = []
+    for w in (8, 12, 16, 17, 20, 24, 30, 31, 32):
+        got = tb_constants(w)
+        for prefix, (variant, terms) in TB_SETS.items():
+            # what the CONST_WIDTH-bit vector holds, read as the signed port value
+            cases["tb_constants"].append({"width": w, "set": prefix, "variant": variant, "terms": terms, "aa": got[prefix]})
+    print("tb constants:", len(cases["tb_constants"]), "sets", flush=True)
+
+
+def update_only_tb():
+    """python tests/golden/make_rtl_golden.py tb: add the testbench constants to the existing case file."""
+    cases = json.load(open(os.path.join(HERE, "rtl_sim_cases.json")))
+    tb_constant_cases(cases)
+    json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
+
+
 def update_only_swapped():
     """python tests/golden/make_rtl_golden.py swapped: add the swapped compositions to the existing files."""
     lib = V.reference_library()
@@ -192,6 +241,7 @@ def main():
         print(key, flush=True)
 
     swapped_cases(lib, arrays, cases)
+    tb_constant_cases(cases)
     np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
     json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
     print("wrote", len(arrays), "arrays")
@@ -200,5 +250,7 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["swapped"]:
         update_only_swapped()
+    elif sys.argv[1:] == ["tb"]:
+        update_only_tb()
     else:
         main()

@@ -292,6 +292,33 @@ def test_hostcheck_atan2_matches_rtl_stream(gold):
 needs_ref = pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference VHDL sources not present")
 
 
+
+def test_testbench_port_constants_equal_the_quantiser(gold):
+    """The reference leaves quantisation to the caller; the rule it uses itself is the arithmetic in the declarative
+    part of its testbench (src/tb/tb_windows.vhd:64-127: CNTm_STDk = conv_std_logic_vector(integer(a_k * S_m), W)).
+    tests/golden/make_rtl_golden.py elaborates that text with the simulator for CONST_WIDTH 8 .. 32; bhw_quantize(rule
+    BHW_RULE_TB) and the oracle's restatement must give the same port values - BASELINE config 3's seven AA words
+    among them."""
+    _, cases = gold
+    tb = cases["tb_constants"]
+    assert len(tb) == 45 and {c["set"] for c in tb} == {"cnt7", "cnt5", "cnt4", "cnt3", "cnt2"}
+    for c in tb:
+        aa, m = bhw.quantize(c["variant"], bhw.RULE_TB, c["width"])
+        assert m == c["terms"]
+        assert [int(a) for a in aa[:m]] == c["aa"], c
+        assert all(int(a) == 0 for a in aa[m:])
+        oa = (C.c_int64 * 11)()
+        wt = C.c_int32(0)
+        assert H.oracle().orc_quantize(c["variant"], bhw.RULE_TB, c["width"], oa, C.byref(wt)) == 0
+        assert wt.value == m and [int(a) for a in oa[:m]] == c["aa"], c
+    cfg3 = next(c for c in tb if c["set"] == "cnt7" and c["width"] == 32)
+    assert cfg3["aa"] == [582441289, 930815217, 468160289, 141272949, 23110934, 1653590, 29379]      # BASELINE.json configs[2]
+    cfg2 = next(c for c in tb if c["set"] == "cnt4" and c["width"] == 17)
+    assert cfg2["aa"] == [47022, 64001, 18518, 1531]                                                 # configs[1]
+    cfg1 = next(c for c in tb if c["set"] == "cnt2" and c["width"] == 16)
+    assert cfg1["aa"] == [17808, 14959]                                                              # configs[0]
+
+
 @pytest.fixture(scope="module")
 def vsim():
     sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
@@ -316,6 +343,12 @@ def test_vectors_reproducible_from_reference_vhdl(gold, vsim):
     out = V.run_atan2(lib, 12, 12, 3, pairs)
     n = len(pairs) + 12 - 2                       # the clocks the shortened run shares with the committed one
     assert [o[0] for o in out][:n] == list(z[c["key"] + "/phi_dt_per_clock"][:n])
+    sys.path.insert(0, GOLD)
+    import make_rtl_golden as G
+    got = G.tb_constants(17)
+    for c in cases["tb_constants"]:
+        if c["width"] == 17:
+            assert got[c["set"]] == c["aa"]
 
 
 @needs_ref

@@ -785,6 +785,10 @@ def run_cuda(args):
             "e2e": e2e,
             "gpu_launches": int(launches * args.steps),
             "gpu_launches_per_step": int(launches),
+            # the reference's one published rate: an entity emits one DT_WIN per clock, "up to
+            # 400 MHz" on a Kintex UltraScale (README.md:15) - per entity instance, other hardware, hence not vs_baseline
+            "reference_fpga": {"gsamples_per_s_per_entity_instance": 0.4, "source": "README.md:15, src/hamming_win.vhd:138-149",
+                               "value_over_it": value / 0.4},
         }
         if world == 1 and not args.no_configs:
             scratch = torch.empty(1 << 28, dtype=torch.int32, device="cuda")

@@ -106,6 +106,34 @@ def update_only_tb():
     json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
 
 
+def precision_cases(lib, arrays, cases, rng):
+    """cordic_dds with its PRECISION generic off the default (src/cordic_dds.vhd:79: "from 1 to 7"; the window entities
+    always leave it at 1, bhw_desc.precision exposes it for bhw_sincos and the windows alike)."""
+    cases["dds_precision"] = []
+    for pw, dw, prec in ((8, 12, 2), (10, 16, 3), (9, 8, 7), (12, 24, 4), (11, 32, 2), (14, 17, 5), (10, 40, 7), (7, 42, 7)):
+        ph = phases_for(pw, rng)
+        out, lat = V.run_dds(lib, "cordic_dds", pw, dw, ph, precision=prec)
+        key = f"ddsprec/cordic_dds/pw{pw}_dw{dw}_p{prec}"
+        arrays[key + "/phases"] = np.array(ph, np.int64)
+        arrays[key + "/sin"] = np.array([o[0] for o in out], np.int64)
+        arrays[key + "/cos"] = np.array([o[1] for o in out], np.int64)
+        cases["dds_precision"].append({"entity": "cordic_dds", "phase_width": pw, "data_width": dw, "precision": prec, "key": key,
+                                       "dt_val_latency": lat})
+        print(key, "latency", lat, flush=True)
+
+
+def update_only_precision():
+    """python tests/golden/make_rtl_golden.py precision: add the PRECISION cases to the existing files."""
+    lib = V.reference_library()
+    z = np.load(os.path.join(HERE, "rtl_sim_vectors.npz"))
+    arrays = {k: z[k] for k in z.files if not k.startswith("ddsprec/")}
+    cases = json.load(open(os.path.join(HERE, "rtl_sim_cases.json")))
+    precision_cases(lib, arrays, cases, np.random.default_rng(20261019))
+    np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
+    print("wrote", len(arrays), "arrays")
+
+
 def update_only_swapped():
     """python tests/golden/make_rtl_golden.py swapped: add the swapped compositions to the existing files."""
     lib = V.reference_library()
@@ -242,6 +270,7 @@ def main():
 
     swapped_cases(lib, arrays, cases)
     tb_constant_cases(cases)
+    precision_cases(lib, arrays, cases, np.random.default_rng(20261019))
     np.savez_compressed(os.path.join(HERE, "rtl_sim_vectors.npz"), **arrays)
     json.dump(cases, open(os.path.join(HERE, "rtl_sim_cases.json"), "w"), indent=1)
     print("wrote", len(arrays), "arrays")
@@ -252,5 +281,7 @@ if __name__ == "__main__":
         update_only_swapped()
     elif sys.argv[1:] == ["tb"]:
         update_only_tb()
+    elif sys.argv[1:] == ["precision"]:
+        update_only_precision()
     else:
         main()

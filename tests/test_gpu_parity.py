@@ -941,8 +941,8 @@ def test_rtl_golden_vectors_on_gpu():
     z = np.load(os.path.join(gold, "rtl_sim_vectors.npz"))
     cases = json.load(open(os.path.join(gold, "rtl_sim_cases.json")))
     sin_of = {"cordic_dds": bhw.SIN_CORDIC, "cordic_dds48": bhw.SIN_CORDIC48, "cordic_dds_scaled": bhw.SIN_CORDIC_SCALED}
-    for c in cases["dds"]:
-        d = bhw.make_desc(2, c["phase_width"], c["data_width"], sin_type=sin_of[c["entity"]])
+    for c in cases["dds"] + cases["dds_precision"]:
+        d = bhw.make_desc(2, c["phase_width"], c["data_width"], sin_type=sin_of[c["entity"]], precision=c.get("precision", 0))
         ph = z[c["key"] + "/phases"]
         if c["phase_width"] <= 20:
             s, co = bhw.sincos(d)

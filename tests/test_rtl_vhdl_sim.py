@@ -55,7 +55,7 @@ def test_case_inventory(gold):
     assert {c["entity"] for c in cases["dds"]} == set(SIN_OF)
     assert {c["entity"] for c in cases["windows"]} == ENTITIES
     assert sum(H.rtl_case_is_taylor(c) for c in cases["windows"]) == 12
-    for grp in ("dds", "windows", "atan2", "taylor", "mult", "windows_swapped"):
+    for grp in ("dds", "windows", "atan2", "taylor", "mult", "windows_swapped", "dds_precision"):
         for c in cases[grp]:
             assert any(f.startswith(c["key"] + "/") for f in z.files), c["key"]
 
@@ -64,9 +64,10 @@ def test_oracle_dds_entities_match_rtl(gold):
     """orc_sincos == DT_SIN / DT_COS of the simulated entity at every recorded phase (src/cordic_dds.vhd:148-257,
     src/cordic_dds48.vhd, src/cordic_dds_scaled.vhd); DT_VAL latency DATA_WIDTH+1 / +3 / +3."""
     z, cases = gold
-    for c in cases["dds"]:
+    assert len(cases["dds_precision"]) == 8 and {c["precision"] for c in cases["dds_precision"]} == {2, 3, 4, 5, 7}
+    for c in cases["dds"] + cases["dds_precision"]:               # ... and cordic_dds with PRECISION 2..7 (:79)
         pw, dw = c["phase_width"], c["data_width"]
-        d = bhw.make_desc(2, pw, dw, sin_type=SIN_OF[c["entity"]])
+        d = bhw.make_desc(2, pw, dw, sin_type=SIN_OF[c["entity"]], precision=c.get("precision", 0))
         ph = z[c["key"] + "/phases"]
         lo, hi = int(ph.min()), int(ph.max())
         got_s, got_c = np.empty(len(ph), np.int64), np.empty(len(ph), np.int64)
@@ -86,8 +87,8 @@ def test_hostcheck_dds_matches_rtl(gold):
     """The product's sin/cos body (host build of bhw_device.cuh) against the same vectors."""
     z, cases = gold
     hc = H.hostcheck()
-    for c in cases["dds"]:
-        d = bhw.make_desc(2, c["phase_width"], c["data_width"], sin_type=SIN_OF[c["entity"]])
+    for c in cases["dds"] + cases["dds_precision"]:
+        d = bhw.make_desc(2, c["phase_width"], c["data_width"], sin_type=SIN_OF[c["entity"]], precision=c.get("precision", 0))
         ph = z[c["key"] + "/phases"]
         s, co = np.empty(1, np.int64), np.empty(1, np.int64)
         for i, p in enumerate(ph):

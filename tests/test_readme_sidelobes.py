@@ -119,6 +119,30 @@ def test_equal_scale_ports_give_the_window_on_a_pedestal():
     assert abs(ped.mean() - (aa0 - (aa0 + 1) // 2) / 4) < 1.0
 
 
+# doc/blackman-harris coef.jpg, "Table 1. Coefficients of minimum sidelobe windows" (the table of Albrecht's ICASSP 2001
+# paper): highest side lobe of the M-term minimum-sidelobe window.  The reference ships entities for M <= 7 only; M = 6 and
+# 8..11 are this library's BHW_WIN_MTERM_* extension (bhw_quantize variants 14..18), which has no reference stream to be
+# pinned against - these figures are what ties the eleven-digit coefficient sets transcribed from the image, and the
+# M-term structure, to something published.
+MIN_SIDELOBE_DB = {2: -43.19, 3: -71.48, 4: -98.17, 5: -125.43, 6: -153.57, 7: -180.47, 8: -207.51, 9: -234.73, 10: -262.87,
+                   11: -289.64}
+
+
+@pytest.mark.parametrize("variant,terms,dw", [(12, 2, 24), (4, 3, 24), (7, 4, 32), (9, 5, 32), (14, 6, 40), (10, 7, 47), (15, 8, 47),
+                                              (16, 9, 47), (17, 10, 47), (18, 11, 47)])
+def test_minimum_sidelobe_sets_of_the_doc_image(variant, terms, dw):
+    for st in (bhw.SIN_CORDIC, bhw.SIN_CORDIC48):
+        d = published_form(bhw.variant_desc(variant, 12, dw, sin_type=st))
+        assert d.win_type == terms
+        got = sidelobe_db(H.orc_window(d), terms)
+        if terms <= 9:
+            assert abs(got - MIN_SIDELOBE_DB[terms]) < 0.15, (terms, st, got)
+        elif terms == 10:       # 47 bits: quantisation starts to show (6 dB per bit)
+            assert abs(got - MIN_SIDELOBE_DB[terms]) < 1.5, (terms, st, got)
+        else:                   # -289.6 dB needs more than the 47 bits the CORDIC entities offer
+            assert -285.0 < got < -270.0, (terms, st, got)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant,pw,dw,level", [(6, 16, 17, -91.4), (2, 14, 16, -31.5), (9, 14, 24, -123.8), (10, 14, 32, -179.5)])
 def test_published_sidelobe_levels_on_the_gpu(variant, pw, dw, level):

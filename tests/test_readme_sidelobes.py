@@ -143,6 +143,18 @@ def test_minimum_sidelobe_sets_of_the_doc_image(variant, terms, dw):
             assert -285.0 < got < -270.0, (terms, st, got)
 
 
+@pytest.mark.parametrize("win_type,nwidth,level", [(1, 24, -41.7), (3, 24, -58.1), (4, 24, -92.0), (5, 32, -125.4), (7, 32, -179.8)])
+def test_hls_model_reaches_the_published_levels_at_equal_scale(win_type, nwidth, level):
+    """The reference's C++ model (hls/windows/win_function.cpp) multiplies by a full-amplitude cosine
+    (m_k = (a_k * c_k) >> (NW-2)), so its equal-scale coefficients give the textbook window as they are.
+    (Type 2, Hann, wraps its centre sample - SURVEY 2.1 F - and type 4 does at NWIDTH 32: left out.)"""
+    import cases
+    d = bhw.variant_desc(cases.HLS_TYPES[win_type], 12, nwidth, model=bhw.MODEL_HLS)
+    got = sidelobe_db(H.orc_window(d), d.win_type)
+    assert abs(got - level) < 0.5, got
+    assert got < README_DB[cases.HLS_TYPES[win_type]] + 1.5
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant,pw,dw,level", [(6, 16, 17, -91.4), (2, 14, 16, -31.5), (9, 14, 24, -123.8), (10, 14, 32, -179.5)])
 def test_published_sidelobe_levels_on_the_gpu(variant, pw, dw, level):

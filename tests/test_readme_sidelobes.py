@@ -66,12 +66,19 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant,dw,level", CASES)
-@pytest.mark.parametrize("sin_type", [bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR])
+def _elaborable(variant, dw, sin_type):
+    return bhw.validate(bhw.variant_desc(variant, 12 if dw <= 32 else 13, dw, sin_type=sin_type)) == 0
+
+
+# every sin/cos source the entity of the variant can be elaborated with at that width (4+ terms have no TAYLOR,
+# cordic_dds_scaled and TAYLOR stop at 32 bits)
+SOURCE_CASES = [(v, dw, lvl, st) for (v, dw, lvl) in CASES
+                for st in (bhw.SIN_CORDIC, bhw.SIN_CORDIC48, bhw.SIN_CORDIC_SCALED, bhw.SIN_TAYLOR) if _elaborable(v, dw, st)]
+
+
+@pytest.mark.parametrize("variant,dw,level,sin_type", SOURCE_CASES)
 def test_published_sidelobe_levels_on_the_oracle(variant, dw, level, sin_type):
     d = bhw.variant_desc(variant, 12 if dw <= 32 else 13, dw, sin_type=sin_type)
-    if bhw.validate(d):
-        pytest.skip("combination the entities do not elaborate")
     d = published_form(d)
     got = sidelobe_db(H.orc_window(d), d.win_type)
     assert abs(got - level) < 0.5, (variant, dw, sin_type, got)
